@@ -1,0 +1,126 @@
+// oracle/shims/umfpack_shim.cpp — TEST INFRASTRUCTURE ONLY (see suitesparse/umfpack.h).
+// Banded LU stand-in for the UMFPACK calls made by reference src/fields.cpp:273-275,311,347,352.
+// The factorisation is lazy (done at the first solve) so that constructing a reference `Fields`
+// object on a large grid stays cheap when the caller never solves.
+#include "suitesparse/umfpack.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+namespace {
+struct Symbolic { int n; };
+struct Numeric
+{
+    int n = 0;
+    std::vector<int> Ap, Ai;
+    std::vector<double> Ax;
+    // factor of M = A^T (sys==UMFPACK_At) or A (sys==UMFPACK_A), band storage lu[row*(2*bw+1) + (col-row+bw)]
+    int factored_sys = -1;
+    int bw = 0;
+    std::vector<double> lu;
+
+    void factor(int sys)
+    {
+        bw = 0;
+        for (int c = 0; c < n; c++)
+            for (int l = Ap[c]; l < Ap[c + 1]; l++)
+                if (Ai[l] >= 0 && Ai[l] < n) bw = std::max(bw, std::abs(Ai[l] - c));
+        const size_t w = 2 * (size_t)bw + 1;
+        lu.assign((size_t)n * w, 0.0);
+        for (int c = 0; c < n; c++)
+            for (int l = Ap[c]; l < Ap[c + 1]; l++)
+            {
+                int r = Ai[l];
+                if (r < 0 || r >= n) continue;   // the reference never emits these for valid geometries
+                // CSC entry A[r][c]; M = A^T has M[c][r]
+                int row = (sys == UMFPACK_At) ? c : r;
+                int col = (sys == UMFPACK_At) ? r : c;
+                lu[(size_t)row * w + (col - row + bw)] += Ax[l];
+            }
+        // Doolittle elimination inside the band, no pivoting
+        for (int k = 0; k < n; k++)
+        {
+            const double piv = lu[(size_t)k * w + bw];
+            const int rmax = std::min(n - 1, k + bw);
+            const int cmax = std::min(n - 1, k + bw);
+            for (int r = k + 1; r <= rmax; r++)
+            {
+                double& lrk = lu[(size_t)r * w + (k - r + bw)];
+                if (lrk == 0.0) continue;
+                lrk /= piv;
+                const double f = lrk;
+                double* rowr = &lu[(size_t)r * w + bw - r];
+                const double* rowk = &lu[(size_t)k * w + bw - k];
+                for (int c = k + 1; c <= cmax; c++) rowr[c] -= f * rowk[c];
+            }
+        }
+        factored_sys = sys;
+    }
+    void solve(int sys, double* X, const double* B)
+    {
+        if (factored_sys != sys) factor(sys);
+        const size_t w = 2 * (size_t)bw + 1;
+        std::vector<double> y(B, B + n);
+        for (int r = 0; r < n; r++)
+        {
+            const int c0 = std::max(0, r - bw);
+            const double* rowr = &lu[(size_t)r * w + bw - r];
+            double s = y[r];
+            for (int c = c0; c < r; c++) s -= rowr[c] * y[c];
+            y[r] = s;
+        }
+        for (int r = n - 1; r >= 0; r--)
+        {
+            const int c1 = std::min(n - 1, r + bw);
+            const double* rowr = &lu[(size_t)r * w + bw - r];
+            double s = y[r];
+            for (int c = r + 1; c <= c1; c++) s -= rowr[c] * y[c];
+            y[r] = s / rowr[r];
+        }
+        std::copy(y.begin(), y.end(), X);
+    }
+};
+}  // namespace
+
+extern "C" {
+int umfpack_di_symbolic(int n_row, int n_col, const int*, const int*, const double*, void** S,
+                        const double*, double*)
+{
+    (void)n_col;
+    Symbolic* s = new Symbolic;
+    s->n = n_row;
+    *S = s;
+    return UMFPACK_OK;
+}
+int umfpack_di_numeric(const int Ap[], const int Ai[], const double Ax[], void* S, void** N,
+                       const double*, double*)
+{
+    Symbolic* s = (Symbolic*)S;
+    Numeric* num = new Numeric;
+    num->n = s->n;
+    num->Ap.assign(Ap, Ap + s->n + 1);
+    num->Ai.assign(Ai, Ai + Ap[s->n]);
+    num->Ax.assign(Ax, Ax + Ap[s->n]);
+    *N = num;
+    return UMFPACK_OK;
+}
+int umfpack_di_solve(int sys, const int*, const int*, const double*, double X[], const double B[],
+                     void* N, const double*, double*)
+{
+    if (!N) return UMFPACK_ERROR_invalid_Numeric_object;
+    ((Numeric*)N)->solve(sys, X, B);
+    return UMFPACK_OK;
+}
+void umfpack_di_free_symbolic(void** S)
+{
+    if (S && *S) { delete (Symbolic*)*S; *S = 0; }
+}
+void umfpack_di_free_numeric(void** N)
+{
+    if (N && *N) { delete (Numeric*)*N; *N = 0; }
+}
+int umfpack_di_save_numeric(void*, char*) { return UMFPACK_ERROR_file_IO; }
+int umfpack_di_load_numeric(void**, char*) { return UMFPACK_ERROR_file_IO; }
+}
