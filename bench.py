@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the PIC/MCC hot path (push + MCC + boundary + deposit, with the Poisson solve
+and the periodic cell sort inside the timed region) in particle-steps/s, on synthetic particle loads of the
+shapes BASELINE.json names.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c3|c1] [--particles P]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the reference's own CPU code on the host cores
+
+Default workload: C4 of BASELINE.json — 2-D self-consistent Ar+/e- discharge, 512x512 grid, 1e8 particles
+per GPU, Poisson solve every step — the one configuration that exercises every part of the metric
+(push + MCC + deposit, solve ms/step).  The other configs are parity-test cases (tests/), selectable here
+with --workload for exploration only.
+
+One step = one Pic::advance (reference src/pic.cpp:330-358).  A "particle-step" is one live particle
+advanced by one step.  Weak scaling: every rank pushes its own --particles shard and the fixed-point charge
+grid is all-reduced (NCCL) before the replicated solve.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BYTES_PER_PARTICLE_STEP = 80.0       # 2D3V fp64: x,z,vx,vy,vz read + written once (SURVEY.md §8d / DESIGN.md)
+WORKLOADS = {
+    "c4": "C4: 2-D self-consistent Ar+/e- discharge, 512x512 grid, Poisson each step, Boris + MCC + deposit",
+    "c2": "C2: 22-pole RF ion trap, 200x200, H- in He/H2 buffer gas, Boris + RF gather + Langevin MCC",
+    "c3": "C3: cylindrical r-z, 200x100, Bz=0.03 T, electrons, self-consistent, Boris",
+    "c1": "C1: e- swarm in He, E=1 kV/m, multi-collision mover (~90 events per particle-step)",
+}
+DEFAULT_PARTICLES = {"c4": 100_000_000, "c2": 1_000_000, "c3": 10_000_000, "c1": 1_000_000}
+BYTES = {"c4": 80.0, "c2": 80.0, "c3": 80.0, "c1": 96.0}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            t = [c.strip() for c in line.split(",")]
+            if len(t) < 9:
+                continue
+            try:
+                sm.append(float(t[1]))
+                mx.append(float(t[2]))
+                power.append(float(t[3]))
+            except ValueError:
+                continue
+            for k, name in enumerate(names):
+                if t[5 + k].lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_deck(workload, particles_per_gpu, world, tmp):
+    from mag2d_b200 import decks
+    n_global = particles_per_gpu * world
+    if workload == "c4":
+        # dV = V/cells with V = n_particles_total/density_total (param.cpp:134-136): the macro-particle
+        # weight follows the GLOBAL count per species so that the physical density stays 1e15 m^-3
+        return decks.deck("c4", tmp, n_particles=particles_per_gpu, n_particles_total=n_global // 2)
+    return decks.deck(workload, tmp, n_particles=particles_per_gpu)
+
+
+def load_particles(sim, workload, d, n):
+    """synthetic load through the device-side Philox loaders (the initscript verbs)"""
+    if workload == "c3":
+        sim.generate(sim.species_index("ELECTRON"), "cylinder", n, 1.0, 3.75e-2, 4e-3, 2e-2)
+    elif workload == "c2":
+        # uniform disk of radius 4 mm in the 22-pole trap (field-free core of the trap)
+        sim.generate(sim.species_index("H_NEG"), "on_disk", n, 1e-2, 1e-2, 4e-3)
+    else:
+        sim.run_initscript(d["initscript"])
+
+
+def bench_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from mag2d_b200.api import Sim
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    wl = args.workload
+    n = args.particles or DEFAULT_PARTICLES[wl]
+    tmp = tempfile.mkdtemp(prefix="mag2d_bench_")
+    d = make_deck(wl, n, world, tmp)
+    stream = torch.cuda.current_stream(dev)
+    sim = Sim(d["config"], d["species_conf"], device=local_rank, stream=stream.cuda_stream, seed=1234 + rank)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(Sim.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        sim.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+    selfconsistent = bool(sim.param["selfconsistent"])
+    load_particles(sim, wl, d, n)
+    part_species = [sim.species_index(s) for s in d["species"]]
+    for s in part_species:
+        sim.sort(s)
+    sort_interval = args.sort_interval
+    sim.set_sort_interval(sort_interval)
+    if selfconsistent:
+        sim.set_solver(cycles_per_step=args.cycles, tol=1e-10, max_cycles=60)
+    sim.advance_init()
+    n_live0 = sum(sim.count(s)[0] for s in part_species)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    sim.advance(args.warmup)
+    barrier()
+    n_live = sum(sim.count(s)[0] for s in part_species)
+    launches0 = sim.kernel_launches()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    # ---- timed region: exactly K steps, device-timed on the launching stream, max over ranks
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    sim.advance(args.steps)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clock_info = clocks.stop() if rank == 0 else None
+    launches = sim.kernel_launches() - launches0
+    n_live_end = sum(sim.count(s)[0] for s in part_species)
+    t = torch.tensor([ms, float(n_live), float(n_live_end)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms = float(tmax[0])
+        n_live_all, n_live_end_all = float(tsum[1]), float(tsum[2])
+    else:
+        n_live_all, n_live_end_all = float(n_live), float(n_live_end)
+    # live particles decay slowly through wall losses: use the mean of the two counts
+    pstep = 0.5 * (n_live_all + n_live_end_all) * args.steps
+    value = pstep / (ms * 1e-3)
+
+    # ---- per-phase device times (events around each phase; adds one sync per step, so it is a separate pass)
+    sim.set_timing(True)
+    sim.advance(args.steps)
+    tm = sim.timers()
+    sim.set_timing(False)
+    push_ms = tm["push"] / args.steps
+    n_now = sum(sim.count(s)[0] for s in part_species)
+    n_push_launches = len(part_species) * (2 if sim.param["rf"] else 1)
+    peak, peak_src = measured_peaks()
+    achieved = BYTES[wl] * n_now / (push_ms * 1e-3) / 1e9 if push_ms > 0 else 0.0
+    solve_info = None
+    if selfconsistent:
+        info = sim.solve(rf=False, tol=1e-10)
+        solve_info = {"ms_per_step": tm["solve"] / args.steps, "vcycles_per_step": args.cycles,
+                      "extra_cycles_to_1e-10": info["cycles"], "resid": info["resid"]}
+
+    # ---- end-to-end through the C ABI with HOST buffers: per step, particles go host -> device from pinned
+    # memory, one Pic::advance runs, particles and the charge grid come back (what a host-resident caller
+    # of Species::advance pays when it keeps the reference's host-side particle array)
+    e2e = None
+    if rank == 0 or world > 1:
+        e2e = bench_e2e(sim, part_species, args, torch, stream, world, dist, dev)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline(wl, d, sim, part_species, args)
+        except Exception as ex:     # the checker must never take the bench down
+            cpu = {"value": None, "unit": "particle-steps/s", "cores": 1, "kind": "unavailable", "sample": repr(ex)}
+    if rank == 0:
+        out = {
+            "metric": "particle-steps/sec (push+MCC+deposit, Poisson solve and periodic cell sort inside the step)",
+            "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic (device-side Philox loaders, seed 1234)",
+            "config": {"workload": WORKLOADS[wl], "particles_per_gpu": n, "live_particles": n_live_all,
+                       "grid": [int(sim.param["x_sampl"]), int(sim.param["z_sampl"])],
+                       "species": d["species"], "sort_interval": sort_interval,
+                       "l2": "inputs larger than L2 (%.1f GB of particle state per GPU)" % (n * 40 / 1e9)
+                       if n * 40 > 200e6 else "particle state fits L2: flush not applied, see roofline note",
+                       "parallelism": "particle shards, %d rank(s), NCCL all-reduce of the int64 charge grid" % world,
+                       "vcycles_per_step": args.cycles if selfconsistent else 0},
+            "gpu_launches": int(launches),
+            "clocks": clock_info,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "k_push_boris (fused gather+push+MCC+boundary+deposit), %d launches/step" % n_push_launches,
+                         "algorithmic_bytes_per_particle_step": BYTES[wl], "push_ms_per_step": push_ms,
+                         "peak_source": peak_src},
+            "phases_ms_per_step": {k: v / args.steps for k, v in tm.items()},
+            "solve": solve_info,
+            "e2e": e2e,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_e2e(sim, part_species, args, torch, stream, world, dist, dev):
+    import ctypes as C
+
+    import numpy as np
+    steps = max(1, args.e2e_steps)
+    bufs = {}
+    h2d = d2h = 0
+    for s in part_species:
+        n_slots = sim.count(s)[1]
+        host = {k: torch.empty(n_slots, dtype=torch.float64).pin_memory() for k in ("x", "z", "vx", "vy", "vz")}
+        alive = np.empty(1, dtype=np.uint8)
+        bufs[s] = (n_slots, host)
+        h2d += 5 * 8 * n_slots
+        d2h += 5 * 8 * n_slots
+    rho_host = torch.empty(sim.M * sim.N, dtype=torch.float64).pin_memory()
+    d2h += 8 * sim.M * sim.N
+    dp = C.POINTER(C.c_double)
+
+    def ptr(t):
+        return C.cast(t.data_ptr(), dp)
+
+    def download(s):
+        n_slots, host = bufs[s]
+        ns = C.c_int64()
+        sim._chk(sim.L.mag2d_particles_download_soa(sim.h, s, n_slots, ptr(host["x"]), None, ptr(host["z"]), ptr(host["vx"]),
+                                                    ptr(host["vy"]), ptr(host["vz"]), None, None, C.byref(ns)))
+
+    def upload(s):
+        n_slots, host = bufs[s]
+        sim._chk(sim.L.mag2d_particles_clear(sim.h, s))
+        sim._chk(sim.L.mag2d_particles_upload_soa(sim.h, s, n_slots, ptr(host["x"]), None, ptr(host["z"]), ptr(host["vx"]),
+                                                  ptr(host["vy"]), ptr(host["vz"]), None))
+    for s in part_species:
+        download(s)          # the host-side particle arrays the caller owns
+    n_live = sum(sim.count(s)[0] for s in part_species)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for s in part_species:
+            upload(s)
+        sim.advance(1)
+        for s in part_species:
+            download(s)
+        sim._chk(sim.L.mag2d_rho_download(sim.h, ptr(rho_host)))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt, float(n_live)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dt, n_live = float(tmax[0]), float(tsum[1])
+    return {"value": n_live * steps / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": dt / steps * 1e3,
+            "path": "mag2d_particles_upload_soa (pinned host) -> mag2d_step -> mag2d_particles_download_soa + mag2d_rho_download"}
+
+
+def reference_run(workload, d, n_cpu, steps, u=None, variant="fast"):
+    """time the reference's own CPU implementation (oracle/_ref) of the particle phase of Pic::advance
+    on a bounded sample of the workload; falls back to the oracle port when oracle/_ref is absent"""
+    import numpy as np
+
+    from mag2d_b200 import config as cfg
+    from oracle import RefHarness, ref_available
+    p = cfg.read_config(d["config"])
+    rng = np.random.default_rng(1234)
+    sp, _ = cfg.read_species(d["species_conf"])
+    names = [s["name"] for s in sp]
+    per = max(1, n_cpu // len(d["species"]))
+
+    def sample(name):
+        s = sp[names.index(name)]
+        vth = np.sqrt(1.380662e-23 * s["temperature"] / s["mass"])
+        aos = np.zeros((per, 7))
+        if workload == "c2":
+            ang = rng.uniform(0, 2 * np.pi, per)
+            rad = np.sqrt(rng.uniform(0, 1, per)) * 4e-3
+            aos[:, 0] = 1e-2 + rad * np.cos(ang)
+            aos[:, 2] = 1e-2 + rad * np.sin(ang)
+        elif workload == "c3":
+            aos[:, 0] = np.sqrt(rng.uniform(0, 1, per)) * 4e-3
+            aos[:, 2] = 3.75e-2 + 2e-2 * (rng.uniform(0, 1, per) - 0.5)
+        else:
+            aos[:, 0] = rng.uniform(0, p["x_max"], per) * (1 - 1e-12)
+            aos[:, 2] = rng.uniform(0, p["z_max"], per) * (1 - 1e-12)
+        aos[:, 3:6] = rng.normal(size=(per, 3)) * vth
+        # cell-sorted like the GPU store, which is also the friendliest order for the CPU caches
+        key = (aos[:, 0] * p["idx"]).astype(np.int64) * int(p["z_sampl"]) + (aos[:, 2] * p["idz"]).astype(np.int64)
+        return aos[np.argsort(key, kind="stable")]
+    if ref_available(variant):
+        # the reference's constructor pre-solves the vacuum field with UMFPACK (pic.cpp:180-187); the shim's
+        # banded LU would need 2 GB and minutes at 512x512, so it is skipped on this timing arm (u = 0 is the
+        # exact vacuum solution of the grounded box) — see oracle/shims/umfpack_shim.cpp
+        os.environ["MAG2D_UMFPACK_SHIM_MAXN"] = "60000"
+        with RefHarness(d["config"], d["species_conf"], seed=1234, variant=variant) as ref:
+            for name in d["species"]:
+                ref.set_particles(ref.species_index(name), sample(name))
+            if u is not None:
+                ref.set_field("u", u)
+            ref.advance_particles(2)       # warm the caches, as the GPU arm's warm-up does
+            n_live = sum(ref.species(ref.species_index(name))["n_particles"] for name in d["species"])
+            wall, cpu = ref.time_advance(steps, particles_only=True)
+            n_end = sum(ref.species(ref.species_index(name))["n_particles"] for name in d["species"])
+        return {"value": 0.5 * (n_live + n_end) * steps / wall, "unit": "particle-steps/s", "cores": 1, "kind": "reference",
+                "sample": "%d particles x %d steps of the same deck, reference sources compiled -Ofast (oracle/_ref), "
+                          "Species::advance of every species + rho sum (pic.cpp:343-354), single thread: the "
+                          "reference's simulation loop is serial; wall %.2f s, user-cpu %.2f s" % (n_live, steps, wall, cpu),
+                "seconds": wall}
+    raise RuntimeError("oracle/_ref is not built on this machine")
+
+
+def cpu_baseline(workload, d, sim, part_species, args):
+    u = sim.get_field("u") if sim.param["selfconsistent"] else None
+    n_cpu = {"c1": 20000}.get(workload, 2_000_000)
+    steps = {"c1": 10}.get(workload, 40)
+    return reference_run(workload, d, n_cpu, steps, u)
+
+
+def bench_reference(args):
+    """--impl reference: the reference's own CPU code on the host cores, same metric/config, rank 0 only"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    n = args.particles or DEFAULT_PARTICLES[wl]
+    tmp = tempfile.mkdtemp(prefix="mag2d_bench_ref_")
+    d = make_deck(wl, n, 1, tmp)
+    n_cpu = {"c1": 20000}.get(wl, 1_000_000)
+    try:
+        for _ in range(max(0, min(args.warmup, 1))):
+            reference_run(wl, d, n_cpu, 2)
+        r = reference_run(wl, d, n_cpu, args.steps)
+    except Exception as ex:
+        print(json.dumps({"impl": "reference", "unavailable": repr(ex)[:200]}))
+        return
+    from mag2d_b200 import config as cfg
+    p = cfg.read_config(d["config"])
+    out = {
+        "impl": "reference",
+        "metric": "particle-steps/sec (push+MCC+deposit, Poisson solve and periodic cell sort inside the step)",
+        "value": r["value"], "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["seconds"] / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic (numpy, seed 1234)",
+        "config": {"workload": WORKLOADS[wl], "particles_per_gpu": n, "grid": [int(p["x_sampl"]), int(p["z_sampl"])],
+                   "species": d["species"], "note": "each step is a bounded sample of %d particles of this workload; "
+                   "the field solve is excluded on this arm (UMFPACK is not available here; SURVEY.md §8c)" % n_cpu},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the workload's named size)")
+    ap.add_argument("--sort-interval", type=int, default=8)
+    ap.add_argument("--cycles", type=int, default=2, help="multigrid V-cycles per step (warm-started)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,192 @@
+/* mag2d_b200.h — C ABI of the B200-native mag2d hot path (libmag2d_b200.so).
+ *
+ * The reference (rouckas/mag2d) has no FFI: its boundary is the C++ class surface that Pic<D> and
+ * the drivers use.  This ABI sits directly underneath that surface; every entry point names the
+ * reference interface it replaces (paths relative to the reference checkout).  The C++ host layer in
+ * mag2d_b200/csrc/host/ (Param, Fields, Species, Pic, plasma2d, test_MCC) and the ctypes binding in
+ * mag2d_b200/api.py are both thin callers of these functions.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer argument is a HOST pointer borrowed for the call
+ *     unless its name ends in _dev;
+ *   - every function returns 0 on success, non-zero on error (mag2d_last_error() has the message);
+ *     no exception crosses the ABI (the reference throws std::runtime_error, e.g. particles.hpp:226);
+ *   - one context per GPU; calls on one context must be serialised by the caller; work is enqueued
+ *     on the context's stream and is asynchronous unless stated (download / sync / solve block);
+ *   - 2-D naming follows the reference: position (x, z), velocity (vx, vz) in plane, vy out of plane
+ *     (azimuthal in cylindrical coordinates); grids are row-major a[i*N + j], i along x/r;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef MAG2D_B200_H
+#define MAG2D_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAG2D_ABI_VERSION 1
+#define MAG2D_MAX_SPECIES 16
+
+typedef struct mag2d_ctx mag2d_ctx;
+
+/* enum values equal the reference's (src/param.hpp:7,20-23; src/parser.hpp:14-15; src/fields.hpp:20) */
+enum { MAG2D_CARTESIAN = 0, MAG2D_CYLINDRICAL = 1, MAG2D_CARTESIAN3D = 2 };
+enum { MAG2D_BOUNDARY_FREE = 0, MAG2D_BOUNDARY_PERIODIC = 1 };
+enum { MAG2D_ADVANCE_BORIS = 0, MAG2D_ADVANCE_MULTICOLL = 1 };
+enum { MAG2D_NEUTRAL = 0, MAG2D_ELECTRON = 1, MAG2D_ION = 2 };
+enum { MAG2D_ELASTIC = 0, MAG2D_LANGEVIN = 1, MAG2D_CX = 2, MAG2D_COULOMB = 3, MAG2D_SUPERELASTIC = 4 };
+enum { MAG2D_FIXED = 0, MAG2D_FIXED_RF = 1, MAG2D_FREE = 2, MAG2D_BOUNDARY = 3 };
+
+/* The subset of the reference's Param (src/param.hpp:24-79) that the hot path reads.  dx, dz, idx,
+ * idz, dV are passed as the host computed them (param.cpp:126-136) so both sides round identically. */
+typedef struct
+{
+    int32_t coord, boundary, mover;
+    int32_t M, N, K;            /* x_sampl, z_sampl, y_sampl (K only for CARTESIAN3D) */
+    double x_max, z_max, y_max; /* domain is [0,x_max] x [0,z_max] (x [0,y_max]) */
+    double dx, dz, dy, idx, idz, idy;
+    int32_t selfconsistent, rf, geometry_empty, electric_field_from_file;
+    double extern_field;
+    double rf_amplitude, rf_U0, rf_omega;
+    int32_t magnetic_field_const, u_smooth;   /* u_smooth: Fields::u_smooth() after every solve (pic.cpp:336) */
+    double Br, Bz, Bt;
+    double dV, macroparticle_factor;
+} mag2d_grid_desc;
+
+/* SpeciesParams (src/parser.hpp:16-28); E_max <= 0 selects 10 kT/q_e (src/particles.hpp:164) */
+typedef struct
+{
+    int32_t type, reserved0;
+    double mass, charge, density, temperature, E_max, dt;
+} mag2d_species_desc;
+
+/* InteractionParams (src/parser.hpp:30-43); the cross-section table of interaction k is
+ * table_E[table_offset .. table_offset+n_table) / table_sigma[...] (eV, m^2); n_table = 0: constant RATE */
+typedef struct
+{
+    int32_t type, primary, secondary, n_table, table_offset, reserved0;
+    double DE_eV, rate, cutoff;
+} mag2d_interaction_desc;
+
+/* binary layout of the reference's t_particle (src/particles.hpp:26-33, 64 bytes), used by
+ * BaseSpecies::save/load files (src/particles.cpp:32-93) */
+typedef struct
+{
+    double x, y, z, vx, vy, vz, time_to_death;
+    uint8_t empty, pad[7];
+} mag2d_particle;
+
+/* ---- life cycle ------------------------------------------------------------------------------ */
+int mag2d_abi_version(void);
+/* thread-local message of the last failing call on this thread */
+const char* mag2d_last_error(void);
+/* Replaces Pic<D>::Pic / Fields::Fields (src/pic.cpp:127-189, src/fields.cpp:115-276).  `stream` is a
+ * cudaStream_t to enqueue on, or NULL for a context-owned non-blocking stream. */
+int mag2d_create(int device, const mag2d_grid_desc* grid, void* stream, mag2d_ctx** out);
+int mag2d_destroy(mag2d_ctx* ctx);
+int mag2d_sync(mag2d_ctx* ctx);
+int mag2d_seed(mag2d_ctx* ctx, uint64_t seed); /* t_random::initialize_seed, src/random.cpp:200-208 */
+
+/* ---- geometry and fields ---------------------------------------------------------------------- */
+/* t_grid mask / voltage (src/fields.hpp:31-55): mask[M*N] of MAG2D_FIXED.., voltage[M*N].  Builds the
+ * multigrid hierarchy that replaces the UMFPACK factorisation of src/fields.cpp:133-275. */
+int mag2d_set_grid(mag2d_ctx* ctx, const uint8_t* mask, const double* voltage);
+/* which: 0 = u, 1 = uRF (Fields::u / uRF host mirrors, src/fields.hpp:60-62) */
+int mag2d_set_potential(mag2d_ctx* ctx, int which, const double* values);
+int mag2d_get_potential(mag2d_ctx* ctx, int which, double* values);
+/* Fields::boundary_solve (rf = 0) / boundary_solve_rf (rf = 1), src/fields.cpp:278-348: scale rho into
+ * the right-hand side, overwrite Dirichlet rows, solve Op(u) = b by multigrid V-cycles until the
+ * max-norm residual drops below tol * max|b| (or max_cycles).  Blocks.  Any out pointer may be NULL. */
+int mag2d_solve(mag2d_ctx* ctx, int rf, double tol, int max_cycles, int* cycles_out, double* resid_out);
+/* solver knobs for mag2d_step: V-cycles per step (0 = iterate to tol) and the tolerance */
+int mag2d_set_solver(mag2d_ctx* ctx, int cycles_per_step, double tol, int max_cycles);
+/* Fields::u_smooth, src/fields.cpp:28-113 */
+int mag2d_u_smooth(mag2d_ctx* ctx, int symmetry, double radius);
+/* Fields::E at n points, src/fields.hpp:124-150 (diagnostics / parity checks) */
+int mag2d_field_E(mag2d_ctx* ctx, int n, const double* x, const double* z, double time, double* Ex, double* Ez);
+
+/* ---- species and collisions ------------------------------------------------------------------- */
+/* Speclist<D>::Speclist (src/pic.cpp:27-80) + BaseSpecies::lifetime_init (src/particles.cpp:142-170) */
+int mag2d_set_species(mag2d_ctx* ctx, int n_species, const mag2d_species_desc* species, int n_interactions,
+                      const mag2d_interaction_desc* interactions, const double* table_E,
+                      const double* table_sigma, int n_table_total);
+/* what: 0 lifetime, 1 v_max, 2 E_max, 3 t (species clock), 4 niter, 5 prob per step */
+int mag2d_species_get(mag2d_ctx* ctx, int species, int what, double* out);
+int mag2d_species_rates(mag2d_ctx* ctx, int species, double* rates_by_species /* [n_species] */);
+/* per-process collision counters of a primary species since the last reset:
+ * counts[target*16 + process], null collisions at counts[n_species*16 + target] */
+int mag2d_collision_counts(mag2d_ctx* ctx, int species, int64_t* counts /* [(n_species+1)*16] */, int reset);
+/* counting costs one global atomic per collision event; off by default */
+int mag2d_set_collision_counting(mag2d_ctx* ctx, int enable);
+
+/* ---- particle store (BaseSpecies::particles / insert / remove, src/particles.hpp:113,223-249) ---- */
+int mag2d_reserve(mag2d_ctx* ctx, int species, int64_t capacity);
+/* append n particles given as the reference's 64-byte AoS records (empty ones are skipped) */
+int mag2d_particles_upload(mag2d_ctx* ctx, int species, const mag2d_particle* aos, int64_t n);
+/* append n particles given as SoA host arrays (y and ttd may be NULL) */
+int mag2d_particles_upload_soa(mag2d_ctx* ctx, int species, int64_t n, const double* x, const double* y,
+                               const double* z, const double* vx, const double* vy, const double* vz,
+                               const double* ttd);
+/* all slots in device order; removed particles are returned with empty = 1 */
+int mag2d_particles_download(mag2d_ctx* ctx, int species, mag2d_particle* aos, int64_t capacity, int64_t* n_slots);
+int mag2d_particles_download_soa(mag2d_ctx* ctx, int species, int64_t capacity, double* x, double* y, double* z,
+                                 double* vx, double* vy, double* vz, double* ttd, uint8_t* alive,
+                                 int64_t* n_slots);
+int mag2d_particles_clear(mag2d_ctx* ctx, int species);
+int mag2d_count(mag2d_ctx* ctx, int species, int64_t* n_alive, int64_t* n_slots); /* n_particles() */
+/* device-side loaders with the context's Philox stream (src/particles.cpp:685-749, 485-510):
+ * kind 0 add_particles_everywhere(n), 1 add_particles_on_disk(n, a=cx, b=cz, c=radius),
+ * 2 add_monoenergetic_particles_on_cylinder_cylindrical(n, a=energy eV, b=centre z, c=radius, d=height) */
+int mag2d_particles_generate(mag2d_ctx* ctx, int species, int kind, int64_t n, double a, double b, double c, double d);
+/* cell sort + compaction of removed particles (replaces the free list, src/particles.hpp:223-247) */
+int mag2d_sort(mag2d_ctx* ctx, int species);
+int mag2d_set_sort_interval(mag2d_ctx* ctx, int steps); /* 0 = never sort inside mag2d_step */
+
+/* ---- stepping --------------------------------------------------------------------------------- */
+/* Pic<D>::advance_init, src/pic.cpp:359-384 */
+int mag2d_advance_init(mag2d_ctx* ctx);
+/* nsteps x Pic<D>::advance, src/pic.cpp:330-358: [solve] -> per species push+MCC+boundary+deposit ->
+ * [rho all-reduce].  Asynchronous. */
+int mag2d_step(mag2d_ctx* ctx, int nsteps);
+/* one Species<D>::advance (src/particles.hpp:342-349) of one species: fused advance_position +
+ * advance_boundary (+ deposit into that species' rho when selfconsistent) */
+int mag2d_species_advance(mag2d_ctx* ctx, int species);
+/* Species<D>::advance_init for one species (half step back), src/particles.hpp:351-355 */
+int mag2d_species_advance_init(mag2d_ctx* ctx, int species);
+/* Species<D>::accumulate, src/particles.hpp:358-367: deposit the current positions */
+int mag2d_species_accumulate(mag2d_ctx* ctx, int species);
+int mag2d_rho_reset(mag2d_ctx* ctx, int species /* -1 = all */);
+/* fixed-point charge grid of one species: sum of Q32 CIC weights (int64 [M*N]) */
+int mag2d_rho_fixed_download(mag2d_ctx* ctx, int species, int64_t* rho_fixed);
+/* Fields::rho in coulombs: sum over species of charge * weights * 2^-32, fixed species order */
+int mag2d_rho_download(mag2d_ctx* ctx, double* rho);
+int mag2d_rho_upload(mag2d_ctx* ctx, int species, const int64_t* rho_fixed);
+
+/* ---- diagnostics ------------------------------------------------------------------------------ */
+/* BaseSpecies::energy_dist_compute (src/particles.cpp:408-414): histogram of kinetic energy in eV,
+ * nbins bins on (0, emax); stats = {n_in_range, sum_in_range, n_total, sum_total} (Histogram, histogram.cpp) */
+int mag2d_energy_hist(mag2d_ctx* ctx, int species, int nbins, double emax, double* hist, double* stats);
+
+/* ---- multi-GPU (new: the reference is single-process) ------------------------------------------- */
+/* fill a 128-byte ncclUniqueId on rank 0; broadcast it out of band; then every rank calls comm_init */
+int mag2d_comm_unique_id(void* id128);
+int mag2d_comm_init(mag2d_ctx* ctx, int rank, int nranks, const void* id128);
+int mag2d_comm_destroy(mag2d_ctx* ctx);
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+/* number of kernels this context has launched since creation */
+int mag2d_kernel_launches(mag2d_ctx* ctx, int64_t* n);
+/* device time in ms of the most recent mag2d_step broken down by phase:
+ * out[0] push+MCC+boundary+deposit, out[1] rhs+solve, out[2] sort, out[3] all-reduce, out[4] total.
+ * Needs mag2d_set_timing(ctx, 1) before the step; blocks until the step has finished. */
+int mag2d_set_timing(mag2d_ctx* ctx, int enable);
+int mag2d_timers(mag2d_ctx* ctx, double* out5);
+/* raw device pointers for zero-copy interop (torch.distributed, CUDA IPC): what = 0 rho_fixed
+ * (all species, int64 [n_species*M*N]), 1 u, 2 uRF */
+int mag2d_device_pointer(mag2d_ctx* ctx, int what, void** ptr_dev, size_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,847 @@
+// abi.cu — the C ABI of include/mag2d_b200.h: context, device memory, species/collision model set-up,
+// particle store management and the per-step orchestration (Pic<D>::advance, src/pic.cpp:330-358).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ctx.hpp"
+
+static thread_local std::string g_last_error;
+void mag2d_set_error(const std::string& msg) { g_last_error = msg; }
+
+#define CHECK_CTX(c)                                   \
+    do {                                               \
+        if (!(c)) { mag2d_set_error("null context"); return 1; } \
+        if (cudaSetDevice((c)->device) != cudaSuccess) { mag2d_set_error("cudaSetDevice failed"); return 1; } \
+    } while (0)
+#define CHECK_SPECIES(c, s)                                                      \
+    do {                                                                         \
+        if ((s) < 0 || (s) >= (int)(c)->sp.size()) { mag2d_set_error("species index out of range"); return 1; } \
+    } while (0)
+
+namespace {
+
+size_t grid_n(const mag2d_ctx* c) { return (size_t)c->g.M * c->g.N; }
+
+__global__ void k_count_alive(const double* __restrict__ x, long long n, unsigned long long* __restrict__ out2)
+{
+    // out2[0] = live particles, out2[1] = 1 + highest live slot
+    unsigned long long cnt = 0, hi = 0;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+        if (particle_alive(x[k])) { cnt++; hi = (unsigned long long)k + 1; }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        cnt += __shfl_xor_sync(MAG2D_FULL_MASK, cnt, o);
+        hi = max(hi, __shfl_xor_sync(MAG2D_FULL_MASK, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (cnt) atomicAdd(out2, cnt);
+        if (hi) atomicMax(out2 + 1, hi);
+    }
+}
+
+// ---- host restatement of the collision-rate bookkeeping (BaseSpecies::lifetime_init, svmax_find,
+// Interaction::sigma_v; src/particles.cpp:142-206, src/particles.hpp:61-83,415-433) -----------------
+struct HostInter
+{
+    mag2d_interaction_desc d;
+    double DE, rate, mu;
+    const double* E;
+    const double* sigma;
+};
+
+double host_table(const double* xd, const double* yd, int n, double x)
+{
+    if (x >= xd[n - 1]) return yd[n - 1];
+    if (x <= xd[0]) return yd[0];
+    int j1 = 0, j2 = n - 1;
+    while (j2 - j1 > 1)
+    {
+        const int j3 = (j1 + j2) / 2;
+        if (x < xd[j3]) j2 = j3;
+        else j1 = j3;
+    }
+    const double w = (x - xd[j1]) / (xd[j2] - xd[j1]);
+    return yd[j1] * (1 - w) + yd[j2] * w;
+}
+
+double host_sigma_v(const HostInter& I, const mag2d_species_desc& prim, const mag2d_species_desc& sec, double v)
+{
+    const double EeV = 0.5 * I.mu * v * v / MAG2D_QE;
+    if (I.d.type == MAG2D_COULOMB)
+    {
+        const double E = EeV * MAG2D_QE;
+        const double lambda_D = sqrt(MAG2D_EPS0 * MAG2D_KB * prim.temperature / (prim.density * prim.charge * prim.charge));
+        const double Lambda = prim.charge * sec.charge / (4 * M_PI * MAG2D_EPS0 * E);
+        return M_PI * Lambda * Lambda * log(lambda_D / Lambda) * v;
+    }
+    if (I.d.n_table > 0) return host_table(I.E, I.sigma, I.d.n_table, EeV) * v;
+    return I.rate;
+}
+
+int free_store(SpeciesStore& S)
+{
+    for (int b = 0; b < 2; b++)
+        for (int a = 0; a < N_ARR; a++)
+            if (S.arr[b][a]) { cudaFree(S.arr[b][a]); S.arr[b][a] = nullptr; }
+    if (S.d_removed) cudaFree(S.d_removed);
+    if (S.d_counts) cudaFree(S.d_counts);
+    if (S.d_blob) cudaFree(S.d_blob);
+    delete S.h_blob;
+    S = SpeciesStore();
+    return 0;
+}
+
+bool needs_array(const mag2d_ctx* c, int a)
+{
+    if (a == ARR_Y) return c->g.coord == MAG2D_CARTESIAN3D;
+    if (a == ARR_TTD) return c->g.mover == MAG2D_ADVANCE_MULTICOLL;
+    return true;
+}
+
+int ensure_capacity(mag2d_ctx* c, SpeciesStore& S, long long need)
+{
+    if (need <= S.capacity) return 0;
+    long long cap = std::max<long long>(need, (long long)(S.capacity * 1.5) + 1024);
+    cap = (cap + 255) / 256 * 256;
+    double* old[N_ARR];
+    for (int a = 0; a < N_ARR; a++) old[a] = S.arr[S.cur][a];
+    // drop the idle slab first (it is re-created lazily by the next sort)
+    for (int a = 0; a < N_ARR; a++)
+        if (S.arr[S.cur ^ 1][a]) { cudaFree(S.arr[S.cur ^ 1][a]); S.arr[S.cur ^ 1][a] = nullptr; }
+    for (int a = 0; a < N_ARR; a++) S.arr[S.cur][a] = nullptr;
+    const long long old_cap = S.capacity;
+    S.capacity = 0;
+    if (store_alloc_slab(c, S, S.cur, cap)) return 1;
+    for (int a = 0; a < N_ARR; a++)
+        if (old[a])
+        {
+            if (S.n_slots > 0)
+                CUDA_OK(cudaMemcpyAsync(S.arr[S.cur][a], old[a], sizeof(double) * (size_t)S.n_slots, cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_OK(cudaStreamSynchronize(c->stream));
+            CUDA_OK(cudaFree(old[a]));
+        }
+    (void)old_cap;
+    return 0;
+}
+
+int upload_blob_header(mag2d_ctx* c, SpeciesStore& S)
+{
+    CUDA_OK(cudaMemcpyAsync(S.d_blob, S.h_blob, offsetof(MccBlob, tab), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+// partner pools follow the particle arrays (realloc, sort flips the slab): refresh when stale
+int refresh_pools(mag2d_ctx* c, int s)
+{
+    SpeciesStore& S = c->sp[s];
+    if (!S.h_blob || !S.h_blob->has_collisions) return 0;
+    bool dirty = false;
+    for (int k = 0; k < S.h_blob->n_targets; k++)
+    {
+        const SpeciesStore& T = c->sp[k];
+        PoolDev want;
+        memset(&want, 0, sizeof(want));
+        const int pool = T.n_slots > 0 ? 1 : 0;   // speclist[k]->particles.size() == 0 -> continuum (particles.cpp:230)
+        if (pool)
+        {
+            want.x = T.arr[T.cur][ARR_X];
+            want.vx = T.arr[T.cur][ARR_VX];
+            want.vy = T.arr[T.cur][ARR_VY];
+            want.vz = T.arr[T.cur][ARR_VZ];
+            want.n = T.n_slots;
+        }
+        if (S.h_blob->t[k].pool != pool || memcmp(&S.h_blob->pool[k], &want, sizeof(want)) != 0)
+        {
+            S.h_blob->t[k].pool = pool;
+            S.h_blob->pool[k] = want;
+            dirty = true;
+        }
+    }
+    if (dirty) return upload_blob_header(c, S);
+    return 0;
+}
+
+int advance_one(mag2d_ctx* c, int s)
+{
+    if (refresh_pools(c, s)) return 1;
+    return launch_species_advance(c, s);
+}
+
+}  // namespace
+
+int store_alloc_slab(mag2d_ctx* c, SpeciesStore& S, int slab, long long capacity)
+{
+    for (int a = 0; a < N_ARR; a++)
+    {
+        if (!needs_array(c, a)) continue;
+        if (S.arr[slab][a]) { cudaFree(S.arr[slab][a]); S.arr[slab][a] = nullptr; }
+        CUDA_OK(cudaMalloc(&S.arr[slab][a], sizeof(double) * (size_t)capacity));
+    }
+    S.capacity = capacity;
+    return 0;
+}
+
+extern "C" {
+
+int mag2d_abi_version(void) { return MAG2D_ABI_VERSION; }
+const char* mag2d_last_error(void) { return g_last_error.c_str(); }
+
+int mag2d_create(int device, const mag2d_grid_desc* grid, void* stream, mag2d_ctx** out)
+{
+    if (!grid || !out) { mag2d_set_error("mag2d_create: null argument"); return 1; }
+    if (grid->coord != MAG2D_CARTESIAN && grid->coord != MAG2D_CYLINDRICAL)
+    {
+        mag2d_set_error("mag2d_create: coord must be CARTESIAN or CYLINDRICAL (CARTESIAN3D: use mag3d_*)");
+        return 1;
+    }
+    if (grid->M < 2 || grid->N < 2) { mag2d_set_error("mag2d_create: grid must be at least 2x2"); return 1; }
+    // Param's own validation (param.cpp:60-64, 91-95)
+    if (grid->selfconsistent && grid->rf) { mag2d_set_error("Param: selfconsistent rf trap not implemented\n"); return 1; }
+    if (grid->selfconsistent && grid->electric_field_from_file)
+    {
+        mag2d_set_error("Param: selfconsistent with electric_field_from_file not implemented");
+        return 1;
+    }
+    if (grid->coord == MAG2D_CYLINDRICAL && grid->boundary != MAG2D_BOUNDARY_FREE)
+    {
+        mag2d_set_error("Param: only FREE boundary condition in cylindrical coords is implemented\n");
+        return 1;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        mag2d_set_error("mag2d_create: no CUDA device available (this library has no CPU path)");
+        return 1;
+    }
+    if (device < 0 || device >= ndev) { mag2d_set_error("mag2d_create: device index out of range"); return 1; }
+    CUDA_OK(cudaSetDevice(device));
+    mag2d_ctx* c = new mag2d_ctx;
+    c->device = device;
+    c->g = *grid;
+    if (stream) c->stream = (cudaStream_t)stream;
+    else
+    {
+        CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->owns_stream = true;
+    }
+    const size_t n = grid_n(c);
+    CUDA_OK(cudaMalloc(&c->d_mask, n));
+    CUDA_OK(cudaMalloc(&c->d_voltage, sizeof(double) * n));
+    CUDA_OK(cudaMalloc(&c->d_u, sizeof(double) * n));
+    CUDA_OK(cudaMalloc(&c->d_uRF, sizeof(double) * n));
+    CUDA_OK(cudaMalloc(&c->d_ueff, sizeof(double) * n));
+    CUDA_OK(cudaMalloc(&c->d_b, sizeof(double) * n));
+    CUDA_OK(cudaMalloc(&c->d_scratch, sizeof(double) * 64));
+    CUDA_OK(cudaMemsetAsync(c->d_u, 0, sizeof(double) * n, c->stream));
+    CUDA_OK(cudaMemsetAsync(c->d_uRF, 0, sizeof(double) * n, c->stream));
+    CUDA_OK(cudaMemsetAsync(c->d_ueff, 0, sizeof(double) * n, c->stream));
+    CUDA_OK(cudaMemsetAsync(c->d_voltage, 0, sizeof(double) * n, c->stream));
+    CUDA_OK(cudaMemsetAsync(c->d_mask, MAG2D_FREE, n, c->stream));
+    for (int q = 0; q < 8; q++) CUDA_OK(cudaEventCreate(&c->ev[q]));
+    *out = c;
+    return 0;
+}
+
+int mag2d_destroy(mag2d_ctx* c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    mag2d_comm_destroy(c);
+    mg_free(c);
+    for (auto& S : c->sp) free_store(S);
+    cudaFree(c->d_mask);
+    cudaFree(c->d_voltage);
+    cudaFree(c->d_u);
+    cudaFree(c->d_uRF);
+    cudaFree(c->d_ueff);
+    cudaFree(c->d_b);
+    cudaFree(c->d_scratch);
+    if (c->d_rho) cudaFree(c->d_rho);
+    if (c->d_charges) cudaFree(c->d_charges);
+    if (c->d_cell_count) cudaFree(c->d_cell_count);
+    if (c->d_cell_offset) cudaFree(c->d_cell_offset);
+    if (c->d_block_sums) cudaFree(c->d_block_sums);
+    if (c->d_rank) cudaFree(c->d_rank);
+    if (c->d_key) cudaFree(c->d_key);
+    for (int q = 0; q < 8; q++)
+        if (c->ev[q]) cudaEventDestroy(c->ev[q]);
+    if (c->owns_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int mag2d_sync(mag2d_ctx* c)
+{
+    CHECK_CTX(c);
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mag2d_seed(mag2d_ctx* c, uint64_t seed)
+{
+    CHECK_CTX(c);
+    c->seed = seed * 0x9E3779B97F4A7C15ULL + 0xD1B54A32D192ED03ULL;
+    return 0;
+}
+
+int mag2d_set_grid(mag2d_ctx* c, const uint8_t* mask, const double* voltage)
+{
+    CHECK_CTX(c);
+    const size_t n = grid_n(c);
+    c->h_mask.assign(mask, mask + n);
+    c->h_voltage.assign(voltage, voltage + n);
+    CUDA_OK(cudaMemcpyAsync(c->d_mask, mask, n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->d_voltage, voltage, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->grid_set = true;
+    return mg_setup(c);
+}
+
+int mag2d_set_potential(mag2d_ctx* c, int which, const double* values)
+{
+    CHECK_CTX(c);
+    double* dst = which == 0 ? c->d_u : c->d_uRF;
+    CUDA_OK(cudaMemcpyAsync(dst, values, sizeof(double) * grid_n(c), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mag2d_get_potential(mag2d_ctx* c, int which, double* values)
+{
+    CHECK_CTX(c);
+    const double* src = which == 0 ? c->d_u : c->d_uRF;
+    CUDA_OK(cudaMemcpyAsync(values, src, sizeof(double) * grid_n(c), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mag2d_solve(mag2d_ctx* c, int rf, double tol, int max_cycles, int* cycles_out, double* resid_out)
+{
+    CHECK_CTX(c);
+    if (c->sp.empty() && !c->d_rho)
+    {
+        // no species yet (the Pic constructor pre-solves the vacuum fields, pic.cpp:180-187): zero charge
+        CUDA_OK(cudaMalloc(&c->d_rho, sizeof(unsigned long long) * grid_n(c)));
+        CUDA_OK(cudaMemsetAsync(c->d_rho, 0, sizeof(unsigned long long) * grid_n(c), c->stream));
+    }
+    return mg_solve(c, rf, tol, max_cycles, 0, cycles_out, resid_out);
+}
+
+int mag2d_set_solver(mag2d_ctx* c, int cycles_per_step, double tol, int max_cycles)
+{
+    CHECK_CTX(c);
+    c->cycles_per_step = cycles_per_step;
+    c->solve_tol = tol;
+    c->max_cycles = max_cycles;
+    return 0;
+}
+
+int mag2d_u_smooth(mag2d_ctx* c, int symmetry, double radius)
+{
+    CHECK_CTX(c);
+    return launch_u_smooth(c, symmetry, radius);
+}
+
+int mag2d_field_E(mag2d_ctx* c, int n, const double* x, const double* z, double time, double* Ex, double* Ez)
+{
+    CHECK_CTX(c);
+    return launch_field_E(c, n, x, z, time, Ex, Ez);
+}
+
+int mag2d_set_species(mag2d_ctx* c, int ns, const mag2d_species_desc* species, int ni,
+                      const mag2d_interaction_desc* inter, const double* table_E, const double* table_sigma,
+                      int n_table_total)
+{
+    CHECK_CTX(c);
+    if (ns < 1 || ns > MAG2D_MAX_SPECIES) { mag2d_set_error("mag2d_set_species: 1..16 species supported"); return 1; }
+    for (auto& S : c->sp) free_store(S);
+    c->sp.assign(ns, SpeciesStore());
+    const size_t n = grid_n(c);
+    if (c->d_rho) cudaFree(c->d_rho);
+    if (c->d_charges) cudaFree(c->d_charges);
+    CUDA_OK(cudaMalloc(&c->d_rho, sizeof(unsigned long long) * n * ns));
+    CUDA_OK(cudaMemsetAsync(c->d_rho, 0, sizeof(unsigned long long) * n * ns, c->stream));
+    CUDA_OK(cudaMalloc(&c->d_charges, sizeof(double) * ns));
+    std::vector<double> charges(ns);
+    for (int i = 0; i < ns; i++)
+    {
+        SpeciesStore& S = c->sp[i];
+        S.desc = species[i];
+        // BaseSpecies ctor (particles.hpp:164,180)
+        S.E_max = species[i].E_max > 0. ? species[i].E_max : species[i].temperature * MAG2D_KB / MAG2D_QE * 10.0;
+        S.v_max = sqrt(2.0 * MAG2D_KB * species[i].temperature / species[i].mass);
+        S.rates.assign(ns, 0.0);
+        charges[i] = species[i].charge;
+        CUDA_OK(cudaMalloc(&S.d_removed, sizeof(unsigned long long)));
+        CUDA_OK(cudaMemsetAsync(S.d_removed, 0, sizeof(unsigned long long), c->stream));
+        CUDA_OK(cudaMalloc(&S.d_counts, sizeof(unsigned long long) * (ns + 1) * 16));
+        CUDA_OK(cudaMemsetAsync(S.d_counts, 0, sizeof(unsigned long long) * (ns + 1) * 16, c->stream));
+    }
+    CUDA_OK(cudaMemcpyAsync(c->d_charges, charges.data(), sizeof(double) * ns, cudaMemcpyHostToDevice, c->stream));
+    // Interaction ctor (particles.hpp:74-83) and the per-primary, per-target lists of Speclist (pic.cpp:46-72)
+    std::vector<std::vector<std::vector<HostInter>>> by(ns, std::vector<std::vector<HostInter>>(ns));
+    for (int k = 0; k < ni; k++)
+    {
+        const mag2d_interaction_desc& d = inter[k];
+        if (d.primary < 0 || d.primary >= ns || d.secondary < 0 || d.secondary >= ns)
+        {
+            mag2d_set_error("Speclist::Speclist: unrecognized primary species of interaction\n");
+            return 1;
+        }
+        if (d.n_table > 0 && (d.table_offset < 0 || d.table_offset + d.n_table > n_table_total))
+        {
+            mag2d_set_error("mag2d_set_species: cross-section table out of range");
+            return 1;
+        }
+        HostInter I;
+        I.d = d;
+        I.DE = d.DE_eV * MAG2D_QE;
+        I.rate = d.rate;
+        if (d.type == MAG2D_LANGEVIN) I.rate *= d.cutoff * d.cutoff;
+        const double m1 = species[d.primary].mass, m2 = species[d.secondary].mass;
+        I.mu = m1 * m2 / (m1 + m2);
+        I.E = d.n_table > 0 ? table_E + d.table_offset : nullptr;
+        I.sigma = d.n_table > 0 ? table_sigma + d.table_offset : nullptr;
+        by[d.primary][d.secondary].push_back(I);
+    }
+    for (int i = 0; i < ns; i++)
+    {
+        SpeciesStore& S = c->sp[i];
+        // lifetime_init (particles.cpp:151-161) with svmax_find (particles.cpp:190-206): 1000 samples of
+        // v in [0, veV(E_max)), v advanced by repeated addition as the reference does
+        const double vmax = sqrt(S.E_max * MAG2D_QE / S.desc.mass * 2.0);
+        double rate = 0;
+        for (int k = 0; k < ns; k++)
+        {
+            const double dv = vmax / 1000;
+            double svmax = 0.0;
+            for (double v = 0; v < vmax; v += dv)
+            {
+                double sv = 0;
+                for (const HostInter& I : by[i][k]) sv += host_sigma_v(I, species[i], species[k], v);
+                if (std::isnan(sv)) continue;
+                if (sv > svmax) svmax = sv;
+            }
+            S.rates[k] = svmax * species[k].density;
+            rate += S.rates[k];
+        }
+        S.lifetime = rate > 0.0 ? 1.0 / rate : INFINITY;
+        // device blob
+        MccBlob* B = new MccBlob;
+        memset(B, 0, sizeof(MccBlob));
+        B->n_targets = ns;
+        B->lifetime = S.lifetime;
+        B->inv_lifetime = rate;
+        B->mass = S.desc.mass;
+        B->charge = S.desc.charge;
+        int ii = 0, nt = 0;
+        std::vector<double> tE, tS;
+        for (int k = 0; k < ns; k++)
+        {
+            MccTarget& T = B->t[k];
+            T.rate_max = S.rates[k];
+            T.density = species[k].density;
+            T.mass = species[k].mass;
+            T.vth = c->sp[k].v_max * M_SQRT1_2;
+            T.first_inter = ii;
+            T.n_inter = (int)by[i][k].size();
+            for (const HostInter& I : by[i][k])
+            {
+                if (ii >= MCC_MAX_I) { mag2d_set_error("mag2d_set_species: more than 32 interactions for one primary species"); delete B; return 1; }
+                MccInter& D = B->in[ii++];
+                D.type = I.d.type;
+                D.n_table = I.d.n_table;
+                D.table_off = nt;
+                D.DE = I.DE;
+                D.rate = I.rate;
+                D.cutoff = I.d.cutoff;
+                D.mu = I.mu;
+                D.half_mu = 0.5 * I.mu;
+                for (int q = 0; q < I.d.n_table; q++) { tE.push_back(I.E[q]); tS.push_back(I.sigma[q]); }
+                nt += I.d.n_table;
+            }
+        }
+        if (nt > MCC_MAX_TAB) { mag2d_set_error("mag2d_set_species: cross-section tables exceed 2048 points for one primary species"); delete B; return 1; }
+        B->n_inter_total = ii;
+        B->n_tab = nt;
+        B->has_collisions = rate > 0.0;
+        for (int q = 0; q < nt; q++) { B->tab[q] = tE[q]; B->tab[nt + q] = tS[q]; }
+        S.h_blob = B;
+        CUDA_OK(cudaMalloc(&S.d_blob, sizeof(MccBlob)));
+        CUDA_OK(cudaMemcpyAsync(S.d_blob, B, sizeof(MccBlob), cudaMemcpyHostToDevice, c->stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mag2d_species_get(mag2d_ctx* c, int s, int what, double* out)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    const SpeciesStore& S = c->sp[s];
+    switch (what)
+    {
+        case 0: *out = S.lifetime; break;
+        case 1: *out = S.v_max; break;
+        case 2: *out = S.E_max; break;
+        case 3: *out = S.t; break;
+        case 4: *out = (double)S.niter; break;
+        case 5: *out = 1.0 - exp(-S.desc.dt / S.lifetime); break;
+        default: mag2d_set_error("mag2d_species_get: unknown selector"); return 1;
+    }
+    return 0;
+}
+
+int mag2d_species_rates(mag2d_ctx* c, int s, double* rates)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    for (size_t k = 0; k < c->sp.size(); k++) rates[k] = c->sp[s].rates[k];
+    return 0;
+}
+
+int mag2d_collision_counts(mag2d_ctx* c, int s, int64_t* counts, int reset)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    const size_t bytes = sizeof(unsigned long long) * (c->sp.size() + 1) * 16;
+    CUDA_OK(cudaMemcpyAsync(counts, c->sp[s].d_counts, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (reset) CUDA_OK(cudaMemsetAsync(c->sp[s].d_counts, 0, bytes, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mag2d_set_collision_counting(mag2d_ctx* c, int enable)
+{
+    CHECK_CTX(c);
+    c->count_collisions = enable != 0;
+    return 0;
+}
+
+int mag2d_reserve(mag2d_ctx* c, int s, int64_t capacity)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    return ensure_capacity(c, c->sp[s], capacity);
+}
+
+int mag2d_particles_upload(mag2d_ctx* c, int s, const mag2d_particle* aos, int64_t n)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    if (n <= 0) return 0;
+    SpeciesStore& S = c->sp[s];
+    if (ensure_capacity(c, S, S.n_slots + n)) return 1;
+    mag2d_particle* d_aos;
+    CUDA_OK(cudaMalloc(&d_aos, sizeof(mag2d_particle) * (size_t)n));
+    CUDA_OK(cudaMemcpyAsync(d_aos, aos, sizeof(mag2d_particle) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    long long added = 0;
+    const int rc = launch_aos_to_soa(c, s, d_aos, n, &added);
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaFree(d_aos));
+    return rc;
+}
+
+int mag2d_particles_upload_soa(mag2d_ctx* c, int s, int64_t n, const double* x, const double* y, const double* z,
+                               const double* vx, const double* vy, const double* vz, const double* ttd)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    if (n <= 0) return 0;
+    SpeciesStore& S = c->sp[s];
+    if (ensure_capacity(c, S, S.n_slots + n)) return 1;
+    const double* src[N_ARR] = {x, z, vx, vy, vz, y, ttd};
+    for (int a = 0; a < N_ARR; a++)
+    {
+        double* dst = S.arr[S.cur][a];
+        if (!dst) continue;
+        if (src[a]) CUDA_OK(cudaMemcpyAsync(dst + S.n_slots, src[a], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        else CUDA_OK(cudaMemsetAsync(dst + S.n_slots, 0, sizeof(double) * (size_t)n, c->stream));
+    }
+    S.n_slots += n;
+    return 0;
+}
+
+int mag2d_particles_download(mag2d_ctx* c, int s, mag2d_particle* aos, int64_t capacity, int64_t* n_slots)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    SpeciesStore& S = c->sp[s];
+    if (n_slots) *n_slots = S.n_slots;
+    if (S.n_slots == 0) return 0;
+    if (capacity < S.n_slots) { mag2d_set_error("mag2d_particles_download: buffer too small"); return 1; }
+    mag2d_particle* d_aos;
+    CUDA_OK(cudaMalloc(&d_aos, sizeof(mag2d_particle) * (size_t)S.n_slots));
+    const int rc = launch_soa_to_aos(c, s, d_aos);
+    if (!rc) CUDA_OK(cudaMemcpyAsync(aos, d_aos, sizeof(mag2d_particle) * (size_t)S.n_slots, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaFree(d_aos));
+    return rc;
+}
+
+int mag2d_particles_download_soa(mag2d_ctx* c, int s, int64_t capacity, double* x, double* y, double* z, double* vx,
+                                 double* vy, double* vz, double* ttd, uint8_t* alive, int64_t* n_slots)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    SpeciesStore& S = c->sp[s];
+    if (n_slots) *n_slots = S.n_slots;
+    if (S.n_slots == 0) return 0;
+    if (capacity < S.n_slots) { mag2d_set_error("mag2d_particles_download_soa: buffer too small"); return 1; }
+    double* dst[N_ARR] = {x, z, vx, vy, vz, y, ttd};
+    for (int a = 0; a < N_ARR; a++)
+    {
+        if (!dst[a]) continue;
+        const double* src = S.arr[S.cur][a];
+        if (src) CUDA_OK(cudaMemcpyAsync(dst[a], src, sizeof(double) * (size_t)S.n_slots, cudaMemcpyDeviceToHost, c->stream));
+        else memset(dst[a], 0, sizeof(double) * (size_t)S.n_slots);
+    }
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (alive)
+    {
+        if (!x) { mag2d_set_error("mag2d_particles_download_soa: alive needs x"); return 1; }
+        for (long long k = 0; k < S.n_slots; k++) alive[k] = x[k] == x[k] ? 1 : 0;
+    }
+    return 0;
+}
+
+int mag2d_particles_clear(mag2d_ctx* c, int s)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    c->sp[s].n_slots = 0;
+    CUDA_OK(cudaMemsetAsync(c->sp[s].d_removed, 0, sizeof(unsigned long long), c->stream));
+    return 0;
+}
+
+int mag2d_count(mag2d_ctx* c, int s, int64_t* n_alive, int64_t* n_slots)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    SpeciesStore& S = c->sp[s];
+    unsigned long long h[2] = {0, 0};
+    if (S.n_slots > 0)
+    {
+        unsigned long long* d = reinterpret_cast<unsigned long long*>(c->d_scratch + 8);
+        CUDA_OK(cudaMemsetAsync(d, 0, sizeof(h), c->stream));
+        const unsigned blocks = (unsigned)std::min<long long>((S.n_slots + 255) / 256, 148 * 16);
+        k_count_alive<<<blocks, 256, 0, c->stream>>>(S.arr[S.cur][ARR_X], S.n_slots, d);
+        c->launches++;
+        CUDA_OK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        S.n_slots = (long long)h[1];   // trailing dead slots (left behind by a compaction) are released
+    }
+    if (n_alive) *n_alive = (int64_t)h[0];
+    if (n_slots) *n_slots = S.n_slots;
+    return 0;
+}
+
+int mag2d_particles_generate(mag2d_ctx* c, int s, int kind, int64_t n, double a, double b, double cc, double d)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    if (kind < 0 || kind > 2) { mag2d_set_error("mag2d_particles_generate: unknown loader"); return 1; }
+    if (kind == 2 && c->g.coord != MAG2D_CYLINDRICAL) { mag2d_set_error("mag2d_particles_generate: loader 2 is cylindrical only"); return 1; }
+    if (kind == 2 && (b < 0 || b > c->g.z_max)) return 0;   // particles.cpp:489
+    SpeciesStore& S = c->sp[s];
+    if (ensure_capacity(c, S, S.n_slots + n)) return 1;
+    return launch_generate(c, s, kind, n, a, b, cc, d);
+}
+
+int mag2d_sort(mag2d_ctx* c, int s)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    SpeciesStore& S = c->sp[s];
+    if (S.n_slots == 0) return 0;
+    if (!S.arr[S.cur ^ 1][ARR_X])
+    {
+        const long long cap = S.capacity;
+        if (store_alloc_slab(c, S, S.cur ^ 1, cap)) return 1;
+    }
+    return launch_sort(c, s);
+}
+
+int mag2d_set_sort_interval(mag2d_ctx* c, int steps)
+{
+    CHECK_CTX(c);
+    c->sort_interval = steps;
+    return 0;
+}
+
+int mag2d_rho_reset(mag2d_ctx* c, int s)
+{
+    CHECK_CTX(c);
+    const size_t n = grid_n(c);
+    if (!c->d_rho) return 0;
+    if (s < 0) CUDA_OK(cudaMemsetAsync(c->d_rho, 0, sizeof(unsigned long long) * n * c->sp.size(), c->stream));
+    else
+    {
+        CHECK_SPECIES(c, s);
+        CUDA_OK(cudaMemsetAsync(c->d_rho + (size_t)s * n, 0, sizeof(unsigned long long) * n, c->stream));
+    }
+    return 0;
+}
+
+int mag2d_species_advance(mag2d_ctx* c, int s)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    return advance_one(c, s);
+}
+
+int mag2d_species_advance_init(mag2d_ctx* c, int s)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    return launch_species_advance_init(c, s);
+}
+
+int mag2d_species_accumulate(mag2d_ctx* c, int s)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    return launch_species_accumulate(c, s);
+}
+
+int mag2d_rho_fixed_download(mag2d_ctx* c, int s, int64_t* rho_fixed)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    const size_t n = grid_n(c);
+    CUDA_OK(cudaMemcpyAsync(rho_fixed, c->d_rho + (size_t)s * n, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mag2d_rho_upload(mag2d_ctx* c, int s, const int64_t* rho_fixed)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    const size_t n = grid_n(c);
+    CUDA_OK(cudaMemcpyAsync(c->d_rho + (size_t)s * n, rho_fixed, sizeof(int64_t) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mag2d_rho_download(mag2d_ctx* c, double* rho)
+{
+    CHECK_CTX(c);
+    if (c->sp.empty()) { mag2d_set_error("mag2d_rho_download: no species"); return 1; }
+    // d_b is scratch between solves
+    if (launch_rho_total(c, c->d_b)) return 1;
+    CUDA_OK(cudaMemcpyAsync(rho, c->d_b, sizeof(double) * grid_n(c), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// Pic<D>::advance_init, src/pic.cpp:359-384
+int mag2d_advance_init(mag2d_ctx* c)
+{
+    CHECK_CTX(c);
+    if (c->g.selfconsistent)
+    {
+        if (mag2d_rho_reset(c, -1)) return 1;
+        for (size_t s = 0; s < c->sp.size(); s++)
+            if (launch_species_accumulate(c, (int)s)) return 1;
+        if (comm_allreduce_rho(c)) return 1;
+        if (mg_solve(c, 0, c->solve_tol, c->max_cycles, 0, nullptr, nullptr)) return 1;
+        if (c->g.u_smooth && launch_u_smooth(c, 0, -1.0)) return 1;
+        // the species grids are kept: they are the charge the first advance() solves with
+    }
+    for (size_t s = 0; s < c->sp.size(); s++)
+        if (launch_species_advance_init(c, (int)s)) return 1;
+    return 0;
+}
+
+// Pic<D>::advance, src/pic.cpp:330-358
+int mag2d_step(mag2d_ctx* c, int nsteps)
+{
+    CHECK_CTX(c);
+    if (c->sp.empty()) { mag2d_set_error("mag2d_step: no species"); return 1; }
+    for (int it = 0; it < nsteps; it++)
+    {
+        if (c->timing) CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
+        if (c->g.selfconsistent)
+        {
+            if (mg_solve(c, 0, c->solve_tol, c->max_cycles, c->cycles_per_step, nullptr, nullptr)) return 1;
+            if (c->g.u_smooth && launch_u_smooth(c, 0, -1.0)) return 1;
+            if (mag2d_rho_reset(c, -1)) return 1;
+        }
+        if (c->timing) CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
+        for (size_t s = 0; s < c->sp.size(); s++)
+            if (advance_one(c, (int)s)) return 1;
+        if (c->timing) CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
+        if (c->g.selfconsistent && comm_allreduce_rho(c)) return 1;
+        if (c->timing) CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
+        if (c->sort_interval > 0)
+            for (size_t s = 0; s < c->sp.size(); s++)
+                if (c->sp[s].n_slots > 0 && c->sp[s].steps_since_sort >= c->sort_interval)
+                    if (mag2d_sort(c, (int)s)) return 1;
+        if (c->timing)
+        {
+            CUDA_OK(cudaEventRecord(c->ev[4], c->stream));
+            CUDA_OK(cudaEventSynchronize(c->ev[4]));
+            float ms;
+            CUDA_OK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->timers[1] += ms;
+            CUDA_OK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->timers[0] += ms;
+            CUDA_OK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->timers[3] += ms;
+            CUDA_OK(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->timers[2] += ms;
+            CUDA_OK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->timers[4] += ms;
+        }
+    }
+    return 0;
+}
+
+int mag2d_energy_hist(mag2d_ctx* c, int s, int nbins, double emax, double* hist, double* stats)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    if (nbins < 1 || nbins > 4096) { mag2d_set_error("mag2d_energy_hist: 1..4096 bins"); return 1; }
+    return launch_energy_hist(c, s, nbins, emax, hist, stats);
+}
+
+int mag2d_kernel_launches(mag2d_ctx* c, int64_t* n)
+{
+    if (!c) { mag2d_set_error("null context"); return 1; }
+    *n = c->launches;
+    return 0;
+}
+
+int mag2d_set_timing(mag2d_ctx* c, int enable)
+{
+    CHECK_CTX(c);
+    c->timing = enable != 0;
+    for (double& t : c->timers) t = 0;
+    return 0;
+}
+
+int mag2d_timers(mag2d_ctx* c, double* out5)
+{
+    CHECK_CTX(c);
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    for (int q = 0; q < 5; q++) out5[q] = c->timers[q];
+    for (double& t : c->timers) t = 0;
+    return 0;
+}
+
+int mag2d_device_pointer(mag2d_ctx* c, int what, void** ptr, size_t* bytes)
+{
+    CHECK_CTX(c);
+    const size_t n = grid_n(c);
+    switch (what)
+    {
+        case 0: *ptr = c->d_rho; *bytes = sizeof(unsigned long long) * n * c->sp.size(); break;
+        case 1: *ptr = c->d_u; *bytes = sizeof(double) * n; break;
+        case 2: *ptr = c->d_uRF; *bytes = sizeof(double) * n; break;
+        default: mag2d_set_error("mag2d_device_pointer: unknown selector"); return 1;
+    }
+    return 0;
+}
+
+}  // extern "C"

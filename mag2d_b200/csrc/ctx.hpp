@@ -1,0 +1,139 @@
+// ctx.hpp — host-side context behind the opaque mag2d_ctx of include/mag2d_b200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mag2d_b200.h"
+#include "common.cuh"
+
+#define ARR_X 0
+#define ARR_Z 1
+#define ARR_VX 2
+#define ARR_VY 3
+#define ARR_VZ 4
+#define ARR_Y 5
+#define ARR_TTD 6
+#define N_ARR 7
+
+struct SpeciesStore
+{
+    mag2d_species_desc desc{};
+    double v_max = 0, E_max = 0, lifetime = INFINITY;
+    std::vector<double> rates;        // rates_by_species
+    // particle slabs: two generations (the sort writes out of place), N_ARR arrays each
+    double* arr[2][N_ARR] = {};
+    int cur = 0;
+    long long capacity = 0;
+    long long n_slots = 0;            // high-water mark of used slots
+    unsigned long long* d_removed = nullptr;   // device counter of removals since the last compaction
+    unsigned long long* d_counts = nullptr;    // collision counters [(ns+1)*16]
+    MccBlob* d_blob = nullptr;
+    MccBlob* h_blob = nullptr;
+    unsigned long long niter = 0;     // BaseSpecies::niter
+    double t = 0;                     // BaseSpecies::t
+    int steps_since_sort = 0;
+};
+
+// one level of the Galerkin multigrid hierarchy (poisson.cu)
+struct MgLevel
+{
+    int M = 0, N = 0;
+    int fx = 1, fz = 1;         // coarsening factor towards the next (coarser) level
+    double* coef = nullptr;     // [9][M*N] stencil coefficients, order (di,dj) = (-1,-1),(-1,0),(-1,1),(0,-1),(0,0),(0,1),(1,-1),(1,0),(1,1)
+    unsigned char* freem = nullptr;  // 1 = unknown, 0 = Dirichlet / eliminated
+    double* u = nullptr;        // solution (level 0: the potential) or error (coarser levels)
+    double* b = nullptr;        // right-hand side (scaled)
+};
+
+struct mag2d_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    mag2d_grid_desc g{};
+    uint64_t seed = 0x9E3779B97F4A7C15ULL;
+    long long launches = 0;
+
+    // grid-sized device arrays
+    unsigned char* d_mask = nullptr;
+    double* d_voltage = nullptr;
+    double* d_u = nullptr;      // also mg[0].u
+    double* d_uRF = nullptr;
+    double* d_ueff = nullptr;
+    double* d_b = nullptr;      // RHS in the reference's scaling (for the residual check)
+    double* d_rowscale = nullptr;  // symmetrising row scale s_i of the cylindrical operator, [M]
+    unsigned long long* d_rho = nullptr;   // [n_species][M*N] fixed-point charge grids
+    double* d_scratch = nullptr;           // reductions
+    bool grid_set = false;
+    std::vector<unsigned char> h_mask;
+    std::vector<double> h_voltage;
+
+    std::vector<MgLevel> mg;
+    int cycles_per_step = 0;
+    double solve_tol = 1e-10;
+    int max_cycles = 60;
+    int last_cycles = 0;
+    double last_resid = 0;
+
+    std::vector<SpeciesStore> sp;
+    double* d_charges = nullptr;  // [n_species]
+    int sort_interval = 0;
+    bool count_collisions = false;
+
+    // sort scratch
+    unsigned int* d_cell_count = nullptr;
+    unsigned int* d_cell_offset = nullptr;
+    unsigned int* d_rank = nullptr;
+    unsigned int* d_key = nullptr;
+    long long rank_capacity = 0;
+    unsigned int* d_block_sums = nullptr;
+
+    // multi-GPU
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[8] = {};
+    double timers[5] = {};
+};
+
+// ---- error plumbing (abi.cu)
+void mag2d_set_error(const std::string& msg);
+#define CUDA_OK(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            mag2d_set_error(std::string(#call) + ": " + cudaGetErrorString(_e));                   \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+// ---- store management (abi.cu)
+int store_alloc_slab(mag2d_ctx* c, SpeciesStore& S, int slab, long long capacity);
+
+// ---- launchers implemented in the kernel translation units
+// push.cu
+int launch_species_advance(mag2d_ctx* c, int s);
+int launch_species_advance_init(mag2d_ctx* c, int s);
+int launch_species_accumulate(mag2d_ctx* c, int s);
+int launch_generate(mag2d_ctx* c, int s, int kind, long long n, double a, double b, double cc, double d);
+int launch_energy_hist(mag2d_ctx* c, int s, int nbins, double emax, double* hist, double* stats);
+int launch_field_E(mag2d_ctx* c, int n, const double* x, const double* z, double time, double* Ex, double* Ez);
+int launch_aos_to_soa(mag2d_ctx* c, int s, const mag2d_particle* d_aos, long long n_in, long long* n_added);
+int launch_soa_to_aos(mag2d_ctx* c, int s, mag2d_particle* d_aos);
+int update_ueff(mag2d_ctx* c, double phase, bool rf);
+// sort.cu
+int launch_sort(mag2d_ctx* c, int s);
+// poisson.cu
+int mg_setup(mag2d_ctx* c);
+void mg_free(mag2d_ctx* c);
+int mg_rhs(mag2d_ctx* c, int rf);          // rho (all species) -> b, Dirichlet rows, scaled copy into mg[0].b
+int mg_vcycle(mag2d_ctx* c);
+int mg_residual(mag2d_ctx* c, double* resid_max, double* b_max);
+int mg_solve(mag2d_ctx* c, int rf, double tol, int max_cycles, int fixed_cycles, int* cycles, double* resid);
+int launch_u_smooth(mag2d_ctx* c, int symmetry, double radius);
+int launch_rho_total(mag2d_ctx* c, double* d_out);
+// comm.cu
+int comm_allreduce_rho(mag2d_ctx* c);

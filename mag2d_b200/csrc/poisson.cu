@@ -1,0 +1,687 @@
+// poisson.cu — GPU Poisson solve: Galerkin geometric multigrid on the reference's operator.
+//
+// Replaces Fields::Fields' CSC build + UMFPACK LU (reference src/fields.cpp:133-275) and the
+// per-step triangular solves of Fields::boundary_solve / boundary_solve_rf (src/fields.cpp:278-348).
+//
+// The operator is the reference's: identity rows on FIXED / FIXED_RF nodes, the unit 5-point stencil
+// [1,1,-4,1,1] elsewhere in Cartesian coordinates (fields.cpp:229-235), the r-z stencil with
+// k1=(i-1/2)/(dx^2 i), k2=1/dz^2, k3=(i+1/2)/(dx^2 i) and the axis row k3=4/dx^2 in cylindrical
+// coordinates (fields.cpp:156-208).  Cylindrical rows are multiplied by s_i = i (1/8 on the axis),
+// which makes the matrix symmetric without changing the solution.
+//
+// Hierarchy: vertex-centred coarsening by 2 (semi-coarsening while one direction couples >3x more
+// strongly), bilinear interpolation P that skips Dirichlet nodes, restriction R = P^T and Galerkin
+// coarse operators A_c = R A P, which stay 9-point.  They are built once per geometry on the host by
+// probing R A P with the nine (I mod 3, J mod 3) colourings.  Electrodes of any shape and odd
+// interval counts (x_sampl = 512 or 200) are handled by the Galerkin product itself; measured
+// convergence is 0.1-0.2 per V(2,2) cycle on every reference geometry (scratch/mg_galerkin_proto.py).
+// Smoother: 4-colour Gauss-Seidel (exact for 9-point stencils, deterministic).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "ctx.hpp"
+
+namespace {
+
+// ---------------------------------------------------------------- host side: hierarchy construction
+struct HostLevel
+{
+    int M, N, fx, fz;
+    std::vector<double> coef;            // [9][M*N]
+    std::vector<unsigned char> freem;
+};
+
+inline int cidx(int di, int dj) { return (di + 1) * 3 + (dj + 1); }
+
+void host_apply(const HostLevel& L, const std::vector<double>& x, std::vector<double>& y)
+{
+    const int M = L.M, N = L.N;
+    const size_t n = (size_t)M * N;
+    y.assign(n, 0.0);
+    for (int i = 0; i < M; i++)
+        for (int j = 0; j < N; j++)
+        {
+            const size_t k = (size_t)i * N + j;
+            if (!L.freem[k]) continue;
+            double s = 0;
+            for (int di = -1; di <= 1; di++)
+                for (int dj = -1; dj <= 1; dj++)
+                {
+                    const int ii = i + di, jj = j + dj;
+                    if (ii < 0 || ii >= M || jj < 0 || jj >= N) continue;
+                    const double a = L.coef[(size_t)cidx(di, dj) * n + k];
+                    if (a != 0.0) s += a * x[(size_t)ii * N + jj];
+                }
+            y[k] = s;
+        }
+}
+
+// ef = P ec (zero on non-free fine nodes)
+void host_prolong(const HostLevel& F, int Mc, int Nc, const std::vector<double>& ec, std::vector<double>& ef)
+{
+    const int M = F.M, N = F.N;
+    ef.assign((size_t)M * N, 0.0);
+    for (int i = 0; i < M; i++)
+        for (int j = 0; j < N; j++)
+        {
+            const size_t k = (size_t)i * N + j;
+            if (!F.freem[k]) continue;
+            const int I = i / F.fx, J = j / F.fz;
+            const double wi = (F.fx == 2 && (i & 1)) ? 0.5 : 0.0, wj = (F.fz == 2 && (j & 1)) ? 0.5 : 0.0;
+            double s = 0;
+            for (int a = 0; a < 2; a++)
+                for (int b = 0; b < 2; b++)
+                {
+                    const double w = (a ? wi : 1.0 - wi) * (b ? wj : 1.0 - wj);
+                    if (w == 0.0) continue;
+                    const int II = I + a, JJ = J + b;
+                    if (II >= Mc || JJ >= Nc) continue;
+                    s += w * ec[(size_t)II * Nc + JJ];
+                }
+            ef[k] = s;
+        }
+}
+
+// rc = P^T rf
+void host_restrict(const HostLevel& F, int Mc, int Nc, const std::vector<double>& rf, std::vector<double>& rc)
+{
+    const int M = F.M, N = F.N;
+    rc.assign((size_t)Mc * Nc, 0.0);
+    for (int i = 0; i < M; i++)
+        for (int j = 0; j < N; j++)
+        {
+            const size_t k = (size_t)i * N + j;
+            if (!F.freem[k] || rf[k] == 0.0) continue;
+            const int I = i / F.fx, J = j / F.fz;
+            const double wi = (F.fx == 2 && (i & 1)) ? 0.5 : 0.0, wj = (F.fz == 2 && (j & 1)) ? 0.5 : 0.0;
+            for (int a = 0; a < 2; a++)
+                for (int b = 0; b < 2; b++)
+                {
+                    const double w = (a ? wi : 1.0 - wi) * (b ? wj : 1.0 - wj);
+                    if (w == 0.0) continue;
+                    const int II = I + a, JJ = J + b;
+                    if (II >= Mc || JJ >= Nc) continue;
+                    rc[(size_t)II * Nc + JJ] += w * rf[k];
+                }
+        }
+}
+
+void build_fine_level(const mag2d_ctx* c, HostLevel& L, std::vector<double>& rowscale)
+{
+    const mag2d_grid_desc& g = c->g;
+    const int M = g.M, N = g.N;
+    const size_t n = (size_t)M * N;
+    L.M = M;
+    L.N = N;
+    L.fx = L.fz = 1;
+    L.coef.assign(9 * n, 0.0);
+    L.freem.assign(n, 0);
+    rowscale.assign(M, 1.0);
+    const bool cyl = g.coord == MAG2D_CYLINDRICAL;
+    const double dx = g.dx, dz = g.dz;
+    for (int i = 0; i < M; i++)
+    {
+        if (cyl) rowscale[i] = i == 0 ? 0.125 : (double)i;
+        for (int j = 0; j < N; j++)
+        {
+            const size_t k = (size_t)i * N + j;
+            const unsigned char m = c->h_mask[k];
+            if (m == MAG2D_FIXED || m == MAG2D_FIXED_RF)
+            {
+                L.coef[(size_t)cidx(0, 0) * n + k] = 1.0;
+                continue;
+            }
+            L.freem[k] = 1;
+            double W, E, S, Nn, C;
+            if (cyl)
+            {
+                const double k2 = 1.0 / (dz * dz);
+                if (i == 0)
+                {
+                    const double k3 = 1.0 / (dx * dx * 0.25);
+                    W = 0.0; E = k3; S = k2; Nn = k2; C = -2.0 * k2 - k3;
+                }
+                else
+                {
+                    const double k1 = (i - 0.5) / (dx * dx * i), k3 = (i + 0.5) / (dx * dx * i);
+                    W = k1; E = k3; S = k2; Nn = k2; C = -2.0 * k2 - k1 - k3;
+                }
+                const double s = rowscale[i];
+                W *= s; E *= s; S *= s; Nn *= s; C *= s;
+            }
+            else
+            {
+                W = E = S = Nn = 1.0;
+                C = -4.0;
+            }
+            if (i > 0) L.coef[(size_t)cidx(-1, 0) * n + k] = W;
+            if (i < M - 1) L.coef[(size_t)cidx(1, 0) * n + k] = E;
+            if (j > 0) L.coef[(size_t)cidx(0, -1) * n + k] = S;
+            if (j < N - 1) L.coef[(size_t)cidx(0, 1) * n + k] = Nn;
+            L.coef[(size_t)cidx(0, 0) * n + k] = C;
+        }
+    }
+}
+
+void build_coarse_level(const HostLevel& F, HostLevel& Cl)
+{
+    const int Mc = (F.M - 1) / F.fx + 1, Nc = (F.N - 1) / F.fz + 1;
+    const size_t nc = (size_t)Mc * Nc;
+    Cl.M = Mc;
+    Cl.N = Nc;
+    Cl.fx = Cl.fz = 1;
+    Cl.coef.assign(9 * nc, 0.0);
+    Cl.freem.assign(nc, 0);
+    std::vector<double> ec(nc), ef, af, y;
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++)
+        {
+            std::fill(ec.begin(), ec.end(), 0.0);
+            for (int I = a; I < Mc; I += 3)
+                for (int J = b; J < Nc; J += 3) ec[(size_t)I * Nc + J] = 1.0;
+            host_prolong(F, Mc, Nc, ec, ef);
+            host_apply(F, ef, af);
+            host_restrict(F, Mc, Nc, af, y);
+            for (int I = 0; I < Mc; I++)
+                for (int J = 0; J < Nc; J++)
+                    for (int di = -1; di <= 1; di++)
+                        for (int dj = -1; dj <= 1; dj++)
+                        {
+                            const int II = I + di, JJ = J + dj;
+                            if (II < 0 || II >= Mc || JJ < 0 || JJ >= Nc) continue;
+                            if (II % 3 != a || JJ % 3 != b) continue;
+                            Cl.coef[(size_t)cidx(di, dj) * nc + (size_t)I * Nc + J] = y[(size_t)I * Nc + J];
+                        }
+        }
+    for (size_t k = 0; k < nc; k++)
+    {
+        const double d = Cl.coef[(size_t)cidx(0, 0) * nc + k];
+        if (std::fabs(d) > 1e-300) Cl.freem[k] = 1;
+        else
+        {
+            for (int q = 0; q < 9; q++) Cl.coef[(size_t)q * nc + k] = 0.0;
+            Cl.coef[(size_t)cidx(0, 0) * nc + k] = 1.0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- device kernels
+struct LevelDev
+{
+    int M, N;
+    const double* __restrict__ coef;
+    const unsigned char* __restrict__ freem;
+    double* __restrict__ u;
+    const double* __restrict__ b;
+};
+
+// (A u)(i,j) excluding the diagonal term; returns the diagonal through diag
+__device__ __forceinline__ double offdiag_sum(const LevelDev& L, int i, int j, double& diag)
+{
+    const int M = L.M, N = L.N;
+    const size_t n = (size_t)M * N, k = (size_t)i * N + j;
+    double s = 0.0;
+#pragma unroll
+    for (int di = -1; di <= 1; di++)
+#pragma unroll
+        for (int dj = -1; dj <= 1; dj++)
+        {
+            const int q = (di + 1) * 3 + (dj + 1);
+            const double a = __ldg(L.coef + (size_t)q * n + k);
+            if (di == 0 && dj == 0) { diag = a; continue; }
+            const int ii = i + di, jj = j + dj;
+            if (a != 0.0 && ii >= 0 && ii < M && jj >= 0 && jj < N) s += a * L.u[(size_t)ii * N + jj];
+        }
+    return s;
+}
+
+// one colour of the 4-colour Gauss-Seidel sweep: colour = (i&1)*2 + (j&1)
+__global__ void k_mg_smooth(const __grid_constant__ LevelDev L, int colour)
+{
+    const int ci = colour >> 1, cj = colour & 1;
+    const int tj = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ti = blockIdx.y * blockDim.y + threadIdx.y;
+    const int i = 2 * ti + ci, j = 2 * tj + cj;
+    if (i >= L.M || j >= L.N) return;
+    const size_t k = (size_t)i * L.N + j;
+    if (!L.freem[k]) return;
+    double diag;
+    const double s = offdiag_sum(L, i, j, diag);
+    L.u[k] = (L.b[k] - s) / diag;
+}
+
+__device__ __forceinline__ double residual_at(const LevelDev& L, int i, int j)
+{
+    const size_t k = (size_t)i * L.N + j;
+    if (!L.freem[k]) return 0.0;
+    double diag;
+    const double s = offdiag_sum(L, i, j, diag);
+    return L.b[k] - s - diag * L.u[k];
+}
+
+// coarse rhs = P^T (b - A u) of the fine level; coarse error initialised to zero
+__global__ void k_mg_restrict(const __grid_constant__ LevelDev F, int fx, int fz, int Mc, int Nc, double* __restrict__ bc,
+                              double* __restrict__ ec)
+{
+    const int J = blockIdx.x * blockDim.x + threadIdx.x;
+    const int I = blockIdx.y * blockDim.y + threadIdx.y;
+    if (I >= Mc || J >= Nc) return;
+    const int i0 = I * fx, j0 = J * fz;
+    double s = 0.0;
+    const int ri = fx == 2 ? 1 : 0, rj = fz == 2 ? 1 : 0;
+    for (int di = -ri; di <= ri; di++)
+        for (int dj = -rj; dj <= rj; dj++)
+        {
+            const int i = i0 + di, j = j0 + dj;
+            if (i < 0 || i >= F.M || j < 0 || j >= F.N) continue;
+            const double w = (di ? 0.5 : 1.0) * (dj ? 0.5 : 1.0);
+            s += w * residual_at(F, i, j);
+        }
+    bc[(size_t)I * Nc + J] = s;
+    ec[(size_t)I * Nc + J] = 0.0;
+}
+
+// fine u += P ec on free nodes
+__global__ void k_mg_prolong(const __grid_constant__ LevelDev F, int fx, int fz, int Mc, int Nc, const double* __restrict__ ec)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= F.M || j >= F.N) return;
+    const size_t k = (size_t)i * F.N + j;
+    if (!F.freem[k]) return;
+    const int I = i / fx, J = j / fz;
+    const double wi = (fx == 2 && (i & 1)) ? 0.5 : 0.0, wj = (fz == 2 && (j & 1)) ? 0.5 : 0.0;
+    double s = (1.0 - wi) * (1.0 - wj) * ec[(size_t)I * Nc + J];
+    if (wi != 0.0 && I + 1 < Mc) s += wi * (1.0 - wj) * ec[(size_t)(I + 1) * Nc + J];
+    if (wj != 0.0 && J + 1 < Nc) s += (1.0 - wi) * wj * ec[(size_t)I * Nc + J + 1];
+    if (wi != 0.0 && wj != 0.0 && I + 1 < Mc && J + 1 < Nc) s += wi * wj * ec[(size_t)(I + 1) * Nc + J + 1];
+    F.u[k] += s;
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v)
+{
+    // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// max-norm of the residual in the reference's (unscaled) equation and max |b|
+__global__ void k_mg_residual_norm(const __grid_constant__ LevelDev L, const double* __restrict__ rowscale,
+                                   const double* __restrict__ b_ref, double* __restrict__ out2)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    double r = 0.0, bm = 0.0;
+    if (i < L.M && j < L.N)
+    {
+        r = fabs(residual_at(L, i, j)) / rowscale[i];
+        bm = fabs(b_ref[(size_t)i * L.N + j]);
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        r = fmax(r, __shfl_xor_sync(MAG2D_FULL_MASK, r, o));
+        bm = fmax(bm, __shfl_xor_sync(MAG2D_FULL_MASK, bm, o));
+    }
+    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0)
+    {
+        atomic_max_nonneg(out2, r);
+        atomic_max_nonneg(out2 + 1, bm);
+    }
+}
+
+// rho (all species, fixed point) -> right-hand side: Fields::boundary_solve / _rf, fields.cpp:278-346.
+// Writes b in the reference's scaling (b_ref), the row-scaled copy used by the hierarchy (b_mg) and
+// the Dirichlet values into u.
+struct RhsArgs
+{
+    int M, N, coord, rf, n_species;
+    double dx, dz, dV, mpf;
+    const unsigned char* mask;
+    const double* voltage;
+    const unsigned long long* rho;   // [n_species][M*N]
+    const double* charges;           // [n_species]
+    const double* rowscale;
+    double* b_ref;
+    double* b_mg;
+    double* u;
+};
+
+__device__ __forceinline__ double rho_coulomb(const unsigned long long* rho, const double* charges, int ns, size_t n, size_t k)
+{
+    double q = 0.0;
+    for (int s = 0; s < ns; s++)
+    {
+        const double c = charges[s];
+        if (c != 0.0) q += c * ((double)(long long)rho[(size_t)s * n + k] * 2.3283064365386963e-10);
+    }
+    return q;
+}
+
+__global__ void k_rhs(const __grid_constant__ RhsArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= A.M || j >= A.N) return;
+    const size_t n = (size_t)A.M * A.N, k = (size_t)i * A.N + j;
+    const unsigned char m = A.mask[k];
+    double b;
+    if (m == MAG2D_FIXED) b = A.rf ? 0.0 : A.voltage[k];
+    else if (m == MAG2D_FIXED_RF) b = A.rf ? A.voltage[k] : 0.0;
+    else
+    {
+        const double rho = rho_coulomb(A.rho, A.charges, A.n_species, n, k);
+        if (A.coord == MAG2D_CYLINDRICAL)
+        {
+            if (i > 0) b = rho * (-1.0 / MAG2D_EPS0 / (M_PI * A.dx * A.dx * 2.0 * i * A.dz) * A.mpf);
+            else b = rho * (-1.0 / MAG2D_EPS0 / (M_PI * A.dx * A.dx * 0.25 * A.dz) * A.mpf);
+        }
+        else
+            b = rho * (-(A.dx * A.dx) / MAG2D_EPS0 / A.dV);
+    }
+    A.b_ref[k] = b;
+    if (m == MAG2D_FIXED || m == MAG2D_FIXED_RF)
+    {
+        A.b_mg[k] = b;
+        A.u[k] = b;
+    }
+    else
+        A.b_mg[k] = b * A.rowscale[i];
+}
+
+__global__ void k_rho_total(const unsigned long long* __restrict__ rho, const double* __restrict__ charges, int ns, size_t n,
+                            double* __restrict__ out)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = rho_coulomb(rho, charges, ns, n, k);
+}
+
+// Fields::u_smooth, fields.cpp:28-113
+__global__ void k_symmetrize(double* __restrict__ u, int M)
+{
+    // one thread per orbit (i <= ic/2, j <= i) of the 8-fold symmetry group; orbits are disjoint
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int ic = M - 1;
+    if (i > ic / 2 || j > i) return;
+    const int N = M;
+#define U(a, b) u[(size_t)(a) * N + (b)]
+    double sum = 0;
+    sum += U(i, j);
+    sum += U(ic - i, j);
+    sum += U(i, ic - j);
+    sum += U(ic - i, ic - j);
+    sum += U(ic - j, ic - i);
+    sum += U(j, i);
+    sum += U(ic - j, i);
+    sum += U(j, ic - i);
+    sum /= 8.0;
+    U(i, j) = sum;
+    U(ic - i, j) = sum;
+    U(i, ic - j) = sum;
+    U(ic - i, ic - j) = sum;
+    U(ic - j, ic - i) = sum;
+    U(j, i) = sum;
+    U(ic - j, i) = sum;
+    U(j, ic - i) = sum;
+#undef U
+}
+
+__global__ void k_smooth9(const double* __restrict__ t, double* __restrict__ u, int M, int N, double radius2)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    // the reference's inner loop runs to j <= lmax-1 and so reads one element past each row end, i.e.
+    // the first element of the next row (flat storage); reproduced, with 0 past the end of the array
+    if (i >= M - 1 || j > N - 1) return;
+    const double icf = (M - 1) / 2.0, jcf = (N - 1) / 2.0;
+    const double r = (i - icf) * (i - icf) + (j - jcf) * (j - jcf);
+    if (radius2 > 0 && r > radius2) return;
+    const long long n = (long long)M * N;
+    auto T = [&](int a, int b) -> double {
+        const long long k = (long long)a * N + b;
+        return k < n ? t[k] : 0.0;
+    };
+    const double sum = T(i, j) + T(i - 1, j) * 0.5 + T(i + 1, j) * 0.5 + T(i, j - 1) * 0.5 + T(i, j + 1) * 0.5 +
+                       T(i - 1, j - 1) * 0.25 + T(i + 1, j - 1) * 0.25 + T(i - 1, j + 1) * 0.25 + T(i + 1, j + 1) * 0.25;
+    u[(size_t)i * N + j] = sum / 4.0;
+}
+
+LevelDev level_view(const MgLevel& L)
+{
+    LevelDev v;
+    v.M = L.M;
+    v.N = L.N;
+    v.coef = L.coef;
+    v.freem = L.freem;
+    v.u = L.u;
+    v.b = L.b;
+    return v;
+}
+
+inline dim3 grid2d(int nj, int ni, dim3 block) { return dim3((nj + block.x - 1) / block.x, (ni + block.y - 1) / block.y); }
+
+int smooth_level(mag2d_ctx* c, const MgLevel& L, int sweeps)
+{
+    const LevelDev v = level_view(L);
+    const dim3 block(32, 8);
+    const dim3 grid = grid2d((L.N + 1) / 2, (L.M + 1) / 2, block);
+    for (int s = 0; s < sweeps; s++)
+        for (int colour = 0; colour < 4; colour++)
+        {
+            k_mg_smooth<<<grid, block, 0, c->stream>>>(v, colour);
+            c->launches++;
+        }
+    return 0;
+}
+
+int vcycle_level(mag2d_ctx* c, size_t l)
+{
+    const MgLevel& L = c->mg[l];
+    if (l + 1 == c->mg.size())
+    {
+        smooth_level(c, L, 30);
+        return 0;
+    }
+    const MgLevel& Cl = c->mg[l + 1];
+    smooth_level(c, L, 2);
+    const dim3 block(32, 8);
+    k_mg_restrict<<<grid2d(Cl.N, Cl.M, block), block, 0, c->stream>>>(level_view(L), L.fx, L.fz, Cl.M, Cl.N, Cl.b, Cl.u);
+    c->launches++;
+    if (vcycle_level(c, l + 1)) return 1;
+    k_mg_prolong<<<grid2d(L.N, L.M, block), block, 0, c->stream>>>(level_view(L), L.fx, L.fz, Cl.M, Cl.N, Cl.u);
+    c->launches++;
+    smooth_level(c, L, 2);
+    return 0;
+}
+
+}  // namespace
+
+void mg_free(mag2d_ctx* c)
+{
+    for (size_t l = 0; l < c->mg.size(); l++)
+    {
+        MgLevel& L = c->mg[l];
+        if (L.coef) cudaFree(L.coef);
+        if (L.freem) cudaFree(L.freem);
+        if (l > 0 && L.u) cudaFree(L.u);
+        if (L.b) cudaFree(L.b);
+    }
+    c->mg.clear();
+    if (c->d_rowscale) { cudaFree(c->d_rowscale); c->d_rowscale = nullptr; }
+}
+
+int mg_setup(mag2d_ctx* c)
+{
+    mg_free(c);
+    const mag2d_grid_desc& g = c->g;
+    std::vector<HostLevel> H(1);
+    std::vector<double> rowscale;
+    build_fine_level(c, H[0], rowscale);
+    const bool cyl = g.coord == MAG2D_CYLINDRICAL;
+    double hx = cyl ? g.dx : 1.0, hz = cyl ? g.dz : 1.0;
+    const int min_size = 5;
+    while (H.size() < 14)
+    {
+        HostLevel& F = H.back();
+        const double ax = 1.0 / (hx * hx), az = 1.0 / (hz * hz);
+        const bool cx = (F.M - 1) / 2 + 1 >= min_size && ax >= 0.3 * az;
+        const bool cz = (F.N - 1) / 2 + 1 >= min_size && az >= 0.3 * ax;
+        if (!cx && !cz) break;
+        F.fx = cx ? 2 : 1;
+        F.fz = cz ? 2 : 1;
+        HostLevel Cl;
+        build_coarse_level(F, Cl);
+        hx *= F.fx;
+        hz *= F.fz;
+        H.push_back(std::move(Cl));
+    }
+    c->mg.resize(H.size());
+    for (size_t l = 0; l < H.size(); l++)
+    {
+        MgLevel& L = c->mg[l];
+        const HostLevel& h = H[l];
+        const size_t n = (size_t)h.M * h.N;
+        L.M = h.M;
+        L.N = h.N;
+        L.fx = h.fx;
+        L.fz = h.fz;
+        CUDA_OK(cudaMalloc(&L.coef, sizeof(double) * 9 * n));
+        CUDA_OK(cudaMalloc(&L.freem, n));
+        CUDA_OK(cudaMalloc(&L.b, sizeof(double) * n));
+        if (l == 0) L.u = c->d_u;
+        else CUDA_OK(cudaMalloc(&L.u, sizeof(double) * n));
+        CUDA_OK(cudaMemcpyAsync(L.coef, h.coef.data(), sizeof(double) * 9 * n, cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(cudaMemcpyAsync(L.freem, h.freem.data(), n, cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(cudaMemsetAsync(L.b, 0, sizeof(double) * n, c->stream));
+        if (l > 0) CUDA_OK(cudaMemsetAsync(L.u, 0, sizeof(double) * n, c->stream));
+    }
+    CUDA_OK(cudaMalloc(&c->d_rowscale, sizeof(double) * g.M));
+    CUDA_OK(cudaMemcpyAsync(c->d_rowscale, rowscale.data(), sizeof(double) * g.M, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mg_rhs(mag2d_ctx* c, int rf)
+{
+    const mag2d_grid_desc& g = c->g;
+    RhsArgs A;
+    A.M = g.M;
+    A.N = g.N;
+    A.coord = g.coord;
+    A.rf = rf;
+    A.n_species = (int)c->sp.size();
+    A.dx = g.dx;
+    A.dz = g.dz;
+    A.dV = g.dV;
+    A.mpf = g.macroparticle_factor;
+    A.mask = c->d_mask;
+    A.voltage = c->d_voltage;
+    A.rho = c->d_rho;
+    A.charges = c->d_charges;
+    A.rowscale = c->d_rowscale;
+    A.b_ref = c->d_b;
+    A.b_mg = c->mg[0].b;
+    A.u = rf ? c->d_uRF : c->d_u;
+    const dim3 block(32, 8);
+    k_rhs<<<grid2d(g.N, g.M, block), block, 0, c->stream>>>(A);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mg_vcycle(mag2d_ctx* c)
+{
+    if (vcycle_level(c, 0)) return 1;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mg_residual(mag2d_ctx* c, double* resid_max, double* b_max)
+{
+    const MgLevel& L = c->mg[0];
+    CUDA_OK(cudaMemsetAsync(c->d_scratch, 0, 2 * sizeof(double), c->stream));
+    const dim3 block(32, 8);
+    k_mg_residual_norm<<<grid2d(L.N, L.M, block), block, 0, c->stream>>>(level_view(L), c->d_rowscale, c->d_b, c->d_scratch);
+    c->launches++;
+    double h[2];
+    CUDA_OK(cudaMemcpyAsync(h, c->d_scratch, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    *resid_max = h[0];
+    *b_max = h[1];
+    return 0;
+}
+
+// solve Op(u) = b for u (rf = 0) or uRF (rf = 1).  fixed_cycles > 0: run exactly that many V-cycles and
+// do not look at the residual (no host synchronisation); otherwise iterate to tol * max|b|.
+int mg_solve(mag2d_ctx* c, int rf, double tol, int max_cycles, int fixed_cycles, int* cycles, double* resid)
+{
+    if (!c->grid_set || c->mg.empty())
+    {
+        mag2d_set_error("mag2d_solve: mag2d_set_grid has not been called");
+        return 1;
+    }
+    // the hierarchy works on mg[0].u; solving for uRF swaps the pointer for the duration of the call
+    double* saved = c->mg[0].u;
+    if (rf) c->mg[0].u = c->d_uRF;
+    int rc = mg_rhs(c, rf);
+    int done = 0;
+    double r = 0.0, bm = 0.0;
+    if (!rc)
+    {
+        if (fixed_cycles > 0)
+        {
+            for (; done < fixed_cycles && !rc; done++) rc = mg_vcycle(c);
+        }
+        else
+        {
+            while (!rc)
+            {
+                rc = mg_residual(c, &r, &bm);
+                if (rc || r <= tol * bm || done >= max_cycles) break;
+                rc = mg_vcycle(c);
+                done++;
+            }
+        }
+    }
+    c->mg[0].u = saved;
+    if (cycles) *cycles = done;
+    if (resid) *resid = bm > 0 ? r / bm : r;
+    c->last_cycles = done;
+    c->last_resid = bm > 0 ? r / bm : r;
+    return rc;
+}
+
+int launch_rho_total(mag2d_ctx* c, double* d_out)
+{
+    const size_t n = (size_t)c->g.M * c->g.N;
+    k_rho_total<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_rho, c->d_charges, (int)c->sp.size(), n, d_out);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_u_smooth(mag2d_ctx* c, int symmetry, double radius)
+{
+    const int M = c->g.M, N = c->g.N;
+    const dim3 block(32, 8);
+    if (symmetry)
+    {
+        if (M != N)
+        {
+            mag2d_set_error("Fields::u_smooth: smoothing of non-square matrix not implemented\n");
+            return 1;
+        }
+        k_symmetrize<<<grid2d(M / 2 + 1, M / 2 + 1, block), block, 0, c->stream>>>(c->d_u, M);
+        c->launches++;
+    }
+    double r2 = radius;
+    if (radius > 0) r2 = (radius / c->g.dx) * (radius / c->g.dx);
+    // uTmp.assign(u): d_ueff is free scratch whenever the field is not an RF field
+    double* tmp = c->d_ueff;
+    CUDA_OK(cudaMemcpyAsync(tmp, c->d_u, sizeof(double) * (size_t)M * N, cudaMemcpyDeviceToDevice, c->stream));
+    k_smooth9<<<grid2d(N - 1, M - 2, block), block, 0, c->stream>>>(tmp, c->d_u, M, N, r2);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,892 @@
+// push.cu — fused particle kernels: field gather + Boris push + null-collision MCC + boundary /
+// electrode absorption + fixed-point CIC deposit, for Cartesian and cylindrical 2D3V species; the
+// multi-collision free-flight mover; the half-step-back initialisation; loaders and diagnostics.
+//
+// Reference loops replaced (paths relative to the reference checkout):
+//   Species<CARTESIAN>::advance_boris      src/particles.cpp:924-995
+//   Species<CYLINDRICAL>::advance_boris    src/particles.cpp:539-621
+//   Species<CARTESIAN>::advance_multicoll  src/particles.cpp:812-859
+//   Species<D>::advance_boris_init         src/particles.cpp:997-1050 / 623-679
+//   Species<D>::advance_boundary           src/particles.hpp:370-411
+//   Field2D::grad / Fields::E              src/Field2D.hpp:80-168, src/fields.hpp:124-150
+//   Field2D::accumulate                    src/Field2D.hpp:45-62
+// The reference makes two passes over an AoS array per species and step; here one kernel reads and
+// writes each live phase-space component once (80 B per particle-step, 2D3V fp64).
+#include <cstdio>
+#include <cstring>
+
+#include "ctx.hpp"
+#include "mcc.cuh"
+
+namespace {
+
+constexpr int PUSH_THREADS = 256;
+
+struct PushArgs
+{
+    GridDev g;
+    SpeciesDev s;
+    ParticlesDev p;
+    const MccBlob* mcc;
+    unsigned long long* counts;    // collision counters or nullptr
+    unsigned long long* removed;   // removal counter
+    unsigned long long seed;
+};
+
+// ---- gather: E = -grad(ueff), the staggered-difference bilinear form of Field2D::grad ----------
+// Edge cases of the reference (i == 0, i == jmax-1, j == 0, j == lmax-1) are folded into the general
+// formula by clamping the neighbour index and pinning the interpolation weight to 1 or 0, which
+// produces the same sums (the dropped terms are exact zeros).
+__device__ __forceinline__ void gather_E(const GridDev& g, double x, double z, double& Ex, double& Ez)
+{
+    const int M = g.M, N = g.N;
+    const double* __restrict__ u = g.ueff;
+    const double X = x * g.idx, Y = z * g.idz;
+    {
+        int i = (int)(X + 0.5);
+        int j = min((int)Y, N - 2);
+        i = max(min(i, M - 1), 0);
+        j = max(j, 0);
+        double fx = X - i + .5;
+        const double fy = Y - j;
+        int im = i - 1, ip = i + 1;
+        if (i == 0) { im = 0; fx = 1.0; }
+        if (i == M - 1) { ip = M - 1; fx = 0.0; }
+        const double* r0 = u + (size_t)im * N + j;
+        const double* r1 = u + (size_t)i * N + j;
+        const double* r2 = u + (size_t)ip * N + j;
+        const double a0 = __ldg(r0), a1 = __ldg(r0 + 1), b0 = __ldg(r1), b1 = __ldg(r1 + 1), c0 = __ldg(r2), c1 = __ldg(r2 + 1);
+        const double g1 = (b0 - a0) * g.idx;
+        const double g2 = (b1 - a1) * g.idx;
+        const double g3 = (c1 - b1) * g.idx;
+        const double g4 = (c0 - b0) * g.idx;
+        Ex = -(g1 * (1 - fx) * (1 - fy) + g2 * (1 - fx) * fy + g3 * fx * fy + g4 * fx * (1 - fy));
+    }
+    {
+        int i = min((int)X, M - 2);
+        int j = (int)(Y + 0.5);
+        i = max(i, 0);
+        j = max(min(j, N - 1), 0);
+        const double fx = X - i;
+        double fy = Y - j + 0.5;
+        int jm = j - 1, jp = j + 1;
+        if (j == 0) { jm = 0; fy = 1.0; }
+        if (j == N - 1) { jp = N - 1; fy = 0.0; }
+        const double* r0 = u + (size_t)i * N;
+        const double* r1 = r0 + N;
+        const double a0 = __ldg(r0 + jm), a1 = __ldg(r0 + j), a2 = __ldg(r0 + jp);
+        const double b0 = __ldg(r1 + jm), b1 = __ldg(r1 + j), b2 = __ldg(r1 + jp);
+        const double g1 = (a1 - a0) * g.idz;
+        const double g2 = (b1 - b0) * g.idz;
+        const double g3 = (b2 - b1) * g.idz;
+        const double g4 = (a2 - a1) * g.idz;
+        Ez = -(g1 * (1 - fx) * (1 - fy) + g2 * (1 - fy) * fx + g3 * fx * fy + g4 * fy * (1 - fx));
+    }
+}
+
+// ---- Boris rotation + half accelerations (velocity part of the movers) ---------------------------
+template <int COORD, bool HASB>
+__device__ __forceinline__ void boris_velocity(const SpeciesDev& s, double Ex, double Ez, double& vx, double& vy, double& vz)
+{
+    vx += Ex * s.hq;
+    vz += Ez * s.hq;
+    if (HASB)
+    {
+        if (COORD == MAG2D_CYLINDRICAL)
+        {
+            // textbook orientation in (r, theta, z), particles.cpp:581-592
+            const double pr = vx + vy * s.tz - vz * s.ty;
+            const double pt = vy + vz * s.tx - vx * s.tz;
+            const double pz = vz + vx * s.ty - vy * s.tx;
+            vx = vx + pt * s.sz - pz * s.sy;
+            vy = vy + pz * s.sx - pr * s.sz;
+            vz = vz + pr * s.sy - pt * s.sx;
+        }
+        else
+        {
+            // right-handed (x, z, y) triad: opposite signs, particles.cpp:964-979
+            const double pr = vx - vy * s.tz + vz * s.ty;
+            const double pz = vz - vx * s.ty + vy * s.tx;
+            const double pt = vy - vz * s.tx + vx * s.tz;
+            vx = vx - pt * s.sz + pz * s.sy;
+            vy = vy - pz * s.sx + pr * s.sz;
+            vz = vz - pr * s.sy + pt * s.sx;
+        }
+    }
+    vx += Ex * s.hq;
+    vz += Ez * s.hq;
+}
+
+// ---- boundary + electrode absorption + fixed-point CIC deposit ------------------------------------
+// Returns false when the particle is removed.  Positions may be wrapped (PERIODIC).
+template <bool DEPOSIT>
+__device__ __forceinline__ bool boundary_deposit(const GridDev& g, double& x, double& z)
+{
+    if (x < 0.0 || x > g.x_max || z < 0.0 || z > g.z_max)
+    {
+        if (g.boundary == MAG2D_BOUNDARY_FREE) return false;
+        x = fmod(x, g.x_max);
+        if (x < 0) x += g.x_max;
+        z = fmod(z, g.z_max);
+        if (z < 0) z += g.z_max;
+    }
+    // products rounded separately (no FMA): the CPU restatement must reproduce the weights bit for bit
+    const double X = __dmul_rn(x, g.idx), Y = __dmul_rn(z, g.idz);
+    int i = (int)X, j = (int)Y;
+    // the reference indexes one node past the grid for x == x_max exactly (fields.hpp:96-100); clamp
+    i = max(min(i, g.M - 2), 0);
+    j = max(min(j, g.N - 2), 0);
+    const size_t k = (size_t)i * g.N + j;
+    if (g.check_mask)
+    {
+        const unsigned char* m = g.mask + k;
+        const bool is_free = (m[0] == MAG2D_FREE) | (m[g.N] == MAG2D_FREE) | (m[1] == MAG2D_FREE) | (m[g.N + 1] == MAG2D_FREE);
+        if (!is_free) return false;
+    }
+    if (DEPOSIT)
+    {
+        const double fu = __dsub_rn(X, (double)i), fv = __dsub_rn(Y, (double)j);
+        const double cu = __dsub_rn(1.0, fu), cv = __dsub_rn(1.0, fv);
+        const unsigned long long w00 = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(cu, cv), 4294967296.0));
+        const unsigned long long w10 = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(fu, cv), 4294967296.0));
+        const unsigned long long w01 = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(cu, fv), 4294967296.0));
+        const unsigned long long w11 = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(fu, fv), 4294967296.0));
+        unsigned long long* r = g.rho + k;
+        atomicAdd(r, w00);
+        atomicAdd(r + g.N, w10);
+        atomicAdd(r + 1, w01);
+        atomicAdd(r + g.N + 1, w11);
+    }
+    return true;
+}
+
+__device__ __forceinline__ void count_removed(unsigned long long* counter, bool removed_now)
+{
+    const unsigned m = __ballot_sync(MAG2D_FULL_MASK, removed_now);
+    if (m && lane_id() == 0) atomicAdd(counter, (unsigned long long)__popc(m));
+}
+
+// ---- the fused Boris step --------------------------------------------------------------------------
+template <int COORD, bool GATHER, bool HASB, bool MCC, bool DEPOSIT>
+__global__ void __launch_bounds__(PUSH_THREADS) k_push_boris(const __grid_constant__ PushArgs A)
+{
+    const long long k = (long long)blockIdx.x * PUSH_THREADS + threadIdx.x;
+    const bool in_range = k < A.p.n;
+    double x = in_range ? A.p.x[k] : dead_marker();
+    const bool live = particle_alive(x);
+    bool removed_now = false;
+    if (live)
+    {
+        double z = A.p.z[k];
+        double vx = A.p.vx[k];
+        double vz = A.p.vz[k];
+        double vy = 0.0;
+        // vy only takes part in the rotation and in collisions; cylindrical always needs it (drift)
+        const bool need_vy = HASB || COORD == MAG2D_CYLINDRICAL;
+        if (need_vy) vy = A.p.vy[k];
+        double Ex = 0.0, Ez = A.g.extern_field;
+        if (GATHER) gather_E(A.g, x, z, Ex, Ez);
+        boris_velocity<COORD, HASB>(A.s, Ex, Ez, vx, vy, vz);
+        const double dt = A.s.dt;
+        if (COORD == MAG2D_CYLINDRICAL)
+        {
+            // Birdsall & Langdon p.338: drift in the local Cartesian frame, rotate back (particles.cpp:599-614)
+            const double x2 = x + vx * dt;
+            const double y2 = vy * dt;
+            x = sqrt(x2 * x2 + y2 * y2);
+            z += vz * dt;
+            double sa = y2 / x, ca = x2 / x;
+            if (x == 0) { sa = 0; ca = 1; }
+            const double t = vx;
+            vx = ca * vx + sa * vy;
+            vy = -sa * t + ca * vy;
+        }
+        else
+        {
+            x += vx * dt;
+            z += vz * dt;
+        }
+        bool vy_dirty = need_vy;
+        if (MCC)
+        {
+            Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)k);
+            const uint4 r0 = rng.block();
+            if (u01(r0.x) < A.s.prob)
+            {
+                if (!need_vy) vy = A.p.vy[k];
+                int target;
+                const int proc = mcc_scatter(A.mcc, rng, vx, vy, vz, target);
+                mcc_count(A.counts, A.mcc->n_targets, target, proc);
+                vy_dirty = true;
+            }
+        }
+        const bool keep = boundary_deposit<DEPOSIT>(A.g, x, z);
+        if (keep)
+        {
+            A.p.x[k] = x;
+            A.p.z[k] = z;
+            A.p.vx[k] = vx;
+            A.p.vz[k] = vz;
+            if (vy_dirty) A.p.vy[k] = vy;
+        }
+        else
+        {
+            A.p.x[k] = dead_marker();
+            removed_now = true;
+        }
+    }
+    count_removed(A.removed, removed_now);
+}
+
+// ---- half step back: Species<D>::advance_boris_init ----------------------------------------------
+template <int COORD, bool GATHER>
+__global__ void __launch_bounds__(PUSH_THREADS) k_push_boris_init(const __grid_constant__ PushArgs A)
+{
+    const long long k = (long long)blockIdx.x * PUSH_THREADS + threadIdx.x;
+    if (k >= A.p.n) return;
+    const double x = A.p.x[k];
+    if (!particle_alive(x)) return;
+    const double z = A.p.z[k];
+    double vx = A.p.vx[k], vy = A.p.vy[k], vz = A.p.vz[k];
+    double Ex = 0.0, Ez = A.g.extern_field;
+    if (GATHER) gather_E(A.g, x, z, Ex, Ez);
+    // A.s holds the init constants: t = B*(-0.5*q*dt/(2m)), hq = (-q/m*dt)/2  (particles.cpp:1010,1028)
+    const SpeciesDev& s = A.s;
+    if (COORD == MAG2D_CYLINDRICAL)
+    {
+        const double pr = vx + vy * s.tz - vz * s.ty;
+        const double pt = vy + vz * s.tx - vx * s.tz;
+        const double pz = vz + vx * s.ty - vy * s.tx;
+        vx = vx + pt * s.sz - pz * s.sy;
+        vy = vy + pz * s.sx - pr * s.sz;
+        vz = vz + pr * s.sy - pt * s.sx;
+    }
+    else
+    {
+        const double pr = vx - vy * s.tz + vz * s.ty;
+        const double pz = vz - vx * s.ty + vy * s.tx;
+        const double pt = vy - vz * s.tx + vx * s.tz;
+        vx = vx - pt * s.sz + pz * s.sy;
+        vy = vy - pz * s.sx + pr * s.sz;
+        vz = vz - pr * s.sy + pt * s.sx;
+    }
+    vx += Ex * s.hq;
+    vz += Ez * s.hq;
+    A.p.vx[k] = vx;
+    A.p.vy[k] = vy;
+    A.p.vz[k] = vz;
+}
+
+// ---- multi-collision free-flight mover: Species<CARTESIAN>::advance_multicoll ---------------------
+// Constant field (0, extern_field); each particle flies to its next null-collision time, scatters,
+// draws a new time_to_death = lifetime*rexp(), until the step is used up (~dt/lifetime events/step).
+// The collision model (a few KB) is staged in shared memory: every event does 2-3 table look-ups.
+__global__ void __launch_bounds__(PUSH_THREADS) k_push_multicoll(const __grid_constant__ PushArgs A, int blob_bytes)
+{
+    extern __shared__ __align__(16) unsigned char smem_blob[];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(A.mcc);
+        uint4* dst = reinterpret_cast<uint4*>(smem_blob);
+        for (int q = threadIdx.x; q < blob_bytes / 16; q += PUSH_THREADS) dst[q] = src[q];
+    }
+    __syncthreads();
+    const MccBlob* B = reinterpret_cast<const MccBlob*>(smem_blob);
+    const long long k = (long long)blockIdx.x * PUSH_THREADS + threadIdx.x;
+    const bool in_range = k < A.p.n;
+    double x = in_range ? A.p.x[k] : dead_marker();
+    bool removed_now = false;
+    if (particle_alive(x))
+    {
+        double z = A.p.z[k], vx = A.p.vx[k], vy = A.p.vy[k], vz = A.p.vz[k], ttd = A.p.ttd[k];
+        const double ax = 0.0 * A.s.qm, az = A.g.extern_field * A.s.qm;
+        const double dt = A.s.dt;
+        Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)k);
+        double local_time = 0.0;
+        while (local_time + ttd < dt)
+        {
+            vx += ax * ttd;
+            vz += az * ttd;
+            // the reference advances the position with the already-updated velocity (particles.cpp:841-844)
+            x += (vx + 0.5 * ax * ttd) * ttd;
+            z += (vz + 0.5 * az * ttd) * ttd;
+            local_time += ttd;
+            int target;
+            const int proc = mcc_scatter(B, rng, vx, vy, vz, target);
+            mcc_count(A.counts, B->n_targets, target, proc);
+            const uint4 r = rng.block();
+            ttd = A.s.lifetime * rexp1(r.x);
+        }
+        const double rest = dt - local_time;
+        vx += ax * rest;
+        vz += az * rest;
+        x += (vx + 0.5 * ax * rest) * rest;
+        z += (vz + 0.5 * az * rest) * rest;
+        ttd -= rest;
+        const bool keep = boundary_deposit<false>(A.g, x, z);
+        if (keep)
+        {
+            A.p.x[k] = x;
+            A.p.z[k] = z;
+            A.p.vx[k] = vx;
+            A.p.vy[k] = vy;
+            A.p.vz[k] = vz;
+            A.p.ttd[k] = ttd;
+        }
+        else
+        {
+            A.p.x[k] = dead_marker();
+            removed_now = true;
+        }
+    }
+    count_removed(A.removed, removed_now);
+}
+
+// ---- Species<D>::accumulate: deposit the current positions ----------------------------------------
+__global__ void __launch_bounds__(PUSH_THREADS) k_accumulate(const __grid_constant__ PushArgs A)
+{
+    const long long k = (long long)blockIdx.x * PUSH_THREADS + threadIdx.x;
+    if (k >= A.p.n) return;
+    double x = A.p.x[k];
+    if (!particle_alive(x)) return;
+    double z = A.p.z[k];
+    GridDev g = A.g;
+    g.check_mask = 0;
+    g.boundary = MAG2D_BOUNDARY_PERIODIC;   // never drop here: accumulate() deposits every live particle
+    boundary_deposit<true>(g, x, z);
+}
+
+__global__ void k_ueff(const double* __restrict__ u, const double* __restrict__ urf, double phase, double* __restrict__ out, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = u[k] + urf[k] * phase;
+}
+
+// Fields::E at arbitrary points (diagnostics, parity tests)
+__global__ void k_field_E(const __grid_constant__ GridDev g, int n, const double* __restrict__ x, const double* __restrict__ z,
+                          double* __restrict__ Ex, double* __restrict__ Ez)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double ex = 0.0, ez = g.extern_field;
+    if (!g.const_E) gather_E(g, x[k], z[k], ex, ez);
+    Ex[k] = ex;
+    Ez[k] = ez;
+}
+
+// ---- device-side loaders (Philox), src/particles.cpp:685-749, 485-510 -----------------------------
+struct GenArgs
+{
+    ParticlesDev p;
+    long long first, n;
+    int kind;
+    double a, b, c, d;
+    double x_max, z_max;
+    double vth;        // v_max / sqrt(2)
+    double lifetime;
+    double vmono;      // veV(energy)
+    unsigned long long seed;
+    int species;
+    int has_ttd;
+};
+
+__global__ void __launch_bounds__(PUSH_THREADS) k_generate(const __grid_constant__ GenArgs G)
+{
+    const long long q = (long long)blockIdx.x * PUSH_THREADS + threadIdx.x;
+    if (q >= G.n) return;
+    const long long k = G.first + q;
+    Rng rng = make_rng(G.seed ^ 0xA5A5A5A55A5A5A5AULL, G.species, 0xFFFFFFFF00000000ULL + (unsigned long long)G.kind, (unsigned long long)k);
+    double x, z, vx, vy, vz;
+    if (G.kind == 0)
+    {
+        const uint4 r = rng.block();
+        x = G.x_max * u01(r.x);
+        z = G.z_max * u01(r.z);
+    }
+    else
+    {
+        // rejection sampling of the unit disk, as add_particles_on_disk does
+        double px, pz;
+        do
+        {
+            const uint4 r = rng.block();
+            px = u01(r.x) - 0.5;
+            pz = u01(r.y) - 0.5;
+        } while (px * px + pz * pz > 0.25);
+        if (G.kind == 1)
+        {
+            x = px * 2 * G.c + G.a;
+            z = pz * 2 * G.c + G.b;
+        }
+        else
+        {
+            const uint4 r = rng.block();
+            x = sqrt(px * px + pz * pz) * G.c * 2;
+            z = G.b + G.d * (u01(r.x) - 0.5);
+        }
+    }
+    if (G.kind == 2)
+    {
+        const uint4 r = rng.block();
+        rot_iso(G.vmono, r.x, r.y, vx, vz, vy);
+    }
+    else
+    {
+        const uint4 r = rng.block();
+        float n0, n1, n2, n3;
+        normal2(r.x, r.y, n0, n1);
+        normal2(r.z, r.w, n2, n3);
+        vx = (double)n0 * G.vth;
+        vy = (double)n1 * G.vth;
+        vz = (double)n2 * G.vth;
+    }
+    const bool inside = x >= 0.0 && x <= G.x_max && z >= 0.0 && z <= G.z_max;
+    G.p.x[k] = inside ? x : dead_marker();
+    G.p.z[k] = z;
+    G.p.vx[k] = vx;
+    G.p.vy[k] = vy;
+    G.p.vz[k] = vz;
+    if (G.has_ttd)
+    {
+        const uint4 r = rng.block();
+        G.p.ttd[k] = G.kind == 0 ? G.lifetime * rexp1(r.x) : 0.0;   // on_disk leaves time_to_death = 0
+    }
+}
+
+// ---- energy histogram: BaseSpecies::energy_dist_compute + Histogram::add (strict bounds) ----------
+__global__ void __launch_bounds__(PUSH_THREADS) k_energy_hist(ParticlesDev p, double half_m_over_qe, int nbins, double emax,
+                                                               unsigned long long* __restrict__ hist, double* __restrict__ sums)
+{
+    extern __shared__ unsigned long long sh[];
+    for (int q = threadIdx.x; q < nbins; q += PUSH_THREADS) sh[q] = 0;
+    __syncthreads();
+    double s_in = 0, s_tot = 0;
+    unsigned long long n_in = 0, n_tot = 0;
+    for (long long k = (long long)blockIdx.x * PUSH_THREADS + threadIdx.x; k < p.n; k += (long long)gridDim.x * PUSH_THREADS)
+    {
+        if (!particle_alive(p.x[k])) continue;
+        const double vx = p.vx[k], vy = p.vy[k], vz = p.vz[k];
+        const double f = (vx * vx + vz * vz + vy * vy) * half_m_over_qe;
+        if (f < emax && f > 0.0)
+        {
+            int j = (int)(f * nbins / emax);
+            j = min(j, nbins - 1);
+            atomicAdd(&sh[j], 1ULL);
+            n_in++;
+            s_in += f;
+        }
+        n_tot++;
+        s_tot += f;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < nbins; q += PUSH_THREADS)
+        if (sh[q]) atomicAdd(&hist[q], sh[q]);
+    // block reduction of the four scalars
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        s_in += __shfl_down_sync(MAG2D_FULL_MASK, s_in, o);
+        s_tot += __shfl_down_sync(MAG2D_FULL_MASK, s_tot, o);
+        n_in += __shfl_down_sync(MAG2D_FULL_MASK, n_in, o);
+        n_tot += __shfl_down_sync(MAG2D_FULL_MASK, n_tot, o);
+    }
+    if (lane_id() == 0)
+    {
+        atomicAdd(&sums[0], (double)n_in);
+        atomicAdd(&sums[1], s_in);
+        atomicAdd(&sums[2], (double)n_tot);
+        atomicAdd(&sums[3], s_tot);
+    }
+}
+
+// ---- AoS (reference t_particle, 64 B) <-> SoA converters ------------------------------------------
+__global__ void k_aos_to_soa(const mag2d_particle* __restrict__ aos, long long n_in, ParticlesDev p, long long first,
+                             int has_y, int has_ttd)
+{
+    // record q lands in slot first+q, so device order == input order; empty records become dead slots
+    // (k_mark_dead) that the next sort compacts away
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_in || aos[q].empty) return;
+    const long long dst = first + q;
+    p.x[dst] = aos[q].x;
+    p.z[dst] = aos[q].z;
+    p.vx[dst] = aos[q].vx;
+    p.vy[dst] = aos[q].vy;
+    p.vz[dst] = aos[q].vz;
+    if (has_y) p.y[dst] = aos[q].y;
+    if (has_ttd) p.ttd[dst] = aos[q].time_to_death;
+}
+
+__global__ void k_mark_dead(ParticlesDev p, const mag2d_particle* __restrict__ aos, long long n_in, long long first)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n_in && aos[q].empty) p.x[first + q] = dead_marker();
+}
+
+__global__ void k_soa_to_aos(ParticlesDev p, mag2d_particle* __restrict__ aos, int has_y, int has_ttd)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= p.n) return;
+    mag2d_particle o;
+    memset(&o, 0, sizeof(o));
+    const double x = p.x[q];
+    o.empty = particle_alive(x) ? 0 : 1;
+    o.x = x;
+    o.z = p.z[q];
+    o.vx = p.vx[q];
+    o.vy = p.vy[q];
+    o.vz = p.vz[q];
+    o.y = has_y ? p.y[q] : 0.0;
+    o.time_to_death = has_ttd ? p.ttd[q] : 0.0;
+    aos[q] = o;
+}
+
+// ---- host helpers ---------------------------------------------------------------------------------
+ParticlesDev particles_view(const SpeciesStore& S)
+{
+    ParticlesDev p;
+    double* const* a = S.arr[S.cur];
+    p.x = a[ARR_X];
+    p.z = a[ARR_Z];
+    p.vx = a[ARR_VX];
+    p.vy = a[ARR_VY];
+    p.vz = a[ARR_VZ];
+    p.y = a[ARR_Y];
+    p.ttd = a[ARR_TTD];
+    p.n = S.n_slots;
+    return p;
+}
+
+GridDev grid_view(const mag2d_ctx* c, int s)
+{
+    GridDev g;
+    memset(&g, 0, sizeof(g));
+    const mag2d_grid_desc& d = c->g;
+    g.coord = d.coord;
+    g.boundary = d.boundary;
+    g.M = d.M;
+    g.N = d.N;
+    g.x_max = d.x_max;
+    g.z_max = d.z_max;
+    g.idx = d.idx;
+    g.idz = d.idz;
+    g.const_E = d.geometry_empty && !d.selfconsistent;
+    g.check_mask = !d.electric_field_from_file;
+    g.deposit = d.selfconsistent;
+    g.extern_field = d.extern_field;
+    g.ueff = d.rf ? c->d_ueff : c->d_u;
+    g.mask = c->d_mask;
+    g.rho = s >= 0 ? c->d_rho + (size_t)s * d.M * d.N : nullptr;
+    return g;
+}
+
+// mymath.cpp:71-76
+double mod_ref(double x, double y)
+{
+    if (x >= 0.0 && x <= y) return x;
+    return x - y * (int)(x / y) + (x < 0 ? y : 0);
+}
+
+// SpeciesDev constants with the reference's expression order (particles.cpp:936-975 / 1010-1040)
+SpeciesDev species_view(const mag2d_ctx* c, int s, bool init)
+{
+    const SpeciesStore& S = c->sp[s];
+    const mag2d_grid_desc& d = c->g;
+    SpeciesDev v;
+    memset(&v, 0, sizeof(v));
+    const double charge = S.desc.charge, mass = S.desc.mass, dt = S.desc.dt;
+    v.dt = dt;
+    const double qmdt = init ? -charge / mass * dt : charge / mass * dt;
+    v.hq = qmdt / 2.0;
+    double tmp = init ? -0.5 * charge * dt / (2.0 * mass) : charge * dt / (2.0 * mass);
+    const double Bx = d.Br, By = d.Bt, Bz = d.Bz;
+    v.tx = Bx * tmp;
+    v.ty = By * tmp;
+    v.tz = Bz * tmp;
+    tmp = 2.0 / (1 + v.tx * v.tx + v.ty * v.ty + v.tz * v.tz);
+    v.sx = v.tx * tmp;
+    v.sy = v.ty * tmp;
+    v.sz = v.tz * tmp;
+    v.has_B = (Bx != 0.0 || By != 0.0 || Bz != 0.0);
+    v.species = s;
+    v.prob = 1.0 - exp(-dt / S.lifetime);
+    v.lifetime = S.lifetime;
+    v.qm = charge / mass;
+    v.step = S.niter;
+    return v;
+}
+
+template <int COORD>
+int launch_boris_variant(mag2d_ctx* c, const PushArgs& A, bool gather, bool hasb, bool mcc, bool deposit, unsigned blocks)
+{
+#define LAUNCH(G, B, Mc, D) k_push_boris<COORD, G, B, Mc, D><<<blocks, PUSH_THREADS, 0, c->stream>>>(A)
+    const int code = (gather ? 8 : 0) | (hasb ? 4 : 0) | (mcc ? 2 : 0) | (deposit ? 1 : 0);
+    switch (code)
+    {
+        case 0: LAUNCH(false, false, false, false); break;
+        case 1: LAUNCH(false, false, false, true); break;
+        case 2: LAUNCH(false, false, true, false); break;
+        case 3: LAUNCH(false, false, true, true); break;
+        case 4: LAUNCH(false, true, false, false); break;
+        case 5: LAUNCH(false, true, false, true); break;
+        case 6: LAUNCH(false, true, true, false); break;
+        case 7: LAUNCH(false, true, true, true); break;
+        case 8: LAUNCH(true, false, false, false); break;
+        case 9: LAUNCH(true, false, false, true); break;
+        case 10: LAUNCH(true, false, true, false); break;
+        case 11: LAUNCH(true, false, true, true); break;
+        case 12: LAUNCH(true, true, false, false); break;
+        case 13: LAUNCH(true, true, false, true); break;
+        case 14: LAUNCH(true, true, true, false); break;
+        default: LAUNCH(true, true, true, true); break;
+    }
+#undef LAUNCH
+    c->launches++;
+    return 0;
+}
+
+}  // namespace
+
+int update_ueff(mag2d_ctx* c, double phase, bool rf)
+{
+    if (!rf) return 0;
+    const int n = c->g.M * c->g.N;
+    k_ueff<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_u, c->d_uRF, phase, c->d_ueff, n);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static double rf_phase(const mag2d_ctx* c, const SpeciesStore& S)
+{
+    // Fields::E: phase = rf_amplitude*cos(mod(rf_omega*time, 1e7*pi)) + rf_U0, time = niter*dt (fields.hpp:140-142)
+    const double time = S.niter * S.desc.dt;
+    double phase = mod_ref(c->g.rf_omega * time, 10000000 * M_PI);
+    return c->g.rf_amplitude * cos(phase) + c->g.rf_U0;
+}
+
+int launch_species_advance(mag2d_ctx* c, int s)
+{
+    SpeciesStore& S = c->sp[s];
+    const mag2d_grid_desc& d = c->g;
+    if (S.n_slots > 0)
+    {
+        if (!d.magnetic_field_const)
+        {
+            mag2d_set_error("magnetic field from file is not implemented (magnetic_field_const = 0)");
+            return 1;
+        }
+        PushArgs A;
+        A.g = grid_view(c, s);
+        A.s = species_view(c, s, false);
+        A.p = particles_view(S);
+        A.mcc = S.d_blob;
+        A.counts = c->count_collisions ? S.d_counts : nullptr;
+        A.removed = S.d_removed;
+        A.seed = c->seed;
+        const unsigned blocks = (unsigned)((S.n_slots + PUSH_THREADS - 1) / PUSH_THREADS);
+        const bool mcc = S.h_blob && S.h_blob->has_collisions && std::isfinite(S.lifetime);
+        if (d.mover == MAG2D_ADVANCE_MULTICOLL)
+        {
+            if (d.coord != MAG2D_CARTESIAN)
+            {
+                mag2d_set_error("Species<CYLINDRICAL>: advance method not implemented\n");
+                return 1;
+            }
+            if (d.Br != 0. || d.Bz != 0. || d.Bt != 0.)
+            {
+                mag2d_set_error("Species<CARTESIAN>::advance_multicoll() implemented for zero B only\n");
+                return 1;
+            }
+            if (d.selfconsistent || !d.geometry_empty)
+            {
+                mag2d_set_error("Species<CARTESIAN>::advance_multicoll() implemented for const extern field only:\n\tset selfconsistent=0 and geometry=EMPTY\n");
+                return 1;
+            }
+            const int blob_bytes = (int)((offsetof(MccBlob, tab) + sizeof(double) * 2 * (size_t)S.h_blob->n_tab + 15) / 16 * 16);
+            static bool attr_set = false;
+            if (!attr_set)
+            {
+                CUDA_OK(cudaFuncSetAttribute(k_push_multicoll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MccBlob)));
+                attr_set = true;
+            }
+            k_push_multicoll<<<blocks, PUSH_THREADS, blob_bytes, c->stream>>>(A, blob_bytes);
+            c->launches++;
+        }
+        else
+        {
+            const bool gather = !A.g.const_E;
+            if (gather && d.rf)
+                if (update_ueff(c, rf_phase(c, S), true)) return 1;
+            if (d.coord == MAG2D_CYLINDRICAL)
+                launch_boris_variant<MAG2D_CYLINDRICAL>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, blocks);
+            else
+                launch_boris_variant<MAG2D_CARTESIAN>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, blocks);
+        }
+        CUDA_OK(cudaGetLastError());
+    }
+    // Species<D>::advance: niter++, t += dt; advance_multicoll advances the clock a second time
+    // (particles.cpp:857-858) — kept so that <name>.dat columns match the reference
+    S.niter++;
+    S.t += S.desc.dt;
+    if (d.mover == MAG2D_ADVANCE_MULTICOLL)
+    {
+        S.niter++;
+        S.t += S.desc.dt;
+    }
+    S.steps_since_sort++;
+    return 0;
+}
+
+int launch_species_advance_init(mag2d_ctx* c, int s)
+{
+    SpeciesStore& S = c->sp[s];
+    const mag2d_grid_desc& d = c->g;
+    if (S.n_slots == 0 || d.mover == MAG2D_ADVANCE_MULTICOLL) return 0;   // particles.cpp:805-806
+    PushArgs A;
+    A.g = grid_view(c, s);
+    A.s = species_view(c, s, true);
+    A.p = particles_view(S);
+    A.mcc = nullptr;
+    A.counts = nullptr;
+    A.removed = S.d_removed;
+    A.seed = c->seed;
+    const unsigned blocks = (unsigned)((S.n_slots + PUSH_THREADS - 1) / PUSH_THREADS);
+    const bool gather = !A.g.const_E;
+    if (gather && d.rf)
+        if (update_ueff(c, rf_phase(c, S), true)) return 1;
+    if (d.coord == MAG2D_CYLINDRICAL)
+    {
+        if (gather) k_push_boris_init<MAG2D_CYLINDRICAL, true><<<blocks, PUSH_THREADS, 0, c->stream>>>(A);
+        else k_push_boris_init<MAG2D_CYLINDRICAL, false><<<blocks, PUSH_THREADS, 0, c->stream>>>(A);
+    }
+    else
+    {
+        if (gather) k_push_boris_init<MAG2D_CARTESIAN, true><<<blocks, PUSH_THREADS, 0, c->stream>>>(A);
+        else k_push_boris_init<MAG2D_CARTESIAN, false><<<blocks, PUSH_THREADS, 0, c->stream>>>(A);
+    }
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_species_accumulate(mag2d_ctx* c, int s)
+{
+    SpeciesStore& S = c->sp[s];
+    if (S.n_slots == 0) return 0;
+    PushArgs A;
+    memset(&A, 0, sizeof(A));
+    A.g = grid_view(c, s);
+    A.p = particles_view(S);
+    const unsigned blocks = (unsigned)((S.n_slots + PUSH_THREADS - 1) / PUSH_THREADS);
+    k_accumulate<<<blocks, PUSH_THREADS, 0, c->stream>>>(A);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_field_E(mag2d_ctx* c, int n, const double* x, const double* z, double time, double* Ex, double* Ez)
+{
+    double *dx, *dz, *dex, *dez;
+    CUDA_OK(cudaMalloc(&dx, sizeof(double) * 4 * (size_t)n));
+    dz = dx + n;
+    dex = dz + n;
+    dez = dex + n;
+    CUDA_OK(cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(dz, z, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    GridDev g = grid_view(c, -1);
+    if (!g.const_E && c->g.rf)
+    {
+        double phase = mod_ref(c->g.rf_omega * time, 10000000 * M_PI);
+        phase = c->g.rf_amplitude * cos(phase) + c->g.rf_U0;
+        if (update_ueff(c, phase, true)) return 1;
+    }
+    k_field_E<<<(n + 255) / 256, 256, 0, c->stream>>>(g, n, dx, dz, dex, dez);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(Ex, dex, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(Ez, dez, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaFree(dx));
+    return 0;
+}
+
+int launch_generate(mag2d_ctx* c, int s, int kind, long long n, double a, double b, double cc, double d)
+{
+    SpeciesStore& S = c->sp[s];
+    if (n <= 0) return 0;
+    GenArgs G;
+    memset(&G, 0, sizeof(G));
+    G.p = particles_view(S);
+    G.first = S.n_slots;
+    G.n = n;
+    G.kind = kind;
+    G.a = a;
+    G.b = b;
+    G.c = cc;
+    G.d = d;
+    G.x_max = c->g.x_max;
+    G.z_max = c->g.z_max;
+    G.vth = S.v_max / M_SQRT2;
+    G.lifetime = std::isfinite(S.lifetime) ? S.lifetime : 0.0;
+    G.vmono = sqrt(a * MAG2D_QE / S.desc.mass * 2.0);
+    G.seed = c->seed;
+    G.species = s;
+    G.has_ttd = S.arr[S.cur][ARR_TTD] != nullptr;
+    const unsigned blocks = (unsigned)((n + PUSH_THREADS - 1) / PUSH_THREADS);
+    k_generate<<<blocks, PUSH_THREADS, 0, c->stream>>>(G);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    S.n_slots += n;
+    return 0;
+}
+
+int launch_energy_hist(mag2d_ctx* c, int s, int nbins, double emax, double* hist, double* stats)
+{
+    SpeciesStore& S = c->sp[s];
+    unsigned long long* dh;
+    double* ds;
+    CUDA_OK(cudaMalloc(&dh, sizeof(unsigned long long) * nbins + sizeof(double) * 4));
+    ds = reinterpret_cast<double*>(dh + nbins);
+    CUDA_OK(cudaMemsetAsync(dh, 0, sizeof(unsigned long long) * nbins + sizeof(double) * 4, c->stream));
+    if (S.n_slots > 0)
+    {
+        const unsigned blocks = (unsigned)std::min<long long>((S.n_slots + PUSH_THREADS - 1) / PUSH_THREADS, 148 * 8);
+        k_energy_hist<<<blocks, PUSH_THREADS, sizeof(unsigned long long) * nbins, c->stream>>>(
+            particles_view(S), S.desc.mass * 0.5 / MAG2D_QE, nbins, emax, dh, ds);
+        c->launches++;
+        CUDA_OK(cudaGetLastError());
+    }
+    std::vector<unsigned long long> hh(nbins);
+    CUDA_OK(cudaMemcpyAsync(hh.data(), dh, sizeof(unsigned long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(stats, ds, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    for (int q = 0; q < nbins; q++) hist[q] = (double)hh[q];
+    CUDA_OK(cudaFree(dh));
+    return 0;
+}
+
+int launch_aos_to_soa(mag2d_ctx* c, int s, const mag2d_particle* d_aos, long long n_in, long long* n_added)
+{
+    SpeciesStore& S = c->sp[s];
+    ParticlesDev p = particles_view(S);
+    const unsigned blocks = (unsigned)((n_in + 255) / 256);
+    const int has_y = S.arr[S.cur][ARR_Y] != nullptr, has_ttd = S.arr[S.cur][ARR_TTD] != nullptr;
+    k_aos_to_soa<<<blocks, 256, 0, c->stream>>>(d_aos, n_in, p, S.n_slots, has_y, has_ttd);
+    k_mark_dead<<<blocks, 256, 0, c->stream>>>(p, d_aos, n_in, S.n_slots);
+    c->launches += 2;
+    CUDA_OK(cudaGetLastError());
+    *n_added = n_in;
+    S.n_slots += n_in;
+    return 0;
+}
+
+int launch_soa_to_aos(mag2d_ctx* c, int s, mag2d_particle* d_aos)
+{
+    SpeciesStore& S = c->sp[s];
+    if (S.n_slots == 0) return 0;
+    const unsigned blocks = (unsigned)((S.n_slots + 255) / 256);
+    const int has_y = S.arr[S.cur][ARR_Y] != nullptr, has_ttd = S.arr[S.cur][ARR_TTD] != nullptr;
+    k_soa_to_aos<<<blocks, 256, 0, c->stream>>>(particles_view(S), d_aos, has_y, has_ttd);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}

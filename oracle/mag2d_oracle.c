@@ -865,6 +865,12 @@ static inline void cic_weights(const orc_grid* g, double x, double z, int* i, in
 {
     *i = (int)(x * g->idx);
     *j = (int)(z * g->idz);
+    /* x == x_max exactly: the reference indexes one node past the grid (Field2D.hpp:55-60 lets
+     * i == jmax-1 through); the build clamps the cell so that the weight goes to the last node */
+    if (*i > g->M - 2) *i = g->M - 2;
+    if (*j > g->N - 2) *j = g->N - 2;
+    if (*i < 0) *i = 0;
+    if (*j < 0) *j = 0;
     double u = x * g->idx - *i;
     double v = z * g->idz - *j;
     w[0] = (1 - u) * (1 - v); /* [i][j]     */

@@ -1,0 +1,334 @@
+"""GPU parity tests: the CUDA path (through the C ABI, mag2d_b200.api.Sim) against the CPU oracle
+(oracle/mag2d_oracle.c), against the committed golden fixtures recorded from the unmodified reference,
+and — when oracle/_ref travelled to this box — against the reference itself.
+
+Tolerances (BASELINE.json north_star / SURVEY.md §8c):
+  trajectories, collisions off, fp64:  <= 1e-12 relative after 1 step, <= 1e-10 after 100 steps
+  deposited grid:                      bit-exact against the fixed-point restatement
+  Poisson solve:                       ||u - u_direct||_inf / ||u_direct||_inf <= 1e-8
+"""
+import os
+
+import numpy as np
+import pytest
+
+from common import Particles, disk_particles, grid_from_param, model_from, needs_ref
+from mag2d_b200 import decks
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_v1.npz"))
+
+
+def _sim(*a, **k):
+    from mag2d_b200.api import Sim
+    return Sim(*a, **k)
+
+
+def relerr(a, b):
+    """max |a-b| per column relative to the column's magnitude"""
+    a, b = np.asarray(a), np.asarray(b)
+    scale = np.maximum(np.abs(b).max(axis=0), 1e-300)
+    return (np.abs(a - b).max(axis=0) / scale).max()
+
+
+# ----------------------------------------------------------------------------------------- fields
+@pytest.mark.parametrize("deck,kw", [
+    ("c2", dict(geometry="RF_8PT", x_sampl=41, z_sampl=41)),
+    ("c2", dict(geometry="RF_22PT", x_sampl=200, z_sampl=200)),
+    ("c2", dict(geometry="RF_QUAD", x_sampl=64, z_sampl=50)),
+    ("c2", dict(geometry="PROBE", x_sampl=101, z_sampl=101, probe_radius=2e-3, u_probe=-7.0)),
+    ("c3", dict(geometry="PENNING_SIMPLE", x_sampl=61, z_sampl=81, selfconsistent=0)),
+    ("c3", dict(geometry="EMPTY", x_sampl=200, z_sampl=100, selfconsistent=0)),
+])
+def test_vacuum_solve_matches_direct_solver(orc, deckdir, deck, kw):
+    d = decks.deck(deck, deckdir, n_particles=10, **kw)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        g = grid_from_param(sim.param)
+        mask, volt = orc.geometry(g, int(sim.param["geometry"]), sim.param["probe_radius"], sim.param["u_probe"])
+        assert np.array_equal(mask, sim.mask)
+        zero = np.zeros((g.M, g.N))
+        u_ref = orc.solve_direct(g, mask, orc.rhs(g, mask, volt, zero, rf=False))
+        urf_ref = orc.solve_direct(g, mask, orc.rhs(g, mask, volt, zero, rf=True))
+        u, urf = sim.get_field("u"), sim.get_field("uRF")
+        assert np.abs(u - u_ref).max() <= 1e-8 * max(np.abs(u_ref).max(), 1e-30), sim.solve_info
+        assert np.abs(urf - urf_ref).max() <= 1e-8 * max(np.abs(urf_ref).max(), 1e-30), sim.solve_info
+        assert sim.solve_info["u"]["cycles"] <= 40
+
+
+def test_solve_with_charge_matches_direct_solver(orc, deckdir):
+    d = decks.deck("c4", deckdir, n_particles=40000, x_sampl=65, z_sampl=65, r_max=6.4e-3, z_max=6.4e-3)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        g = grid_from_param(sim.param)
+        ie = sim.species_index("ELECTRON")
+        ii = sim.species_index("ARGON_POS")
+        rng = np.random.default_rng(5)
+        ae = disk_particles(rng, 20000, 3.2e-3, 3.2e-3, 2.5e-3, 6e5)
+        ai = disk_particles(rng, 20000, 3.0e-3, 3.3e-3, 2.0e-3, 300.0)
+        sim.set_particles(ie, ae)
+        sim.set_particles(ii, ai)
+        sim.species_accumulate(ie)
+        sim.species_accumulate(ii)
+        info = sim.solve(rf=False)
+        rho = sim.get_field("rho")
+        mask, volt = orc.geometry(g, 0)
+        u_ref = orc.solve_direct(g, mask, orc.rhs(g, mask, volt, rho))
+        assert np.abs(sim.get_field("u") - u_ref).max() <= 1e-8 * np.abs(u_ref).max(), info
+
+
+def test_gather_matches_oracle_and_golden(orc, deckdir):
+    d = decks.deck("c2", deckdir, n_particles=10, geometry="RF_8PT", x_sampl=41, z_sampl=41, Bt=0.01, Bz=0.02, Br=0.005)
+    with _sim(d["config"], d["species_conf"], presolve=False) as sim:
+        k = "c2_RF_8PT_"
+        sim.set_field("u", G[k + "u"])
+        sim.set_field("uRF", G[k + "uRF"])
+        x, z = G[k + "E_xz"]
+        ex, ez = sim.field_E(x, z, 3.3e-8)
+        scale = np.abs(G[k + "E"]).max()
+        assert np.abs(np.stack([ex, ez]) - G[k + "E"]).max() <= 1e-12 * scale
+
+
+# ----------------------------------------------------------------------------------- trajectories
+@pytest.mark.parametrize("geo", ["RF_8PT", "RF_22PT"])
+def test_boris_cartesian_trajectory_vs_golden_reference(deckdir, geo):
+    # the golden run forced lifetime = inf on the reference side; here the gas densities are zero
+    d2 = decks.deck("c2", deckdir + "_nocoll", n_particles=10, collisions=False, geometry=geo, x_sampl=41, z_sampl=41,
+                    Bt=0.01, Bz=0.02, Br=0.005)
+    with _sim(d2["config"], d2["species_conf"], presolve=False) as sim2:
+        k = "c2_%s_" % geo
+        h = sim2.species_index("H_NEG")
+        assert not np.isfinite(sim2.species_get(h, "lifetime"))
+        sim2.set_field("u", G[k + "u"])
+        sim2.set_field("uRF", G[k + "uRF"])
+        # the golden run started at niter = 17 (RF phase): advance the species clock on an empty store
+        for _ in range(17):
+            sim2.species_advance(h)
+        assert sim2.species_get(h, "niter") == 17
+        sim2.set_particles(h, G[k + "boris_in"])
+        sim2.species_advance_init(h)
+        out = sim2.get_particles(h)
+        assert relerr(out[:, 3:6], G[k + "boris_init"][:, 3:6]) <= 1e-12
+        sim2.species_advance(h)
+        out = sim2.get_particles(h)
+        ref1 = G[k + "boris_1"]
+        # after one step nothing has been removed yet in the reference either (boundary ran only at the end)
+        alive = out[:, 7] > 0
+        assert relerr(out[alive][:, [0, 2, 3, 4, 5]], ref1[alive][:, [0, 2, 3, 4, 5]]) <= 1e-12
+        for _ in range(99):
+            sim2.species_advance(h)
+        out = sim2.get_particles(h)
+        ref100 = G[k + "boris_100"]
+        both = (out[:, 7] > 0) & (ref100[:, 7] > 0)
+        assert both.sum() >= 0.9 * (ref100[:, 7] > 0).sum()
+        assert relerr(out[both][:, [0, 2, 3, 4, 5]], ref100[both][:, [0, 2, 3, 4, 5]]) <= 1e-10
+        # removal decisions agree except for particles within rounding of an electrode cell edge
+        assert np.sum((out[:, 7] > 0) != (ref100[:, 7] > 0)) <= 2
+
+
+def test_boris_cartesian_vs_oracle_large(orc, deckdir):
+    d = decks.deck("c2", deckdir + "_nc", n_particles=10, collisions=False, geometry="RF_22PT", x_sampl=200, z_sampl=200, Bz=0.05)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        g = grid_from_param(sim.param)
+        m, names = model_from(orc, d["species_conf"])
+        h = names.index("H_NEG")
+        u, urf = sim.get_field("u"), sim.get_field("uRF")
+        aos = disk_particles(np.random.default_rng(9), 20000, 1e-2, 1e-2, 6.5e-3, 1500.0)
+        sim.set_particles(h, aos)
+        P = Particles.from_aos7(aos)
+        mask = sim.mask
+        for step in range(20):
+            sim.species_advance(h)
+            orc.advance_boris(g, u, urf, m, h, P, niter=step, rng=None)
+            orc.advance_boundary(g, mask, m.get(h, "charge"), P)
+        out = sim.get_particles(h)
+        both = (out[:, 7] > 0) & (P.alive > 0)
+        assert np.sum((out[:, 7] > 0) != (P.alive > 0)) <= 3
+        assert 0 < both.sum() < 20000          # some ions hit the rods
+        assert relerr(out[both][:, [0, 2, 3, 4, 5]], P.aos7()[both][:, [0, 2, 3, 4, 5]]) <= 1e-11
+
+
+def test_cylindrical_selfconsistent_loop_vs_golden_reference(orc, deckdir):
+    d = decks.deck("c3", deckdir, n_particles=500, x_sampl=41, z_sampl=51)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        ie = sim.species_index("ELECTRON")
+        sim.set_particles(ie, G["c3_in"])
+        sim.advance_init()
+        u0 = sim.get_field("u")
+        assert np.abs(u0 - G["c3_u0"]).max() <= 1e-8 * np.abs(G["c3_u0"]).max()
+        out = sim.get_particles(ie)
+        assert relerr(out[:, 3:6], G["c3_init"][:, 3:6]) <= 1e-9     # E from an iterative solve: 1e-8 * |E| dt q/m
+        sim.advance(5)
+        out = sim.get_particles(ie)
+        ref = G["c3_out"]
+        assert np.array_equal(out[:, 7], ref[:, 7])
+        assert relerr(out[:, [0, 2, 3, 4, 5]], ref[:, [0, 2, 3, 4, 5]]) <= 1e-8
+        assert np.abs(sim.get_field("u") - G["c3_u5"]).max() <= 1e-7 * np.abs(G["c3_u5"]).max()
+        # deposit: bit-exact against the fixed-point restatement on the device's own positions
+        g = grid_from_param(sim.param)
+        fixed, _ = orc.deposit_fixed(g, out[:, 0].copy(), out[:, 2].copy(), out[:, 7].astype(np.uint8))
+        assert np.array_equal(sim.rho_fixed(ie), fixed)
+        qe = sim.species[ie]["charge"]
+        assert np.abs(sim.get_field("rho") - G["c3_rho5"]).max() <= 500 * 2.0 ** -33 * abs(qe) + 1e-6 * abs(qe)
+
+
+def test_cartesian_selfconsistent_loop_vs_oracle(orc, deckdir):
+    """two particle species, deposit + solve every step, collisions off (gas density 0)"""
+    d = decks.deck("c4", deckdir + "_nc", n_particles=20000, collisions=False, x_sampl=33, z_sampl=33, r_max=3.2e-3, z_max=3.2e-3)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        g = grid_from_param(sim.param)
+        m, names = model_from(orc, d["species_conf"])
+        ii, ie = names.index("ARGON_POS"), names.index("ELECTRON")
+        mask, volt = orc.geometry(g, 0)
+        rng = np.random.default_rng(7)
+        ai = disk_particles(rng, 10000, 1.6e-3, 1.6e-3, 1.4e-3, 300.0)
+        ae = disk_particles(rng, 10000, 1.7e-3, 1.6e-3, 1.4e-3, 6e5)
+        sim.set_particles(ii, ai)
+        sim.set_particles(ie, ae)
+        Pi, Pe = Particles.from_aos7(ai), Particles.from_aos7(ae)
+        qi, qe = m.get(ii, "charge"), m.get(ie, "charge")
+        sim.advance_init()
+        rho_i, _ = orc.deposit_fp64(g, qi, Pi.x, Pi.z)
+        rho_e, _ = orc.deposit_fp64(g, qe, Pe.x, Pe.z)
+        rho = rho_i + rho_e
+        u = orc.solve_direct(g, mask, orc.rhs(g, mask, volt, rho))
+        urf = np.zeros_like(u)
+        orc.advance_boris_init(g, u, urf, m, ii, Pi)
+        orc.advance_boris_init(g, u, urf, m, ie, Pe)
+        for step in range(5):
+            sim.advance(1)
+            u = orc.solve_direct(g, mask, orc.rhs(g, mask, volt, rho))
+            rho_i[:] = 0
+            rho_e[:] = 0
+            orc.advance_boris(g, u, urf, m, ii, Pi, niter=step, rng=None)
+            orc.advance_boundary(g, mask, qi, Pi, rho=rho_i)
+            orc.advance_boris(g, u, urf, m, ie, Pe, niter=step, rng=None)
+            orc.advance_boundary(g, mask, qe, Pe, rho=rho_e)
+            rho = rho_i + rho_e
+        oi, oe = sim.get_particles(ii), sim.get_particles(ie)
+        assert np.array_equal(oi[:, 7], Pi.alive) and np.array_equal(oe[:, 7], Pe.alive)
+        assert relerr(oe[:, [0, 2, 3, 4, 5]], Pe.aos7()[:, [0, 2, 3, 4, 5]]) <= 1e-7
+        assert relerr(oi[:, [0, 2, 3, 4, 5]], Pi.aos7()[:, [0, 2, 3, 4, 5]]) <= 1e-7
+        # fixed-point grids are bit-exact for the device's own particle set
+        for s, o in ((ii, oi), (ie, oe)):
+            fixed, _ = orc.deposit_fixed(g, o[:, 0].copy(), o[:, 2].copy(), o[:, 7].astype(np.uint8))
+            assert np.array_equal(sim.rho_fixed(s), fixed)
+        assert np.abs(sim.get_field("rho") - rho).max() <= 20000 * 2.0 ** -33 * abs(qe) + 1e-6 * abs(qe)
+
+
+# ---------------------------------------------------------------------------------------- deposit
+def test_deposit_bit_exact_and_order_independent(orc, deckdir):
+    d = decks.deck("c4", deckdir, n_particles=200000, x_sampl=129, z_sampl=97, r_max=1.28e-2, z_max=0.96e-2)
+    with _sim(d["config"], d["species_conf"], presolve=False) as sim:
+        g = grid_from_param(sim.param)
+        ie = sim.species_index("ELECTRON")
+        rng = np.random.default_rng(11)
+        n = 200000
+        x = rng.uniform(0, 1.28e-2, n)
+        z = rng.uniform(0, 0.96e-2, n)
+        x[:3] = [0.0, 1.28e-2, 1.28e-2]        # corners and the x == x_max edge
+        z[:3] = [0.0, 0.96e-2, 0.0]
+        v = np.zeros(n)
+        sim.add_particles_soa(ie, x, z, v, v, v)
+        sim.species_accumulate(ie)
+        a = sim.rho_fixed(ie)
+        ref, bad = orc.deposit_fixed(g, x, z)
+        assert bad == 0 and np.array_equal(a, ref)
+        assert abs(int(a.sum()) - n * 2 ** 32) <= 2 * n          # charge conserved to 2 ulps per particle
+        # any order / any partition over "ranks": integer sums are associative
+        sim.rho_reset()
+        sim.L.mag2d_particles_clear(sim.h, ie)
+        perm = rng.permutation(n)
+        sim.add_particles_soa(ie, x[perm], z[perm], v, v, v)
+        sim.species_accumulate(ie)
+        assert np.array_equal(sim.rho_fixed(ie), ref)
+        halves = [orc.deposit_fixed(g, x[s], z[s])[0] for s in (slice(0, n // 3), slice(n // 3, n))]
+        assert np.array_equal(halves[0] + halves[1], ref)
+        # distance to the reference's sequential fp64 grid
+        f, _ = orc.deposit_fp64(g, 1.0, x, z)
+        assert np.abs(a * 2.0 ** -32 - f).max() <= 200 * 2.0 ** -33
+
+
+# --------------------------------------------------------------------------- boundary / store / sort
+def test_periodic_wrap_and_free_removal(orc, deckdir):
+    for boundary in ("PERIODIC", "FREE"):
+        d = decks.deck("c1", deckdir, n_particles=100, collisions=False, boundary=boundary, mover="ADVANCE_BORIS",
+                       x_sampl=5, z_sampl=5, extern_field=0.0)
+        with _sim(d["config"], d["species_conf"]) as sim:
+            g = grid_from_param(sim.param)
+            m, names = model_from(orc, d["species_conf"])
+            e = names.index("ELECTRON")
+            rng = np.random.default_rng(2)
+            n = 4000
+            aos = np.zeros((n, 7))
+            aos[:, 0] = rng.uniform(0, 2e-2, n)
+            aos[:, 2] = rng.uniform(0, 2e-2, n)
+            aos[:, 3:6] = rng.normal(size=(n, 3)) * 4e5      # v*dt = 4 mm: many leave the 2 cm box
+            sim.set_particles(e, aos)
+            P = Particles.from_aos7(aos)
+            u = np.zeros((g.M, g.N))
+            for step in range(3):
+                sim.species_advance(e)
+                orc.advance_boris(g, u, u, m, e, P, niter=step, rng=None)
+                orc.advance_boundary(g, sim.mask, m.get(e, "charge"), P)
+            out = sim.get_particles(e)
+            assert np.array_equal(out[:, 7], P.alive)
+            alive = P.alive > 0
+            assert relerr(out[alive][:, [0, 2, 3, 5]], P.aos7()[alive][:, [0, 2, 3, 5]]) <= 1e-12
+            n_alive, n_slots = sim.count(e)
+            assert n_alive == alive.sum()
+            if boundary == "FREE":
+                assert n_alive < n
+
+
+def test_cell_sort_compacts_and_preserves_the_particle_set(orc, deckdir):
+    d = decks.deck("c4", deckdir, n_particles=100000, x_sampl=65, z_sampl=49, r_max=6.4e-3, z_max=4.8e-3)
+    with _sim(d["config"], d["species_conf"], presolve=False) as sim:
+        g = grid_from_param(sim.param)
+        ie = sim.species_index("ELECTRON")
+        rng = np.random.default_rng(3)
+        n = 100000
+        x = rng.uniform(0, 6.4e-3, n)
+        z = rng.uniform(0, 4.8e-3, n)
+        x[::7] = np.nan                                  # removed particles keep their slot until the sort
+        vx, vy, vz = rng.normal(size=(3, n))
+        sim.add_particles_soa(ie, x, z, vx, vy, vz)
+        sim.species_accumulate(ie)
+        before = sim.rho_fixed(ie)
+        sim.sort(ie)
+        n_alive, n_slots = sim.count(ie)
+        live = ~np.isnan(x)
+        assert n_alive == live.sum() and n_slots == n_alive        # compacted
+        out = sim.get_particles(ie)
+        assert np.all(out[:, 7] == 1)
+        key = (np.minimum((out[:, 0] * g.idx).astype(int), g.M - 2) * (g.N - 1)
+               + np.minimum((out[:, 2] * g.idz).astype(int), g.N - 2))
+        assert np.all(np.diff(key) >= 0)                         # cell-sorted
+        a = np.stack([x, z, vx, vy, vz], axis=1)[live]
+        b = out[:, [0, 2, 3, 4, 5]]
+        assert np.array_equal(a[np.lexsort(a.T[::-1])], b[np.lexsort(b.T[::-1])])   # same multiset, bit for bit
+        sim.rho_reset()
+        sim.species_accumulate(ie)
+        assert np.array_equal(sim.rho_fixed(ie), before)         # deposit does not depend on particle order
+
+
+# ------------------------------------------------------------------------------- reference, live
+@pytest.mark.skipif(not needs_ref, reason="oracle/_ref not present on this machine")
+def test_live_reference_rf_trap_100_steps(deckdir):
+    from oracle import RefHarness
+    d = decks.deck("c2", deckdir + "_live", n_particles=10, collisions=False, geometry="RF_22PT", x_sampl=101, z_sampl=101)
+    aos = disk_particles(np.random.default_rng(4), 5000, 1e-2, 1e-2, 5e-3, 1500.0)
+    with RefHarness(d["config"], d["species_conf"], seed=5) as ref, _sim(d["config"], d["species_conf"]) as sim:
+        h = ref.species_index("H_NEG")
+        assert np.abs(sim.get_field("uRF") - ref.get_field("uRF")).max() <= 1e-8
+        sim.set_field("u", ref.get_field("u"))
+        sim.set_field("uRF", ref.get_field("uRF"))
+        ref.set_particles(h, aos)
+        sim.set_particles(h, aos)
+        ref.advance_init()
+        sim.advance_init()
+        ref.advance(100)
+        sim.advance(100)
+        a, b = sim.get_particles(h), ref.get_particles(h)
+        both = (a[:, 7] > 0) & (b[:, 7] > 0)
+        assert np.sum((a[:, 7] > 0) != (b[:, 7] > 0)) <= 2
+        assert relerr(a[both][:, [0, 2, 3, 4, 5]], b[both][:, [0, 2, 3, 4, 5]]) <= 1e-10
