@@ -96,8 +96,9 @@ int mag2d_set_grid(mag2d_ctx* ctx, const uint8_t* mask, const double* voltage);
 int mag2d_set_potential(mag2d_ctx* ctx, int which, const double* values);
 int mag2d_get_potential(mag2d_ctx* ctx, int which, double* values);
 /* Fields::boundary_solve (rf = 0) / boundary_solve_rf (rf = 1), src/fields.cpp:278-348: scale rho into
- * the right-hand side, overwrite Dirichlet rows, solve Op(u) = b by multigrid V-cycles until the
- * max-norm residual drops below tol * max|b| (or max_cycles).  Blocks.  Any out pointer may be NULL. */
+ * the right-hand side, overwrite Dirichlet rows, solve Op(u) = b by multigrid V-cycles until the largest
+ * Jacobi update max_k |r_k / a_kk| drops below tol * max_k |u_k| (or max_cycles).  Blocks.  resid_out
+ * receives that ratio.  Any out pointer may be NULL. */
 int mag2d_solve(mag2d_ctx* ctx, int rf, double tol, int max_cycles, int* cycles_out, double* resid_out);
 /* solver knobs for mag2d_step: V-cycles per step (0 = iterate to tol) and the tolerance */
 int mag2d_set_solver(mag2d_ctx* ctx, int cycles_per_step, double tol, int max_cycles);

@@ -144,7 +144,7 @@ class Sim:
     """One simulation on one GPU: the calls a ``Pic<D>`` user makes (src/test.cpp:50-66)."""
 
     def __init__(self, config, species_conf, overrides=None, device=0, stream=None, seed=1234, presolve=True,
-                 solver_tol=1e-11):
+                 solver_tol=1e-13):
         self.L = lib()
         self.param = cfg.read_config(config, overrides)
         self.species, self.interactions = cfg.read_species(species_conf)
@@ -317,7 +317,7 @@ class Sim:
                                      C.byref(cyc), C.byref(res)))
         return dict(cycles=cyc.value, resid=res.value)
 
-    def set_solver(self, cycles_per_step=0, tol=1e-11, max_cycles=100):
+    def set_solver(self, cycles_per_step=0, tol=1e-13, max_cycles=100):
         self._chk(self.L.mag2d_set_solver(self.h, cycles_per_step, tol, max_cycles))
 
     def get_field(self, which):

@@ -634,7 +634,6 @@ int mag2d_count(mag2d_ctx* c, int s, int64_t* n_alive, int64_t* n_slots)
         c->launches++;
         CUDA_OK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(cudaStreamSynchronize(c->stream));
-        S.n_slots = (long long)h[1];   // trailing dead slots (left behind by a compaction) are released
     }
     if (n_alive) *n_alive = (int64_t)h[0];
     if (n_slots) *n_slots = S.n_slots;
@@ -653,9 +652,8 @@ int mag2d_particles_generate(mag2d_ctx* c, int s, int kind, int64_t n, double a,
     return launch_generate(c, s, kind, n, a, b, cc, d);
 }
 
-int mag2d_sort(mag2d_ctx* c, int s)
+static int sort_species(mag2d_ctx* c, int s, bool trim)
 {
-    CHECK_CTX(c);
     CHECK_SPECIES(c, s);
     SpeciesStore& S = c->sp[s];
     if (S.n_slots == 0) return 0;
@@ -664,7 +662,14 @@ int mag2d_sort(mag2d_ctx* c, int s)
         const long long cap = S.capacity;
         if (store_alloc_slab(c, S, S.cur ^ 1, cap)) return 1;
     }
-    return launch_sort(c, s);
+    return launch_sort(c, s, trim);
+}
+
+int mag2d_sort(mag2d_ctx* c, int s)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    return sort_species(c, s, true);
 }
 
 int mag2d_set_sort_interval(mag2d_ctx* c, int steps)
@@ -782,7 +787,7 @@ int mag2d_step(mag2d_ctx* c, int nsteps)
         if (c->sort_interval > 0)
             for (size_t s = 0; s < c->sp.size(); s++)
                 if (c->sp[s].n_slots > 0 && c->sp[s].steps_since_sort >= c->sort_interval)
-                    if (mag2d_sort(c, (int)s)) return 1;
+                    if (sort_species(c, (int)s, false)) return 1;
         if (c->timing)
         {
             CUDA_OK(cudaEventRecord(c->ev[4], c->stream));

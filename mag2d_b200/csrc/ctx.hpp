@@ -71,7 +71,7 @@ struct mag2d_ctx
 
     std::vector<MgLevel> mg;
     int cycles_per_step = 0;
-    double solve_tol = 1e-10;
+    double solve_tol = 1e-13;
     int max_cycles = 60;
     int last_cycles = 0;
     double last_resid = 0;
@@ -125,13 +125,13 @@ int launch_aos_to_soa(mag2d_ctx* c, int s, const mag2d_particle* d_aos, long lon
 int launch_soa_to_aos(mag2d_ctx* c, int s, mag2d_particle* d_aos);
 int update_ueff(mag2d_ctx* c, double phase, bool rf);
 // sort.cu
-int launch_sort(mag2d_ctx* c, int s);
+int launch_sort(mag2d_ctx* c, int s, bool trim);
 // poisson.cu
 int mg_setup(mag2d_ctx* c);
 void mg_free(mag2d_ctx* c);
 int mg_rhs(mag2d_ctx* c, int rf);          // rho (all species) -> b, Dirichlet rows, scaled copy into mg[0].b
 int mg_vcycle(mag2d_ctx* c);
-int mg_residual(mag2d_ctx* c, double* resid_max, double* b_max);
+int mg_residual(mag2d_ctx* c, double* resid_max, double* u_max);
 int mg_solve(mag2d_ctx* c, int rf, double tol, int max_cycles, int fixed_cycles, int* cycles, double* resid);
 int launch_u_smooth(mag2d_ctx* c, int symmetry, double radius);
 int launch_rho_total(mag2d_ctx* c, double* d_out);

@@ -306,27 +306,34 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v)
     atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
-// max-norm of the residual in the reference's (unscaled) equation and max |b|
-__global__ void k_mg_residual_norm(const __grid_constant__ LevelDev L, const double* __restrict__ rowscale,
-                                   const double* __restrict__ b_ref, double* __restrict__ out2)
+// Convergence measure: max_k |r_k / a_kk| (the size of the Jacobi update, in volts; row scaling cancels)
+// and max_k |u_k|.  Rows of the cylindrical operator carry coefficients ~1e9 and the Dirichlet rows
+// coefficients of 1, so a plain residual norm against max|b| would mix units.
+__global__ void k_mg_residual_norm(const __grid_constant__ LevelDev L, double* __restrict__ out2)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    double r = 0.0, bm = 0.0;
+    double r = 0.0, um = 0.0;
     if (i < L.M && j < L.N)
     {
-        r = fabs(residual_at(L, i, j)) / rowscale[i];
-        bm = fabs(b_ref[(size_t)i * L.N + j]);
+        const size_t k = (size_t)i * L.N + j;
+        um = fabs(L.u[k]);
+        if (L.freem[k])
+        {
+            double diag;
+            const double s = offdiag_sum(L, i, j, diag);
+            r = fabs((L.b[k] - s - diag * L.u[k]) / diag);
+        }
     }
     for (int o = 16; o > 0; o >>= 1)
     {
         r = fmax(r, __shfl_xor_sync(MAG2D_FULL_MASK, r, o));
-        bm = fmax(bm, __shfl_xor_sync(MAG2D_FULL_MASK, bm, o));
+        um = fmax(um, __shfl_xor_sync(MAG2D_FULL_MASK, um, o));
     }
     if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0)
     {
         atomic_max_nonneg(out2, r);
-        atomic_max_nonneg(out2 + 1, bm);
+        atomic_max_nonneg(out2 + 1, um);
     }
 }
 
@@ -597,23 +604,24 @@ int mg_vcycle(mag2d_ctx* c)
     return 0;
 }
 
-int mg_residual(mag2d_ctx* c, double* resid_max, double* b_max)
+int mg_residual(mag2d_ctx* c, double* resid_max, double* u_max)
 {
     const MgLevel& L = c->mg[0];
     CUDA_OK(cudaMemsetAsync(c->d_scratch, 0, 2 * sizeof(double), c->stream));
     const dim3 block(32, 8);
-    k_mg_residual_norm<<<grid2d(L.N, L.M, block), block, 0, c->stream>>>(level_view(L), c->d_rowscale, c->d_b, c->d_scratch);
+    k_mg_residual_norm<<<grid2d(L.N, L.M, block), block, 0, c->stream>>>(level_view(L), c->d_scratch);
     c->launches++;
     double h[2];
     CUDA_OK(cudaMemcpyAsync(h, c->d_scratch, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     *resid_max = h[0];
-    *b_max = h[1];
+    *u_max = h[1];
     return 0;
 }
 
 // solve Op(u) = b for u (rf = 0) or uRF (rf = 1).  fixed_cycles > 0: run exactly that many V-cycles and
-// do not look at the residual (no host synchronisation); otherwise iterate to tol * max|b|.
+// do not look at the residual (no host synchronisation); otherwise iterate until the largest Jacobi
+// update max|r_k/a_kk| is below tol * max|u|.
 int mg_solve(mag2d_ctx* c, int rf, double tol, int max_cycles, int fixed_cycles, int* cycles, double* resid)
 {
     if (!c->grid_set || c->mg.empty())

@@ -43,15 +43,20 @@ __device__ __forceinline__ void gather_E(const GridDev& g, double x, double z, d
     const double* __restrict__ u = g.ueff;
     const double X = x * g.idx, Y = z * g.idz;
     {
-        int i = (int)(X + 0.5);
+        // NB the edge tests are done on the double, not on the clamped integer: ptxas 12.9 fuses
+        // "min(i, M-1) ... i == M-1" into one VIMNMX.RELU with a predicate output that is always
+        // true on sm_100a (observed on B200: fx came out 0 for every particle), see DESIGN.md
+        const double Xs = X + 0.5;
+        const bool lo = Xs < 1.0, hi = Xs >= (double)(M - 1);
+        int i = (int)Xs;
         int j = min((int)Y, N - 2);
         i = max(min(i, M - 1), 0);
         j = max(j, 0);
         double fx = X - i + .5;
         const double fy = Y - j;
         int im = i - 1, ip = i + 1;
-        if (i == 0) { im = 0; fx = 1.0; }
-        if (i == M - 1) { ip = M - 1; fx = 0.0; }
+        if (lo) { im = i; fx = 1.0; }
+        if (hi) { ip = i; fx = 0.0; }
         const double* r0 = u + (size_t)im * N + j;
         const double* r1 = u + (size_t)i * N + j;
         const double* r2 = u + (size_t)ip * N + j;
@@ -63,15 +68,17 @@ __device__ __forceinline__ void gather_E(const GridDev& g, double x, double z, d
         Ex = -(g1 * (1 - fx) * (1 - fy) + g2 * (1 - fx) * fy + g3 * fx * fy + g4 * fx * (1 - fy));
     }
     {
+        const double Ys = Y + 0.5;
+        const bool lo = Ys < 1.0, hi = Ys >= (double)(N - 1);
         int i = min((int)X, M - 2);
-        int j = (int)(Y + 0.5);
+        int j = (int)Ys;
         i = max(i, 0);
         j = max(min(j, N - 1), 0);
         const double fx = X - i;
         double fy = Y - j + 0.5;
         int jm = j - 1, jp = j + 1;
-        if (j == 0) { jm = 0; fy = 1.0; }
-        if (j == N - 1) { jp = N - 1; fy = 0.0; }
+        if (lo) { jm = j; fy = 1.0; }
+        if (hi) { jp = j; fy = 0.0; }
         const double* r0 = u + (size_t)i * N;
         const double* r1 = r0 + N;
         const double a0 = __ldg(r0 + jm), a1 = __ldg(r0 + j), a2 = __ldg(r0 + jp);

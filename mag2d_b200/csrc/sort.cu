@@ -161,7 +161,7 @@ __global__ void k_fill_dead(double* __restrict__ x, const unsigned long long* __
 
 }  // namespace
 
-int launch_sort(mag2d_ctx* c, int s)
+int launch_sort(mag2d_ctx* c, int s, bool trim)
 {
     SpeciesStore& S = c->sp[s];
     const long long n = S.n_slots;
@@ -210,5 +210,14 @@ int launch_sort(mag2d_ctx* c, int s)
     CUDA_OK(cudaMemsetAsync(S.d_removed, 0, sizeof(unsigned long long), c->stream));
     S.cur ^= 1;
     S.steps_since_sort = 0;
+    if (trim)
+    {
+        // explicit mag2d_sort: release the dead tail now (one host sync); sorts issued from inside
+        // mag2d_step stay asynchronous and keep the old slot count as an upper bound
+        unsigned long long total = 0;
+        CUDA_OK(cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        S.n_slots = (long long)total;
+    }
     return 0;
 }

@@ -132,7 +132,7 @@ def test_boris_cartesian_vs_oracle_large(orc, deckdir):
         m, names = model_from(orc, d["species_conf"])
         h = names.index("H_NEG")
         u, urf = sim.get_field("u"), sim.get_field("uRF")
-        aos = disk_particles(np.random.default_rng(9), 20000, 1e-2, 1e-2, 6.5e-3, 1500.0)
+        aos = disk_particles(np.random.default_rng(9), 20000, 1e-2, 1e-2, 7.8e-3, 1500.0)   # reaches into the rods
         sim.set_particles(h, aos)
         P = Particles.from_aos7(aos)
         mask = sim.mask
