@@ -266,6 +266,7 @@ int mag2d_destroy(mag2d_ctx* c)
     if (c->d_cell_count) cudaFree(c->d_cell_count);
     if (c->d_cell_offset) cudaFree(c->d_cell_offset);
     if (c->d_block_sums) cudaFree(c->d_block_sums);
+    if (c->d_coll_count) cudaFree(c->d_coll_count);
     if (c->d_rank) cudaFree(c->d_rank);
     if (c->d_key) cudaFree(c->d_key);
     for (int q = 0; q < 8; q++)

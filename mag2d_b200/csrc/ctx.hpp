@@ -88,6 +88,7 @@ struct mag2d_ctx
     unsigned int* d_key = nullptr;
     long long rank_capacity = 0;
     unsigned int* d_block_sums = nullptr;
+    unsigned int* d_coll_count = nullptr;
 
     // multi-GPU
     void* nccl_comm = nullptr;
@@ -124,6 +125,7 @@ int launch_field_E(mag2d_ctx* c, int n, const double* x, const double* z, double
 int launch_aos_to_soa(mag2d_ctx* c, int s, const mag2d_particle* d_aos, long long n_in, long long* n_added);
 int launch_soa_to_aos(mag2d_ctx* c, int s, mag2d_particle* d_aos);
 int update_ueff(mag2d_ctx* c, double phase, bool rf);
+int ensure_particle_scratch(mag2d_ctx* c, long long capacity);
 // sort.cu
 int launch_sort(mag2d_ctx* c, int s, bool trim);
 // poisson.cu

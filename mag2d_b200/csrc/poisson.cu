@@ -211,10 +211,10 @@ void build_coarse_level(const HostLevel& F, HostLevel& Cl)
 struct LevelDev
 {
     int M, N;
-    const double* __restrict__ coef;
+    const double* __restrict__ coef;         // never written on the device
     const unsigned char* __restrict__ freem;
-    double* __restrict__ u;
-    const double* __restrict__ b;
+    double* u;     // u and b are written and re-read inside k_mg_coarse: no __restrict__, no read-only path
+    double* b;
 };
 
 // (A u)(i,j) excluding the diagonal term; returns the diagonal through diag
@@ -468,37 +468,192 @@ LevelDev level_view(const MgLevel& L)
 
 inline dim3 grid2d(int nj, int ni, dim3 block) { return dim3((nj + block.x - 1) / block.x, (ni + block.y - 1) / block.y); }
 
-int smooth_level(mag2d_ctx* c, const MgLevel& L, int sweeps)
+// ---- tile smoother: SWEEPS full 4-colour Gauss-Seidel sweeps in ONE launch ---------------------------
+// Each CTA owns a TILE x TILE block of nodes and loads it with a halo of HALO = 4*SWEEPS nodes into shared
+// memory.  Colour step s may update every node at distance >= s+1 from the edge of the loaded block (its
+// neighbours are still exact there), so after 4*SWEEPS colour steps the owned tile holds exactly the values
+// the global 4-colour sweep would have produced: same iteration, same bits, 4*SWEEPS times fewer launches,
+// at the price of recomputing the halo ((TILE+2*HALO)^2 / TILE^2 = 2.25x arithmetic for SWEEPS = 2).
+constexpr int MG_TILE = 32;
+template <int SWEEPS>
+__global__ void __launch_bounds__(256) k_mg_smooth_tile(const __grid_constant__ LevelDev L)
 {
-    const LevelDev v = level_view(L);
-    const dim3 block(32, 8);
-    const dim3 grid = grid2d((L.N + 1) / 2, (L.M + 1) / 2, block);
+    constexpr int HALO = 4 * SWEEPS, W = MG_TILE + 2 * HALO;
+    __shared__ double su[W][W + 1];
+    const int M = L.M, N = L.N;
+    const size_t n = (size_t)M * N;
+    const int i0 = blockIdx.y * MG_TILE - HALO, j0 = blockIdx.x * MG_TILE - HALO;
+    for (int q = threadIdx.x; q < W * W; q += 256)
+    {
+        const int li = q / W, lj = q - li * W;
+        const int gi = i0 + li, gj = j0 + lj;
+        su[li][lj] = (gi >= 0 && gi < M && gj >= 0 && gj < N) ? L.u[(size_t)gi * N + gj] : 0.0;
+    }
+    __syncthreads();
+    for (int step = 0; step < 4 * SWEEPS; step++)
+    {
+        const int colour = step & 3;
+        const int lo = step + 1, hi = W - 2 - step;      // updatable local range [lo, hi]
+        const int span = hi - lo + 1;
+        for (int q = threadIdx.x; q < span * span; q += 256)
+        {
+            const int li = lo + q / span, lj = lo + q % span;
+            const int gi = i0 + li, gj = j0 + lj;
+            if (gi < 0 || gi >= M || gj < 0 || gj >= N) continue;
+            if ((((gi & 1) << 1) | (gj & 1)) != colour) continue;
+            const size_t k = (size_t)gi * N + gj;
+            if (!L.freem[k]) continue;
+            double acc = 0.0, diag = 1.0;
+#pragma unroll
+            for (int di = -1; di <= 1; di++)
+#pragma unroll
+                for (int dj = -1; dj <= 1; dj++)
+                {
+                    const double a = __ldg(L.coef + (size_t)((di + 1) * 3 + (dj + 1)) * n + k);
+                    if (di == 0 && dj == 0) diag = a;
+                    else acc += a * su[li + di][lj + dj];
+                }
+            su[li][lj] = (L.b[k] - acc) / diag;
+        }
+        __syncthreads();
+    }
+    for (int q = threadIdx.x; q < MG_TILE * MG_TILE; q += 256)
+    {
+        const int li = HALO + q / MG_TILE, lj = HALO + q % MG_TILE;
+        const int gi = i0 + li, gj = j0 + lj;
+        if (gi < M && gj < N)
+        {
+            const size_t k = (size_t)gi * N + gj;
+            if (L.freem[k]) L.u[k] = su[li][lj];
+        }
+    }
+}
+
+// ---- the coarse part of the V-cycle in ONE single-CTA launch -----------------------------------------
+// All levels with at most MG_COARSE_NODES nodes are visited by one thread block that walks down
+// (pre-smooth, restrict), solves the coarsest level with many sweeps and walks back up (prolong,
+// post-smooth) with __syncthreads() between colour steps.  The arrays stay in L1/L2.
+constexpr int MG_COARSE_NODES = 4225;     // 65 x 65
+constexpr int MG_MAX_LEVELS = 14;
+struct CoarseArgs
+{
+    LevelDev L[MG_MAX_LEVELS];
+    int fx[MG_MAX_LEVELS], fz[MG_MAX_LEVELS];
+    int first, count;      // levels [first, first+count)
+    int nu1, nu2, nu_coarsest;
+};
+
+__device__ __forceinline__ void cta_smooth(const LevelDev& L, int sweeps)
+{
+    const int M = L.M, N = L.N;
+    const int half_n = (N + 1) >> 1, half_m = (M + 1) >> 1;
     for (int s = 0; s < sweeps; s++)
         for (int colour = 0; colour < 4; colour++)
         {
-            k_mg_smooth<<<grid, block, 0, c->stream>>>(v, colour);
-            c->launches++;
+            const int ci = colour >> 1, cj = colour & 1;
+            for (int q = threadIdx.x; q < half_m * half_n; q += blockDim.x)
+            {
+                const int i = 2 * (q / half_n) + ci, j = 2 * (q % half_n) + cj;
+                if (i >= M || j >= N) continue;
+                const size_t k = (size_t)i * N + j;
+                if (!L.freem[k]) continue;
+                double diag;
+                const double acc = offdiag_sum(L, i, j, diag);
+                L.u[k] = (L.b[k] - acc) / diag;
+            }
+            __syncthreads();
         }
+}
+
+__global__ void __launch_bounds__(1024) k_mg_coarse(const __grid_constant__ CoarseArgs A)
+{
+    const int last = A.first + A.count - 1;
+    for (int l = A.first; l < last; l++)
+    {
+        const LevelDev& F = A.L[l];
+        const LevelDev& Cl = A.L[l + 1];
+        cta_smooth(F, A.nu1);
+        const int fx = A.fx[l], fz = A.fz[l];
+        const int ri = fx == 2 ? 1 : 0, rj = fz == 2 ? 1 : 0;
+        for (int q = threadIdx.x; q < Cl.M * Cl.N; q += blockDim.x)
+        {
+            const int I = q / Cl.N, J = q % Cl.N;
+            double s = 0.0;
+            for (int di = -ri; di <= ri; di++)
+                for (int dj = -rj; dj <= rj; dj++)
+                {
+                    const int i = I * fx + di, j = J * fz + dj;
+                    if (i < 0 || i >= F.M || j < 0 || j >= F.N) continue;
+                    s += (di ? 0.5 : 1.0) * (dj ? 0.5 : 1.0) * residual_at(F, i, j);
+                }
+            Cl.b[q] = s;
+            Cl.u[q] = 0.0;
+        }
+        __syncthreads();
+    }
+    cta_smooth(A.L[last], A.nu_coarsest);
+    for (int l = last - 1; l >= A.first; l--)
+    {
+        const LevelDev& F = A.L[l];
+        const LevelDev& Cl = A.L[l + 1];
+        const int fx = A.fx[l], fz = A.fz[l];
+        for (int q = threadIdx.x; q < F.M * F.N; q += blockDim.x)
+        {
+            if (!F.freem[q]) continue;
+            const int i = q / F.N, j = q % F.N;
+            const int I = i / fx, J = j / fz;
+            const double wi = (fx == 2 && (i & 1)) ? 0.5 : 0.0, wj = (fz == 2 && (j & 1)) ? 0.5 : 0.0;
+            double s = (1.0 - wi) * (1.0 - wj) * Cl.u[(size_t)I * Cl.N + J];
+            if (wi != 0.0 && I + 1 < Cl.M) s += wi * (1.0 - wj) * Cl.u[(size_t)(I + 1) * Cl.N + J];
+            if (wj != 0.0 && J + 1 < Cl.N) s += (1.0 - wi) * wj * Cl.u[(size_t)I * Cl.N + J + 1];
+            if (wi != 0.0 && wj != 0.0 && I + 1 < Cl.M && J + 1 < Cl.N) s += wi * wj * Cl.u[(size_t)(I + 1) * Cl.N + J + 1];
+            F.u[q] += s;
+        }
+        __syncthreads();
+        cta_smooth(F, A.nu2);
+    }
+}
+
+int smooth_level(mag2d_ctx* c, const MgLevel& L)
+{
+    const dim3 grid((L.N + MG_TILE - 1) / MG_TILE, (L.M + MG_TILE - 1) / MG_TILE);
+    k_mg_smooth_tile<2><<<grid, 256, 0, c->stream>>>(level_view(L));
+    c->launches++;
+    return 0;
+}
+
+int coarse_vcycle(mag2d_ctx* c, size_t first)
+{
+    CoarseArgs A;
+    memset(&A, 0, sizeof(A));
+    A.first = (int)first;
+    A.count = (int)(c->mg.size() - first);
+    for (size_t l = first; l < c->mg.size(); l++)
+    {
+        A.L[l] = level_view(c->mg[l]);
+        A.fx[l] = c->mg[l].fx;
+        A.fz[l] = c->mg[l].fz;
+    }
+    A.nu1 = A.nu2 = 2;
+    A.nu_coarsest = 30;
+    k_mg_coarse<<<1, 1024, 0, c->stream>>>(A);
+    c->launches++;
     return 0;
 }
 
 int vcycle_level(mag2d_ctx* c, size_t l)
 {
     const MgLevel& L = c->mg[l];
-    if (l + 1 == c->mg.size())
-    {
-        smooth_level(c, L, 30);
-        return 0;
-    }
+    if ((size_t)L.M * L.N <= (size_t)MG_COARSE_NODES || l + 1 == c->mg.size()) return coarse_vcycle(c, l);
     const MgLevel& Cl = c->mg[l + 1];
-    smooth_level(c, L, 2);
+    smooth_level(c, L);
     const dim3 block(32, 8);
     k_mg_restrict<<<grid2d(Cl.N, Cl.M, block), block, 0, c->stream>>>(level_view(L), L.fx, L.fz, Cl.M, Cl.N, Cl.b, Cl.u);
     c->launches++;
     if (vcycle_level(c, l + 1)) return 1;
     k_mg_prolong<<<grid2d(L.N, L.M, block), block, 0, c->stream>>>(level_view(L), L.fx, L.fz, Cl.M, Cl.N, Cl.u);
     c->launches++;
-    smooth_level(c, L, 2);
+    smooth_level(c, L);
     return 0;
 }
 

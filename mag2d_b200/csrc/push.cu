@@ -31,6 +31,8 @@ struct PushArgs
     unsigned long long* counts;    // collision counters or nullptr
     unsigned long long* removed;   // removal counter
     unsigned long long seed;
+    unsigned* coll_list;           // slots whose Bernoulli test fired this step (processed by k_mcc_collide)
+    unsigned* coll_count;
 };
 
 // ---- gather: E = -grad(ueff), the staggered-difference bilinear form of Field2D::grad ----------
@@ -124,10 +126,12 @@ __device__ __forceinline__ void boris_velocity(const SpeciesDev& s, double Ex, d
     vz += Ez * s.hq;
 }
 
-// ---- boundary + electrode absorption + fixed-point CIC deposit ------------------------------------
-// Returns false when the particle is removed.  Positions may be wrapped (PERIODIC).
+// ---- boundary + electrode absorption + fixed-point CIC weights --------------------------------------
+// Returns false when the particle is removed.  Positions may be wrapped (PERIODIC).  When DEPOSIT, node
+// receives the index of the cell's lower-left node and w the four Q32 weights (Field2D.hpp:57-60 order:
+// [i][j], [i+1][j], [i][j+1], [i+1][j+1]).
 template <bool DEPOSIT>
-__device__ __forceinline__ bool boundary_deposit(const GridDev& g, double& x, double& z)
+__device__ __forceinline__ bool boundary_weights(const GridDev& g, double& x, double& z, unsigned& node, unsigned long long (&w)[4])
 {
     if (x < 0.0 || x > g.x_max || z < 0.0 || z > g.z_max)
     {
@@ -154,17 +158,57 @@ __device__ __forceinline__ bool boundary_deposit(const GridDev& g, double& x, do
     {
         const double fu = __dsub_rn(X, (double)i), fv = __dsub_rn(Y, (double)j);
         const double cu = __dsub_rn(1.0, fu), cv = __dsub_rn(1.0, fv);
-        const unsigned long long w00 = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(cu, cv), 4294967296.0));
-        const unsigned long long w10 = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(fu, cv), 4294967296.0));
-        const unsigned long long w01 = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(cu, fv), 4294967296.0));
-        const unsigned long long w11 = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(fu, fv), 4294967296.0));
-        unsigned long long* r = g.rho + k;
-        atomicAdd(r, w00);
-        atomicAdd(r + g.N, w10);
-        atomicAdd(r + 1, w01);
-        atomicAdd(r + g.N + 1, w11);
+        w[0] = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(cu, cv), 4294967296.0));
+        w[1] = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(fu, cv), 4294967296.0));
+        w[2] = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(cu, fv), 4294967296.0));
+        w[3] = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(fu, fv), 4294967296.0));
+        node = (unsigned)k;
     }
     return true;
+}
+
+// ---- warp-aggregated scatter of the fixed-point weights ----------------------------------------------
+// Must be called by all 32 lanes.  Particles are cell-sorted, so the lanes of a warp share a handful of
+// cells: for each distinct cell the four weights are summed across its lanes with REDUX (two 32-bit
+// pieces per weight: hi = w >> 16 <= 2^16, lo < 2^16, so 32 lanes cannot overflow) and lanes 0..3 issue one
+// RED.ADD.64 each.  Integer sums are associative: the grid is bit-identical to the unaggregated scatter.
+// After MAX_RUNS distinct cells the remaining lanes fall back to their own four REDs (unsorted input).
+__device__ __forceinline__ void warp_deposit(unsigned long long* __restrict__ rho, int N, bool valid, unsigned node,
+                                             const unsigned long long (&w)[4])
+{
+    constexpr int MAX_RUNS = 8;
+    const unsigned lane = lane_id();
+    unsigned remaining = __ballot_sync(MAG2D_FULL_MASK, valid);
+    for (int it = 0; remaining && it < MAX_RUNS; it++)
+    {
+        const int src = __ffs(remaining) - 1;
+        const unsigned k0 = __shfl_sync(MAG2D_FULL_MASK, node, src);
+        const bool mine = valid && node == k0;
+        const unsigned m = __ballot_sync(MAG2D_FULL_MASK, mine);
+        unsigned long long t[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            const unsigned lo = __reduce_add_sync(MAG2D_FULL_MASK, mine ? (unsigned)(w[q] & 0xFFFFu) : 0u);
+            const unsigned hi = __reduce_add_sync(MAG2D_FULL_MASK, mine ? (unsigned)(w[q] >> 16) : 0u);
+            t[q] = ((unsigned long long)hi << 16) + lo;
+        }
+        if (lane < 4)
+        {
+            const unsigned long long v = lane == 0 ? t[0] : lane == 1 ? t[1] : lane == 2 ? t[2] : t[3];
+            const size_t off = (size_t)k0 + (lane & 1 ? (size_t)N : 0) + (lane >> 1);
+            atomicAdd(rho + off, v);
+        }
+        remaining &= ~m;
+    }
+    if (valid && ((remaining >> lane) & 1u))
+    {
+        unsigned long long* r = rho + node;
+        atomicAdd(r, w[0]);
+        atomicAdd(r + N, w[1]);
+        atomicAdd(r + 1, w[2]);
+        atomicAdd(r + N + 1, w[3]);
+    }
 }
 
 __device__ __forceinline__ void count_removed(unsigned long long* counter, bool removed_now)
@@ -174,6 +218,11 @@ __device__ __forceinline__ void count_removed(unsigned long long* counter, bool 
 }
 
 // ---- the fused Boris step --------------------------------------------------------------------------
+// One thread per particle slot.  Collisions: only the Bernoulli test of the null-collision method
+// (uni() < 1-exp(-dt/lifetime), particles.cpp:990) runs here; the slots that fire are appended to a list
+// and scattered by k_mcc_collide afterwards.  That is legal because scatter() only changes the velocity,
+// which neither the boundary test nor the deposit reads, and it keeps the rarely-taken, register-hungry
+// collision kinematics out of this bandwidth-bound kernel.
 template <int COORD, bool GATHER, bool HASB, bool MCC, bool DEPOSIT>
 __global__ void __launch_bounds__(PUSH_THREADS) k_push_boris(const __grid_constant__ PushArgs A)
 {
@@ -181,7 +230,9 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push_boris(const __grid_consta
     const bool in_range = k < A.p.n;
     double x = in_range ? A.p.x[k] : dead_marker();
     const bool live = particle_alive(x);
-    bool removed_now = false;
+    bool removed_now = false, keep = false, hit = false;
+    unsigned node = 0;
+    unsigned long long w[4] = {0, 0, 0, 0};
     if (live)
     {
         double z = A.p.z[k];
@@ -213,28 +264,20 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push_boris(const __grid_consta
             x += vx * dt;
             z += vz * dt;
         }
-        bool vy_dirty = need_vy;
         if (MCC)
         {
             Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)k);
             const uint4 r0 = rng.block();
-            if (u01(r0.x) < A.s.prob)
-            {
-                if (!need_vy) vy = A.p.vy[k];
-                int target;
-                const int proc = mcc_scatter(A.mcc, rng, vx, vy, vz, target);
-                mcc_count(A.counts, A.mcc->n_targets, target, proc);
-                vy_dirty = true;
-            }
+            hit = u01(r0.x) < A.s.prob;
         }
-        const bool keep = boundary_deposit<DEPOSIT>(A.g, x, z);
+        keep = boundary_weights<DEPOSIT>(A.g, x, z, node, w);
         if (keep)
         {
             A.p.x[k] = x;
             A.p.z[k] = z;
             A.p.vx[k] = vx;
             A.p.vz[k] = vz;
-            if (vy_dirty) A.p.vy[k] = vy;
+            if (need_vy) A.p.vy[k] = vy;
         }
         else
         {
@@ -242,7 +285,45 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push_boris(const __grid_consta
             removed_now = true;
         }
     }
+    if (DEPOSIT) warp_deposit(A.g.rho, A.g.N, keep, node, w);
+    if (MCC)
+    {
+        // warp-aggregated append to the collision list
+        hit = hit && keep;
+        const unsigned m = __ballot_sync(MAG2D_FULL_MASK, hit);
+        if (m)
+        {
+            const unsigned lane = lane_id();
+            const int leader = __ffs(m) - 1;
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(A.coll_count, (unsigned)__popc(m));
+            base = __shfl_sync(MAG2D_FULL_MASK, base, leader);
+            if (hit) A.coll_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)k;
+        }
+    }
     count_removed(A.removed, removed_now);
+}
+
+// second pass of the Boris movers: BaseSpecies::scatter for the slots whose Bernoulli test fired
+__global__ void __launch_bounds__(128) k_mcc_collide(const __grid_constant__ PushArgs A)
+{
+    const unsigned n = *A.coll_count;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
+    {
+        const long long k = A.coll_list[q];
+        double vx = A.p.vx[k], vy = A.p.vy[k], vz = A.p.vz[k];
+        Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)k);
+        rng.draw = 1;     // block 0 was consumed by the Bernoulli test
+        int target;
+        const int proc = mcc_scatter(A.mcc, rng, vx, vy, vz, target);
+        mcc_count(A.counts, A.mcc->n_targets, target, proc);
+        if (proc >= 0)
+        {
+            A.p.vx[k] = vx;
+            A.p.vy[k] = vy;
+            A.p.vz[k] = vz;
+        }
+    }
 }
 
 // ---- half step back: Species<D>::advance_boris_init ----------------------------------------------
@@ -329,7 +410,9 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push_multicoll(const __grid_co
         x += (vx + 0.5 * ax * rest) * rest;
         z += (vz + 0.5 * az * rest) * rest;
         ttd -= rest;
-        const bool keep = boundary_deposit<false>(A.g, x, z);
+        unsigned node;
+        unsigned long long w[4];
+        const bool keep = boundary_weights<false>(A.g, x, z, node, w);
         if (keep)
         {
             A.p.x[k] = x;
@@ -352,14 +435,19 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push_multicoll(const __grid_co
 __global__ void __launch_bounds__(PUSH_THREADS) k_accumulate(const __grid_constant__ PushArgs A)
 {
     const long long k = (long long)blockIdx.x * PUSH_THREADS + threadIdx.x;
-    if (k >= A.p.n) return;
-    double x = A.p.x[k];
-    if (!particle_alive(x)) return;
-    double z = A.p.z[k];
-    GridDev g = A.g;
-    g.check_mask = 0;
-    g.boundary = MAG2D_BOUNDARY_PERIODIC;   // never drop here: accumulate() deposits every live particle
-    boundary_deposit<true>(g, x, z);
+    double x = k < A.p.n ? A.p.x[k] : dead_marker();
+    bool valid = particle_alive(x);
+    unsigned node = 0;
+    unsigned long long w[4] = {0, 0, 0, 0};
+    if (valid)
+    {
+        double z = A.p.z[k];
+        GridDev g = A.g;
+        g.check_mask = 0;
+        g.boundary = MAG2D_BOUNDARY_PERIODIC;   // never drop here: accumulate() deposits every live particle
+        valid = boundary_weights<true>(g, x, z, node, w);
+    }
+    warp_deposit(A.g.rho, A.g.N, valid, node, w);
 }
 
 __global__ void k_ueff(const double* __restrict__ u, const double* __restrict__ urf, double phase, double* __restrict__ out, int n)
@@ -652,6 +740,20 @@ int launch_boris_variant(mag2d_ctx* c, const PushArgs& A, bool gather, bool hasb
 
 }  // namespace
 
+// per-slot scratch shared by the sort (keys, ranks) and the push (collision list)
+int ensure_particle_scratch(mag2d_ctx* c, long long capacity)
+{
+    if (!c->d_coll_count) CUDA_OK(cudaMalloc(&c->d_coll_count, sizeof(unsigned)));
+    if (c->rank_capacity >= capacity) return 0;
+    if (c->d_rank) cudaFree(c->d_rank);
+    if (c->d_key) cudaFree(c->d_key);
+    c->d_rank = c->d_key = nullptr;
+    CUDA_OK(cudaMalloc(&c->d_rank, sizeof(unsigned) * (size_t)capacity));
+    CUDA_OK(cudaMalloc(&c->d_key, sizeof(unsigned) * (size_t)capacity));
+    c->rank_capacity = capacity;
+    return 0;
+}
+
 int update_ueff(mag2d_ctx* c, double phase, bool rf)
 {
     if (!rf) return 0;
@@ -689,6 +791,8 @@ int launch_species_advance(mag2d_ctx* c, int s)
         A.counts = c->count_collisions ? S.d_counts : nullptr;
         A.removed = S.d_removed;
         A.seed = c->seed;
+        A.coll_list = nullptr;
+        A.coll_count = nullptr;
         const unsigned blocks = (unsigned)((S.n_slots + PUSH_THREADS - 1) / PUSH_THREADS);
         const bool mcc = S.h_blob && S.h_blob->has_collisions && std::isfinite(S.lifetime);
         if (d.mover == MAG2D_ADVANCE_MULTICOLL)
@@ -723,10 +827,22 @@ int launch_species_advance(mag2d_ctx* c, int s)
             const bool gather = !A.g.const_E;
             if (gather && d.rf)
                 if (update_ueff(c, rf_phase(c, S), true)) return 1;
+            if (mcc)
+            {
+                if (ensure_particle_scratch(c, S.capacity)) return 1;
+                A.coll_list = c->d_key;          // the sort's key buffer is idle during a push
+                A.coll_count = c->d_coll_count;
+                CUDA_OK(cudaMemsetAsync(c->d_coll_count, 0, sizeof(unsigned), c->stream));
+            }
             if (d.coord == MAG2D_CYLINDRICAL)
                 launch_boris_variant<MAG2D_CYLINDRICAL>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, blocks);
             else
                 launch_boris_variant<MAG2D_CARTESIAN>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, blocks);
+            if (mcc)
+            {
+                k_mcc_collide<<<148 * 8, 128, 0, c->stream>>>(A);
+                c->launches++;
+            }
         }
         CUDA_OK(cudaGetLastError());
     }

@@ -175,14 +175,7 @@ int launch_sort(mag2d_ctx* c, int s, bool trim)
         CUDA_OK(cudaMalloc(&c->d_cell_offset, sizeof(unsigned) * (size_t)ncells));
         CUDA_OK(cudaMalloc(&c->d_block_sums, sizeof(unsigned) * (size_t)(ntiles + 2) + 16));
     }
-    if (c->rank_capacity < n)
-    {
-        if (c->d_rank) cudaFree(c->d_rank);
-        if (c->d_key) cudaFree(c->d_key);
-        CUDA_OK(cudaMalloc(&c->d_rank, sizeof(unsigned) * (size_t)S.capacity));
-        CUDA_OK(cudaMalloc(&c->d_key, sizeof(unsigned) * (size_t)S.capacity));
-        c->rank_capacity = S.capacity;
-    }
+    if (ensure_particle_scratch(c, S.capacity)) return 1;
     const int ntiles = (ncells + SCAN_TILE - 1) / SCAN_TILE;
     unsigned long long* d_total = reinterpret_cast<unsigned long long*>(c->d_block_sums + ((ntiles + 1) / 2 * 2 + 2));
     double* const* cur = S.arr[S.cur];
