@@ -66,7 +66,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -143,7 +143,9 @@ def bench_ours(args):
     n = args.particles or DEFAULT_PARTICLES[wl]
     tmp = tempfile.mkdtemp(prefix="mag2d_bench_")
     d = make_deck(wl, n, world, tmp)
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated (non-default) stream: the context enqueues on it and the timing events are recorded on it
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     sim = Sim(d["config"], d["species_conf"], device=local_rank, stream=stream.cuda_stream, seed=1234 + rank)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device=dev)
@@ -322,7 +324,25 @@ def bench_e2e(sim, part_species, args, torch, stream, world, dist, dev):
             "path": "mag2d_particles_upload_soa (pinned host) -> mag2d_step -> mag2d_particles_download_soa + mag2d_rho_download"}
 
 
+class _StdoutToStderr:
+    """the reference prints progress on C++ stdout (seed, loader echoes); keep bench.py's stdout to ONE JSON line"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def reference_run(workload, d, n_cpu, steps, u=None, variant="fast"):
+    with _StdoutToStderr():
+        return _reference_run(workload, d, n_cpu, steps, u, variant)
+
+
+def _reference_run(workload, d, n_cpu, steps, u=None, variant="fast"):
     """time the reference's own CPU implementation (oracle/_ref) of the particle phase of Pic::advance
     on a bounded sample of the workload; falls back to the oracle port when oracle/_ref is absent"""
     import numpy as np
@@ -420,7 +440,7 @@ def bench_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--steps", type=int, default=48)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))

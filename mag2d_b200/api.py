@@ -153,6 +153,8 @@ class Sim:
         self.M, self.N = int(p["x_sampl"]), int(p["z_sampl"])
         self.grid = grid_desc_from_param(p)
         h = C.c_void_p()
+        # stream: a cudaStream_t handle (int); None -> the context owns a private non-blocking stream.  The
+        # legacy default stream (handle 0) cannot be named through this argument.
         self._chk(self.L.mag2d_create(device, C.byref(self.grid), C.c_void_p(stream) if stream else None, C.byref(h)))
         self.h = h
         self.L.mag2d_seed(self.h, seed)
