@@ -234,6 +234,12 @@ int mag2d_create(int device, const mag2d_grid_desc* grid, void* stream, mag2d_ct
     CUDA_OK(cudaMalloc(&c->d_u, sizeof(double) * n));
     CUDA_OK(cudaMalloc(&c->d_uRF, sizeof(double) * n));
     CUDA_OK(cudaMalloc(&c->d_ueff, sizeof(double) * n));
+    CUDA_OK(cudaMalloc(&c->d_gx, sizeof(double) * n));
+    CUDA_OK(cudaMalloc(&c->d_gz, sizeof(double) * n));
+    CUDA_OK(cudaMalloc(&c->d_cfree, n));
+    CUDA_OK(cudaMemsetAsync(c->d_cfree, 1, n, c->stream));
+    CUDA_OK(cudaMemsetAsync(c->d_gx, 0, sizeof(double) * n, c->stream));
+    CUDA_OK(cudaMemsetAsync(c->d_gz, 0, sizeof(double) * n, c->stream));
     CUDA_OK(cudaMalloc(&c->d_b, sizeof(double) * n));
     CUDA_OK(cudaMalloc(&c->d_scratch, sizeof(double) * 64));
     CUDA_OK(cudaMemsetAsync(c->d_u, 0, sizeof(double) * n, c->stream));
@@ -259,6 +265,9 @@ int mag2d_destroy(mag2d_ctx* c)
     cudaFree(c->d_u);
     cudaFree(c->d_uRF);
     cudaFree(c->d_ueff);
+    cudaFree(c->d_gx);
+    cudaFree(c->d_gz);
+    cudaFree(c->d_cfree);
     cudaFree(c->d_b);
     cudaFree(c->d_scratch);
     if (c->d_rho) cudaFree(c->d_rho);
@@ -298,6 +307,16 @@ int mag2d_set_grid(mag2d_ctx* c, const uint8_t* mask, const double* voltage)
     c->h_voltage.assign(voltage, voltage + n);
     CUDA_OK(cudaMemcpyAsync(c->d_mask, mask, n, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaMemcpyAsync(c->d_voltage, voltage, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    // t_grid::is_free per cell (fields.hpp:94-101): a particle survives when any corner of its cell is FREE
+    std::vector<unsigned char> cfree(n, 0);
+    const int M = c->g.M, N = c->g.N;
+    for (int i = 0; i + 1 < M; i++)
+        for (int j = 0; j + 1 < N; j++)
+        {
+            const size_t k = (size_t)i * N + j;
+            cfree[k] = mask[k] == MAG2D_FREE || mask[k + N] == MAG2D_FREE || mask[k + 1] == MAG2D_FREE || mask[k + N + 1] == MAG2D_FREE;
+        }
+    CUDA_OK(cudaMemcpyAsync(c->d_cfree, cfree.data(), n, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     c->grid_set = true;
     return mg_setup(c);

@@ -27,8 +27,14 @@ struct GridDev
     int deposit;          // selfconsistent                                             (particles.hpp:408)
     int pad0;
     double extern_field;
-    const double* __restrict__ ueff;          // u + phase*uRF of this step, [M*N]
-    const unsigned char* __restrict__ mask;   // [M*N]
+    // edge-centred field differences of this step's potential ue = u + phase*uRF (k_edge_fields):
+    //   gx[i][j] = (ue[i][j] - ue[i-1][j]) * idx   (row 0 is zero)
+    //   gz[i][j] = (ue[i][j] - ue[i][j-1]) * idz   (column 0 is zero)
+    // exactly the g1..g4 terms of Field2D::grad, evaluated once per node instead of once per particle
+    const double* __restrict__ gx;
+    const double* __restrict__ gz;
+    // cfree[i*N+j] = 1 when any corner of cell (i,j) is a FREE node: t_grid::is_free (fields.hpp:94-101)
+    const unsigned char* __restrict__ cfree;
     unsigned long long* __restrict__ rho;      // fixed-point charge grid of this species, [M*N]
 };
 

@@ -60,7 +60,10 @@ struct mag2d_ctx
     double* d_voltage = nullptr;
     double* d_u = nullptr;      // also mg[0].u
     double* d_uRF = nullptr;
-    double* d_ueff = nullptr;
+    double* d_ueff = nullptr;   // grid-sized scratch (u_smooth)
+    double* d_gx = nullptr;     // edge-centred field differences of the current step (push.cu: k_edge_fields)
+    double* d_gz = nullptr;
+    unsigned char* d_cfree = nullptr;   // per-cell "has a FREE corner" flag (t_grid::is_free)
     double* d_b = nullptr;      // RHS in the reference's scaling (for the residual check)
     double* d_rowscale = nullptr;  // symmetrising row scale s_i of the cylindrical operator, [M]
     unsigned long long* d_rho = nullptr;   // [n_species][M*N] fixed-point charge grids

@@ -35,60 +35,56 @@ struct PushArgs
     unsigned* coll_count;
 };
 
-// ---- gather: E = -grad(ueff), the staggered-difference bilinear form of Field2D::grad ----------
-// Edge cases of the reference (i == 0, i == jmax-1, j == 0, j == lmax-1) are folded into the general
-// formula by clamping the neighbour index and pinning the interpolation weight to 1 or 0, which
-// produces the same sums (the dropped terms are exact zeros).
+// ---- gather: E = -grad(ue), the staggered-difference bilinear form of Field2D::grad ----------------
+// The reference differences the potential around every particle; here the differences live in the
+// precomputed edge fields gx/gz (same operations, same rounding) and the particle only interpolates:
+// 8 loads instead of 12.  Edge cases of the reference (i == 0, i == jmax-1, j == 0, j == lmax-1) are
+// folded into the general formula by pinning the interpolation weight to 1 or 0 (the dropped terms are
+// exact zeros).  Float->int conversions are the expensive part on this pipe mix, so each axis is
+// converted once: (int)(X + 0.5) is derived from (int)X and the fraction.  The two differ only when X
+// lies within one ulp below a half-integer, where both stencils interpolate the same edge value.
 __device__ __forceinline__ void gather_E(const GridDev& g, double x, double z, double& Ex, double& Ez)
 {
     const int M = g.M, N = g.N;
-    const double* __restrict__ u = g.ueff;
     const double X = x * g.idx, Y = z * g.idz;
+    int ix = (int)X, jy = (int)Y;
+    ix = max(min(ix, M - 1), 0);
+    jy = max(min(jy, N - 1), 0);
+    const double dix = (double)ix, djy = (double)jy;
+    const double fxc = X - dix, fyc = Y - djy;          // cell fractions
+    const bool upx = fxc >= 0.5, upy = fyc >= 0.5;
     {
-        // NB the edge tests are done on the double, not on the clamped integer: ptxas 12.9 fuses
-        // "min(i, M-1) ... i == M-1" into one VIMNMX.RELU with a predicate output that is always
-        // true on sm_100a (observed on B200: fx came out 0 for every particle), see DESIGN.md
+        // x component: i = (int)(X + 0.5), j = min((int)Y, N-2)
+        const int i = min(ix + (upx ? 1 : 0), M - 1);
+        const int j = min(jy, N - 2);
+        double fx = X - (dix + (upx ? 1.0 : 0.0)) + .5;
+        const double fy = Y - fmin(djy, (double)(N - 2));
+        // NB edge tests on the double, not on the clamped integer: ptxas 12.9 fuses "min(i, M-1) ... i ==
+        // M-1" into a VIMNMX.RELU predicate that came out always-true on sm_100a
         const double Xs = X + 0.5;
         const bool lo = Xs < 1.0, hi = Xs >= (double)(M - 1);
-        int i = (int)Xs;
-        int j = min((int)Y, N - 2);
-        i = max(min(i, M - 1), 0);
-        j = max(j, 0);
-        double fx = X - i + .5;
-        const double fy = Y - j;
-        int im = i - 1, ip = i + 1;
-        if (lo) { im = i; fx = 1.0; }
-        if (hi) { ip = i; fx = 0.0; }
-        const double* r0 = u + (size_t)im * N + j;
-        const double* r1 = u + (size_t)i * N + j;
-        const double* r2 = u + (size_t)ip * N + j;
-        const double a0 = __ldg(r0), a1 = __ldg(r0 + 1), b0 = __ldg(r1), b1 = __ldg(r1 + 1), c0 = __ldg(r2), c1 = __ldg(r2 + 1);
-        const double g1 = (b0 - a0) * g.idx;
-        const double g2 = (b1 - a1) * g.idx;
-        const double g3 = (c1 - b1) * g.idx;
-        const double g4 = (c0 - b0) * g.idx;
+        if (lo) fx = 1.0;
+        if (hi) fx = 0.0;
+        const int ip = hi ? i : i + 1;
+        const double* r1 = g.gx + (size_t)i * N + j;
+        const double* r2 = g.gx + (size_t)ip * N + j;
+        const double g1 = __ldg(r1), g2 = __ldg(r1 + 1), g4 = __ldg(r2), g3 = __ldg(r2 + 1);
         Ex = -(g1 * (1 - fx) * (1 - fy) + g2 * (1 - fx) * fy + g3 * fx * fy + g4 * fx * (1 - fy));
     }
     {
+        // z component: i = min((int)X, M-2), j = (int)(Y + 0.5)
+        const int i = min(ix, M - 2);
+        const int j = min(jy + (upy ? 1 : 0), N - 1);
+        const double fx = X - fmin(dix, (double)(M - 2));
+        double fy = Y - (djy + (upy ? 1.0 : 0.0)) + 0.5;
         const double Ys = Y + 0.5;
         const bool lo = Ys < 1.0, hi = Ys >= (double)(N - 1);
-        int i = min((int)X, M - 2);
-        int j = (int)Ys;
-        i = max(i, 0);
-        j = max(min(j, N - 1), 0);
-        const double fx = X - i;
-        double fy = Y - j + 0.5;
-        int jm = j - 1, jp = j + 1;
-        if (lo) { jm = j; fy = 1.0; }
-        if (hi) { jp = j; fy = 0.0; }
-        const double* r0 = u + (size_t)i * N;
+        if (lo) fy = 1.0;
+        if (hi) fy = 0.0;
+        const int jp = hi ? j : j + 1;
+        const double* r0 = g.gz + (size_t)i * N;
         const double* r1 = r0 + N;
-        const double a0 = __ldg(r0 + jm), a1 = __ldg(r0 + j), a2 = __ldg(r0 + jp);
-        const double b0 = __ldg(r1 + jm), b1 = __ldg(r1 + j), b2 = __ldg(r1 + jp);
-        const double g1 = (a1 - a0) * g.idz;
-        const double g2 = (b1 - b0) * g.idz;
-        const double g3 = (b2 - b1) * g.idz;
-        const double g4 = (a2 - a1) * g.idz;
+        const double g1 = __ldg(r0 + j), g4 = __ldg(r0 + jp), g2 = __ldg(r1 + j), g3 = __ldg(r1 + jp);
         Ez = -(g1 * (1 - fx) * (1 - fy) + g2 * (1 - fy) * fx + g3 * fx * fy + g4 * fy * (1 - fx));
     }
 }
@@ -126,6 +122,16 @@ __device__ __forceinline__ void boris_velocity(const SpeciesDev& s, double Ex, d
     vz += Ez * s.hq;
 }
 
+// round-to-nearest-even of w * 2^32 for 0 <= w <= 1 (the Q32 rule of the fixed-point deposit) without the
+// slow F2I.S64 path: adding 1.5 * 2^52 leaves the integer in the low mantissa bits; the scaling by 2^32 is
+// exact, so this equals llrint(w * 4294967296.0) of the CPU restatement bit for bit
+__device__ __forceinline__ unsigned long long q32_rn(double w)
+{
+    const double magic = 6755399441055744.0;   // 1.5 * 2^52
+    const double t = __dadd_rn(__dmul_rn(w, 4294967296.0), magic);
+    return (unsigned long long)(__double_as_longlong(t) - __double_as_longlong(magic));
+}
+
 // ---- boundary + electrode absorption + fixed-point CIC weights --------------------------------------
 // Returns false when the particle is removed.  Positions may be wrapped (PERIODIC).  When DEPOSIT, node
 // receives the index of the cell's lower-left node and w the four Q32 weights (Field2D.hpp:57-60 order:
@@ -148,20 +154,15 @@ __device__ __forceinline__ bool boundary_weights(const GridDev& g, double& x, do
     i = max(min(i, g.M - 2), 0);
     j = max(min(j, g.N - 2), 0);
     const size_t k = (size_t)i * g.N + j;
-    if (g.check_mask)
-    {
-        const unsigned char* m = g.mask + k;
-        const bool is_free = (m[0] == MAG2D_FREE) | (m[g.N] == MAG2D_FREE) | (m[1] == MAG2D_FREE) | (m[g.N + 1] == MAG2D_FREE);
-        if (!is_free) return false;
-    }
+    if (g.check_mask && !g.cfree[k]) return false;
     if (DEPOSIT)
     {
         const double fu = __dsub_rn(X, (double)i), fv = __dsub_rn(Y, (double)j);
         const double cu = __dsub_rn(1.0, fu), cv = __dsub_rn(1.0, fv);
-        w[0] = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(cu, cv), 4294967296.0));
-        w[1] = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(fu, cv), 4294967296.0));
-        w[2] = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(cu, fv), 4294967296.0));
-        w[3] = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(fu, fv), 4294967296.0));
+        w[0] = q32_rn(__dmul_rn(cu, cv));
+        w[1] = q32_rn(__dmul_rn(fu, cv));
+        w[2] = q32_rn(__dmul_rn(cu, fv));
+        w[3] = q32_rn(__dmul_rn(fu, fv));
         node = (unsigned)k;
     }
     return true;
@@ -218,90 +219,171 @@ __device__ __forceinline__ void count_removed(unsigned long long* counter, bool 
 }
 
 // ---- the fused Boris step --------------------------------------------------------------------------
-// One thread per particle slot.  Collisions: only the Bernoulli test of the null-collision method
-// (uni() < 1-exp(-dt/lifetime), particles.cpp:990) runs here; the slots that fire are appended to a list
-// and scattered by k_mcc_collide afterwards.  That is legal because scatter() only changes the velocity,
-// which neither the boundary test nor the deposit reads, and it keeps the rarely-taken, register-hungry
-// collision kinematics out of this bandwidth-bound kernel.
+// A warp owns a tile of 128 consecutive slots; lane l handles the pairs (2l, 2l+1) and (64+2l, 64+2l+1)
+// of the tile, so that every array is moved with 128-bit loads/stores that a warp issues fully coalesced
+// (512 B per instruction).  Four particles per thread amortise the Philox block (one word per particle),
+// the address arithmetic and — because neighbouring slots sit in the same cell after the sort — the
+// charge scatter: a thread first merges the weights of its own particles that share a cell, then the
+// warp merges equal cells across lanes (warp_deposit).
+//
+// Collisions: only the Bernoulli test of the null-collision method (uni() < 1-exp(-dt/lifetime),
+// particles.cpp:990) runs here; the slots that fire are appended to a list and scattered by k_mcc_collide
+// afterwards.  That is legal because scatter() only changes the velocity, which neither the boundary test
+// nor the deposit reads, and it keeps the rarely-taken, register-hungry collision kinematics out of this
+// kernel.
+constexpr int PPT = 4;                       // particles per thread
+constexpr int TILE = 32 * PPT;               // slots per warp
+
 template <int COORD, bool GATHER, bool HASB, bool MCC, bool DEPOSIT>
 __global__ void __launch_bounds__(PUSH_THREADS) k_push_boris(const __grid_constant__ PushArgs A)
 {
-    const long long k = (long long)blockIdx.x * PUSH_THREADS + threadIdx.x;
-    const bool in_range = k < A.p.n;
-    double x = in_range ? A.p.x[k] : dead_marker();
-    const bool live = particle_alive(x);
-    bool removed_now = false, keep = false, hit = false;
-    unsigned node = 0;
-    unsigned long long w[4] = {0, 0, 0, 0};
-    if (live)
+    const unsigned lane = lane_id();
+    const long long warp_id = ((long long)blockIdx.x * PUSH_THREADS + threadIdx.x) >> 5;
+    const long long base = warp_id * TILE + 2 * lane;     // slot of this thread's first pair
+    const long long n = A.p.n;
+    constexpr bool need_vy = HASB || COORD == MAG2D_CYLINDRICAL;
+    double x[PPT], z[PPT], vx[PPT], vz[PPT], vy[PPT];
+    // arrays are allocated in multiples of 256 slots, so a whole tile is always readable
+    if (base - 2 * lane < n)
     {
-        double z = A.p.z[k];
-        double vx = A.p.vx[k];
-        double vz = A.p.vz[k];
-        double vy = 0.0;
-        // vy only takes part in the rotation and in collisions; cylindrical always needs it (drift)
-        const bool need_vy = HASB || COORD == MAG2D_CYLINDRICAL;
-        if (need_vy) vy = A.p.vy[k];
-        double Ex = 0.0, Ez = A.g.extern_field;
-        if (GATHER) gather_E(A.g, x, z, Ex, Ez);
-        boris_velocity<COORD, HASB>(A.s, Ex, Ez, vx, vy, vz);
-        const double dt = A.s.dt;
-        if (COORD == MAG2D_CYLINDRICAL)
+#pragma unroll
+        for (int p = 0; p < PPT / 2; p++)
         {
-            // Birdsall & Langdon p.338: drift in the local Cartesian frame, rotate back (particles.cpp:599-614)
-            const double x2 = x + vx * dt;
-            const double y2 = vy * dt;
-            x = sqrt(x2 * x2 + y2 * y2);
-            z += vz * dt;
-            double sa = y2 / x, ca = x2 / x;
-            if (x == 0) { sa = 0; ca = 1; }
-            const double t = vx;
-            vx = ca * vx + sa * vy;
-            vy = -sa * t + ca * vy;
-        }
-        else
-        {
-            x += vx * dt;
-            z += vz * dt;
-        }
-        if (MCC)
-        {
-            Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)k);
-            const uint4 r0 = rng.block();
-            hit = u01(r0.x) < A.s.prob;
-        }
-        keep = boundary_weights<DEPOSIT>(A.g, x, z, node, w);
-        if (keep)
-        {
-            A.p.x[k] = x;
-            A.p.z[k] = z;
-            A.p.vx[k] = vx;
-            A.p.vz[k] = vz;
-            if (need_vy) A.p.vy[k] = vy;
-        }
-        else
-        {
-            A.p.x[k] = dead_marker();
-            removed_now = true;
+            const long long k = base + 64 * p;
+            const double2 a = *reinterpret_cast<const double2*>(A.p.x + k);
+            const double2 b = *reinterpret_cast<const double2*>(A.p.z + k);
+            const double2 c = *reinterpret_cast<const double2*>(A.p.vx + k);
+            const double2 d = *reinterpret_cast<const double2*>(A.p.vz + k);
+            x[2 * p] = a.x; x[2 * p + 1] = a.y;
+            z[2 * p] = b.x; z[2 * p + 1] = b.y;
+            vx[2 * p] = c.x; vx[2 * p + 1] = c.y;
+            vz[2 * p] = d.x; vz[2 * p + 1] = d.y;
+            if (need_vy)
+            {
+                const double2 e = *reinterpret_cast<const double2*>(A.p.vy + k);
+                vy[2 * p] = e.x; vy[2 * p + 1] = e.y;
+            }
+            else
+                vy[2 * p] = vy[2 * p + 1] = 0.0;
         }
     }
-    if (DEPOSIT) warp_deposit(A.g.rho, A.g.N, keep, node, w);
+    else
+    {
+#pragma unroll
+        for (int q = 0; q < PPT; q++) x[q] = dead_marker();
+    }
+    uint4 rnd = make_uint4(0, 0, 0, 0);
     if (MCC)
     {
-        // warp-aggregated append to the collision list
-        hit = hit && keep;
-        const unsigned m = __ballot_sync(MAG2D_FULL_MASK, hit);
-        if (m)
+        Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)base);
+        rnd = rng.block();
+    }
+    bool keep[PPT];
+    unsigned node[PPT];
+    unsigned long long w[PPT][4];
+    unsigned hit_mask = 0, removed = 0;
+#pragma unroll
+    for (int q = 0; q < PPT; q++)
+    {
+        const long long k = base + 64 * (q >> 1) + (q & 1);
+        keep[q] = false;
+        node[q] = 0;
+        w[q][0] = w[q][1] = w[q][2] = w[q][3] = 0;
+        const bool live = k < n && particle_alive(x[q]);
+        if (live)
         {
-            const unsigned lane = lane_id();
-            const int leader = __ffs(m) - 1;
-            unsigned base = 0;
-            if ((int)lane == leader) base = atomicAdd(A.coll_count, (unsigned)__popc(m));
-            base = __shfl_sync(MAG2D_FULL_MASK, base, leader);
-            if (hit) A.coll_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)k;
+            double Ex = 0.0, Ez = A.g.extern_field;
+            if (GATHER) gather_E(A.g, x[q], z[q], Ex, Ez);
+            boris_velocity<COORD, HASB>(A.s, Ex, Ez, vx[q], vy[q], vz[q]);
+            const double dt = A.s.dt;
+            if (COORD == MAG2D_CYLINDRICAL)
+            {
+                // Birdsall & Langdon p.338: drift in the local Cartesian frame, rotate back (particles.cpp:599-614)
+                const double x2 = x[q] + vx[q] * dt;
+                const double y2 = vy[q] * dt;
+                x[q] = sqrt(x2 * x2 + y2 * y2);
+                z[q] += vz[q] * dt;
+                double sa = y2 / x[q], ca = x2 / x[q];
+                if (x[q] == 0) { sa = 0; ca = 1; }
+                const double t = vx[q];
+                vx[q] = ca * vx[q] + sa * vy[q];
+                vy[q] = -sa * t + ca * vy[q];
+            }
+            else
+            {
+                x[q] += vx[q] * dt;
+                z[q] += vz[q] * dt;
+            }
+            keep[q] = boundary_weights<DEPOSIT>(A.g, x[q], z[q], node[q], w[q]);
+            if (!keep[q])
+            {
+                x[q] = dead_marker();
+                removed++;
+            }
+            else if (MCC)
+            {
+                const unsigned word = q == 0 ? rnd.x : q == 1 ? rnd.y : q == 2 ? rnd.z : rnd.w;
+                if (u01(word) < A.s.prob) hit_mask |= 1u << q;
+            }
         }
     }
-    count_removed(A.removed, removed_now);
+    if (base - 2 * lane < n)
+    {
+#pragma unroll
+        for (int p = 0; p < PPT / 2; p++)
+        {
+            const long long k = base + 64 * p;
+            *reinterpret_cast<double2*>(A.p.x + k) = make_double2(x[2 * p], x[2 * p + 1]);
+            *reinterpret_cast<double2*>(A.p.z + k) = make_double2(z[2 * p], z[2 * p + 1]);
+            *reinterpret_cast<double2*>(A.p.vx + k) = make_double2(vx[2 * p], vx[2 * p + 1]);
+            *reinterpret_cast<double2*>(A.p.vz + k) = make_double2(vz[2 * p], vz[2 * p + 1]);
+            if (need_vy) *reinterpret_cast<double2*>(A.p.vy + k) = make_double2(vy[2 * p], vy[2 * p + 1]);
+        }
+    }
+    if (DEPOSIT)
+    {
+        // thread-level merge of equal cells (slots 2l,2l+1 and 64+2l,64+2l+1 are neighbours in sorted order)
+#pragma unroll
+        for (int q = 1; q < PPT; q++)
+        {
+            const int r = (q & 1) ? q - 1 : 0;      // 1->0, 2->0, 3->2
+            if (keep[q] && keep[r] && node[q] == node[r])
+            {
+#pragma unroll
+                for (int c = 0; c < 4; c++) w[r][c] += w[q][c];
+                keep[q] = false;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < PPT; q++) warp_deposit(A.g.rho, A.g.N, keep[q], node[q], w[q]);
+    }
+    if (MCC)
+    {
+        // warp-aggregated append of the firing slots to the collision list
+        const unsigned cnt = __popc(hit_mask);
+        unsigned incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned t = __shfl_up_sync(MAG2D_FULL_MASK, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        const unsigned total = __shfl_sync(MAG2D_FULL_MASK, incl, 31);
+        if (total)
+        {
+            unsigned start = 0;
+            if (lane == 31) start = atomicAdd(A.coll_count, total);
+            start = __shfl_sync(MAG2D_FULL_MASK, start, 31) + incl - cnt;
+#pragma unroll
+            for (int q = 0; q < PPT; q++)
+                if (hit_mask & (1u << q)) A.coll_list[start++] = (unsigned)(base + 64 * (q >> 1) + (q & 1));
+        }
+    }
+    // removal counter: one atomic per warp
+    unsigned rsum = removed;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(MAG2D_FULL_MASK, rsum, o);
+    if (rsum && lane == 0) atomicAdd(A.removed, (unsigned long long)rsum);
 }
 
 // second pass of the Boris movers: BaseSpecies::scatter for the slots whose Bernoulli test fired
@@ -450,10 +532,19 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_accumulate(const __grid_consta
     warp_deposit(A.g.rho, A.g.N, valid, node, w);
 }
 
-__global__ void k_ueff(const double* __restrict__ u, const double* __restrict__ urf, double phase, double* __restrict__ out, int n)
+// edge-centred differences of ue = u + phase*uRF: the g1..g4 terms of Field2D::grad (Field2D.hpp:97-100,
+// 141-144), once per node and step instead of once per particle
+__global__ void k_edge_fields(const double* __restrict__ u, const double* __restrict__ urf, double phase, int rf, int M, int N,
+                              double idx, double idz, double* __restrict__ gx, double* __restrict__ gz)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) out[k] = u[k] + urf[k] * phase;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= M || j >= N) return;
+    const size_t k = (size_t)i * N + j;
+    auto ue = [&](size_t q) { return rf ? u[q] + urf[q] * phase : u[q]; };
+    const double c = ue(k);
+    gx[k] = i > 0 ? (c - ue(k - N)) * idx : 0.0;
+    gz[k] = j > 0 ? (c - ue(k - 1)) * idz : 0.0;
 }
 
 // Fields::E at arbitrary points (diagnostics, parity tests)
@@ -667,8 +758,9 @@ GridDev grid_view(const mag2d_ctx* c, int s)
     g.check_mask = !d.electric_field_from_file;
     g.deposit = d.selfconsistent;
     g.extern_field = d.extern_field;
-    g.ueff = d.rf ? c->d_ueff : c->d_u;
-    g.mask = c->d_mask;
+    g.gx = c->d_gx;
+    g.gz = c->d_gz;
+    g.cfree = c->d_cfree;
     g.rho = s >= 0 ? c->d_rho + (size_t)s * d.M * d.N : nullptr;
     return g;
 }
@@ -756,9 +848,9 @@ int ensure_particle_scratch(mag2d_ctx* c, long long capacity)
 
 int update_ueff(mag2d_ctx* c, double phase, bool rf)
 {
-    if (!rf) return 0;
-    const int n = c->g.M * c->g.N;
-    k_ueff<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_u, c->d_uRF, phase, c->d_ueff, n);
+    const int M = c->g.M, N = c->g.N;
+    const dim3 block(32, 8), grid((N + 31) / 32, (M + 7) / 8);
+    k_edge_fields<<<grid, block, 0, c->stream>>>(c->d_u, c->d_uRF, phase, rf ? 1 : 0, M, N, c->g.idx, c->g.idz, c->d_gx, c->d_gz);
     c->launches++;
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -794,6 +886,7 @@ int launch_species_advance(mag2d_ctx* c, int s)
         A.coll_list = nullptr;
         A.coll_count = nullptr;
         const unsigned blocks = (unsigned)((S.n_slots + PUSH_THREADS - 1) / PUSH_THREADS);
+        const unsigned tile_blocks = (unsigned)((S.n_slots + PUSH_THREADS * PPT - 1) / (PUSH_THREADS * PPT));
         const bool mcc = S.h_blob && S.h_blob->has_collisions && std::isfinite(S.lifetime);
         if (d.mover == MAG2D_ADVANCE_MULTICOLL)
         {
@@ -825,8 +918,8 @@ int launch_species_advance(mag2d_ctx* c, int s)
         else
         {
             const bool gather = !A.g.const_E;
-            if (gather && d.rf)
-                if (update_ueff(c, rf_phase(c, S), true)) return 1;
+            if (gather)
+                if (update_ueff(c, d.rf ? rf_phase(c, S) : 0.0, d.rf != 0)) return 1;
             if (mcc)
             {
                 if (ensure_particle_scratch(c, S.capacity)) return 1;
@@ -835,9 +928,9 @@ int launch_species_advance(mag2d_ctx* c, int s)
                 CUDA_OK(cudaMemsetAsync(c->d_coll_count, 0, sizeof(unsigned), c->stream));
             }
             if (d.coord == MAG2D_CYLINDRICAL)
-                launch_boris_variant<MAG2D_CYLINDRICAL>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, blocks);
+                launch_boris_variant<MAG2D_CYLINDRICAL>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, tile_blocks);
             else
-                launch_boris_variant<MAG2D_CARTESIAN>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, blocks);
+                launch_boris_variant<MAG2D_CARTESIAN>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, tile_blocks);
             if (mcc)
             {
                 k_mcc_collide<<<148 * 8, 128, 0, c->stream>>>(A);
@@ -874,8 +967,8 @@ int launch_species_advance_init(mag2d_ctx* c, int s)
     A.seed = c->seed;
     const unsigned blocks = (unsigned)((S.n_slots + PUSH_THREADS - 1) / PUSH_THREADS);
     const bool gather = !A.g.const_E;
-    if (gather && d.rf)
-        if (update_ueff(c, rf_phase(c, S), true)) return 1;
+    if (gather)
+        if (update_ueff(c, d.rf ? rf_phase(c, S) : 0.0, d.rf != 0)) return 1;
     if (d.coord == MAG2D_CYLINDRICAL)
     {
         if (gather) k_push_boris_init<MAG2D_CYLINDRICAL, true><<<blocks, PUSH_THREADS, 0, c->stream>>>(A);
@@ -916,11 +1009,11 @@ int launch_field_E(mag2d_ctx* c, int n, const double* x, const double* z, double
     CUDA_OK(cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaMemcpyAsync(dz, z, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     GridDev g = grid_view(c, -1);
-    if (!g.const_E && c->g.rf)
+    if (!g.const_E)
     {
         double phase = mod_ref(c->g.rf_omega * time, 10000000 * M_PI);
         phase = c->g.rf_amplitude * cos(phase) + c->g.rf_U0;
-        if (update_ueff(c, phase, true)) return 1;
+        if (update_ueff(c, phase, c->g.rf != 0)) return 1;
     }
     k_field_E<<<(n + 255) / 256, 256, 0, c->stream>>>(g, n, dx, dz, dex, dez);
     c->launches++;

@@ -20,19 +20,37 @@ __global__ void k_sort_count(const double* __restrict__ x, const double* __restr
                              int M, int N, unsigned* __restrict__ count, unsigned* __restrict__ key, unsigned* __restrict__ rank)
 {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const double px = x[k];
+    const double px = k < n ? x[k] : dead_marker();
+    const bool valid = particle_alive(px);
     unsigned ky = INVALID_KEY, rk = 0;
-    if (particle_alive(px))
+    if (valid)
     {
         int i = (int)(px * idx), j = (int)(z[k] * idz);
         i = max(min(i, M - 2), 0);
         j = max(min(j, N - 2), 0);
         ky = (unsigned)i * (unsigned)(N - 1) + (unsigned)j;
-        rk = atomicAdd(&count[ky], 1u);
     }
-    key[k] = ky;
-    rank[k] = rk;
+    // warp-aggregated ticket: the store is already almost sorted, so the lanes of a warp share a few cells;
+    // one atomic per (warp, cell) instead of one per particle, ranks handed out in lane order
+    const unsigned lane = lane_id();
+    unsigned remaining = __ballot_sync(MAG2D_FULL_MASK, valid);
+    while (remaining)
+    {
+        const int src = __ffs(remaining) - 1;
+        const unsigned k0 = __shfl_sync(MAG2D_FULL_MASK, ky, src);
+        const bool mine = valid && ky == k0;
+        const unsigned m = __ballot_sync(MAG2D_FULL_MASK, mine);
+        unsigned base = 0;
+        if ((int)lane == src) base = atomicAdd(&count[k0], (unsigned)__popc(m));
+        base = __shfl_sync(MAG2D_FULL_MASK, base, src);
+        if (mine) rk = base + __popc(m & ((1u << lane) - 1u));
+        remaining &= ~m;
+    }
+    if (k < n)
+    {
+        key[k] = ky;
+        rank[k] = rk;
+    }
 }
 
 // exclusive scan, level 1: per-tile scan + tile sums
@@ -155,8 +173,8 @@ __global__ void k_sort_scatter(const __grid_constant__ PermArgs P, long long n, 
 // slots behind the compacted particles become dead markers
 __global__ void k_fill_dead(double* __restrict__ x, const unsigned long long* __restrict__ total, long long n)
 {
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x + (long long)*total;
-    if (k < n) x[k] = dead_marker();
+    for (long long k = (long long)*total + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+        x[k] = dead_marker();
 }
 
 }  // namespace
@@ -197,7 +215,7 @@ int launch_sort(mag2d_ctx* c, int s, bool trim)
         }
     for (int a = P.n_arr; a < N_ARR; a++) { P.src[a] = nullptr; P.dst[a] = nullptr; }
     k_sort_scatter<<<pblocks, 256, 0, c->stream>>>(P, n, c->d_key, c->d_rank, c->d_cell_offset);
-    k_fill_dead<<<pblocks, 256, 0, c->stream>>>(oth[ARR_X], d_total, n);
+    k_fill_dead<<<148 * 4, 256, 0, c->stream>>>(oth[ARR_X], d_total, n);
     c->launches += 6;
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemsetAsync(S.d_removed, 0, sizeof(unsigned long long), c->stream));
