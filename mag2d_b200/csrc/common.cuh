@@ -27,6 +27,7 @@ struct GridDev
     int deposit;          // selfconsistent                                             (particles.hpp:408)
     int pad0;
     double extern_field;
+    double dM1, dM2, dN1, dN2;   // (double)(M-1), (M-2), (N-1), (N-2): int->double conversions are slow
     // edge-centred field differences of this step's potential ue = u + phase*uRF (k_edge_fields):
     //   gx[i][j] = (ue[i][j] - ue[i-1][j]) * idx   (row 0 is zero)
     //   gz[i][j] = (ue[i][j] - ue[i][j-1]) * idz   (column 0 is zero)

@@ -51,41 +51,38 @@ __device__ __forceinline__ void gather_E(const GridDev& g, double x, double z, d
     ix = max(min(ix, M - 1), 0);
     jy = max(min(jy, N - 1), 0);
     const double dix = (double)ix, djy = (double)jy;
-    const double fxc = X - dix, fyc = Y - djy;          // cell fractions
-    const bool upx = fxc >= 0.5, upy = fyc >= 0.5;
+    const bool upx = X - dix >= 0.5, upy = Y - djy >= 0.5;
+    // NB edge tests on the double, not on the clamped integer: ptxas 12.9 fuses "min(i, M-1) ... i == M-1"
+    // into a VIMNMX.RELU predicate that came out always-true on sm_100a
+    const double Xs = X + 0.5, Ys = Y + 0.5;
+    const bool xlo = Xs < 1.0, xhi = Xs >= g.dM1, zlo = Ys < 1.0, zhi = Ys >= g.dN1;
     {
         // x component: i = (int)(X + 0.5), j = min((int)Y, N-2)
         const int i = min(ix + (upx ? 1 : 0), M - 1);
         const int j = min(jy, N - 2);
-        double fx = X - (dix + (upx ? 1.0 : 0.0)) + .5;
-        const double fy = Y - fmin(djy, (double)(N - 2));
-        // NB edge tests on the double, not on the clamped integer: ptxas 12.9 fuses "min(i, M-1) ... i ==
-        // M-1" into a VIMNMX.RELU predicate that came out always-true on sm_100a
-        const double Xs = X + 0.5;
-        const bool lo = Xs < 1.0, hi = Xs >= (double)(M - 1);
-        if (lo) fx = 1.0;
-        if (hi) fx = 0.0;
-        const int ip = hi ? i : i + 1;
-        const double* r1 = g.gx + (size_t)i * N + j;
-        const double* r2 = g.gx + (size_t)ip * N + j;
+        double fx = X - (upx ? dix + 1.0 : dix) + .5;
+        const double fy = Y - fmin(djy, g.dN2);
+        fx = xlo ? 1.0 : fx;
+        fx = xhi ? 0.0 : fx;
+        const double* r1 = g.gx + ((unsigned)i * (unsigned)N + (unsigned)j);
+        const double* r2 = r1 + (xhi ? 0 : N);
         const double g1 = __ldg(r1), g2 = __ldg(r1 + 1), g4 = __ldg(r2), g3 = __ldg(r2 + 1);
-        Ex = -(g1 * (1 - fx) * (1 - fy) + g2 * (1 - fx) * fy + g3 * fx * fy + g4 * fx * (1 - fy));
+        const double cx = 1 - fx, cy = 1 - fy;
+        Ex = -(g1 * cx * cy + g2 * cx * fy + g3 * fx * fy + g4 * fx * cy);
     }
     {
         // z component: i = min((int)X, M-2), j = (int)(Y + 0.5)
         const int i = min(ix, M - 2);
         const int j = min(jy + (upy ? 1 : 0), N - 1);
-        const double fx = X - fmin(dix, (double)(M - 2));
-        double fy = Y - (djy + (upy ? 1.0 : 0.0)) + 0.5;
-        const double Ys = Y + 0.5;
-        const bool lo = Ys < 1.0, hi = Ys >= (double)(N - 1);
-        if (lo) fy = 1.0;
-        if (hi) fy = 0.0;
-        const int jp = hi ? j : j + 1;
-        const double* r0 = g.gz + (size_t)i * N;
-        const double* r1 = r0 + N;
-        const double g1 = __ldg(r0 + j), g4 = __ldg(r0 + jp), g2 = __ldg(r1 + j), g3 = __ldg(r1 + jp);
-        Ez = -(g1 * (1 - fx) * (1 - fy) + g2 * (1 - fy) * fx + g3 * fx * fy + g4 * fy * (1 - fx));
+        const double fx = X - fmin(dix, g.dM2);
+        double fy = Y - (upy ? djy + 1.0 : djy) + 0.5;
+        fy = zlo ? 1.0 : fy;
+        fy = zhi ? 0.0 : fy;
+        const double* r0 = g.gz + ((unsigned)i * (unsigned)N + (unsigned)j);
+        const int jo = zhi ? 0 : 1;
+        const double g1 = __ldg(r0), g4 = __ldg(r0 + jo), g2 = __ldg(r0 + N), g3 = __ldg(r0 + N + jo);
+        const double cx = 1 - fx, cy = 1 - fy;
+        Ez = -(g1 * cx * cy + g2 * cy * fx + g3 * fx * fy + g4 * fy * cx);
     }
 }
 
@@ -139,9 +136,9 @@ __device__ __forceinline__ unsigned long long q32_rn(double w)
 template <bool DEPOSIT>
 __device__ __forceinline__ bool boundary_weights(const GridDev& g, double& x, double& z, unsigned& node, unsigned long long (&w)[4])
 {
-    if (x < 0.0 || x > g.x_max || z < 0.0 || z > g.z_max)
+    if (!(x >= 0.0 && x <= g.x_max && z >= 0.0 && z <= g.z_max))
     {
-        if (g.boundary == MAG2D_BOUNDARY_FREE) return false;
+        if (g.boundary == MAG2D_BOUNDARY_FREE || !(x == x && z == z)) return false;
         x = fmod(x, g.x_max);
         if (x < 0) x += g.x_max;
         z = fmod(z, g.z_max);
@@ -174,36 +171,43 @@ __device__ __forceinline__ bool boundary_weights(const GridDev& g, double& x, do
 // pieces per weight: hi = w >> 16 <= 2^16, lo < 2^16, so 32 lanes cannot overflow) and lanes 0..3 issue one
 // RED.ADD.64 each.  Integer sums are associative: the grid is bit-identical to the unaggregated scatter.
 // After MAX_RUNS distinct cells the remaining lanes fall back to their own four REDs (unsorted input).
+template <int MAX_RUNS>
 __device__ __forceinline__ void warp_deposit(unsigned long long* __restrict__ rho, int N, bool valid, unsigned node,
                                              const unsigned long long (&w)[4])
 {
-    constexpr int MAX_RUNS = 8;
     const unsigned lane = lane_id();
     unsigned remaining = __ballot_sync(MAG2D_FULL_MASK, valid);
+    if (remaining == 0) return;
+    // 32-bit pieces once per entry: hi = w >> 16 (<= 2^16), lo = w & 0xffff
+    unsigned piece[8];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+    {
+        piece[2 * q] = (unsigned)(w[q] & 0xFFFFu);
+        piece[2 * q + 1] = (unsigned)(w[q] >> 16);
+    }
+#pragma unroll 1
     for (int it = 0; remaining && it < MAX_RUNS; it++)
     {
         const int src = __ffs(remaining) - 1;
         const unsigned k0 = __shfl_sync(MAG2D_FULL_MASK, node, src);
         const bool mine = valid && node == k0;
         const unsigned m = __ballot_sync(MAG2D_FULL_MASK, mine);
-        unsigned long long t[4];
+        unsigned sum[8];
 #pragma unroll
-        for (int q = 0; q < 4; q++)
-        {
-            const unsigned lo = __reduce_add_sync(MAG2D_FULL_MASK, mine ? (unsigned)(w[q] & 0xFFFFu) : 0u);
-            const unsigned hi = __reduce_add_sync(MAG2D_FULL_MASK, mine ? (unsigned)(w[q] >> 16) : 0u);
-            t[q] = ((unsigned long long)hi << 16) + lo;
-        }
+        for (int q = 0; q < 8; q++) sum[q] = __reduce_add_sync(MAG2D_FULL_MASK, mine ? piece[q] : 0u);
         if (lane < 4)
         {
-            const unsigned long long v = lane == 0 ? t[0] : lane == 1 ? t[1] : lane == 2 ? t[2] : t[3];
-            const size_t off = (size_t)k0 + (lane & 1 ? (size_t)N : 0) + (lane >> 1);
-            atomicAdd(rho + off, v);
+            const unsigned lo = lane == 0 ? sum[0] : lane == 1 ? sum[2] : lane == 2 ? sum[4] : sum[6];
+            const unsigned hi = lane == 0 ? sum[1] : lane == 1 ? sum[3] : lane == 2 ? sum[5] : sum[7];
+            const unsigned off = k0 + (lane & 1 ? (unsigned)N : 0u) + (lane >> 1);
+            atomicAdd(rho + off, ((unsigned long long)hi << 16) + lo);
         }
         remaining &= ~m;
     }
     if (valid && ((remaining >> lane) & 1u))
     {
+        // left-overs (particles that drifted away from the cells the warp mostly sits in): own REDs
         unsigned long long* r = rho + node;
         atomicAdd(r, w[0]);
         atomicAdd(r + N, w[1]);
@@ -233,144 +237,118 @@ __device__ __forceinline__ void count_removed(unsigned long long* counter, bool 
 // kernel.
 constexpr int PPT = 4;                       // particles per thread
 constexpr int TILE = 32 * PPT;               // slots per warp
+constexpr int DEPOSIT_RUNS = 4;              // cells per warp call that get the REDUX treatment
 
 template <int COORD, bool GATHER, bool HASB, bool MCC, bool DEPOSIT>
-__global__ void __launch_bounds__(PUSH_THREADS) k_push_boris(const __grid_constant__ PushArgs A)
+__global__ void __launch_bounds__(PUSH_THREADS, 3) k_push_boris(const __grid_constant__ PushArgs A)
 {
     const unsigned lane = lane_id();
     const long long warp_id = ((long long)blockIdx.x * PUSH_THREADS + threadIdx.x) >> 5;
-    const long long base = warp_id * TILE + 2 * lane;     // slot of this thread's first pair
+    const long long tile0 = warp_id * TILE;
     const long long n = A.p.n;
+    if (tile0 >= n) return;                   // warp-uniform; arrays are allocated in multiples of 256 slots
+    const long long base = tile0 + 2 * lane;  // slot of this thread's first pair
     constexpr bool need_vy = HASB || COORD == MAG2D_CYLINDRICAL;
-    double x[PPT], z[PPT], vx[PPT], vz[PPT], vy[PPT];
-    // arrays are allocated in multiples of 256 slots, so a whole tile is always readable
-    if (base - 2 * lane < n)
-    {
-#pragma unroll
-        for (int p = 0; p < PPT / 2; p++)
-        {
-            const long long k = base + 64 * p;
-            const double2 a = *reinterpret_cast<const double2*>(A.p.x + k);
-            const double2 b = *reinterpret_cast<const double2*>(A.p.z + k);
-            const double2 c = *reinterpret_cast<const double2*>(A.p.vx + k);
-            const double2 d = *reinterpret_cast<const double2*>(A.p.vz + k);
-            x[2 * p] = a.x; x[2 * p + 1] = a.y;
-            z[2 * p] = b.x; z[2 * p + 1] = b.y;
-            vx[2 * p] = c.x; vx[2 * p + 1] = c.y;
-            vz[2 * p] = d.x; vz[2 * p + 1] = d.y;
-            if (need_vy)
-            {
-                const double2 e = *reinterpret_cast<const double2*>(A.p.vy + k);
-                vy[2 * p] = e.x; vy[2 * p + 1] = e.y;
-            }
-            else
-                vy[2 * p] = vy[2 * p + 1] = 0.0;
-        }
-    }
-    else
-    {
-#pragma unroll
-        for (int q = 0; q < PPT; q++) x[q] = dead_marker();
-    }
     uint4 rnd = make_uint4(0, 0, 0, 0);
     if (MCC)
     {
         Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)base);
         rnd = rng.block();
     }
-    bool keep[PPT];
-    unsigned node[PPT];
-    unsigned long long w[PPT][4];
+    const double dt = A.s.dt;
     unsigned hit_mask = 0, removed = 0;
 #pragma unroll
-    for (int q = 0; q < PPT; q++)
+    for (int p = 0; p < PPT / 2; p++)
     {
-        const long long k = base + 64 * (q >> 1) + (q & 1);
-        keep[q] = false;
-        node[q] = 0;
-        w[q][0] = w[q][1] = w[q][2] = w[q][3] = 0;
-        const bool live = k < n && particle_alive(x[q]);
-        if (live)
+        const long long k = base + 64 * p;
+        double x[2], z[2], vx[2], vz[2], vy[2];
         {
+            const double2 a = *reinterpret_cast<const double2*>(A.p.x + k);
+            const double2 b = *reinterpret_cast<const double2*>(A.p.z + k);
+            const double2 c = *reinterpret_cast<const double2*>(A.p.vx + k);
+            const double2 d = *reinterpret_cast<const double2*>(A.p.vz + k);
+            x[0] = a.x; x[1] = a.y; z[0] = b.x; z[1] = b.y;
+            vx[0] = c.x; vx[1] = c.y; vz[0] = d.x; vz[1] = d.y;
+            vy[0] = vy[1] = 0.0;
+            if (need_vy)
+            {
+                const double2 e = *reinterpret_cast<const double2*>(A.p.vy + k);
+                vy[0] = e.x; vy[1] = e.y;
+            }
+        }
+        bool keep[2];
+        unsigned node[2];
+        unsigned long long w[2][4];
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+        {
+            // removed slots (x = NaN) and the slots past n are pushed like everybody else — NaNs and garbage
+            // only ever index clamped cells — and masked out at the end: no divergent branch in the hot path
+            const bool live = (k + e < n) && particle_alive(x[e]);
             double Ex = 0.0, Ez = A.g.extern_field;
-            if (GATHER) gather_E(A.g, x[q], z[q], Ex, Ez);
-            boris_velocity<COORD, HASB>(A.s, Ex, Ez, vx[q], vy[q], vz[q]);
-            const double dt = A.s.dt;
+            if (GATHER) gather_E(A.g, x[e], z[e], Ex, Ez);
+            boris_velocity<COORD, HASB>(A.s, Ex, Ez, vx[e], vy[e], vz[e]);
             if (COORD == MAG2D_CYLINDRICAL)
             {
                 // Birdsall & Langdon p.338: drift in the local Cartesian frame, rotate back (particles.cpp:599-614)
-                const double x2 = x[q] + vx[q] * dt;
-                const double y2 = vy[q] * dt;
-                x[q] = sqrt(x2 * x2 + y2 * y2);
-                z[q] += vz[q] * dt;
-                double sa = y2 / x[q], ca = x2 / x[q];
-                if (x[q] == 0) { sa = 0; ca = 1; }
-                const double t = vx[q];
-                vx[q] = ca * vx[q] + sa * vy[q];
-                vy[q] = -sa * t + ca * vy[q];
+                const double x2 = x[e] + vx[e] * dt;
+                const double y2 = vy[e] * dt;
+                x[e] = sqrt(x2 * x2 + y2 * y2);
+                z[e] += vz[e] * dt;
+                double sa = y2 / x[e], ca = x2 / x[e];
+                if (x[e] == 0) { sa = 0; ca = 1; }
+                const double t = vx[e];
+                vx[e] = ca * vx[e] + sa * vy[e];
+                vy[e] = -sa * t + ca * vy[e];
             }
             else
             {
-                x[q] += vx[q] * dt;
-                z[q] += vz[q] * dt;
+                x[e] += vx[e] * dt;
+                z[e] += vz[e] * dt;
             }
-            keep[q] = boundary_weights<DEPOSIT>(A.g, x[q], z[q], node[q], w[q]);
-            if (!keep[q])
+            const bool inside = boundary_weights<DEPOSIT>(A.g, x[e], z[e], node[e], w[e]);
+            keep[e] = live && inside;
+            removed += (live && !inside) ? 1u : 0u;
+            if (!keep[e]) x[e] = dead_marker();
+            if (MCC)
             {
-                x[q] = dead_marker();
-                removed++;
-            }
-            else if (MCC)
-            {
+                const int q = 2 * p + e;
                 const unsigned word = q == 0 ? rnd.x : q == 1 ? rnd.y : q == 2 ? rnd.z : rnd.w;
-                if (u01(word) < A.s.prob) hit_mask |= 1u << q;
+                if (keep[e] && u01(word) < A.s.prob) hit_mask |= 1u << q;
             }
         }
-    }
-    if (base - 2 * lane < n)
-    {
-#pragma unroll
-        for (int p = 0; p < PPT / 2; p++)
+        *reinterpret_cast<double2*>(A.p.x + k) = make_double2(x[0], x[1]);
+        *reinterpret_cast<double2*>(A.p.z + k) = make_double2(z[0], z[1]);
+        *reinterpret_cast<double2*>(A.p.vx + k) = make_double2(vx[0], vx[1]);
+        *reinterpret_cast<double2*>(A.p.vz + k) = make_double2(vz[0], vz[1]);
+        if (need_vy) *reinterpret_cast<double2*>(A.p.vy + k) = make_double2(vy[0], vy[1]);
+        if (DEPOSIT)
         {
-            const long long k = base + 64 * p;
-            *reinterpret_cast<double2*>(A.p.x + k) = make_double2(x[2 * p], x[2 * p + 1]);
-            *reinterpret_cast<double2*>(A.p.z + k) = make_double2(z[2 * p], z[2 * p + 1]);
-            *reinterpret_cast<double2*>(A.p.vx + k) = make_double2(vx[2 * p], vx[2 * p + 1]);
-            *reinterpret_cast<double2*>(A.p.vz + k) = make_double2(vz[2 * p], vz[2 * p + 1]);
-            if (need_vy) *reinterpret_cast<double2*>(A.p.vy + k) = make_double2(vy[2 * p], vy[2 * p + 1]);
-        }
-    }
-    if (DEPOSIT)
-    {
-        // thread-level merge of equal cells (slots 2l,2l+1 and 64+2l,64+2l+1 are neighbours in sorted order)
-#pragma unroll
-        for (int q = 1; q < PPT; q++)
-        {
-            const int r = (q & 1) ? q - 1 : 0;      // 1->0, 2->0, 3->2
-            if (keep[q] && keep[r] && node[q] == node[r])
+            // neighbouring slots share a cell after the sort: merge the pair, then merge across the warp
+            if (keep[0] && keep[1] && node[0] == node[1])
             {
 #pragma unroll
-                for (int c = 0; c < 4; c++) w[r][c] += w[q][c];
-                keep[q] = false;
+                for (int c = 0; c < 4; c++) w[0][c] += w[1][c];
+                keep[1] = false;
             }
+            warp_deposit<DEPOSIT_RUNS>(A.g.rho, A.g.N, keep[0], node[0], w[0]);
+            warp_deposit<DEPOSIT_RUNS>(A.g.rho, A.g.N, keep[1], node[1], w[1]);
         }
-#pragma unroll
-        for (int q = 0; q < PPT; q++) warp_deposit(A.g.rho, A.g.N, keep[q], node[q], w[q]);
     }
     if (MCC)
     {
         // warp-aggregated append of the firing slots to the collision list
         const unsigned cnt = __popc(hit_mask);
-        unsigned incl = cnt;
+        if (__any_sync(MAG2D_FULL_MASK, cnt != 0))
+        {
+            unsigned incl = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            const unsigned t = __shfl_up_sync(MAG2D_FULL_MASK, incl, o);
-            if (lane >= (unsigned)o) incl += t;
-        }
-        const unsigned total = __shfl_sync(MAG2D_FULL_MASK, incl, 31);
-        if (total)
-        {
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const unsigned t = __shfl_up_sync(MAG2D_FULL_MASK, incl, o);
+                if (lane >= (unsigned)o) incl += t;
+            }
+            const unsigned total = __shfl_sync(MAG2D_FULL_MASK, incl, 31);
             unsigned start = 0;
             if (lane == 31) start = atomicAdd(A.coll_count, total);
             start = __shfl_sync(MAG2D_FULL_MASK, start, 31) + incl - cnt;
@@ -379,11 +357,14 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push_boris(const __grid_consta
                 if (hit_mask & (1u << q)) A.coll_list[start++] = (unsigned)(base + 64 * (q >> 1) + (q & 1));
         }
     }
-    // removal counter: one atomic per warp
-    unsigned rsum = removed;
+    // removal counter: one atomic per warp, only when something was removed
+    if (__any_sync(MAG2D_FULL_MASK, removed != 0))
+    {
+        unsigned rsum = removed;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(MAG2D_FULL_MASK, rsum, o);
-    if (rsum && lane == 0) atomicAdd(A.removed, (unsigned long long)rsum);
+        for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(MAG2D_FULL_MASK, rsum, o);
+        if (lane == 0) atomicAdd(A.removed, (unsigned long long)rsum);
+    }
 }
 
 // second pass of the Boris movers: BaseSpecies::scatter for the slots whose Bernoulli test fired
@@ -529,7 +510,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_accumulate(const __grid_consta
         g.boundary = MAG2D_BOUNDARY_PERIODIC;   // never drop here: accumulate() deposits every live particle
         valid = boundary_weights<true>(g, x, z, node, w);
     }
-    warp_deposit(A.g.rho, A.g.N, valid, node, w);
+    warp_deposit<8>(A.g.rho, A.g.N, valid, node, w);
 }
 
 // edge-centred differences of ue = u + phase*uRF: the g1..g4 terms of Field2D::grad (Field2D.hpp:97-100,
@@ -758,6 +739,10 @@ GridDev grid_view(const mag2d_ctx* c, int s)
     g.check_mask = !d.electric_field_from_file;
     g.deposit = d.selfconsistent;
     g.extern_field = d.extern_field;
+    g.dM1 = (double)(d.M - 1);
+    g.dM2 = (double)(d.M - 2);
+    g.dN1 = (double)(d.N - 1);
+    g.dN2 = (double)(d.N - 2);
     g.gx = c->d_gx;
     g.gz = c->d_gz;
     g.cfree = c->d_cfree;
