@@ -102,6 +102,9 @@ int mag2d_get_potential(mag2d_ctx* ctx, int which, double* values);
 int mag2d_solve(mag2d_ctx* ctx, int rf, double tol, int max_cycles, int* cycles_out, double* resid_out);
 /* solver knobs for mag2d_step: V-cycles per step (0 = iterate to tol) and the tolerance */
 int mag2d_set_solver(mag2d_ctx* ctx, int cycles_per_step, double tol, int max_cycles);
+/* V-cycles used and convergence measure reached by the most recent solve (also the one inside mag2d_step
+ * when cycles_per_step == 0; with a fixed cycle count the residual is not evaluated and reads 0) */
+int mag2d_solver_stats(mag2d_ctx* ctx, int* last_cycles, double* last_resid);
 /* Fields::u_smooth, src/fields.cpp:28-113 */
 int mag2d_u_smooth(mag2d_ctx* ctx, int symmetry, double radius);
 /* Fields::E at n points, src/fields.hpp:124-150 (diagnostics / parity checks) */

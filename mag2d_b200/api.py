@@ -15,7 +15,7 @@ from . import config as cfg
 from . import geometry
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmag2d_b200.so")
+LIB_PATH = os.environ.get("MAG2D_B200_LIB") or os.path.join(HERE, "libmag2d_b200.so")   # env: tuning builds
 
 dp = C.POINTER(C.c_double)
 i64p = C.POINTER(C.c_int64)
@@ -80,6 +80,7 @@ def lib():
     L.mag2d_get_potential.argtypes = [vp, C.c_int, dp]
     L.mag2d_solve.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp]
     L.mag2d_set_solver.argtypes = [vp, C.c_int, C.c_double, C.c_int]
+    L.mag2d_solver_stats.argtypes = [vp, C.POINTER(C.c_int), dp]
     L.mag2d_u_smooth.argtypes = [vp, C.c_int, C.c_double]
     L.mag2d_field_E.argtypes = [vp, C.c_int, dp, dp, C.c_double, dp, dp]
     L.mag2d_set_species.argtypes = [vp, C.c_int, C.POINTER(SpeciesDesc), C.c_int, C.POINTER(InteractionDesc), dp, dp, C.c_int]
@@ -321,6 +322,11 @@ class Sim:
 
     def set_solver(self, cycles_per_step=0, tol=1e-13, max_cycles=100):
         self._chk(self.L.mag2d_set_solver(self.h, cycles_per_step, tol, max_cycles))
+
+    def solver_stats(self):
+        cyc, res = C.c_int(), C.c_double()
+        self._chk(self.L.mag2d_solver_stats(self.h, C.byref(cyc), C.byref(res)))
+        return dict(cycles=cyc.value, resid=res.value)
 
     def get_field(self, which):
         if which == "mask":

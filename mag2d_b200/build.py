@@ -35,13 +35,18 @@ def _deps():
     return out
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra=(), out=None):
+    """extra: additional nvcc flags (tuning experiments), out: alternative output path"""
+    global LIB, OBJ
+    if out:
+        LIB = out
+        OBJ = out + ".build"
     newest = max(os.path.getmtime(p) for p in _deps())
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     common = [_nvcc(), "-O3", "-std=c++17", "-lineinfo", "-ccbin", _ccbin(), "-Xcompiler", "-fPIC",
-              "--cudart", "shared"] + ARCH
+              "--cudart", "shared"] + ARCH + list(extra)
     if verbose:
         common += ["-Xptxas", "-v"]
 
@@ -65,4 +70,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    out = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")), None)
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, extra=extra, out=out))

@@ -361,6 +361,14 @@ int mag2d_set_solver(mag2d_ctx* c, int cycles_per_step, double tol, int max_cycl
     return 0;
 }
 
+int mag2d_solver_stats(mag2d_ctx* c, int* last_cycles, double* last_resid)
+{
+    CHECK_CTX(c);
+    if (last_cycles) *last_cycles = c->last_cycles;
+    if (last_resid) *last_resid = c->last_resid;
+    return 0;
+}
+
 int mag2d_u_smooth(mag2d_ctx* c, int symmetry, double radius)
 {
     CHECK_CTX(c);

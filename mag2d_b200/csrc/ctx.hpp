@@ -73,6 +73,7 @@ struct mag2d_ctx
     std::vector<double> h_voltage;
 
     std::vector<MgLevel> mg;
+    double* d_mg_inv = nullptr;   // dense inverse of the coarsest-level operator
     int cycles_per_step = 0;
     double solve_tol = 1e-13;
     int max_cycles = 60;

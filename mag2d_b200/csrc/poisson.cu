@@ -476,44 +476,57 @@ inline dim3 grid2d(int nj, int ni, dim3 block) { return dim3((nj + block.x - 1) 
 // at the price of recomputing the halo ((TILE+2*HALO)^2 / TILE^2 = 2.25x arithmetic for SWEEPS = 2).
 constexpr int MG_TILE = 32;
 template <int SWEEPS>
-__global__ void __launch_bounds__(256) k_mg_smooth_tile(const __grid_constant__ LevelDev L)
+struct MgTileCfg
 {
-    constexpr int HALO = 4 * SWEEPS, W = MG_TILE + 2 * HALO;
-    __shared__ double su[W][W + 1];
+    static constexpr int HALO = 4 * SWEEPS, W = MG_TILE + 2 * HALO, NODES = W * W;
+    // shared memory: u, b and the nine coefficient planes of the loaded block, plus the free flags
+    static constexpr size_t SMEM = sizeof(double) * 11 * NODES + NODES;
+};
+
+template <int SWEEPS>
+__global__ void __launch_bounds__(256, 1) k_mg_smooth_tile(const __grid_constant__ LevelDev L)
+{
+    using Cfg = MgTileCfg<SWEEPS>;
+    constexpr int HALO = Cfg::HALO, W = Cfg::W, NODES = Cfg::NODES;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* su = reinterpret_cast<double*>(smem_raw);      // [NODES]
+    double* sb = su + NODES;                               // [NODES]
+    double* sc = sb + NODES;                               // [9][NODES]
+    unsigned char* sf = reinterpret_cast<unsigned char*>(sc + 9 * NODES);
     const int M = L.M, N = L.N;
     const size_t n = (size_t)M * N;
     const int i0 = blockIdx.y * MG_TILE - HALO, j0 = blockIdx.x * MG_TILE - HALO;
-    for (int q = threadIdx.x; q < W * W; q += 256)
+    // stage the whole block once (coalesced along j); everything after this runs out of shared memory
+    for (int q = threadIdx.x; q < NODES; q += 256)
     {
         const int li = q / W, lj = q - li * W;
         const int gi = i0 + li, gj = j0 + lj;
-        su[li][lj] = (gi >= 0 && gi < M && gj >= 0 && gj < N) ? L.u[(size_t)gi * N + gj] : 0.0;
+        const bool in = gi >= 0 && gi < M && gj >= 0 && gj < N;
+        const size_t k = in ? (size_t)gi * N + gj : 0;
+        su[q] = in ? L.u[k] : 0.0;
+        sb[q] = in ? L.b[k] : 0.0;
+        sf[q] = in ? L.freem[k] : 0;
+#pragma unroll
+        for (int c = 0; c < 9; c++) sc[c * NODES + q] = in ? __ldg(L.coef + (size_t)c * n + k) : 0.0;
     }
     __syncthreads();
     for (int step = 0; step < 4 * SWEEPS; step++)
     {
         const int colour = step & 3;
-        const int lo = step + 1, hi = W - 2 - step;      // updatable local range [lo, hi]
-        const int span = hi - lo + 1;
-        for (int q = threadIdx.x; q < span * span; q += 256)
+        const int ci = colour >> 1, cj = colour & 1;
+        // nodes of this colour inside the still-exact region [lo, hi]^2, enumerated without gaps
+        const int lo = step + 1, hi = W - 2 - step;
+        const int fi = lo + (((i0 + lo) & 1) != ci), fj = lo + (((j0 + lo) & 1) != cj);   // first local row/col of the colour
+        const int ni = fi > hi ? 0 : (hi - fi) / 2 + 1, nj = fj > hi ? 0 : (hi - fj) / 2 + 1;
+        for (int q = threadIdx.x; q < ni * nj; q += 256)
         {
-            const int li = lo + q / span, lj = lo + q % span;
-            const int gi = i0 + li, gj = j0 + lj;
-            if (gi < 0 || gi >= M || gj < 0 || gj >= N) continue;
-            if ((((gi & 1) << 1) | (gj & 1)) != colour) continue;
-            const size_t k = (size_t)gi * N + gj;
-            if (!L.freem[k]) continue;
-            double acc = 0.0, diag = 1.0;
-#pragma unroll
-            for (int di = -1; di <= 1; di++)
-#pragma unroll
-                for (int dj = -1; dj <= 1; dj++)
-                {
-                    const double a = __ldg(L.coef + (size_t)((di + 1) * 3 + (dj + 1)) * n + k);
-                    if (di == 0 && dj == 0) diag = a;
-                    else acc += a * su[li + di][lj + dj];
-                }
-            su[li][lj] = (L.b[k] - acc) / diag;
+            const int li = fi + 2 * (q / nj), lj = fj + 2 * (q % nj);
+            const int p = li * W + lj;
+            if (!sf[p]) continue;
+            const double acc = sc[0 * NODES + p] * su[p - W - 1] + sc[1 * NODES + p] * su[p - W] + sc[2 * NODES + p] * su[p - W + 1] +
+                               sc[3 * NODES + p] * su[p - 1] + sc[5 * NODES + p] * su[p + 1] + sc[6 * NODES + p] * su[p + W - 1] +
+                               sc[7 * NODES + p] * su[p + W] + sc[8 * NODES + p] * su[p + W + 1];
+            su[p] = (sb[p] - acc) / sc[4 * NODES + p];
         }
         __syncthreads();
     }
@@ -521,11 +534,8 @@ __global__ void __launch_bounds__(256) k_mg_smooth_tile(const __grid_constant__ 
     {
         const int li = HALO + q / MG_TILE, lj = HALO + q % MG_TILE;
         const int gi = i0 + li, gj = j0 + lj;
-        if (gi < M && gj < N)
-        {
-            const size_t k = (size_t)gi * N + gj;
-            if (L.freem[k]) L.u[k] = su[li][lj];
-        }
+        const int p = li * W + lj;
+        if (gi < M && gj < N && sf[p]) L.u[(size_t)gi * N + gj] = su[p];
     }
 }
 
@@ -541,6 +551,7 @@ struct CoarseArgs
     int fx[MG_MAX_LEVELS], fz[MG_MAX_LEVELS];
     int first, count;      // levels [first, first+count)
     int nu1, nu2, nu_coarsest;
+    const double* inv;     // dense inverse of the coarsest operator (row-major n x n) or nullptr
 };
 
 __device__ __forceinline__ void cta_smooth(const LevelDev& L, int sweeps)
@@ -591,7 +602,22 @@ __global__ void __launch_bounds__(1024) k_mg_coarse(const __grid_constant__ Coar
         }
         __syncthreads();
     }
-    cta_smooth(A.L[last], A.nu_coarsest);
+    if (A.inv)
+    {
+        // exact coarsest solve: e = A^-1 b with the host-computed dense inverse (n <= 256 unknowns)
+        const LevelDev& Cz = A.L[last];
+        const int nz = Cz.M * Cz.N;
+        for (int q = threadIdx.x; q < nz; q += blockDim.x)
+        {
+            const double* row = A.inv + (size_t)q * nz;
+            double acc = 0.0;
+            for (int r = 0; r < nz; r++) acc += row[r] * Cz.b[r];
+            Cz.u[q] = acc;
+        }
+        __syncthreads();
+    }
+    else
+        cta_smooth(A.L[last], A.nu_coarsest);
     for (int l = last - 1; l >= A.first; l--)
     {
         const LevelDev& F = A.L[l];
@@ -616,8 +642,14 @@ __global__ void __launch_bounds__(1024) k_mg_coarse(const __grid_constant__ Coar
 
 int smooth_level(mag2d_ctx* c, const MgLevel& L)
 {
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        CUDA_OK(cudaFuncSetAttribute(k_mg_smooth_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MgTileCfg<2>::SMEM));
+        attr_set = true;
+    }
     const dim3 grid((L.N + MG_TILE - 1) / MG_TILE, (L.M + MG_TILE - 1) / MG_TILE);
-    k_mg_smooth_tile<2><<<grid, 256, 0, c->stream>>>(level_view(L));
+    k_mg_smooth_tile<2><<<grid, 256, MgTileCfg<2>::SMEM, c->stream>>>(level_view(L));
     c->launches++;
     return 0;
 }
@@ -636,6 +668,7 @@ int coarse_vcycle(mag2d_ctx* c, size_t first)
     }
     A.nu1 = A.nu2 = 2;
     A.nu_coarsest = 30;
+    A.inv = c->d_mg_inv;
     k_mg_coarse<<<1, 1024, 0, c->stream>>>(A);
     c->launches++;
     return 0;
@@ -671,6 +704,7 @@ void mg_free(mag2d_ctx* c)
     }
     c->mg.clear();
     if (c->d_rowscale) { cudaFree(c->d_rowscale); c->d_rowscale = nullptr; }
+    if (c->d_mg_inv) { cudaFree(c->d_mg_inv); c->d_mg_inv = nullptr; }
 }
 
 int mg_setup(mag2d_ctx* c)
@@ -717,6 +751,60 @@ int mg_setup(mag2d_ctx* c)
         CUDA_OK(cudaMemcpyAsync(L.freem, h.freem.data(), n, cudaMemcpyHostToDevice, c->stream));
         CUDA_OK(cudaMemsetAsync(L.b, 0, sizeof(double) * n, c->stream));
         if (l > 0) CUDA_OK(cudaMemsetAsync(L.u, 0, sizeof(double) * n, c->stream));
+    }
+    // dense inverse of the coarsest operator (Gauss-Jordan with partial pivoting on the host)
+    {
+        const HostLevel& Z = H.back();
+        const int nz = Z.M * Z.N;
+        if (nz <= 256 && H.size() > 1)
+        {
+            std::vector<double> a((size_t)nz * nz, 0.0), inv((size_t)nz * nz, 0.0);
+            for (int i = 0; i < Z.M; i++)
+                for (int j = 0; j < Z.N; j++)
+                {
+                    const int k = i * Z.N + j;
+                    if (!Z.freem[k]) { a[(size_t)k * nz + k] = 1.0; continue; }
+                    for (int di = -1; di <= 1; di++)
+                        for (int dj = -1; dj <= 1; dj++)
+                        {
+                            const int ii = i + di, jj = j + dj;
+                            if (ii < 0 || ii >= Z.M || jj < 0 || jj >= Z.N) continue;
+                            const int kk = ii * Z.N + jj;
+                            if (kk != k && !Z.freem[kk]) continue;      // eliminated unknowns carry zero error
+                            a[(size_t)k * nz + kk] = Z.coef[(size_t)cidx(di, dj) * nz + k];
+                        }
+                }
+            for (int k = 0; k < nz; k++) inv[(size_t)k * nz + k] = 1.0;
+            bool ok = true;
+            for (int col = 0; col < nz && ok; col++)
+            {
+                int piv = col;
+                for (int r = col + 1; r < nz; r++)
+                    if (std::fabs(a[(size_t)r * nz + col]) > std::fabs(a[(size_t)piv * nz + col])) piv = r;
+                if (std::fabs(a[(size_t)piv * nz + col]) < 1e-300) { ok = false; break; }
+                if (piv != col)
+                    for (int q = 0; q < nz; q++)
+                    {
+                        std::swap(a[(size_t)piv * nz + q], a[(size_t)col * nz + q]);
+                        std::swap(inv[(size_t)piv * nz + q], inv[(size_t)col * nz + q]);
+                    }
+                const double d = 1.0 / a[(size_t)col * nz + col];
+                for (int q = 0; q < nz; q++) { a[(size_t)col * nz + q] *= d; inv[(size_t)col * nz + q] *= d; }
+                for (int r = 0; r < nz; r++)
+                {
+                    if (r == col) continue;
+                    const double f = a[(size_t)r * nz + col];
+                    if (f == 0.0) continue;
+                    for (int q = 0; q < nz; q++) { a[(size_t)r * nz + q] -= f * a[(size_t)col * nz + q]; inv[(size_t)r * nz + q] -= f * inv[(size_t)col * nz + q]; }
+                }
+            }
+            if (ok)
+            {
+                CUDA_OK(cudaMalloc(&c->d_mg_inv, sizeof(double) * (size_t)nz * nz));
+                CUDA_OK(cudaMemcpyAsync(c->d_mg_inv, inv.data(), sizeof(double) * (size_t)nz * nz, cudaMemcpyHostToDevice, c->stream));
+                CUDA_OK(cudaStreamSynchronize(c->stream));
+            }
+        }
     }
     CUDA_OK(cudaMalloc(&c->d_rowscale, sizeof(double) * g.M));
     CUDA_OK(cudaMemcpyAsync(c->d_rowscale, rowscale.data(), sizeof(double) * g.M, cudaMemcpyHostToDevice, c->stream));

@@ -237,10 +237,16 @@ __device__ __forceinline__ void count_removed(unsigned long long* counter, bool 
 // kernel.
 constexpr int PPT = 4;                       // particles per thread
 constexpr int TILE = 32 * PPT;               // slots per warp
-constexpr int DEPOSIT_RUNS = 4;              // cells per warp call that get the REDUX treatment
+#ifndef MAG2D_DEPOSIT_RUNS
+#define MAG2D_DEPOSIT_RUNS 4
+#endif
+#ifndef MAG2D_PUSH_MIN_BLOCKS
+#define MAG2D_PUSH_MIN_BLOCKS 4   // 64 registers: measured 2.00 ms vs 2.16 ms (3 blocks, 80 regs) on C4
+#endif
+constexpr int DEPOSIT_RUNS = MAG2D_DEPOSIT_RUNS;   // cells per warp call that get the REDUX treatment
 
 template <int COORD, bool GATHER, bool HASB, bool MCC, bool DEPOSIT>
-__global__ void __launch_bounds__(PUSH_THREADS, 3) k_push_boris(const __grid_constant__ PushArgs A)
+__global__ void __launch_bounds__(PUSH_THREADS, MAG2D_PUSH_MIN_BLOCKS) k_push_boris(const __grid_constant__ PushArgs A)
 {
     const unsigned lane = lane_id();
     const long long warp_id = ((long long)blockIdx.x * PUSH_THREADS + threadIdx.x) >> 5;

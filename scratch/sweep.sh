@@ -1,0 +1,8 @@
+#!/bin/bash
+# tuning sweep (scratch): prints push/sort/solve ms per step for library variants and sort intervals
+run() { python bench.py --steps 24 --warmup 8 --no-cpu-baseline --e2e-steps 0 "$@" 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); p=d['phases_ms_per_step']
+print('  value %.3e  ms/step %.3f  push %.3f sort %.3f solve %.3f frac %.3f'%(d['value'],d['ms_per_step'],p['push'],p['sort'],p['solve'],d['roofline']['frac']))"; }
+for lib in scratch/variants/lib_*.so; do echo "$lib"; MAG2D_B200_LIB=$PWD/$lib run; done
+for si in 4 6 12 16; do echo "default lib sort-interval $si"; run --sort-interval $si; done
