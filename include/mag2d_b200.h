@@ -100,7 +100,9 @@ int mag2d_get_potential(mag2d_ctx* ctx, int which, double* values);
  * Jacobi update max_k |r_k / a_kk| drops below tol * max_k |u_k| (or max_cycles).  Blocks.  resid_out
  * receives that ratio.  Any out pointer may be NULL. */
 int mag2d_solve(mag2d_ctx* ctx, int rf, double tol, int max_cycles, int* cycles_out, double* resid_out);
-/* solver knobs for mag2d_step: V-cycles per step (0 = iterate to tol) and the tolerance */
+/* solver knobs for mag2d_step: V-cycles per step (0 = iterate to tol, one host sync per cycle; n > 0 = exactly
+ * n cycles, no sync, residual monitored on the device; n < 0 = |n| cycles started from the time-extrapolated
+ * guess 2u_n - u_{n-1}) and the tolerance of the iterate-to-tol mode */
 int mag2d_set_solver(mag2d_ctx* ctx, int cycles_per_step, double tol, int max_cycles);
 /* V-cycles used and convergence measure reached by the most recent solve (also the one inside mag2d_step
  * when cycles_per_step == 0; with a fixed cycle count the residual is not evaluated and reads 0) */

@@ -242,6 +242,7 @@ int mag2d_create(int device, const mag2d_grid_desc* grid, void* stream, mag2d_ct
     CUDA_OK(cudaMemsetAsync(c->d_gz, 0, sizeof(double) * n, c->stream));
     CUDA_OK(cudaMalloc(&c->d_b, sizeof(double) * n));
     CUDA_OK(cudaMalloc(&c->d_scratch, sizeof(double) * 64));
+    CUDA_OK(cudaMemsetAsync(c->d_scratch, 0, sizeof(double) * 64, c->stream));
     CUDA_OK(cudaMemsetAsync(c->d_u, 0, sizeof(double) * n, c->stream));
     CUDA_OK(cudaMemsetAsync(c->d_uRF, 0, sizeof(double) * n, c->stream));
     CUDA_OK(cudaMemsetAsync(c->d_ueff, 0, sizeof(double) * n, c->stream));
@@ -270,6 +271,7 @@ int mag2d_destroy(mag2d_ctx* c)
     cudaFree(c->d_cfree);
     cudaFree(c->d_b);
     cudaFree(c->d_scratch);
+    if (c->d_u_prev) cudaFree(c->d_u_prev);
     if (c->d_rho) cudaFree(c->d_rho);
     if (c->d_charges) cudaFree(c->d_charges);
     if (c->d_cell_count) cudaFree(c->d_cell_count);
@@ -355,15 +357,28 @@ int mag2d_solve(mag2d_ctx* c, int rf, double tol, int max_cycles, int* cycles_ou
 int mag2d_set_solver(mag2d_ctx* c, int cycles_per_step, double tol, int max_cycles)
 {
     CHECK_CTX(c);
-    c->cycles_per_step = cycles_per_step;
+    // a negative cycle count selects |cycles| V-cycles per step with the time-extrapolated first guess
+    c->extrapolate = cycles_per_step < 0;
+    c->cycles_per_step = cycles_per_step < 0 ? -cycles_per_step : cycles_per_step;
     c->solve_tol = tol;
     c->max_cycles = max_cycles;
+    c->have_prev = false;
     return 0;
 }
 
 int mag2d_solver_stats(mag2d_ctx* c, int* last_cycles, double* last_resid)
 {
     CHECK_CTX(c);
+    if (c->monitor_armed)
+    {
+        // fixed-cycle solves do not look at the residual themselves: read (and reset) the running maxima
+        double h[2];
+        CUDA_OK(cudaMemcpyAsync(h, c->d_scratch + 16, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaMemsetAsync(c->d_scratch + 16, 0, sizeof(h), c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        c->last_resid = h[1] > 0 ? h[0] / h[1] : h[0];
+        c->monitor_armed = false;
+    }
     if (last_cycles) *last_cycles = c->last_cycles;
     if (last_resid) *last_resid = c->last_resid;
     return 0;

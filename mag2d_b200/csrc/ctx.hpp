@@ -78,6 +78,10 @@ struct mag2d_ctx
     double solve_tol = 1e-13;
     int max_cycles = 60;
     int last_cycles = 0;
+    bool extrapolate = false;     // 2u_n - u_{n-1} as the initial guess of the in-step solve
+    bool have_prev = false;
+    double* d_u_prev = nullptr;
+    bool monitor_armed = false;   // d_scratch[16..17] hold running max |r/a_kk| and max |u| of fixed-cycle solves
     double last_resid = 0;
 
     std::vector<SpeciesStore> sp;

@@ -454,6 +454,22 @@ __global__ void k_smooth9(const double* __restrict__ t, double* __restrict__ u, 
     u[(size_t)i * N + j] = sum / 4.0;
 }
 
+// initial guess for the next solve by linear extrapolation in time: u <- 2u - u_prev on the unknowns
+__global__ void k_extrapolate(double* __restrict__ u, double* __restrict__ u_prev, const unsigned char* __restrict__ freem, size_t n)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double cur = u[k];
+    if (freem[k]) u[k] = 2.0 * cur - u_prev[k];
+    u_prev[k] = cur;
+}
+
+__global__ void k_copy(double* __restrict__ dst, const double* __restrict__ src, size_t n)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) dst[k] = src[k];
+}
+
 LevelDev level_view(const MgLevel& L)
 {
     LevelDev v;
@@ -878,11 +894,28 @@ int mg_solve(mag2d_ctx* c, int rf, double tol, int max_cycles, int fixed_cycles,
     int rc = mg_rhs(c, rf);
     int done = 0;
     double r = 0.0, bm = 0.0;
+    if (!rc && !rf && c->extrapolate)
+    {
+        // warm start: the potential changes smoothly from step to step (omega_p dt << 1), so 2u_n - u_{n-1}
+        // is a better first guess than u_n
+        const size_t n = (size_t)c->g.M * c->g.N;
+        if (!c->d_u_prev) CUDA_OK(cudaMalloc(&c->d_u_prev, sizeof(double) * n));
+        if (c->have_prev) k_extrapolate<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_u, c->d_u_prev, c->mg[0].freem, n);
+        else k_copy<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_u_prev, c->d_u, n);
+        c->have_prev = true;
+        c->launches++;
+    }
     if (!rc)
     {
         if (fixed_cycles > 0)
         {
             for (; done < fixed_cycles && !rc; done++) rc = mg_vcycle(c);
+            // residual monitor without a host sync: the running maxima are read by mag2d_solver_stats
+            const MgLevel& L = c->mg[0];
+            const dim3 block(32, 8);
+            k_mg_residual_norm<<<grid2d(L.N, L.M, block), block, 0, c->stream>>>(level_view(L), c->d_scratch + 16);
+            c->launches++;
+            c->monitor_armed = true;
         }
         else
         {
