@@ -1127,18 +1127,22 @@ void orc_u_smooth(const orc_grid* g, int symmetry, double radius, double* u)
     memcpy(t, u, sizeof(double) * (size_t)M * N);
 #define T(i, j) t[(size_t)(i) * N + (j)]
     double icf = ic / 2.0, jcf = jc / 2.0;
-    /* NB the reference's inner bound is j <= lmax-1, i.e. it reads one column past each row end
-     * (the next row's first element); the last column is left untouched here instead */
+    /* NB the reference's inner bound is j <= lmax-1 (fields.cpp:88): for the last column it reads one
+     * element past the row end, i.e. the first element of the next row of the contiguous array, and one
+     * past the array end for the very last node.  Reproduced with flat indexing; 0 past the end. */
+    const long nn = (long)M * N;
+#define TF(i, j) (((long)(i) * N + (j)) < nn ? t[(long)(i) * N + (j)] : 0.0)
     for (int i = 1; i < M - 1; i++)
-        for (int j = 1; j < N - 1; j++)
+        for (int j = 1; j <= N - 1; j++)
         {
             double r = sqr(i - icf) + sqr(j - jcf);
             if (radius > 0 && r > radius) continue;
-            double sum = T(i, j) + T(i - 1, j) * 0.5 + T(i + 1, j) * 0.5 + T(i, j - 1) * 0.5 + T(i, j + 1) * 0.5 +
-                         T(i - 1, j - 1) * 0.25 + T(i + 1, j - 1) * 0.25 + T(i - 1, j + 1) * 0.25 +
-                         T(i + 1, j + 1) * 0.25;
+            double sum = TF(i, j) + TF(i - 1, j) * 0.5 + TF(i + 1, j) * 0.5 + TF(i, j - 1) * 0.5 + TF(i, j + 1) * 0.5 +
+                         TF(i - 1, j - 1) * 0.25 + TF(i + 1, j - 1) * 0.25 + TF(i - 1, j + 1) * 0.25 +
+                         TF(i + 1, j + 1) * 0.25;
             U(i, j) = sum / 4.0;
         }
+#undef TF
 #undef T
 #undef U
     free(t);

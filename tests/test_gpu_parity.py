@@ -332,3 +332,50 @@ def test_live_reference_rf_trap_100_steps(deckdir):
         both = (a[:, 7] > 0) & (b[:, 7] > 0)
         assert np.sum((a[:, 7] > 0) != (b[:, 7] > 0)) <= 2
         assert relerr(a[both][:, [0, 2, 3, 4, 5]], b[both][:, [0, 2, 3, 4, 5]]) <= 1e-10
+
+
+# ------------------------------------------------------------------------------ next rows (§8f)
+def test_u_smooth_matches_oracle(orc, deckdir):
+    d = decks.deck("c4", deckdir + "_sm", n_particles=4000, geometry="TUBE", probe_radius=1.4e-3, u_smooth=1,
+                   x_sampl=33, z_sampl=33, r_max=3.2e-3, z_max=3.2e-3)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        g = grid_from_param(sim.param)
+        u = np.random.default_rng(2).normal(size=(g.M, g.N))
+        sim.set_field("u", u)
+        sim.u_smooth()
+        assert np.abs(sim.get_field("u") - orc.u_smooth(g, u)).max() <= 1e-15
+        sim.set_field("u", u)
+        sim.u_smooth(symmetry=True, radius=1.0e-3)
+        assert np.abs(sim.get_field("u") - orc.u_smooth(g, u, symmetry=True, radius=1.0e-3)).max() <= 1e-15
+
+
+def test_energy_histogram_matches_reference_histogram_rule(deckdir):
+    # Histogram::add (histogram.cpp:21-33): strict bounds, bin = (int)((f-min)*n/(max-min)), totals include outliers
+    d = decks.deck("c1", deckdir, n_particles=100)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        e = sim.species_index("ELECTRON")
+        rng = np.random.default_rng(4)
+        n = 50000
+        aos = np.zeros((n, 7))
+        aos[:, 0] = aos[:, 2] = 1e-2
+        aos[:, 3:6] = rng.normal(size=(n, 3)) * 1.2e6
+        sim.set_particles(e, aos)
+        hist, st = sim.energy_hist(e, nbins=200, emax=30.0)
+        f = (aos[:, 3] ** 2 + aos[:, 5] ** 2 + aos[:, 4] ** 2) * 9.11e-31 * 0.5 / 1.602189e-19
+        inside = (f < 30.0) & (f > 0.0)
+        want = np.bincount((f[inside] * 200 / 30.0).astype(int), minlength=200)
+        assert np.array_equal(hist, want)
+        assert st["n_tot"] == n and st["n_in"] == inside.sum()
+        assert abs(st["sum_tot"] - f.sum()) <= 1e-9 * f.sum()
+
+
+def test_device_loaders_fill_the_domain_statistically(deckdir):
+    d = decks.deck("c4", deckdir, n_particles=200000, x_sampl=65, z_sampl=65, r_max=6.4e-3, z_max=6.4e-3)
+    with _sim(d["config"], d["species_conf"], presolve=False) as sim:
+        sim.run_initscript(d["initscript"])
+        for name, T, m in (("ARGON_POS", 300.0, 6.68173e-26), ("ELECTRON", 23200.0, 9.11e-31)):
+            p = sim.get_particles(sim.species_index(name))
+            assert p.shape[0] == 100000 and p[:, 7].all()
+            assert abs(p[:, 0].mean() / 6.4e-3 - 0.5) < 0.01 and abs(p[:, 2].mean() / 6.4e-3 - 0.5) < 0.01
+            vth = np.sqrt(1.380662e-23 * T / m)              # each component: rnor * v_max / sqrt(2)
+            assert abs(p[:, 3:6].std() / vth - 1.0) < 0.01
