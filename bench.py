@@ -40,6 +40,18 @@ DEFAULT_PARTICLES = {"c4": 100_000_000, "c2": 1_000_000, "c3": 10_000_000, "c1":
 BYTES = {"c4": 80.0, "c2": 80.0, "c3": 80.0, "c1": 96.0}
 
 
+def measured_traffic(workload, n_particles):
+    """DRAM bytes per push launch from the committed `ncu --set full` capture (profiles/r1_push_dram.json holds
+    dram__bytes_read.sum + dram__bytes_write.sum per particle of the profiled launches), scaled to this run's
+    particles per launch; None when the workload was not profiled"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_push_dram.json")) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_per_particle_step"][workload]) * n_particles
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -161,7 +173,9 @@ def bench_ours(args):
     sort_interval = args.sort_interval
     sim.set_sort_interval(sort_interval)
     if selfconsistent:
+        sim.set_solver_kind(args.solver)
         sim.set_solver(cycles_per_step=args.cycles, tol=1e-12, max_cycles=60)
+    direct = selfconsistent and sim.solver_is_direct()
     sim.advance_init()
     n_live0 = sum(sim.count(s)[0] for s in part_species)
 
@@ -217,7 +231,13 @@ def bench_ours(args):
     peak, peak_src = measured_peaks()
     achieved = BYTES[wl] * n_now / (push_ms * 1e-3) / 1e9 if push_ms > 0 else 0.0
     solve_info = None
-    if selfconsistent:
+    if direct:
+        solve_info = {"kind": "direct: sine transform along z (FP64 matrix product) x tridiagonal solve per mode along x "
+                              "(the grid has no internal electrodes); exact to round-off like the reference's LU",
+                      "ms_per_step": tm["solve"] / args.steps, "vcycles_per_step": 0,
+                      "max_resid_over_timed_steps": monitored_resid,
+                      "resid_def": "max|r_k/a_kk| / max|u| (largest Jacobi update relative to the potential)"}
+    elif selfconsistent:
         # how far from converged is the field after the fixed number of warm-started V-cycles per step?
         info = sim.solve(rf=False, tol=1e-12)
         # and how many cycles does a step need when it iterates to the tolerance (one host sync per cycle)?
@@ -227,7 +247,8 @@ def bench_ours(args):
             sim.advance(1)
             need.append(sim.solver_stats()["cycles"])
         sim.set_solver(cycles_per_step=args.cycles, tol=1e-12, max_cycles=60)
-        solve_info = {"ms_per_step": tm["solve"] / args.steps, "vcycles_per_step": abs(args.cycles),
+        solve_info = {"kind": "geometric multigrid (Galerkin coarse operators), fixed V-cycles per step",
+                      "ms_per_step": tm["solve"] / args.steps, "vcycles_per_step": abs(args.cycles),
                       "first_guess": "2u_n - u_(n-1)" if args.cycles < 0 else "u_n",
                       "ms_per_vcycle": tm["solve"] / args.steps / max(abs(args.cycles), 1),
                       "max_resid_over_timed_steps": monitored_resid,
@@ -261,11 +282,13 @@ def bench_ours(args):
                        "l2": "inputs larger than L2 (%.1f GB of particle state per GPU)" % (n * 40 / 1e9)
                        if n * 40 > 200e6 else "particle state fits L2: flush not applied, see roofline note",
                        "parallelism": "particle shards, %d rank(s), NCCL all-reduce of the int64 charge grid" % world,
-                       "vcycles_per_step": abs(args.cycles) if selfconsistent else 0},
+                       "poisson": ("direct (sine transform x tridiagonal)" if direct else "multigrid, %d V-cycles/step" % abs(args.cycles))
+                       if selfconsistent else "none (vacuum field solved once)"},
             "gpu_launches": int(launches),
             "clocks": clock_info,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": measured_traffic(wl, n_now / n_push_launches),
+                         "algorithmic_bytes_per_launch": BYTES[wl] * n_now / n_push_launches,
                          "kernel": "k_push_boris (fused gather+push+MCC+boundary+deposit), %d launches/step" % n_push_launches,
                          "algorithmic_bytes_per_particle_step": BYTES[wl], "push_ms_per_step": push_ms,
                          "peak_source": peak_src},
@@ -414,8 +437,8 @@ def _reference_run(workload, d, n_cpu, steps, u=None, variant="fast"):
 
 def cpu_baseline(workload, d, sim, part_species, args):
     u = sim.get_field("u") if sim.param["selfconsistent"] else None
-    n_cpu = {"c1": 20000}.get(workload, 2_000_000)
-    steps = {"c1": 10}.get(workload, 40)
+    n_cpu = {"c1": 40000}.get(workload, 4_000_000)      # about 10 s of single-thread work
+    steps = {"c1": 25}.get(workload, 100)
     return reference_run(workload, d, n_cpu, steps, u)
 
 
@@ -428,7 +451,7 @@ def bench_reference(args):
     n = args.particles or DEFAULT_PARTICLES[wl]
     tmp = tempfile.mkdtemp(prefix="mag2d_bench_ref_")
     d = make_deck(wl, n, 1, tmp)
-    n_cpu = {"c1": 20000}.get(wl, 1_000_000)
+    n_cpu = {"c1": 20000}.get(wl, 4_000_000)
     try:
         for _ in range(max(0, min(args.warmup, 1))):
             reference_run(wl, d, n_cpu, 2)
@@ -464,6 +487,8 @@ def main():
     ap.add_argument("--sort-interval", type=int, default=8)
     ap.add_argument("--cycles", type=int, default=-3,
                     help="multigrid V-cycles per step; negative: |n| cycles from the time-extrapolated guess 2u_n - u_(n-1)")
+    ap.add_argument("--solver", default="auto", choices=["auto", "multigrid", "direct"],
+                    help="Poisson solver of the self-consistent step (auto: direct when the grid separates)")
     ap.add_argument("--solve-tol", type=float, default=1e-10)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -104,6 +104,18 @@ int mag2d_solve(mag2d_ctx* ctx, int rf, double tol, int max_cycles, int* cycles_
  * n cycles, no sync, residual monitored on the device; n < 0 = |n| cycles started from the time-extrapolated
  * guess 2u_n - u_{n-1}) and the tolerance of the iterate-to-tol mode */
 int mag2d_set_solver(mag2d_ctx* ctx, int cycles_per_step, double tol, int max_cycles);
+/* which Poisson solver stands in for the reference's UMFPACK factorisation (src/fields.cpp:169-329).
+ * MAG2D_SOLVER_AUTO: the direct sine-transform x tridiagonal solver when the grid separates (every grid row is an
+ * electrode over its whole length or free between two Dirichlet end nodes: geometry EMPTY), multigrid otherwise;
+ * MAG2D_SOLVER_MULTIGRID: always multigrid; MAG2D_SOLVER_DIRECT: error unless the grid separates.  The direct
+ * solver is exact to round-off, so cycles_per_step / tol do not apply to it (solver_stats reports 0 cycles and
+ * the measured residual). */
+#define MAG2D_SOLVER_AUTO 0
+#define MAG2D_SOLVER_MULTIGRID 1
+#define MAG2D_SOLVER_DIRECT 2
+int mag2d_set_solver_kind(mag2d_ctx* ctx, int kind);
+/* 1 when the direct solver is the one in use for the current grid and kind, else 0 */
+int mag2d_solver_is_direct(mag2d_ctx* ctx);
 /* V-cycles used and convergence measure reached by the most recent solve (also the one inside mag2d_step
  * when cycles_per_step == 0; with a fixed cycle count the residual is not evaluated and reads 0) */
 int mag2d_solver_stats(mag2d_ctx* ctx, int* last_cycles, double* last_resid);

@@ -80,6 +80,8 @@ def lib():
     L.mag2d_get_potential.argtypes = [vp, C.c_int, dp]
     L.mag2d_solve.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp]
     L.mag2d_set_solver.argtypes = [vp, C.c_int, C.c_double, C.c_int]
+    L.mag2d_set_solver_kind.argtypes = [vp, C.c_int]
+    L.mag2d_solver_is_direct.argtypes = [vp]
     L.mag2d_solver_stats.argtypes = [vp, C.POINTER(C.c_int), dp]
     L.mag2d_u_smooth.argtypes = [vp, C.c_int, C.c_double]
     L.mag2d_field_E.argtypes = [vp, C.c_int, dp, dp, C.c_double, dp, dp]
@@ -322,6 +324,13 @@ class Sim:
 
     def set_solver(self, cycles_per_step=0, tol=1e-13, max_cycles=100):
         self._chk(self.L.mag2d_set_solver(self.h, cycles_per_step, tol, max_cycles))
+
+    def set_solver_kind(self, kind):
+        """'auto' (direct sine-transform solver when the grid separates, else multigrid), 'multigrid' or 'direct'"""
+        self._chk(self.L.mag2d_set_solver_kind(self.h, {"auto": 0, "multigrid": 1, "mg": 1, "direct": 2}[kind]))
+
+    def solver_is_direct(self):
+        return bool(self.L.mag2d_solver_is_direct(self.h))
 
     def solver_stats(self):
         cyc, res = C.c_int(), C.c_double()

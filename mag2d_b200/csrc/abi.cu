@@ -260,6 +260,7 @@ int mag2d_destroy(mag2d_ctx* c)
     cudaStreamSynchronize(c->stream);
     mag2d_comm_destroy(c);
     mg_free(c);
+    direct_free(c);
     for (auto& S : c->sp) free_store(S);
     cudaFree(c->d_mask);
     cudaFree(c->d_voltage);
@@ -321,7 +322,8 @@ int mag2d_set_grid(mag2d_ctx* c, const uint8_t* mask, const double* voltage)
     CUDA_OK(cudaMemcpyAsync(c->d_cfree, cfree.data(), n, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     c->grid_set = true;
-    return mg_setup(c);
+    if (mg_setup(c)) return 1;
+    return direct_setup(c);
 }
 
 int mag2d_set_potential(mag2d_ctx* c, int which, const double* values)
@@ -364,6 +366,30 @@ int mag2d_set_solver(mag2d_ctx* c, int cycles_per_step, double tol, int max_cycl
     c->max_cycles = max_cycles;
     c->have_prev = false;
     return 0;
+}
+
+int mag2d_set_solver_kind(mag2d_ctx* c, int kind)
+{
+    CHECK_CTX(c);
+    if (kind < MAG2D_SOLVER_AUTO || kind > MAG2D_SOLVER_DIRECT)
+    {
+        mag2d_set_error("mag2d_set_solver_kind: unknown solver kind");
+        return 1;
+    }
+    if (kind == MAG2D_SOLVER_DIRECT && !c->direct.ok)
+    {
+        mag2d_set_error("mag2d_set_solver_kind: the grid does not separate (electrodes inside free rows); use the multigrid solver");
+        return 1;
+    }
+    c->solver_kind = kind;
+    c->have_prev = false;
+    return 0;
+}
+
+int mag2d_solver_is_direct(mag2d_ctx* c)
+{
+    if (!c) return 0;
+    return c->direct.ok && c->solver_kind != MAG2D_SOLVER_MULTIGRID;
 }
 
 int mag2d_solver_stats(mag2d_ctx* c, int* last_cycles, double* last_resid)
@@ -817,7 +843,9 @@ int mag2d_step(mag2d_ctx* c, int nsteps)
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
         if (c->g.selfconsistent)
         {
-            if (mg_solve(c, 0, c->solve_tol, c->max_cycles, c->cycles_per_step, nullptr, nullptr)) return 1;
+            // the direct solver needs no convergence test: never synchronise with the host inside the step
+            const bool direct = c->direct.ok && c->solver_kind != MAG2D_SOLVER_MULTIGRID;
+            if (mg_solve(c, 0, c->solve_tol, c->max_cycles, direct && !c->cycles_per_step ? 1 : c->cycles_per_step, nullptr, nullptr)) return 1;
             if (c->g.u_smooth && launch_u_smooth(c, 0, -1.0)) return 1;
             if (mag2d_rho_reset(c, -1)) return 1;
         }

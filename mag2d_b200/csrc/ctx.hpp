@@ -46,6 +46,20 @@ struct MgLevel
     double* b = nullptr;        // right-hand side (scaled)
 };
 
+// separable direct solver (poisson_direct.cu): sine transform along z, tridiagonal solves along x / r
+struct DirectSolver
+{
+    bool ok = false;            // the grid separates (every row is an electrode or free between Dirichlet ends)
+    int n = 0;                  // N - 2
+    double* S = nullptr;        // [n][n] sine matrix
+    double* lower = nullptr;    // [M][n] Thomas factors per mode
+    double* inv = nullptr;
+    double* upper = nullptr;
+    double* hat = nullptr;      // [M][n] transformed right-hand side / solution
+    unsigned char* rowfree = nullptr;
+    double* k2 = nullptr;
+};
+
 struct mag2d_ctx
 {
     int device = 0;
@@ -74,6 +88,8 @@ struct mag2d_ctx
 
     std::vector<MgLevel> mg;
     double* d_mg_inv = nullptr;   // dense inverse of the coarsest-level operator
+    DirectSolver direct;
+    int solver_kind = MAG2D_SOLVER_AUTO;
     int cycles_per_step = 0;
     double solve_tol = 1e-13;
     int max_cycles = 60;
@@ -144,6 +160,10 @@ int mg_vcycle(mag2d_ctx* c);
 int mg_residual(mag2d_ctx* c, double* resid_max, double* u_max);
 int mg_solve(mag2d_ctx* c, int rf, double tol, int max_cycles, int fixed_cycles, int* cycles, double* resid);
 int launch_u_smooth(mag2d_ctx* c, int symmetry, double radius);
+// poisson_direct.cu
+int direct_setup(mag2d_ctx* c);
+void direct_free(mag2d_ctx* c);
+int direct_solve(mag2d_ctx* c, double* u);
 int launch_rho_total(mag2d_ctx* c, double* d_out);
 // comm.cu
 int comm_allreduce_rho(mag2d_ctx* c);

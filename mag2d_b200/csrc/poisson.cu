@@ -894,7 +894,25 @@ int mg_solve(mag2d_ctx* c, int rf, double tol, int max_cycles, int fixed_cycles,
     int rc = mg_rhs(c, rf);
     int done = 0;
     double r = 0.0, bm = 0.0;
-    if (!rc && !rf && c->extrapolate)
+    const bool direct = c->direct.ok && c->solver_kind != MAG2D_SOLVER_MULTIGRID;
+    if (!rc && direct)
+    {
+        rc = direct_solve(c, c->mg[0].u);
+        if (!rc)
+        {
+            if (fixed_cycles != 0)
+            {
+                const MgLevel& L = c->mg[0];
+                const dim3 block(32, 8);
+                k_mg_residual_norm<<<grid2d(L.N, L.M, block), block, 0, c->stream>>>(level_view(L), c->d_scratch + 16);
+                c->launches++;
+                c->monitor_armed = true;
+            }
+            else
+                rc = mg_residual(c, &r, &bm);
+        }
+    }
+    else if (!rc && !rf && c->extrapolate)
     {
         // warm start: the potential changes smoothly from step to step (omega_p dt << 1), so 2u_n - u_{n-1}
         // is a better first guess than u_n
@@ -905,7 +923,7 @@ int mg_solve(mag2d_ctx* c, int rf, double tol, int max_cycles, int fixed_cycles,
         c->have_prev = true;
         c->launches++;
     }
-    if (!rc)
+    if (!rc && !direct)
     {
         if (fixed_cycles > 0)
         {

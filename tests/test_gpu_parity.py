@@ -76,6 +76,45 @@ def test_solve_with_charge_matches_direct_solver(orc, deckdir):
         assert np.abs(sim.get_field("u") - u_ref).max() <= 1e-8 * np.abs(u_ref).max(), info
 
 
+@pytest.mark.parametrize("deck,kw,species", [
+    ("c4", dict(x_sampl=80, z_sampl=65, r_max=7.9e-3, z_max=6.4e-3), ("ELECTRON", "ARGON_POS")),
+    ("c3", dict(geometry="EMPTY", x_sampl=97, z_sampl=130), None),
+])
+def test_direct_and_multigrid_solvers_agree_with_oracle(orc, deckdir, deck, kw, species):
+    """grids whose electrodes are whole rows use the sine-transform x tridiagonal direct solver (auto);
+    it has to reproduce the reference's LU to round-off, and the multigrid forced on the same system to 1e-8"""
+    d = decks.deck(deck, deckdir, n_particles=40000, **kw)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        g = grid_from_param(sim.param)
+        assert sim.solver_is_direct()
+        rng = np.random.default_rng(11)
+        names = species or [n for n in d["species"]]
+        for q, name in enumerate(names):
+            a = disk_particles(rng, 20000, 0.45 * g.x_max, 0.5 * g.z_max, 0.3 * min(g.x_max, g.z_max), 300.0 * (1 + 100 * q))
+            i = sim.species_index(name)
+            sim.set_particles(i, a)
+            sim.species_accumulate(i)
+        mask, volt = orc.geometry(g, int(sim.param["geometry"]), sim.param["probe_radius"], sim.param["u_probe"])
+        rho = sim.get_field("rho")
+        assert np.abs(rho).max() > 0
+        u_ref = orc.solve_direct(g, mask, orc.rhs(g, mask, volt, rho))
+        info = sim.solve(rf=False)
+        u_direct = sim.get_field("u")
+        assert info["cycles"] == 0 and info["resid"] < 1e-10, info
+        assert np.abs(u_direct - u_ref).max() <= 1e-9 * np.abs(u_ref).max(), info
+        sim.set_solver_kind("multigrid")
+        assert not sim.solver_is_direct()
+        sim.set_field("u", np.zeros_like(u_ref))
+        info = sim.solve(rf=False)
+        assert info["cycles"] > 0
+        assert np.abs(sim.get_field("u") - u_ref).max() <= 1e-8 * np.abs(u_ref).max(), info
+    d = decks.deck("c2", deckdir, n_particles=10, geometry="PROBE", x_sampl=41, z_sampl=41, probe_radius=2e-3)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        assert not sim.solver_is_direct()
+        with pytest.raises(Exception, match="does not separate"):
+            sim.set_solver_kind("direct")
+
+
 def test_gather_matches_oracle_and_golden(orc, deckdir):
     d = decks.deck("c2", deckdir, n_particles=10, geometry="RF_8PT", x_sampl=41, z_sampl=41, Bt=0.01, Bz=0.02, Br=0.005)
     with _sim(d["config"], d["species_conf"], presolve=False) as sim:

@@ -105,7 +105,7 @@ def test_plasma2d_driver_matches_python_front_end(host_bins, tmp_path):
     out = str(tmp_path / "out_cpp")
     log = run_driver(host_bins, "plasma2d_b200", d, out)
     assert "plot 20" in log
-    for f in ("out.dat", "potential.dat", "config.txt", "species_conf.txt", "initscript.txt", "energy_dist_ELECTRON.dat", "rho_ARGON_POS.dat"):
+    for f in ("out.dat", "potential.dat", "config.txt", "species_conf.txt", "initscript.txt", "ELECTRON_energy_dist.dat", "ARGON_POS_rho.dat"):
         assert os.path.exists(os.path.join(out, f)), f
     pot = np.loadtxt(os.path.join(out, "potential.dat"))
     with Sim(d["config"], d["species_conf"]) as sim:
@@ -125,5 +125,5 @@ def test_test_mcc_driver_runs_c1(host_bins, tmp_path):
     out = str(tmp_path / "out_mcc")
     log = run_driver(host_bins, "test_MCC_b200", d, out)
     assert "ms / iteration" in log
-    e = np.loadtxt(os.path.join(out, "energy_dist_ELECTRON.dat"))
+    e = np.loadtxt(os.path.join(out, "ELECTRON_energy_dist.dat"))
     assert e.shape[1] >= 2 and e[:, 1].sum() > 0
