@@ -51,11 +51,13 @@ struct DirectSolver
 {
     bool ok = false;            // the grid separates (every row is an electrode or free between Dirichlet ends)
     int n = 0;                  // N - 2
+    int ld = 0;                 // n rounded up to a multiple of 32: leading dimension of every [.][n] array below
+    double* bp = nullptr;       // [M][ld] right-hand side of the interior columns (written by k_rhs)
     double* S = nullptr;        // [n][n] sine matrix
-    double* lower = nullptr;    // [M][n] Thomas factors per mode
-    double* inv = nullptr;
-    double* upper = nullptr;
-    double* hat = nullptr;      // [M][n] transformed right-hand side / solution
+    double* fwd = nullptr;      // [M][ld][2] forward sweep pairs (hat/den, lower/den)
+    double* inv = nullptr;      // [M][ld] 1/den, applied in the forward product's epilogue
+    double* bwd = nullptr;      // [M][ld][2] backward sweep pairs (y, upper/den)
+    double* hat = nullptr;      // [M][ld] transformed solution
     unsigned char* rowfree = nullptr;
     double* k2 = nullptr;
 };
@@ -90,6 +92,7 @@ struct mag2d_ctx
     double* d_mg_inv = nullptr;   // dense inverse of the coarsest-level operator
     DirectSolver direct;
     int solver_kind = MAG2D_SOLVER_AUTO;
+    unsigned long long direct_calls = 0;
     int cycles_per_step = 0;
     double solve_tol = 1e-13;
     int max_cycles = 60;

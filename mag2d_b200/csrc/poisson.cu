@@ -352,7 +352,18 @@ struct RhsArgs
     double* b_ref;
     double* b_mg;
     double* u;
+    // direct solver (poisson_direct.cu): interior columns with the Dirichlet end nodes moved to the right-hand side
+    double* bp;
+    int ld;
+    const unsigned char* rowfree;
+    const double* k2row;
 };
+
+__device__ __forceinline__ double dirichlet_value(unsigned char m, double voltage, int rf)
+{
+    if (m == MAG2D_FIXED) return rf ? 0.0 : voltage;
+    return rf ? voltage : 0.0;      // MAG2D_FIXED_RF
+}
 
 __device__ __forceinline__ double rho_coulomb(const unsigned long long* rho, const double* charges, int ns, size_t n, size_t k)
 {
@@ -387,6 +398,16 @@ __global__ void k_rhs(const __grid_constant__ RhsArgs A)
             b = rho * (-(A.dx * A.dx) / MAG2D_EPS0 / A.dV);
     }
     A.b_ref[k] = b;
+    if (A.bp && j >= 1 && j <= A.N - 2)
+    {
+        double v = b;
+        if (A.rowfree[i])
+        {
+            if (j == 1) v -= A.k2row[i] * dirichlet_value(A.mask[k - 1], A.voltage[k - 1], A.rf);
+            if (j == A.N - 2) v -= A.k2row[i] * dirichlet_value(A.mask[k + 1], A.voltage[k + 1], A.rf);
+        }
+        A.bp[(size_t)i * A.ld + j - 1] = v;
+    }
     if (m == MAG2D_FIXED || m == MAG2D_FIXED_RF)
     {
         A.b_mg[k] = b;
@@ -848,6 +869,11 @@ int mg_rhs(mag2d_ctx* c, int rf)
     A.rowscale = c->d_rowscale;
     A.b_ref = c->d_b;
     A.b_mg = c->mg[0].b;
+    const bool direct = c->direct.ok && c->solver_kind != MAG2D_SOLVER_MULTIGRID;
+    A.bp = direct ? c->direct.bp : nullptr;
+    A.ld = c->direct.ld;
+    A.rowfree = c->direct.rowfree;
+    A.k2row = c->direct.k2;
     A.u = rf ? c->d_uRF : c->d_u;
     const dim3 block(32, 8);
     k_rhs<<<grid2d(g.N, g.M, block), block, 0, c->stream>>>(A);
@@ -902,6 +928,8 @@ int mg_solve(mag2d_ctx* c, int rf, double tol, int max_cycles, int fixed_cycles,
         {
             if (fixed_cycles != 0)
             {
+                // in-step solve: the result is exact to round-off, so the residual is only sampled (every 32nd step)
+                if (c->direct_calls++ % 32 != 0) goto direct_done;
                 const MgLevel& L = c->mg[0];
                 const dim3 block(32, 8);
                 k_mg_residual_norm<<<grid2d(L.N, L.M, block), block, 0, c->stream>>>(level_view(L), c->d_scratch + 16);
@@ -911,6 +939,7 @@ int mg_solve(mag2d_ctx* c, int rf, double tol, int max_cycles, int fixed_cycles,
             else
                 rc = mg_residual(c, &r, &bm);
         }
+    direct_done:;
     }
     else if (!rc && !rf && c->extrapolate)
     {

@@ -17,155 +17,210 @@
 
 namespace {
 
-constexpr int GM_TM = 64, GM_TN = 32, GM_TK = 16, GM_THREADS = 128;   // CTA tile 64x32, 4x4 per thread
+// FP64 matrix product C = A x S on the CUDA cores: CTA tile 64 x 32, 4 x 4 outputs per thread, K in chunks of 32
+// streamed through a 3-stage cp.async ring (the operands are L2-resident, the ring hides the L2 latency).
+// All operands are padded to ld = a multiple of 32 columns with zeros, so the K loop has no bounds tests.
+constexpr int GM_TM = 64, GM_TN = 32, GM_KC = 32, GM_THREADS = 128, GM_STAGES = 3;
+constexpr int GM_LDA = GM_KC + 2;                                    // smem row stride of the A tile (doubles)
+constexpr int GM_STAGE_DOUBLES = GM_TM * GM_LDA + GM_KC * GM_TN;
+constexpr int GM_SMEM = GM_STAGES * GM_STAGE_DOUBLES * (int)sizeof(double);
 
-struct DirectArgs
+struct GemmArgs
 {
-    int M, N, n;              // n = N - 2 interior columns
-    const double* b;          // [M][N] right-hand side in the reference's scaling (k_rhs); electrode nodes hold their voltage
-    const double* S;          // [n][n] sine matrix
-    const unsigned char* rowfree;   // [M]
-    const double* k2;         // [M] z-coupling of row i (0 on electrode rows)
-    double* hat;              // [M][n] transformed rows
-    double* u;                // [M][N] potential
-    double scale;             // 2/(n+1)
+    int M, ld, n;                   // rows, padded leading dimension of A / S / hat, live columns
+    const double* A;                // [M][ld]
+    const double* S;                // [ld][ld] sine matrix, zero padded
+    const double* inv;              // FORWARD: [M][ld] 1/den of the Thomas factorisation, folded into the epilogue
+    const unsigned char* rowfree;   // INVERSE: electrode rows keep the voltages k_rhs wrote
+    double* C;                      // FORWARD: value slots of the pair array [M][ld][2];  INVERSE: u + 1 with row stride ldc
+    int ldc;
+    double scale;
 };
 
-// element (i, jj) of B': the right-hand side of interior column j = jj+1 with the two Dirichlet end nodes moved over
-__device__ __forceinline__ double bprime(const DirectArgs& A, int i, int jj)
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
-    const double* row = A.b + (size_t)i * A.N;
-    double v = row[jj + 1];
-    if (A.rowfree[i])
-    {
-        if (jj == 0) v -= A.k2[i] * row[0];
-        if (jj == A.n - 1) v -= A.k2[i] * row[A.N - 1];
-    }
-    return v;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem) : "memory");
 }
-
-// C = A x S with A either B' (FORWARD) or hat (inverse; result scaled and scattered into u's interior columns)
-template <bool FORWARD>
-__global__ void __launch_bounds__(GM_THREADS) k_direct_gemm(const __grid_constant__ DirectArgs A)
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem)
 {
-    __shared__ __align__(32) double sa[2][GM_TK][GM_TM + 4];   // A tile stored k-major so that a thread's 4 rows are contiguous
-    __shared__ __align__(32) double sb[2][GM_TK][GM_TN];
-    const int n = A.n, M = A.M;
-    const int i0 = blockIdx.y * GM_TM, j0 = blockIdx.x * GM_TN;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool FORWARD>
+__global__ void __launch_bounds__(GM_THREADS) k_direct_gemm(const __grid_constant__ GemmArgs G)
+{
+    extern __shared__ __align__(16) double gm_smem[];
     const int t = threadIdx.x;
-    const int tr = (t / 8) * 4, tc = (t % 8) * 4;     // 16 x 8 threads, 4 x 4 outputs each
-    double acc[4][4] = {};
-    auto load = [&](int buf, int k0) {
-        // A tile: 64 rows x 16 k, 1024 elements, 8 per thread; consecutive threads read consecutive k (coalesced rows)
-        for (int e = t; e < GM_TM * GM_TK; e += GM_THREADS)
+    const int i0 = blockIdx.y * GM_TM, j0 = blockIdx.x * GM_TN;
+    const int tr = (t / 8) * 4, tc = (t % 8) * 4;
+    const int nk = G.ld / GM_KC;
+    auto issue = [&](int kb) {
+        double* sa = gm_smem + (kb % GM_STAGES) * GM_STAGE_DOUBLES;
+        double* sb = sa + GM_TM * GM_LDA;
+        const int k0 = kb * GM_KC;
+        // A tile: 64 rows x 32 doubles = 1024 16-byte pieces, 8 per thread (16 pieces per row)
+#pragma unroll
+        for (int q = 0; q < 8; q++)
         {
-            const int r = e / GM_TK, k = e % GM_TK;
-            const int i = i0 + r, kk = k0 + k;
-            double v = 0.0;
-            if (i < M && kk < n) v = FORWARD ? bprime(A, i, kk) : A.hat[(size_t)i * n + kk];
-            sa[buf][k][r] = v;
+            const int e = t + q * GM_THREADS, r = e >> 4, c2 = (e & 15) * 2;
+            const int i = min(i0 + r, G.M - 1);
+            cp_async16(sa + r * GM_LDA + c2, G.A + (size_t)i * G.ld + k0 + c2);
         }
-        for (int e = t; e < GM_TK * GM_TN; e += GM_THREADS)
+        // S tile: 32 k x 32 columns = 512 pieces, 4 per thread
+#pragma unroll
+        for (int q = 0; q < 4; q++)
         {
-            const int k = e / GM_TN, cidx = e % GM_TN;
-            const int kk = k0 + k, j = j0 + cidx;
-            sb[buf][k][cidx] = (kk < n && j < n) ? A.S[(size_t)kk * n + j] : 0.0;
+            const int e = t + q * GM_THREADS, r = e >> 4, c2 = (e & 15) * 2;
+            cp_async16(sb + r * GM_TN + c2, G.S + (size_t)(k0 + r) * G.ld + j0 + c2);
         }
     };
-    const int nk = (n + GM_TK - 1) / GM_TK;
-    load(0, 0);
-    __syncthreads();
+    double acc[4][4] = {};
+    for (int s = 0; s < GM_STAGES - 1; s++)
+    {
+        if (s < nk) issue(s);
+        cp_async_commit();
+    }
     for (int kb = 0; kb < nk; kb++)
     {
-        const int buf = kb & 1;
-        if (kb + 1 < nk) load(buf ^ 1, (kb + 1) * GM_TK);
-#pragma unroll
-        for (int k = 0; k < GM_TK; k++)
+        cp_async_wait<GM_STAGES - 2>();
+        __syncthreads();                               // tile kb landed for everyone; tile kb-1's buffer is free
+        if (kb + GM_STAGES - 1 < nk) issue(kb + GM_STAGES - 1);
+        cp_async_commit();
+        const double* sa = gm_smem + (kb % GM_STAGES) * GM_STAGE_DOUBLES;
+        const double* sb = sa + GM_TM * GM_LDA;
+#pragma unroll 8
+        for (int k = 0; k < GM_KC; k++)
         {
-            const double4 a4 = *reinterpret_cast<const double4*>(&sa[buf][k][tr]);
-            const double4 b4 = *reinterpret_cast<const double4*>(&sb[buf][k][tc]);
-            const double a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+            double a[4], b[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++) a[p] = sa[(tr + p) * GM_LDA + k];
+            const double2 b01 = *reinterpret_cast<const double2*>(sb + k * GM_TN + tc);
+            const double2 b23 = *reinterpret_cast<const double2*>(sb + k * GM_TN + tc + 2);
+            b[0] = b01.x; b[1] = b01.y; b[2] = b23.x; b[3] = b23.y;
 #pragma unroll
             for (int p = 0; p < 4; p++)
 #pragma unroll
                 for (int q = 0; q < 4; q++) acc[p][q] = fma(a[p], b[q], acc[p][q]);
         }
-        __syncthreads();
     }
 #pragma unroll
     for (int p = 0; p < 4; p++)
     {
         const int i = i0 + tr + p;
-        if (i >= M) continue;
-        if (!FORWARD && !A.rowfree[i]) continue;      // electrode rows keep the voltages k_rhs wrote
-#pragma unroll
-        for (int q = 0; q < 4; q++)
+        if (i >= G.M) continue;
+        if (FORWARD)
         {
-            const int j = j0 + tc + q;
-            if (j >= n) continue;
-            if (FORWARD) A.hat[(size_t)i * n + j] = acc[p][q];
-            else A.u[(size_t)i * A.N + j + 1] = acc[p][q] * A.scale;
+            // p = hat / den goes into the value slots of the forward pair array [i][k][2]
+            const size_t e = (size_t)i * G.ld + j0 + tc;
+            const double2 i01 = *reinterpret_cast<const double2*>(G.inv + e), i23 = *reinterpret_cast<const double2*>(G.inv + e + 2);
+            G.C[2 * e] = acc[p][0] * i01.x;
+            G.C[2 * e + 2] = acc[p][1] * i01.y;
+            G.C[2 * e + 4] = acc[p][2] * i23.x;
+            G.C[2 * e + 6] = acc[p][3] * i23.y;
+        }
+        else
+        {
+            if (!G.rowfree[i]) continue;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const int j = j0 + tc + q;
+                if (j < G.n) G.C[(size_t)i * G.ldc + j] = acc[p][q] * G.scale;
+            }
         }
     }
 }
 
-// Thomas sweeps, one thread per sine mode; lower[i][k] = a_i/den, inv = 1/den, upper = c_i/den precomputed on the host
-__global__ void k_direct_tridiag(int M, int n, const double* __restrict__ lower, const double* __restrict__ inv,
-                                 const double* __restrict__ upper, double* __restrict__ hat)
+// Thomas sweeps, one sine mode per lane of warp 0: y_i = p_i - lower_i y_(i-1) with p = hat/den already formed by the
+// forward product's epilogue, then x_i = y_i - upper_i x_(i+1).  The recurrence is one DFMA per row, so the sweep is
+// bound by the issue latency of the single warp that owns a mode: it must execute nothing but LDS.128 / DFMA / STG.
+// Warps 1..3 are the producers: they stream the (value, coefficient) pairs, interleaved in memory as [row][mode][2],
+// through a cp.async ring of TD_STAGES chunks of TD_ROWS rows (512 contiguous bytes per row).
+constexpr int TD_ROWS = 32, TD_STAGES = 4, TD_THREADS = 128;
+constexpr int TD_STAGE_DOUBLES = TD_ROWS * 64;
+constexpr int TD_SMEM = TD_STAGES * TD_STAGE_DOUBLES * (int)sizeof(double);
+
+// pair: [M][ld][2] (value, coefficient); BACKWARD walks the rows downwards.  OUT_STRIDE 2 writes the result into the
+// value slots of the other pair array (forward sweep -> y), 1 into the plain [M][ld] array (backward sweep -> x)
+template <bool BACKWARD, int OUT_STRIDE>
+__device__ __forceinline__ void tridiag_sweep(int M, int ld, int k0, const double* __restrict__ pair, double* __restrict__ out, double* sm)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    const int t = threadIdx.x, lane = t & 31;
+    const int nchunks = (M + TD_ROWS - 1) / TD_ROWS;
+    auto issue = [&](int chunk) {
+        double* st = sm + (chunk % TD_STAGES) * TD_STAGE_DOUBLES;
+        // 32 rows x 32 pieces of 16 bytes, spread over the 96 producer threads
+        for (int e = t - 32; e < TD_ROWS * 32; e += TD_THREADS - 32)
+        {
+            const int r = e >> 5, c16 = e & 31;
+            const int q = chunk * TD_ROWS + r;
+            if (q >= M) break;
+            const int i = BACKWARD ? M - 1 - q : q;
+            cp_async16(st + r * 64 + c16 * 2, pair + ((size_t)i * ld + k0 + c16) * 2);
+        }
+    };
+    if (t >= 32)
+        for (int s = 0; s < TD_STAGES - 1; s++)
+        {
+            if (s < nchunks) issue(s);
+            cp_async_commit();
+        }
     double y = 0.0;
-    constexpr int U = 8;
-    int i = 0;
-    for (; i + U <= M; i += U)
+    for (int chunk = 0; chunk < nchunks; chunk++)
     {
-        double bi[U], li[U];
-#pragma unroll
-        for (int q = 0; q < U; q++)
+        if (t >= 32) cp_async_wait<TD_STAGES - 2>();
+        __syncthreads();            // chunk landed; everybody is done with chunk - 1, whose buffer is refilled below
+        if (t >= 32)
         {
-            const size_t e = (size_t)(i + q) * n + k;
-            bi[q] = hat[e] * inv[e];
-            li[q] = lower[e];
+            if (chunk + TD_STAGES - 1 < nchunks) issue(chunk + TD_STAGES - 1);
+            cp_async_commit();
         }
-#pragma unroll
-        for (int q = 0; q < U; q++)
+        else
         {
-            y = fma(-li[q], y, bi[q]);
-            hat[(size_t)(i + q) * n + k] = y;
-        }
-    }
-    for (; i < M; i++)
-    {
-        const size_t e = (size_t)i * n + k;
-        y = fma(-lower[e], y, hat[e] * inv[e]);
-        hat[e] = y;
-    }
-    double x = 0.0;
-    i = M - 1;
-    for (; i - U + 1 >= 0; i -= U)
-    {
-        double yi[U], ui[U];
+            const double2* st = reinterpret_cast<const double2*>(sm + (chunk % TD_STAGES) * TD_STAGE_DOUBLES) + lane;
+            const int q0 = chunk * TD_ROWS;
+            const int rows = min(TD_ROWS, M - q0);
+            const long long step = (BACKWARD ? -(long long)ld : (long long)ld) * OUT_STRIDE;
+            double* o = out + ((size_t)(BACKWARD ? M - 1 - q0 : q0) * ld + k0 + lane) * OUT_STRIDE;
+            if (rows == TD_ROWS)
+            {
 #pragma unroll
-        for (int q = 0; q < U; q++)
-        {
-            const size_t e = (size_t)(i - q) * n + k;
-            yi[q] = hat[e];
-            ui[q] = upper[e];
-        }
-#pragma unroll
-        for (int q = 0; q < U; q++)
-        {
-            x = fma(-ui[q], x, yi[q]);
-            hat[(size_t)(i - q) * n + k] = x;
+                for (int r = 0; r < TD_ROWS; r++)
+                {
+                    const double2 pc = st[r * 32];
+                    y = fma(-pc.y, y, pc.x);
+                    *o = y;
+                    o += step;
+                }
+            }
+            else
+                for (int r = 0; r < rows; r++)
+                {
+                    const double2 pc = st[r * 32];
+                    y = fma(-pc.y, y, pc.x);
+                    *o = y;
+                    o += step;
+                }
         }
     }
-    for (; i >= 0; i--)
-    {
-        const size_t e = (size_t)i * n + k;
-        x = fma(-upper[e], x, hat[e]);
-        hat[e] = x;
-    }
+    if (t >= 32) cp_async_wait<0>();
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TD_THREADS) k_direct_tridiag(int M, int ld, const double* __restrict__ fwd, double* __restrict__ bwd,
+                                                               double* __restrict__ x)
+{
+    extern __shared__ __align__(16) double td_smem[];
+    const int k0 = blockIdx.x * 32;
+    tridiag_sweep<false, 2>(M, ld, k0, fwd, bwd, td_smem);
+    __threadfence();          // the backward sweep re-reads the y values through the async copy path
+    __syncthreads();
+    tridiag_sweep<true, 1>(M, ld, k0, bwd, x, td_smem);
 }
 
 }  // namespace
@@ -174,10 +229,11 @@ void direct_free(mag2d_ctx* c)
 {
     DirectSolver& D = c->direct;
     cudaFree(D.S);
-    cudaFree(D.lower);
+    cudaFree(D.fwd);
     cudaFree(D.inv);
-    cudaFree(D.upper);
+    cudaFree(D.bwd);
     cudaFree(D.hat);
+    cudaFree(D.bp);
     cudaFree(D.rowfree);
     cudaFree(D.k2);
     D = DirectSolver();
@@ -230,14 +286,16 @@ int direct_setup(mag2d_ctx* c)
         if (i == 0) W[i] = 0.0;
         if (i == M - 1) E[i] = 0.0;
     }
-    std::vector<double> S((size_t)n * n), lower((size_t)M * n), inv((size_t)M * n), upper((size_t)M * n);
+    // every [.][ld] array is zero padded to a multiple of 32 columns: the kernels then need no column bounds tests
+    const int ld = (n + 31) / 32 * 32;
+    std::vector<double> S((size_t)ld * ld, 0.0), lower((size_t)M * ld, 0.0), inv((size_t)M * ld, 0.0), upper((size_t)M * ld, 0.0);
     for (int j = 0; j < n; j++)
         for (int k = j; k < n; k++)
         {
             // reduce the argument exactly before calling sin: (j+1)(k+1) mod 2(n+1)
             const long long p = (long long)(j + 1) * (k + 1) % (2LL * (n + 1));
             const double s = (double)sinl(M_PIl * (long double)p / (long double)(n + 1));
-            S[(size_t)j * n + k] = S[(size_t)k * n + j] = s;
+            S[(size_t)j * ld + k] = S[(size_t)k * ld + j] = s;
         }
     for (int k = 0; k < n; k++)
     {
@@ -248,7 +306,7 @@ int direct_setup(mag2d_ctx* c)
             const double d = rowfree[i] ? C[i] + k2[i] * lam : 1.0;
             const double den = d - W[i] * cp_prev;
             if (!(std::fabs(den) > 1e-300)) return 0;
-            const size_t e = (size_t)i * n + k;
+            const size_t e = (size_t)i * ld + k;
             inv[e] = 1.0 / den;
             lower[e] = W[i] / den;
             upper[e] = E[i] / den;
@@ -257,17 +315,31 @@ int direct_setup(mag2d_ctx* c)
     }
     DirectSolver& D = c->direct;
     D.n = n;
+    D.ld = ld;
     CUDA_OK(cudaMalloc(&D.S, sizeof(double) * S.size()));
-    CUDA_OK(cudaMalloc(&D.lower, sizeof(double) * lower.size()));
+    // (value, coefficient) pairs of the two sweeps: the coefficient slots are filled once, here
+    std::vector<double> fwd(2 * lower.size(), 0.0), bwd(2 * upper.size(), 0.0);
+    for (size_t e = 0; e < lower.size(); e++)
+    {
+        fwd[2 * e + 1] = lower[e];
+        bwd[2 * e + 1] = upper[e];
+    }
+    CUDA_OK(cudaMalloc(&D.fwd, sizeof(double) * fwd.size()));
     CUDA_OK(cudaMalloc(&D.inv, sizeof(double) * inv.size()));
-    CUDA_OK(cudaMalloc(&D.upper, sizeof(double) * upper.size()));
+    CUDA_OK(cudaMalloc(&D.bwd, sizeof(double) * bwd.size()));
     CUDA_OK(cudaMalloc(&D.hat, sizeof(double) * lower.size()));
+    CUDA_OK(cudaMalloc(&D.bp, sizeof(double) * lower.size()));
+    CUDA_OK(cudaMemsetAsync(D.hat, 0, sizeof(double) * lower.size(), c->stream));
+    CUDA_OK(cudaMemsetAsync(D.bp, 0, sizeof(double) * lower.size(), c->stream));
+    CUDA_OK(cudaFuncSetAttribute(k_direct_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM));
+    CUDA_OK(cudaFuncSetAttribute(k_direct_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM));
+    CUDA_OK(cudaFuncSetAttribute(k_direct_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM));
     CUDA_OK(cudaMalloc(&D.rowfree, M));
     CUDA_OK(cudaMalloc(&D.k2, sizeof(double) * M));
     CUDA_OK(cudaMemcpyAsync(D.S, S.data(), sizeof(double) * S.size(), cudaMemcpyHostToDevice, c->stream));
-    CUDA_OK(cudaMemcpyAsync(D.lower, lower.data(), sizeof(double) * lower.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(D.fwd, fwd.data(), sizeof(double) * fwd.size(), cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaMemcpyAsync(D.inv, inv.data(), sizeof(double) * inv.size(), cudaMemcpyHostToDevice, c->stream));
-    CUDA_OK(cudaMemcpyAsync(D.upper, upper.data(), sizeof(double) * upper.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(D.bwd, bwd.data(), sizeof(double) * bwd.size(), cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaMemcpyAsync(D.rowfree, rowfree.data(), M, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaMemcpyAsync(D.k2, k2.data(), sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -275,25 +347,29 @@ int direct_setup(mag2d_ctx* c)
     return 0;
 }
 
-// u (or uRF) <- solution of the system whose right-hand side k_rhs left in c->d_b
+// u (or uRF) <- solution of the system whose right-hand side k_rhs left in c->direct.bp (B': interior columns, the
+// Dirichlet end nodes already moved to the right-hand side; electrode rows hold their voltages)
 int direct_solve(mag2d_ctx* c, double* u)
 {
     const DirectSolver& D = c->direct;
-    DirectArgs A;
-    A.M = c->g.M;
-    A.N = c->g.N;
-    A.n = D.n;
-    A.b = c->d_b;
-    A.S = D.S;
-    A.rowfree = D.rowfree;
-    A.k2 = D.k2;
-    A.hat = D.hat;
-    A.u = u;
-    A.scale = 2.0 / (D.n + 1);
-    const dim3 grid((D.n + GM_TN - 1) / GM_TN, (A.M + GM_TM - 1) / GM_TM);
-    k_direct_gemm<true><<<grid, GM_THREADS, 0, c->stream>>>(A);
-    k_direct_tridiag<<<(D.n + 31) / 32, 32, 0, c->stream>>>(A.M, D.n, D.lower, D.inv, D.upper, D.hat);
-    k_direct_gemm<false><<<grid, GM_THREADS, 0, c->stream>>>(A);
+    GemmArgs G;
+    G.M = c->g.M;
+    G.ld = D.ld;
+    G.n = D.n;
+    G.S = D.S;
+    G.inv = D.inv;
+    G.rowfree = D.rowfree;
+    G.scale = 2.0 / (D.n + 1);
+    const dim3 grid(D.ld / GM_TN, (G.M + GM_TM - 1) / GM_TM);
+    G.A = D.bp;
+    G.C = D.fwd;
+    G.ldc = D.ld;
+    k_direct_gemm<true><<<grid, GM_THREADS, GM_SMEM, c->stream>>>(G);
+    k_direct_tridiag<<<D.ld / 32, TD_THREADS, TD_SMEM, c->stream>>>(G.M, D.ld, D.fwd, D.bwd, D.hat);
+    G.A = D.hat;
+    G.C = u + 1;
+    G.ldc = c->g.N;
+    k_direct_gemm<false><<<grid, GM_THREADS, GM_SMEM, c->stream>>>(G);
     c->launches += 3;
     CUDA_OK(cudaGetLastError());
     return 0;
