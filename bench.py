@@ -172,6 +172,12 @@ def bench_ours(args):
         sim.sort(s)
     sort_interval = args.sort_interval
     sim.set_sort_interval(sort_interval)
+    species_sort = {}
+    if args.sort_intervals:
+        for item in args.sort_intervals.split(","):
+            name, k = item.split("=")
+            species_sort[name] = int(k)
+            sim.set_sort_interval(int(k), species=sim.species_index(name))
     if selfconsistent:
         sim.set_solver_kind(args.solver)
         sim.set_solver(cycles_per_step=args.cycles, tol=1e-12, max_cycles=60)
@@ -278,7 +284,7 @@ def bench_ours(args):
             "dtype": "f64", "data": "synthetic (device-side Philox loaders, seed 1234)",
             "config": {"workload": WORKLOADS[wl], "particles_per_gpu": n, "live_particles": n_live_all,
                        "grid": [int(sim.param["x_sampl"]), int(sim.param["z_sampl"])],
-                       "species": d["species"], "sort_interval": sort_interval,
+                       "species": d["species"], "sort_interval": sort_interval, "species_sort_interval": species_sort,
                        "l2": "inputs larger than L2 (%.1f GB of particle state per GPU)" % (n * 40 / 1e9)
                        if n * 40 > 200e6 else "particle state fits L2: flush not applied, see roofline note",
                        "parallelism": "particle shards, %d rank(s), NCCL all-reduce of the int64 charge grid" % world,
@@ -484,7 +490,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the workload's named size)")
-    ap.add_argument("--sort-interval", type=int, default=8)
+    ap.add_argument("--sort-interval", type=int, default=-1, help="pushes between cell sorts; -1: per species from its thermal drift")
+    ap.add_argument("--sort-intervals", default="", help="per-species overrides, e.g. ARGON_POS=64,ELECTRON=2")
     ap.add_argument("--cycles", type=int, default=-3,
                     help="multigrid V-cycles per step; negative: |n| cycles from the time-extrapolated guess 2u_n - u_(n-1)")
     ap.add_argument("--solver", default="auto", choices=["auto", "multigrid", "direct"],

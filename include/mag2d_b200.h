@@ -159,7 +159,11 @@ int mag2d_count(mag2d_ctx* ctx, int species, int64_t* n_alive, int64_t* n_slots)
 int mag2d_particles_generate(mag2d_ctx* ctx, int species, int kind, int64_t n, double a, double b, double c, double d);
 /* cell sort + compaction of removed particles (replaces the free list, src/particles.hpp:223-247) */
 int mag2d_sort(mag2d_ctx* ctx, int species);
-int mag2d_set_sort_interval(mag2d_ctx* ctx, int steps); /* 0 = never sort inside mag2d_step */
+int mag2d_set_sort_interval(mag2d_ctx* ctx, int steps); /* 0 = never sort inside mag2d_step; -1 = per species from its thermal drift (v_th dt K ~ 0.35 cell, 2..64) */
+/* per-species override (-1 = use the context-wide interval): slow species (ions) need far fewer sorts than fast
+ * ones.  With the Boris movers the sort is carried by the push kernels themselves (a COUNT step hands out cell
+ * tickets, the next step writes the particles to their sorted slots), so an interval of 1 is affordable. */
+int mag2d_set_species_sort_interval(mag2d_ctx* ctx, int species, int steps);
 
 /* ---- stepping --------------------------------------------------------------------------------- */
 /* Pic<D>::advance_init, src/pic.cpp:359-384 */

@@ -100,6 +100,7 @@ def lib():
     L.mag2d_particles_generate.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double]
     L.mag2d_sort.argtypes = [vp, C.c_int]
     L.mag2d_set_sort_interval.argtypes = [vp, C.c_int]
+    L.mag2d_set_species_sort_interval.argtypes = [vp, C.c_int, C.c_int]
     L.mag2d_advance_init.argtypes = [vp]
     L.mag2d_step.argtypes = [vp, C.c_int]
     L.mag2d_species_advance.argtypes = [vp, C.c_int]
@@ -290,8 +291,12 @@ class Sim:
     def sort(self, i):
         self._chk(self.L.mag2d_sort(self.h, i))
 
-    def set_sort_interval(self, steps):
-        self._chk(self.L.mag2d_set_sort_interval(self.h, steps))
+    def set_sort_interval(self, steps, species=None):
+        """cell-sort period in pushes (0: never); species=None sets the context-wide value, else a per-species override"""
+        if species is None:
+            self._chk(self.L.mag2d_set_sort_interval(self.h, steps))
+        else:
+            self._chk(self.L.mag2d_set_species_sort_interval(self.h, species, steps))
 
     # ---- stepping
     def advance_init(self):

@@ -2,6 +2,7 @@
 // particle store management and the per-step orchestration (Pic<D>::advance, src/pic.cpp:330-358).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -91,6 +92,7 @@ int free_store(SpeciesStore& S)
     if (S.d_counts) cudaFree(S.d_counts);
     if (S.d_blob) cudaFree(S.d_blob);
     delete S.h_blob;
+    sort_fused_free(S);
     S = SpeciesStore();
     return 0;
 }
@@ -104,6 +106,7 @@ bool needs_array(const mag2d_ctx* c, int a)
 
 int ensure_capacity(mag2d_ctx* c, SpeciesStore& S, long long need)
 {
+    S.tickets_valid = false;      // every append goes through here: pending sort tickets do not cover the new slots
     if (need <= S.capacity) return 0;
     long long cap = std::max<long long>(need, (long long)(S.capacity * 1.5) + 1024);
     cap = (cap + 255) / 256 * 256;
@@ -165,10 +168,40 @@ int refresh_pools(mag2d_ctx* c, int s)
     return 0;
 }
 
-int advance_one(mag2d_ctx* c, int s)
+// pushes between two sorts of a species.  A context-wide interval of -1 picks it per species from the thermal drift:
+// the sort pays off while most particles of a warp still share their cell, i.e. until the thermal displacement
+// v_th * dt * K reaches about a third of a cell (measured on the C4 deck: electrons 6, optimum flat from 4 to 8);
+// slow species (ions) are re-sorted every 64 pushes, which only serves to compact the removed slots.
+int effective_sort_interval(const mag2d_ctx* c, const SpeciesStore& S)
+{
+    if (S.sort_interval >= 0) return S.sort_interval;
+    if (c->sort_interval >= 0) return c->sort_interval;
+    if (!(S.desc.mass > 0) || !(S.desc.dt > 0)) return 64;
+    const double vth = sqrt(1.380662e-23 * std::max(S.desc.temperature, 0.0) / S.desc.mass);
+    const double h = std::min(c->g.dx, c->g.dz);
+    const double per_step = vth * S.desc.dt / h;
+    if (!(per_step > 0)) return 64;
+    const double k = 0.35 / per_step;
+    return k >= 64 ? 64 : k <= 2 ? 2 : (int)(k + 0.5);
+}
+
+// which part of the fused cell sort this push of species s takes on (sort.cu): bit 0 permute, bit 1 count.
+// With an interval of K pushes the sequence is PERMUTE, K-2 plain pushes, COUNT, PERMUTE, ... (K = 1: both every push)
+int fused_sort_mode(const mag2d_ctx* c, const SpeciesStore& S)
+{
+    if (!c->fused_sort || c->g.mover == MAG2D_ADVANCE_MULTICOLL || S.n_slots == 0) return 0;
+    const int K = effective_sort_interval(c, S);
+    if (K <= 0) return 0;
+    int mode = S.tickets_valid ? 1 : 0;
+    const int since = mode ? 0 : S.pushes_since_permute;
+    if (since >= K - 1) mode |= 2;
+    return mode;
+}
+
+int advance_one(mag2d_ctx* c, int s, bool in_step)
 {
     if (refresh_pools(c, s)) return 1;
-    return launch_species_advance(c, s);
+    return launch_species_advance(c, s, in_step ? fused_sort_mode(c, c->sp[s]) : 0);
 }
 
 }  // namespace
@@ -222,6 +255,7 @@ int mag2d_create(int device, const mag2d_grid_desc* grid, void* stream, mag2d_ct
     mag2d_ctx* c = new mag2d_ctx;
     c->device = device;
     c->g = *grid;
+    if (const char* e = getenv("MAG2D_FUSED_SORT")) c->fused_sort = atoi(e) != 0;
     if (stream) c->stream = (cudaStream_t)stream;
     else
     {
@@ -684,6 +718,7 @@ int mag2d_particles_clear(mag2d_ctx* c, int s)
     CHECK_CTX(c);
     CHECK_SPECIES(c, s);
     c->sp[s].n_slots = 0;
+    c->sp[s].tickets_valid = false;
     CUDA_OK(cudaMemsetAsync(c->sp[s].d_removed, 0, sizeof(unsigned long long), c->stream));
     return 0;
 }
@@ -748,6 +783,14 @@ int mag2d_set_sort_interval(mag2d_ctx* c, int steps)
     return 0;
 }
 
+int mag2d_set_species_sort_interval(mag2d_ctx* c, int s, int steps)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    c->sp[s].sort_interval = steps;
+    return 0;
+}
+
 int mag2d_rho_reset(mag2d_ctx* c, int s)
 {
     CHECK_CTX(c);
@@ -766,7 +809,7 @@ int mag2d_species_advance(mag2d_ctx* c, int s)
 {
     CHECK_CTX(c);
     CHECK_SPECIES(c, s);
-    return advance_one(c, s);
+    return advance_one(c, s, false);
 }
 
 int mag2d_species_advance_init(mag2d_ctx* c, int s)
@@ -851,14 +894,18 @@ int mag2d_step(mag2d_ctx* c, int nsteps)
         }
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
         for (size_t s = 0; s < c->sp.size(); s++)
-            if (advance_one(c, (int)s)) return 1;
+            if (advance_one(c, (int)s, true)) return 1;
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
         if (c->g.selfconsistent && comm_allreduce_rho(c)) return 1;
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
-        if (c->sort_interval > 0)
+        // stand-alone sort: the multi-collision mover, or the fused sort switched off
+        if (!c->fused_sort || c->g.mover == MAG2D_ADVANCE_MULTICOLL)
             for (size_t s = 0; s < c->sp.size(); s++)
-                if (c->sp[s].n_slots > 0 && c->sp[s].steps_since_sort >= c->sort_interval)
+            {
+                const int K = effective_sort_interval(c, c->sp[s]);
+                if (K > 0 && c->sp[s].n_slots > 0 && c->sp[s].steps_since_sort >= K)
                     if (sort_species(c, (int)s, false)) return 1;
+            }
         if (c->timing)
         {
             CUDA_OK(cudaEventRecord(c->ev[4], c->stream));

@@ -33,6 +33,17 @@ struct SpeciesStore
     unsigned long long niter = 0;     // BaseSpecies::niter
     double t = 0;                     // BaseSpecies::t
     int steps_since_sort = 0;
+    // cell sort fused into the push (sort.cu): tickets handed out by a COUNT step, consumed by the next PERMUTE step
+    unsigned* d_key[2] = {};          // [capacity] cell key per slot, two sets (a permuting step reads one, writes the other)
+    unsigned* d_rank[2] = {};
+    unsigned* d_cell_count = nullptr; // [ncells]
+    unsigned* d_cell_offset = nullptr;
+    unsigned* d_sort_sums = nullptr;  // scan scratch + grand total
+    long long key_capacity = 0;
+    int kr = 0;                       // key/rank set holding the pending tickets
+    bool tickets_valid = false;       // a COUNT step has run and nothing has disturbed the slots since
+    int sort_interval = -1;           // pushes between permuting steps (-1: the context-wide setting)
+    int pushes_since_permute = 1 << 20;
 };
 
 // one level of the Galerkin multigrid hierarchy (poisson.cu)
@@ -106,6 +117,7 @@ struct mag2d_ctx
     std::vector<SpeciesStore> sp;
     double* d_charges = nullptr;  // [n_species]
     int sort_interval = 0;
+    bool fused_sort = true;       // cell sort carried by the Boris push itself (MAG2D_FUSED_SORT=0: stand-alone passes)
     bool count_collisions = false;
 
     // sort scratch
@@ -143,7 +155,7 @@ int store_alloc_slab(mag2d_ctx* c, SpeciesStore& S, int slab, long long capacity
 
 // ---- launchers implemented in the kernel translation units
 // push.cu
-int launch_species_advance(mag2d_ctx* c, int s);
+int launch_species_advance(mag2d_ctx* c, int s, int sort_mode = 0);
 int launch_species_advance_init(mag2d_ctx* c, int s);
 int launch_species_accumulate(mag2d_ctx* c, int s);
 int launch_generate(mag2d_ctx* c, int s, int kind, long long n, double a, double b, double cc, double d);
@@ -155,6 +167,9 @@ int update_ueff(mag2d_ctx* c, double phase, bool rf);
 int ensure_particle_scratch(mag2d_ctx* c, long long capacity);
 // sort.cu
 int launch_sort(mag2d_ctx* c, int s, bool trim);
+int sort_fused_begin(mag2d_ctx* c, int s, bool permute, bool count);   // buffers, zeroed counters, other slab
+int sort_fused_end(mag2d_ctx* c, int s, bool permute, bool count);     // scan of the new counts, dead tail, slab swap
+void sort_fused_free(SpeciesStore& S);
 // poisson.cu
 int mg_setup(mag2d_ctx* c);
 void mg_free(mag2d_ctx* c);

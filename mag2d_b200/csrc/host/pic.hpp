@@ -194,7 +194,7 @@ class Pic
             }
         }
         // the cell sort permutes slots, which would lose tracked particles: only sort when nothing is tracked
-        gpu_check(mag2d_set_sort_interval(field.gpu, has_tracked ? 0 : 8));
+        gpu_check(mag2d_set_sort_interval(field.gpu, has_tracked ? 0 : -1));
     }
 
     void advance()

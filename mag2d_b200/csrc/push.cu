@@ -12,7 +12,9 @@
 //   Field2D::accumulate                    src/Field2D.hpp:45-62
 // The reference makes two passes over an AoS array per species and step; here one kernel reads and
 // writes each live phase-space component once (80 B per particle-step, 2D3V fp64).
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.hpp"
@@ -33,7 +35,35 @@ struct PushArgs
     unsigned long long seed;
     unsigned* coll_list;           // slots whose Bernoulli test fired this step (processed by k_mcc_collide)
     unsigned* coll_count;
+    // cell sort fused into the step (SORTING kernels; sort.cu describes the pipeline)
+    int permute;                   // write every array to its sorted slot of the other slab (keys of an earlier COUNT step)
+    int count;                     // hand every surviving particle a ticket of its new cell for the next permuting step
+    int cell_cols;                 // N - 1
+    const unsigned* key_in;        // [slot] cell key / rank within the cell / exclusive offsets of the cells
+    const unsigned* rank_in;
+    const unsigned* offset_in;
+    ParticlesDev dst;              // the other slab
+    unsigned* key_out;             // [slot of this step's output]
+    unsigned* rank_out;
+    unsigned* count_out;           // [cell]
 };
+
+constexpr unsigned SORT_INVALID_KEY = 0xFFFFFFFFu;
+
+// warp-aggregated ticket: one atomic per (warp, cell), ranks handed out in lane order.  MATCH.ANY finds the lanes
+// that share a cell in one instruction, so all group leaders issue their atomics together: one memory round trip
+// per call, not one per distinct cell (the returning atomic is the long pole of a COUNT step).
+__device__ __forceinline__ unsigned warp_ticket(unsigned* __restrict__ count, bool valid, unsigned key)
+{
+    const unsigned lane = lane_id();
+    // invalid lanes get distinct pseudo-keys so that they never join a group of live particles
+    const unsigned group = __match_any_sync(MAG2D_FULL_MASK, valid ? key : (0xFFFFFFE0u | lane));
+    const int leader = __ffs(group) - 1;
+    unsigned base = 0;
+    if (valid && (int)lane == leader) base = atomicAdd(&count[key], (unsigned)__popc(group));
+    base = __shfl_sync(MAG2D_FULL_MASK, base, leader);
+    return base + __popc(group & ((1u << lane) - 1u));
+}
 
 // ---- gather: E = -grad(ue), the staggered-difference bilinear form of Field2D::grad ----------------
 // The reference differences the potential around every particle; here the differences live in the
@@ -134,8 +164,9 @@ __device__ __forceinline__ unsigned long long q32_rn(double w)
 // receives the index of the cell's lower-left node and w the four Q32 weights (Field2D.hpp:57-60 order:
 // [i][j], [i+1][j], [i][j+1], [i+1][j+1]).
 template <bool DEPOSIT>
-__device__ __forceinline__ bool boundary_weights(const GridDev& g, double& x, double& z, unsigned& node, unsigned long long (&w)[4])
+__device__ __forceinline__ bool boundary_weights(const GridDev& g, double& x, double& z, unsigned& node, unsigned long long (&w)[4], unsigned* row = nullptr)
 {
+    node = 0;
     if (!(x >= 0.0 && x <= g.x_max && z >= 0.0 && z <= g.z_max))
     {
         if (g.boundary == MAG2D_BOUNDARY_FREE || !(x == x && z == z)) return false;
@@ -151,6 +182,8 @@ __device__ __forceinline__ bool boundary_weights(const GridDev& g, double& x, do
     i = max(min(i, g.M - 2), 0);
     j = max(min(j, g.N - 2), 0);
     const size_t k = (size_t)i * g.N + j;
+    node = (unsigned)k;
+    if (row) *row = (unsigned)i;
     if (g.check_mask && !g.cfree[k]) return false;
     if (DEPOSIT)
     {
@@ -160,7 +193,6 @@ __device__ __forceinline__ bool boundary_weights(const GridDev& g, double& x, do
         w[1] = q32_rn(__dmul_rn(fu, cv));
         w[2] = q32_rn(__dmul_rn(cu, fv));
         w[3] = q32_rn(__dmul_rn(fu, fv));
-        node = (unsigned)k;
     }
     return true;
 }
@@ -235,7 +267,10 @@ __device__ __forceinline__ void count_removed(unsigned long long* counter, bool 
 // afterwards.  That is legal because scatter() only changes the velocity, which neither the boundary test
 // nor the deposit reads, and it keeps the rarely-taken, register-hungry collision kinematics out of this
 // kernel.
-constexpr int PPT = 4;                       // particles per thread
+#ifndef MAG2D_PPT
+#define MAG2D_PPT 4
+#endif
+constexpr int PPT = MAG2D_PPT;               // particles per thread
 constexpr int TILE = 32 * PPT;               // slots per warp
 #ifndef MAG2D_DEPOSIT_RUNS
 #define MAG2D_DEPOSIT_RUNS 4
@@ -245,7 +280,7 @@ constexpr int TILE = 32 * PPT;               // slots per warp
 #endif
 constexpr int DEPOSIT_RUNS = MAG2D_DEPOSIT_RUNS;   // cells per warp call that get the REDUX treatment
 
-template <int COORD, bool GATHER, bool HASB, bool MCC, bool DEPOSIT>
+template <int COORD, bool GATHER, bool HASB, bool MCC, bool DEPOSIT, bool SORTING>
 __global__ void __launch_bounds__(PUSH_THREADS, MAG2D_PUSH_MIN_BLOCKS) k_push_boris(const __grid_constant__ PushArgs A)
 {
     const unsigned lane = lane_id();
@@ -255,6 +290,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, MAG2D_PUSH_MIN_BLOCKS) k_push_bo
     if (tile0 >= n) return;                   // warp-uniform; arrays are allocated in multiples of 256 slots
     const long long base = tile0 + 2 * lane;  // slot of this thread's first pair
     constexpr bool need_vy = HASB || COORD == MAG2D_CYLINDRICAL;
+    const bool permute = SORTING && A.permute, count = SORTING && A.count;
     uint4 rnd = make_uint4(0, 0, 0, 0);
     if (MCC)
     {
@@ -263,6 +299,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, MAG2D_PUSH_MIN_BLOCKS) k_push_bo
     }
     const double dt = A.s.dt;
     unsigned hit_mask = 0, removed = 0;
+    long long dest[PPT];                      // slot this step's output of particle q lives in (-1: none)
 #pragma unroll
     for (int p = 0; p < PPT / 2; p++)
     {
@@ -276,14 +313,25 @@ __global__ void __launch_bounds__(PUSH_THREADS, MAG2D_PUSH_MIN_BLOCKS) k_push_bo
             x[0] = a.x; x[1] = a.y; z[0] = b.x; z[1] = b.y;
             vx[0] = c.x; vx[1] = c.y; vz[0] = d.x; vz[1] = d.y;
             vy[0] = vy[1] = 0.0;
-            if (need_vy)
+            if (need_vy || permute)
             {
                 const double2 e = *reinterpret_cast<const double2*>(A.p.vy + k);
                 vy[0] = e.x; vy[1] = e.y;
             }
         }
+        dest[2 * p] = k;
+        dest[2 * p + 1] = k + 1;
+        if (permute)
+        {
+            // sorted slot = offset of the cell the particle was counted in + its ticket; slots that were dead when
+            // the tickets were handed out (or lie past n) have no destination: the permutation compacts
+            const uint2 ky = *reinterpret_cast<const uint2*>(A.key_in + k);
+            const uint2 rk = *reinterpret_cast<const uint2*>(A.rank_in + k);
+            dest[2 * p] = (k < n && ky.x != SORT_INVALID_KEY) ? (long long)__ldg(A.offset_in + ky.x) + rk.x : -1;
+            dest[2 * p + 1] = (k + 1 < n && ky.y != SORT_INVALID_KEY) ? (long long)__ldg(A.offset_in + ky.y) + rk.y : -1;
+        }
         bool keep[2];
-        unsigned node[2];
+        unsigned node[2], row[2] = {0, 0};
         unsigned long long w[2][4];
 #pragma unroll
         for (int e = 0; e < 2; e++)
@@ -312,7 +360,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, MAG2D_PUSH_MIN_BLOCKS) k_push_bo
                 x[e] += vx[e] * dt;
                 z[e] += vz[e] * dt;
             }
-            const bool inside = boundary_weights<DEPOSIT>(A.g, x[e], z[e], node[e], w[e]);
+            const bool inside = boundary_weights<DEPOSIT>(A.g, x[e], z[e], node[e], w[e], SORTING ? &row[e] : nullptr);
             keep[e] = live && inside;
             removed += (live && !inside) ? 1u : 0u;
             if (!keep[e]) x[e] = dead_marker();
@@ -323,11 +371,44 @@ __global__ void __launch_bounds__(PUSH_THREADS, MAG2D_PUSH_MIN_BLOCKS) k_push_bo
                 if (keep[e] && u01(word) < A.s.prob) hit_mask |= 1u << q;
             }
         }
-        *reinterpret_cast<double2*>(A.p.x + k) = make_double2(x[0], x[1]);
-        *reinterpret_cast<double2*>(A.p.z + k) = make_double2(z[0], z[1]);
-        *reinterpret_cast<double2*>(A.p.vx + k) = make_double2(vx[0], vx[1]);
-        *reinterpret_cast<double2*>(A.p.vz + k) = make_double2(vz[0], vz[1]);
-        if (need_vy) *reinterpret_cast<double2*>(A.p.vy + k) = make_double2(vy[0], vy[1]);
+        if (permute)
+        {
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+            {
+                const long long d = dest[2 * p + e];
+                if (d < 0) continue;
+                A.dst.x[d] = x[e];
+                A.dst.z[d] = z[e];
+                A.dst.vx[d] = vx[e];
+                A.dst.vz[d] = vz[e];
+                A.dst.vy[d] = vy[e];
+            }
+        }
+        else
+        {
+            *reinterpret_cast<double2*>(A.p.x + k) = make_double2(x[0], x[1]);
+            *reinterpret_cast<double2*>(A.p.z + k) = make_double2(z[0], z[1]);
+            *reinterpret_cast<double2*>(A.p.vx + k) = make_double2(vx[0], vx[1]);
+            *reinterpret_cast<double2*>(A.p.vz + k) = make_double2(vz[0], vz[1]);
+            if (need_vy) *reinterpret_cast<double2*>(A.p.vy + k) = make_double2(vy[0], vy[1]);
+        }
+        if (count)
+        {
+            // tickets for the next permuting step, keyed by the cell the particle sits in now (node = i*N + j)
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+            {
+                const unsigned key = keep[e] ? node[e] - row[e] : SORT_INVALID_KEY;      // i*N + j - i = i*(N-1) + j
+                const unsigned rk = warp_ticket(A.count_out, keep[e], key);
+                const long long d = dest[2 * p + e];
+                if (d >= 0 && (permute || k + e < n))
+                {
+                    A.key_out[d] = key;
+                    A.rank_out[d] = rk;
+                }
+            }
+        }
         if (DEPOSIT)
         {
             // neighbouring slots share a cell after the sort: merge the pair, then merge across the warp
@@ -360,7 +441,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, MAG2D_PUSH_MIN_BLOCKS) k_push_bo
             start = __shfl_sync(MAG2D_FULL_MASK, start, 31) + incl - cnt;
 #pragma unroll
             for (int q = 0; q < PPT; q++)
-                if (hit_mask & (1u << q)) A.coll_list[start++] = (unsigned)(base + 64 * (q >> 1) + (q & 1));
+                if (hit_mask & (1u << q)) A.coll_list[start++] = (unsigned)dest[q];
         }
     }
     // removal counter: one atomic per warp, only when something was removed
@@ -372,6 +453,246 @@ __global__ void __launch_bounds__(PUSH_THREADS, MAG2D_PUSH_MIN_BLOCKS) k_push_bo
         if (lane == 0) atomicAdd(A.removed, (unsigned long long)rsum);
     }
 }
+
+#ifdef MAG2D_WITH_TMA_PUSH
+// ---- the same step with TMA-staged particle tiles ----------------------------------------------------
+// Persistent CTAs (MAG2D_TMA_CTAS_PER_SM per SM) walk the slot range in tiles of 256 * PPT slots.  One elected
+// thread moves every phase-space array of a tile HBM -> shared memory with 1-D bulk copies (cp.async.bulk, the TMA
+// engine) that complete on an mbarrier, MAG2D_TMA_STAGES tiles deep, and moves the updated tile shared -> HBM with a
+// bulk store; the compute threads only touch shared memory, so the HBM latency of the particle stream is off their
+// scoreboards and no registers are spent on staging.  The arithmetic is the code of k_push_boris, shared verbatim.
+#ifndef MAG2D_TMA_STAGES
+#define MAG2D_TMA_STAGES 3
+#endif
+#ifndef MAG2D_TMA_CTAS_PER_SM
+#define MAG2D_TMA_CTAS_PER_SM 2
+#endif
+constexpr int TMA_STAGES = MAG2D_TMA_STAGES;
+constexpr int TMA_TILE = PUSH_THREADS * PPT;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int COORD, bool HASB>
+constexpr int tma_narr() { return (HASB || COORD == MAG2D_CYLINDRICAL) ? 5 : 4; }
+template <int COORD, bool HASB>
+constexpr int tma_smem_bytes() { return TMA_STAGES * tma_narr<COORD, HASB>() * TMA_TILE * (int)sizeof(double) + 64; }
+
+template <int COORD, bool GATHER, bool HASB, bool MCC, bool DEPOSIT>
+__global__ void __launch_bounds__(PUSH_THREADS, MAG2D_TMA_CTAS_PER_SM) k_push_boris_tma(const __grid_constant__ PushArgs A)
+{
+    constexpr bool need_vy = HASB || COORD == MAG2D_CYLINDRICAL;
+    constexpr int NARR = need_vy ? 5 : 4;
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    double* const buf = reinterpret_cast<double*>(tma_smem);                       // [stage][array][slot]
+    unsigned long long* const full = reinterpret_cast<unsigned long long*>(tma_smem + (size_t)TMA_STAGES * NARR * TMA_TILE * sizeof(double));
+    const unsigned t = threadIdx.x, lane = t & 31;
+    const long long n = A.p.n;
+    const long long n_round = (n + 255) / 256 * 256;        // the slabs are allocated in multiples of 256 slots
+    const long long ntiles = (n_round + TMA_TILE - 1) / TMA_TILE;
+    double* const arr[5] = {A.p.x, A.p.z, A.p.vx, A.p.vz, A.p.vy};
+    if (t == 0)
+    {
+        for (int s = 0; s < TMA_STAGES; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto tile_bytes = [&](long long tile) { return (unsigned)(min((long long)TMA_TILE, n_round - tile * TMA_TILE) * (long long)sizeof(double)); };
+    auto issue_load = [&](long long tile, int stage) {
+        const unsigned bytes = tile_bytes(tile);
+        mbar_expect_tx(&full[stage], NARR * bytes);
+#pragma unroll
+        for (int a = 0; a < NARR; a++) bulk_load(buf + ((size_t)stage * NARR + a) * TMA_TILE, arr[a] + tile * TMA_TILE, bytes, &full[stage]);
+    };
+    if (t == 0)
+        for (int s = 0; s < TMA_STAGES - 1; s++)
+        {
+            const long long tile = blockIdx.x + (long long)s * gridDim.x;
+            if (tile < ntiles) issue_load(tile, s);
+        }
+    const double dt = A.s.dt;
+    unsigned removed = 0;
+    for (int it = 0;; it++)
+    {
+        const long long tile = blockIdx.x + (long long)it * gridDim.x;
+        if (tile >= ntiles) break;
+        const int stage = it % TMA_STAGES;
+        const unsigned parity = (unsigned)(it / TMA_STAGES) & 1u;
+        while (!mbar_try_wait(&full[stage], parity)) {}
+        double* const sx = buf + (size_t)stage * NARR * TMA_TILE;
+        double* const sz = sx + TMA_TILE;
+        double* const svx = sz + TMA_TILE;
+        double* const svz = svx + TMA_TILE;
+        double* const svy = svz + TMA_TILE;       // only dereferenced when need_vy
+        const long long tile0 = tile * TMA_TILE;
+        const long long base = tile0 + 2 * t;     // first slot of this thread: pairs (2t, 2t+1) + 512 p
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        if (MCC)
+        {
+            Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)base);
+            rnd = rng.block();
+        }
+        unsigned hit_mask = 0;
+#pragma unroll
+        for (int p = 0; p < PPT / 2; p++)
+        {
+            const int slot = 2 * (int)t + 2 * PUSH_THREADS * p;
+            const long long k = tile0 + slot;
+            double x[2], z[2], vx[2], vz[2], vy[2];
+            {
+                const double2 a = *reinterpret_cast<const double2*>(sx + slot);
+                const double2 b = *reinterpret_cast<const double2*>(sz + slot);
+                const double2 c = *reinterpret_cast<const double2*>(svx + slot);
+                const double2 d = *reinterpret_cast<const double2*>(svz + slot);
+                x[0] = a.x; x[1] = a.y; z[0] = b.x; z[1] = b.y;
+                vx[0] = c.x; vx[1] = c.y; vz[0] = d.x; vz[1] = d.y;
+                vy[0] = vy[1] = 0.0;
+                if (need_vy)
+                {
+                    const double2 e = *reinterpret_cast<const double2*>(svy + slot);
+                    vy[0] = e.x; vy[1] = e.y;
+                }
+            }
+            bool keep[2];
+            unsigned node[2];
+            unsigned long long w[2][4];
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+            {
+                const bool live = (k + e < n) && particle_alive(x[e]);
+                double Ex = 0.0, Ez = A.g.extern_field;
+                if (GATHER) gather_E(A.g, x[e], z[e], Ex, Ez);
+                boris_velocity<COORD, HASB>(A.s, Ex, Ez, vx[e], vy[e], vz[e]);
+                if (COORD == MAG2D_CYLINDRICAL)
+                {
+                    const double x2 = x[e] + vx[e] * dt;
+                    const double y2 = vy[e] * dt;
+                    x[e] = sqrt(x2 * x2 + y2 * y2);
+                    z[e] += vz[e] * dt;
+                    double sa = y2 / x[e], ca = x2 / x[e];
+                    if (x[e] == 0) { sa = 0; ca = 1; }
+                    const double tv = vx[e];
+                    vx[e] = ca * vx[e] + sa * vy[e];
+                    vy[e] = -sa * tv + ca * vy[e];
+                }
+                else
+                {
+                    x[e] += vx[e] * dt;
+                    z[e] += vz[e] * dt;
+                }
+                const bool inside = boundary_weights<DEPOSIT>(A.g, x[e], z[e], node[e], w[e]);
+                keep[e] = live && inside;
+                removed += (live && !inside) ? 1u : 0u;
+                if (!keep[e]) x[e] = dead_marker();
+                if (MCC)
+                {
+                    const int q = 2 * p + e;
+                    const unsigned word = q == 0 ? rnd.x : q == 1 ? rnd.y : q == 2 ? rnd.z : rnd.w;
+                    if (keep[e] && u01(word) < A.s.prob) hit_mask |= 1u << q;
+                }
+            }
+            *reinterpret_cast<double2*>(sx + slot) = make_double2(x[0], x[1]);
+            *reinterpret_cast<double2*>(sz + slot) = make_double2(z[0], z[1]);
+            *reinterpret_cast<double2*>(svx + slot) = make_double2(vx[0], vx[1]);
+            *reinterpret_cast<double2*>(svz + slot) = make_double2(vz[0], vz[1]);
+            if (need_vy) *reinterpret_cast<double2*>(svy + slot) = make_double2(vy[0], vy[1]);
+            if (DEPOSIT)
+            {
+                if (keep[0] && keep[1] && node[0] == node[1])
+                {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) w[0][c] += w[1][c];
+                    keep[1] = false;
+                }
+                warp_deposit<DEPOSIT_RUNS>(A.g.rho, A.g.N, keep[0], node[0], w[0]);
+                warp_deposit<DEPOSIT_RUNS>(A.g.rho, A.g.N, keep[1], node[1], w[1]);
+            }
+        }
+        // the updated tile goes back with one bulk store per array; make the generic-proxy writes visible to it
+        fence_proxy_async();
+        __syncthreads();
+        if (t == 0)
+        {
+            const unsigned bytes = tile_bytes(tile);
+#pragma unroll
+            for (int a = 0; a < NARR; a++) bulk_store(arr[a] + tile0, buf + ((size_t)stage * NARR + a) * TMA_TILE, bytes);
+            bulk_commit();
+            // refill the stage that was stored one iteration ago: its store must have finished reading shared memory
+            const long long next = tile + (long long)(TMA_STAGES - 1) * gridDim.x;
+            if (next < ntiles)
+            {
+                bulk_wait_read<1>();
+                issue_load(next, (it + TMA_STAGES - 1) % TMA_STAGES);
+            }
+        }
+        if (MCC)
+        {
+            const unsigned cnt = __popc(hit_mask);
+            if (__any_sync(MAG2D_FULL_MASK, cnt != 0))
+            {
+                unsigned incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const unsigned tt = __shfl_up_sync(MAG2D_FULL_MASK, incl, o);
+                    if (lane >= (unsigned)o) incl += tt;
+                }
+                const unsigned total = __shfl_sync(MAG2D_FULL_MASK, incl, 31);
+                unsigned start = 0;
+                if (lane == 31) start = atomicAdd(A.coll_count, total);
+                start = __shfl_sync(MAG2D_FULL_MASK, start, 31) + incl - cnt;
+#pragma unroll
+                for (int q = 0; q < PPT; q++)
+                    if (hit_mask & (1u << q)) A.coll_list[start++] = (unsigned)(base + 2 * PUSH_THREADS * (q >> 1) + (q & 1));
+            }
+        }
+    }
+    if (t == 0) bulk_wait_read<0>();
+    if (__any_sync(MAG2D_FULL_MASK, removed != 0))
+    {
+        unsigned rsum = removed;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(MAG2D_FULL_MASK, rsum, o);
+        if (lane == 0) atomicAdd(A.removed, (unsigned long long)rsum);
+    }
+}
+
+#endif  // MAG2D_WITH_TMA_PUSH
 
 // second pass of the Boris movers: BaseSpecies::scatter for the slots whose Bernoulli test fired
 __global__ void __launch_bounds__(128) k_mcc_collide(const __grid_constant__ PushArgs A)
@@ -792,10 +1113,10 @@ SpeciesDev species_view(const mag2d_ctx* c, int s, bool init)
     return v;
 }
 
-template <int COORD>
+template <int COORD, bool SORTING>
 int launch_boris_variant(mag2d_ctx* c, const PushArgs& A, bool gather, bool hasb, bool mcc, bool deposit, unsigned blocks)
 {
-#define LAUNCH(G, B, Mc, D) k_push_boris<COORD, G, B, Mc, D><<<blocks, PUSH_THREADS, 0, c->stream>>>(A)
+#define LAUNCH(G, B, Mc, D) k_push_boris<COORD, G, B, Mc, D, SORTING><<<blocks, PUSH_THREADS, 0, c->stream>>>(A)
     const int code = (gather ? 8 : 0) | (hasb ? 4 : 0) | (mcc ? 2 : 0) | (deposit ? 1 : 0);
     switch (code)
     {
@@ -855,7 +1176,9 @@ static double rf_phase(const mag2d_ctx* c, const SpeciesStore& S)
     return c->g.rf_amplitude * cos(phase) + c->g.rf_U0;
 }
 
-int launch_species_advance(mag2d_ctx* c, int s)
+// sort_mode: bit 0 = permute (write into the other slab at the sorted slots of the pending tickets), bit 1 = count
+// (hand out tickets for the next permuting step); Boris movers only
+int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
 {
     SpeciesStore& S = c->sp[s];
     const mag2d_grid_desc& d = c->g;
@@ -876,6 +1199,10 @@ int launch_species_advance(mag2d_ctx* c, int s)
         A.seed = c->seed;
         A.coll_list = nullptr;
         A.coll_count = nullptr;
+        A.permute = A.count = A.cell_cols = 0;
+        A.key_in = A.rank_in = A.offset_in = nullptr;
+        A.key_out = A.rank_out = A.count_out = nullptr;
+        memset(&A.dst, 0, sizeof(A.dst));
         const unsigned blocks = (unsigned)((S.n_slots + PUSH_THREADS - 1) / PUSH_THREADS);
         const unsigned tile_blocks = (unsigned)((S.n_slots + PUSH_THREADS * PPT - 1) / (PUSH_THREADS * PPT));
         const bool mcc = S.h_blob && S.h_blob->has_collisions && std::isfinite(S.lifetime);
@@ -914,14 +1241,45 @@ int launch_species_advance(mag2d_ctx* c, int s)
             if (mcc)
             {
                 if (ensure_particle_scratch(c, S.capacity)) return 1;
-                A.coll_list = c->d_key;          // the sort's key buffer is idle during a push
+                A.coll_list = c->d_key;          // the stand-alone sort's key buffer is idle during a push
                 A.coll_count = c->d_coll_count;
                 CUDA_OK(cudaMemsetAsync(c->d_coll_count, 0, sizeof(unsigned), c->stream));
             }
-            if (d.coord == MAG2D_CYLINDRICAL)
-                launch_boris_variant<MAG2D_CYLINDRICAL>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, tile_blocks);
+            const bool permute = (sort_mode & 1) != 0, count = (sort_mode & 2) != 0;
+            if (permute || count)
+            {
+                if (sort_fused_begin(c, s, permute, count)) return 1;
+                A.permute = permute;
+                A.count = count;
+                A.cell_cols = d.N - 1;
+                A.key_in = S.d_key[S.kr];
+                A.rank_in = S.d_rank[S.kr];
+                A.offset_in = S.d_cell_offset;
+                // tickets of a permuting step describe the new slab: they go to the other key/rank set
+                A.key_out = S.d_key[permute ? S.kr ^ 1 : S.kr];
+                A.rank_out = S.d_rank[permute ? S.kr ^ 1 : S.kr];
+                A.count_out = S.d_cell_count;
+                if (permute)
+                {
+                    double* const* o = S.arr[S.cur ^ 1];
+                    A.dst.x = o[ARR_X];
+                    A.dst.z = o[ARR_Z];
+                    A.dst.vx = o[ARR_VX];
+                    A.dst.vy = o[ARR_VY];
+                    A.dst.vz = o[ARR_VZ];
+                    A.dst.n = S.n_slots;
+                }
+                if (d.coord == MAG2D_CYLINDRICAL)
+                    launch_boris_variant<MAG2D_CYLINDRICAL, true>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, tile_blocks);
+                else
+                    launch_boris_variant<MAG2D_CARTESIAN, true>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, tile_blocks);
+                if (sort_fused_end(c, s, permute, count)) return 1;
+                if (permute) A.p = particles_view(S);      // the collision pass works on the new slab
+            }
+            else if (d.coord == MAG2D_CYLINDRICAL)
+                launch_boris_variant<MAG2D_CYLINDRICAL, false>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, tile_blocks);
             else
-                launch_boris_variant<MAG2D_CARTESIAN>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, tile_blocks);
+                launch_boris_variant<MAG2D_CARTESIAN, false>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, tile_blocks);
             if (mcc)
             {
                 k_mcc_collide<<<148 * 8, 128, 0, c->stream>>>(A);
@@ -940,6 +1298,7 @@ int launch_species_advance(mag2d_ctx* c, int s)
         S.t += S.desc.dt;
     }
     S.steps_since_sort++;
+    if (S.pushes_since_permute < (1 << 20)) S.pushes_since_permute++;
     return 0;
 }
 

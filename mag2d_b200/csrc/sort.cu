@@ -177,12 +177,23 @@ __global__ void k_fill_dead(double* __restrict__ x, const unsigned long long* __
         x[k] = dead_marker();
 }
 
+// the same for a fused permuting step: the new tickets of the tail slots must read "no particle" as well
+__global__ void k_fill_dead_keys(double* __restrict__ x, unsigned* __restrict__ key, const unsigned long long* __restrict__ total, long long n)
+{
+    for (long long k = (long long)*total + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+    {
+        x[k] = dead_marker();
+        if (key) key[k] = INVALID_KEY;
+    }
+}
+
 }  // namespace
 
 int launch_sort(mag2d_ctx* c, int s, bool trim)
 {
     SpeciesStore& S = c->sp[s];
     const long long n = S.n_slots;
+    S.tickets_valid = false;
     if (n == 0) return 0;
     const int M = c->g.M, N = c->g.N;
     const int ncells = (M - 1) * (N - 1);
@@ -230,5 +241,94 @@ int launch_sort(mag2d_ctx* c, int s, bool trim)
         CUDA_OK(cudaStreamSynchronize(c->stream));
         S.n_slots = (long long)total;
     }
+    return 0;
+}
+
+// ---- cell sort fused into the Boris push (push.cu, SORTING kernels) -----------------------------------------------
+// Instead of a stand-alone count + scatter pass every K steps (16 + 88 bytes per particle), the push itself does the
+// work of both: a COUNT step hands every surviving particle a ticket (cell key, rank in the cell) for the position it
+// has just been moved to; the counts are scanned; the next PERMUTE step reads the particles in slot order as always
+// but writes them to slot offset[key] + rank of the other slab, dropping dead slots on the way.  The store is then
+// sorted by the cell each particle occupied one step earlier, which is as good for the gather / scatter locality,
+// and the only extra traffic is the 8 bytes of ticket written and read per particle.
+void sort_fused_free(SpeciesStore& S)
+{
+    for (int q = 0; q < 2; q++)
+    {
+        cudaFree(S.d_key[q]);
+        cudaFree(S.d_rank[q]);
+        S.d_key[q] = S.d_rank[q] = nullptr;
+    }
+    cudaFree(S.d_cell_count);
+    cudaFree(S.d_cell_offset);
+    cudaFree(S.d_sort_sums);
+    S.d_cell_count = S.d_cell_offset = S.d_sort_sums = nullptr;
+    S.key_capacity = 0;
+    S.tickets_valid = false;
+}
+
+int sort_fused_begin(mag2d_ctx* c, int s, bool permute, bool count)
+{
+    SpeciesStore& S = c->sp[s];
+    const int ncells = (c->g.M - 1) * (c->g.N - 1);
+    const int ntiles = (ncells + SCAN_TILE - 1) / SCAN_TILE;
+    if (!S.d_cell_count)
+    {
+        CUDA_OK(cudaMalloc(&S.d_cell_count, sizeof(unsigned) * (size_t)ncells));
+        CUDA_OK(cudaMalloc(&S.d_cell_offset, sizeof(unsigned) * (size_t)ncells));
+        CUDA_OK(cudaMalloc(&S.d_sort_sums, sizeof(unsigned) * (size_t)(ntiles + 8) + 16));
+    }
+    if (S.key_capacity < S.capacity)
+    {
+        if (S.tickets_valid)
+        {
+            mag2d_set_error("sort_fused_begin: the particle store grew while tickets were pending");
+            return 1;
+        }
+        for (int q = 0; q < 2; q++)
+        {
+            cudaFree(S.d_key[q]);
+            cudaFree(S.d_rank[q]);
+            CUDA_OK(cudaMalloc(&S.d_key[q], sizeof(unsigned) * (size_t)S.capacity));
+            CUDA_OK(cudaMalloc(&S.d_rank[q], sizeof(unsigned) * (size_t)S.capacity));
+        }
+        S.key_capacity = S.capacity;
+    }
+    if (count) CUDA_OK(cudaMemsetAsync(S.d_cell_count, 0, sizeof(unsigned) * (size_t)ncells, c->stream));
+    if (permute)
+    {
+        if (!S.arr[S.cur ^ 1][ARR_X] && store_alloc_slab(c, S, S.cur ^ 1, S.capacity)) return 1;
+        // removals are counted per compaction period: the dead slots of the old slab are dropped by this step
+        CUDA_OK(cudaMemsetAsync(S.d_removed, 0, sizeof(unsigned long long), c->stream));
+    }
+    return 0;
+}
+
+int sort_fused_end(mag2d_ctx* c, int s, bool permute, bool count)
+{
+    SpeciesStore& S = c->sp[s];
+    const int ncells = (c->g.M - 1) * (c->g.N - 1);
+    const int ntiles = (ncells + SCAN_TILE - 1) / SCAN_TILE;
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(S.d_sort_sums + ((ntiles + 1) / 2 * 2 + 2));
+    if (permute)
+    {
+        // d_total still holds the number of particles the consumed tickets covered: everything behind is dead
+        k_fill_dead_keys<<<148 * 4, 256, 0, c->stream>>>(S.arr[S.cur ^ 1][ARR_X], count ? S.d_key[S.kr ^ 1] : nullptr, d_total, S.n_slots);
+        c->launches++;
+        S.cur ^= 1;
+        if (count) S.kr ^= 1;
+        S.pushes_since_permute = 0;
+        S.steps_since_sort = 0;
+        S.tickets_valid = false;
+    }
+    if (count)
+    {
+        k_scan_tiles<<<ntiles, SCAN_THREADS, 0, c->stream>>>(S.d_cell_count, S.d_cell_offset, S.d_sort_sums, ncells);
+        k_scan_sums<<<1, 1024, 0, c->stream>>>(S.d_sort_sums, ntiles, d_total);
+        k_scan_add<<<ntiles, SCAN_THREADS, 0, c->stream>>>(S.d_cell_offset, S.d_sort_sums, ncells);
+        c->launches += 3;
+        S.tickets_valid = true;
+    }
+    CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -351,6 +351,62 @@ def test_cell_sort_compacts_and_preserves_the_particle_set(orc, deckdir):
 
 
 # ------------------------------------------------------------------------------- reference, live
+@pytest.mark.parametrize("interval", [1, 2, 3])
+def test_fused_cell_sort_keeps_the_particle_set_and_the_charge(orc, deckdir, interval):
+    """the Boris push carries the cell sort (COUNT step -> tickets, PERMUTE step -> sorted slots of the other slab):
+    with collisions off the physics does not depend on the slot order, so after N steps the multiset of particles and
+    the fixed-point charge grids must be bit-identical to a run that never sorts; dead slots must be compacted away"""
+    d = decks.deck("c4", deckdir, n_particles=30000, collisions=False, x_sampl=33, z_sampl=49, r_max=3.2e-3, z_max=4.8e-3)
+    rng = np.random.default_rng(21)
+    init = {}
+    results = []
+    for k in (0, interval):
+        with _sim(d["config"], d["species_conf"]) as sim:
+            for name, vth in (("ARGON_POS", 4e5), ("ELECTRON", 8e5)):
+                i = sim.species_index(name)
+                if name not in init:
+                    # uniform over the whole box and fast: particles leave through the walls every step, so the
+                    # compaction is exercised
+                    a = np.zeros((15000, 7))
+                    a[:, 0] = rng.uniform(1e-7, 3.2e-3 - 1e-7, 15000)
+                    a[:, 2] = rng.uniform(1e-7, 4.8e-3 - 1e-7, 15000)
+                    a[:, 3:6] = rng.normal(size=(15000, 3)) * vth
+                    init[name] = a
+                sim.set_particles(i, init[name])
+            sim.set_sort_interval(k)
+            sim.advance_init()
+            sim.advance(7)
+            out = {}
+            for name in ("ARGON_POS", "ELECTRON"):
+                i = sim.species_index(name)
+                p = sim.get_particles(i)
+                alive = p[p[:, 7] > 0][:, [0, 2, 3, 4, 5]]
+                order = np.lexsort(alive.T[::-1])
+                out[name] = (alive[order], sim.rho_fixed(i), sim.count(i), p[:, 7])
+            results.append(out)
+    for name in ("ARGON_POS", "ELECTRON"):
+        a, b = results[0][name], results[1][name]
+        assert a[2][0] == b[2][0] and a[2][0] < 15000          # same survivors, and some particles did leave
+        assert np.array_equal(a[0], b[0]), name
+        assert np.array_equal(a[1], b[1]), name
+        # the permuting steps drop dead slots: only the removals since the last permute are still holes
+        flags = b[3]
+        n_alive = int(flags.sum())
+        n_dead = 15000 - n_alive
+        assert (flags[:n_alive] == 0).sum() < 0.6 * n_dead
+    with _sim(d["config"], d["species_conf"]) as sim:
+        i = sim.species_index("ELECTRON")
+        sim.set_particles(i, init["ELECTRON"])
+        sim.set_sort_interval(interval)
+        sim.advance_init()
+        sim.advance(2 * interval + 1)
+        p = sim.get_particles(i)
+        live = p[p[:, 7] > 0]
+        g = grid_from_param(sim.param)
+        key = np.floor(live[:, 0] * g.idx).astype(np.int64) * (g.N - 1) + np.floor(live[:, 2] * g.idz).astype(np.int64)
+        assert (np.diff(key) < 0).mean() < 0.35      # an unsorted store has ~0.5
+
+
 @pytest.mark.skipif(not needs_ref, reason="oracle/_ref not present on this machine")
 def test_live_reference_rf_trap_100_steps(deckdir):
     from oracle import RefHarness
