@@ -7,5 +7,5 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 legs may import this package — as the checker, never as the thing measured or shipped.  The product
 (``mag2d_b200``) must not import it and fails loudly when its CUDA library is missing.
 """
-from .pyoracle import Oracle, OrcGrid, build_oracle  # noqa: F401
-from .pyref import RefHarness, ref_available, REF_DIR  # noqa: F401
+from .pyoracle import Oracle, Oracle3, Orc3Grid, OrcGrid, build_oracle  # noqa: F401
+from .pyref import Ref3D, RefHarness, ref_available, REF_DIR  # noqa: F401

@@ -66,12 +66,11 @@ class OrcRng(C.Structure):
 
 def build_oracle(force=False):
     """Compile the restatement (gcc, -O2 -ffp-contract=off).  Building the checker is not using it."""
-    src = os.path.join(HERE, "mag2d_oracle.c")
-    hdr = os.path.join(HERE, "mag2d_oracle.h")
-    if (not force and os.path.exists(LIB)
-            and os.path.getmtime(LIB) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+    srcs = [os.path.join(HERE, f) for f in ("mag2d_oracle.c", "mag3d_oracle.c")]
+    deps = srcs + [os.path.join(HERE, f) for f in ("mag2d_oracle.h", "mag3d_oracle.h")]
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(f) for f in deps):
         return LIB
-    subprocess.check_call(["/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc", "-std=c11", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", LIB, src, "-lm"])
+    subprocess.check_call(["/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc", "-std=c11", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", LIB] + srcs + ["-lm"])
     return LIB
 
 
@@ -336,3 +335,109 @@ class Oracle:
         voltage = np.zeros((g.M, g.N))
         self.lib.orc_geometry(C.byref(g), geometry, probe_radius, u_probe, _u8(mask), _d(voltage))
         return mask, voltage
+
+
+# ---------------------------------------------------------------------------------------------- 3-D
+class Orc3Grid(C.Structure):
+    _fields_ = [("imax", C.c_int), ("jmax", C.c_int), ("kmax", C.c_int),
+                ("idx", C.c_double), ("idy", C.c_double), ("idz", C.c_double),
+                ("x_max", C.c_double), ("y_max", C.c_double), ("z_max", C.c_double),
+                ("boundary", C.c_int), ("macroparticle_factor", C.c_double)]
+
+    @classmethod
+    def make(cls, dims, idx, idy, idz, x_max, y_max, z_max, boundary=0, mpf=1.0):
+        g = cls()
+        g.imax, g.jmax, g.kmax = (int(v) for v in dims)
+        g.idx, g.idy, g.idz = idx, idy, idz
+        g.x_max, g.y_max, g.z_max = x_max, y_max, z_max
+        g.boundary = boundary
+        g.macroparticle_factor = mpf
+        return g
+
+    @property
+    def shape(self):
+        return (self.imax, self.jmax, self.kmax)
+
+
+class Oracle3:
+    """ctypes view of oracle/mag3d_oracle.c (the restatement of the reference's 3-D path)"""
+
+    def __init__(self):
+        build_oracle()
+        lib = C.CDLL(LIB)
+        self.lib = lib
+        G = C.POINTER(Orc3Grid)
+        i8p = C.POINTER(C.c_int8)
+        i64p = C.POINTER(C.c_int64)
+        self._i8p, self._i64p = i8p, i64p
+        lib.orc3_geometry.argtypes = [G, i8p, dp]
+        lib.orc3_is_free.argtypes = [G, i8p, C.c_double, C.c_double, C.c_double]
+        lib.orc3_accumulate.argtypes = [G, dp, C.c_double, C.c_double, C.c_double, C.c_double]
+        lib.orc3_deposit_fixed.argtypes = [G, C.c_int, dp, dp, dp, u8p, i64p]
+        lib.orc3_interpolate.restype = C.c_double
+        lib.orc3_interpolate.argtypes = [G, dp, C.c_double, C.c_double, C.c_double]
+        lib.orc3_grad.argtypes = [G, dp, C.c_double, C.c_double, C.c_double, dp, dp, dp]
+        lib.orc3_rhs.argtypes = [G, i8p, dp, dp]
+        lib.orc3_apply_operator.argtypes = [G, i8p, dp, dp]
+        lib.orc3_solve_direct.argtypes = [G, i8p, dp, dp]
+        lib.orc3_advance.argtypes = [G, dp, i8p] + [C.c_double] * 6 + [C.c_int] + [dp] * 6 + [u8p, dp, i64p]
+
+    def geometry(self, g):
+        mask = np.zeros(g.shape, dtype=np.int8)
+        volt = np.zeros(g.shape)
+        self.lib.orc3_geometry(C.byref(g), mask.ctypes.data_as(self._i8p), _d(volt))
+        return mask, volt
+
+    def is_free(self, g, mask, x, y, z):
+        m = mask.ctypes.data_as(self._i8p)
+        return np.array([self.lib.orc3_is_free(C.byref(g), m, a, b, c) for a, b, c in zip(x, y, z)], dtype=np.int32)
+
+    def accumulate(self, g, charge, x, y, z):
+        rho = np.zeros(g.shape)
+        bad = sum(self.lib.orc3_accumulate(C.byref(g), _d(rho), charge, a, b, c) != 0 for a, b, c in zip(x, y, z))
+        return rho, bad
+
+    def deposit_fixed(self, g, x, y, z, alive=None):
+        out = np.zeros(g.shape, dtype=np.int64)
+        x, y, z = (np.ascontiguousarray(v, dtype=np.float64) for v in (x, y, z))
+        al = None if alive is None else np.ascontiguousarray(alive, dtype=np.uint8)
+        bad = self.lib.orc3_deposit_fixed(C.byref(g), len(x), _d(x), _d(y), _d(z), None if al is None else _u8(al),
+                                          out.ctypes.data_as(self._i64p))
+        return out, bad
+
+    def grad(self, g, u, x, y, z):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        out = np.zeros((len(x), 3))
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        for p in range(len(x)):
+            self.lib.orc3_grad(C.byref(g), _d(u), x[p], y[p], z[p], C.byref(a), C.byref(b), C.byref(c))
+            out[p] = (a.value, b.value, c.value)
+        return out
+
+    def interpolate(self, g, u, x, y, z):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        return np.array([self.lib.orc3_interpolate(C.byref(g), _d(u), a, b, c) for a, b, c in zip(x, y, z)])
+
+    def rhs(self, g, mask, voltage, rho):
+        b = np.array(rho, dtype=np.float64, copy=True)
+        self.lib.orc3_rhs(C.byref(g), mask.ctypes.data_as(self._i8p), _d(np.ascontiguousarray(voltage)), _d(b))
+        return b
+
+    def apply_operator(self, g, mask, u):
+        y = np.zeros(g.shape)
+        self.lib.orc3_apply_operator(C.byref(g), mask.ctypes.data_as(self._i8p), _d(np.ascontiguousarray(u)), _d(y))
+        return y
+
+    def solve_direct(self, g, mask, b):
+        u = np.zeros(g.shape)
+        rc = self.lib.orc3_solve_direct(C.byref(g), mask.ctypes.data_as(self._i8p), _d(np.ascontiguousarray(b)), _d(u))
+        assert rc == 0
+        return u
+
+    def advance(self, g, u, mask, charge, mass, dt, B, soa, alive, rho=None, rho_fixed=None):
+        """soa: dict of contiguous float64 arrays x,y,z,vx,vy,vz (updated in place); alive uint8 (in place)"""
+        n = len(alive)
+        return self.lib.orc3_advance(C.byref(g), _d(np.ascontiguousarray(u)), mask.ctypes.data_as(self._i8p), charge, mass, dt,
+                                     B[0], B[1], B[2], n, _d(soa["x"]), _d(soa["y"]), _d(soa["z"]), _d(soa["vx"]),
+                                     _d(soa["vy"]), _d(soa["vz"]), _u8(alive), None if rho is None else _d(rho),
+                                     None if rho_fixed is None else rho_fixed.ctypes.data_as(self._i64p))

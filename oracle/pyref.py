@@ -268,3 +268,96 @@ class RefHarness:
         a = np.ascontiguousarray(v3, dtype=np.float64).copy()
         self.lib.ref_rng_deflect(self.h, float(angle), a.shape[0], _dp(a))
         return a
+
+
+# ---------------------------------------------------------------------------------------------- 3-D
+class Ref3D:
+    """the compilable part of the reference's 3-D code (Field3D, Geometry, Solver) through oracle/ref3d_harness.cpp"""
+
+    def __init__(self, config, with_solver=True):
+        path = os.path.join(REF_DIR, "libmag3d_ref.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle/_ref/libmag3d_ref.so is not built (make -C oracle ref)")
+        L = C.CDLL(path)
+        self.lib = L
+        dp_ = C.POINTER(C.c_double)
+        ip = C.POINTER(C.c_int)
+        i8p = C.POINTER(C.c_int8)
+        L.ref3_create.restype = C.c_void_p
+        L.ref3_create.argtypes = [C.c_char_p, C.c_int]
+        L.ref3_error.restype = C.c_char_p
+        L.ref3_error.argtypes = [C.c_void_p]
+        L.ref3_destroy.argtypes = [C.c_void_p]
+        L.ref3_dims.argtypes = [C.c_void_p, ip, dp_]
+        L.ref3_mask.argtypes = [C.c_void_p, i8p, dp_]
+        L.ref3_is_free.argtypes = [C.c_void_p, C.c_int, dp_, dp_, dp_, ip]
+        L.ref3_accumulate.argtypes = [C.c_void_p, C.c_int, C.c_double, dp_, dp_, dp_]
+        L.ref3_get.argtypes = [C.c_void_p, C.c_int, dp_]
+        L.ref3_set.argtypes = [C.c_void_p, C.c_int, dp_]
+        L.ref3_grad.argtypes = [C.c_void_p, C.c_int, dp_, dp_, dp_, dp_, dp_, dp_, dp_]
+        L.ref3_solve.argtypes = [C.c_void_p]
+        L.ref3_interpolate.argtypes = [C.c_void_p, C.c_int, dp_, dp_, dp_, dp_]
+        self.h = L.ref3_create(config.encode(), 1 if with_solver else 0)
+        err = L.ref3_error(self.h).decode()
+        if err:
+            raise RuntimeError(err)
+        dims = (C.c_int * 3)()
+        d = (C.c_double * 10)()
+        L.ref3_dims(self.h, dims, d)
+        self.shape = tuple(dims)
+        (self.dx, self.dy, self.dz, self.idx, self.idy, self.idz, self.x_max, self.y_max, self.z_max,
+         self.macroparticle_factor) = list(d)
+
+    def close(self):
+        if self.h:
+            self.lib.ref3_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def mask(self):
+        m = np.zeros(self.shape, dtype=np.int8)
+        v = np.zeros(self.shape)
+        self.lib.ref3_mask(self.h, m.ctypes.data_as(C.POINTER(C.c_int8)), _dp(v))
+        return m, v
+
+    def is_free(self, x, y, z):
+        out = np.zeros(len(x), dtype=np.int32)
+        x, y, z = (np.ascontiguousarray(v, dtype=np.float64) for v in (x, y, z))
+        self.lib.ref3_is_free(self.h, len(x), _dp(x), _dp(y), _dp(z), out.ctypes.data_as(C.POINTER(C.c_int)))
+        return out
+
+    def accumulate(self, charge, x, y, z):
+        x, y, z = (np.ascontiguousarray(v, dtype=np.float64) for v in (x, y, z))
+        return self.lib.ref3_accumulate(self.h, len(x), charge, _dp(x), _dp(y), _dp(z))
+
+    def get(self, which):
+        out = np.zeros(self.shape)
+        self.lib.ref3_get(self.h, {"u": 0, "rho": 1}[which], _dp(out))
+        return out
+
+    def set(self, which, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.shape == self.shape
+        self.lib.ref3_set(self.h, {"u": 0, "rho": 1}[which], _dp(a))
+
+    def grad(self, x, y, z):
+        x, y, z = (np.ascontiguousarray(v, dtype=np.float64) for v in (x, y, z))
+        n = len(x)
+        gx, gy, gz, val = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+        self.lib.ref3_grad(self.h, n, _dp(x), _dp(y), _dp(z), _dp(gx), _dp(gy), _dp(gz), _dp(val))
+        return np.stack([gx, gy, gz], axis=1), val
+
+    def interpolate(self, x, y, z):
+        x, y, z = (np.ascontiguousarray(v, dtype=np.float64) for v in (x, y, z))
+        val = np.zeros(len(x))
+        self.lib.ref3_interpolate(self.h, len(x), _dp(x), _dp(y), _dp(z), _dp(val))
+        return val
+
+    def solve(self):
+        assert self.lib.ref3_solve(self.h) == 0
+        return self.get("u")
