@@ -35,9 +35,10 @@ WORKLOADS = {
     "c2": "C2: 22-pole RF ion trap, 200x200, H- in He/H2 buffer gas, Boris + RF gather + Langevin MCC",
     "c3": "C3: cylindrical r-z, 200x100, Bz=0.03 T, electrons, self-consistent, Boris",
     "c1": "C1: e- swarm in He, E=1 kV/m, multi-collision mover (~90 events per particle-step)",
+    "c5": "C5: 3-D self-consistent electron cloud in Ar, 256^3 grid, Poisson each step, Boris + MCC + 8-node deposit",
 }
-DEFAULT_PARTICLES = {"c4": 100_000_000, "c2": 1_000_000, "c3": 10_000_000, "c1": 1_000_000}
-BYTES = {"c4": 80.0, "c2": 80.0, "c3": 80.0, "c1": 96.0}
+DEFAULT_PARTICLES = {"c4": 100_000_000, "c2": 1_000_000, "c3": 10_000_000, "c1": 1_000_000, "c5": 125_000_000}
+BYTES = {"c4": 80.0, "c2": 80.0, "c3": 80.0, "c1": 96.0, "c5": 96.0}
 
 
 def measured_traffic(workload, n_particles):
@@ -120,6 +121,10 @@ def make_deck(workload, particles_per_gpu, world, tmp):
         # dV = V/cells with V = n_particles_total/density_total (param.cpp:134-136): the macro-particle
         # weight follows the GLOBAL count per species so that the physical density stays 1e15 m^-3
         return decks.deck("c4", tmp, n_particles=particles_per_gpu, n_particles_total=n_global // 2)
+    if workload == "c5":
+        # the macro-particle volume follows the GLOBAL count (Param derives dy from it, param.cpp:133-137)
+        L, dy = 1e-4 * 255, 1e-4
+        return decks.deck("c5", tmp, n_particles=particles_per_gpu, n_particles_total=n_global, density_total=n_global / (L * L * dy))
     return decks.deck(workload, tmp, n_particles=particles_per_gpu)
 
 
@@ -130,6 +135,8 @@ def load_particles(sim, workload, d, n):
     elif workload == "c2":
         # uniform disk of radius 4 mm in the 22-pole trap (field-free core of the trap)
         sim.generate(sim.species_index("H_NEG"), "on_disk", n, 1e-2, 1e-2, 4e-3)
+    elif workload == "c5":
+        sim.generate(sim.species_index("ELECTRON"), "everywhere", n)
     else:
         sim.run_initscript(d["initscript"])
 
@@ -182,6 +189,7 @@ def bench_ours(args):
         sim.set_solver_kind(args.solver)
         sim.set_solver(cycles_per_step=args.cycles, tol=1e-12, max_cycles=60)
     direct = selfconsistent and sim.solver_is_direct()
+    three_d = wl == "c5"
     sim.advance_init()
     n_live0 = sum(sim.count(s)[0] for s in part_species)
 
@@ -210,6 +218,8 @@ def bench_ours(args):
     ms = e0.elapsed_time(e1)
     clock_info = clocks.stop() if rank == 0 else None
     monitored_resid = sim.solver_stats()["resid"] if selfconsistent else None
+    if three_d:
+        monitored_resid = sim.solve()["resid"]       # measured after the timed region (the 3-D step does not monitor)
     launches = sim.kernel_launches() - launches0
     n_live_end = sum(sim.count(s)[0] for s in part_species)
     t = torch.tensor([ms, float(n_live), float(n_live_end)], dtype=torch.float64, device=dev)
@@ -238,8 +248,11 @@ def bench_ours(args):
     achieved = BYTES[wl] * n_now / (push_ms * 1e-3) / 1e9 if push_ms > 0 else 0.0
     solve_info = None
     if direct:
-        solve_info = {"kind": "direct: sine transform along z (FP64 matrix product) x tridiagonal solve per mode along x "
-                              "(the grid has no internal electrodes); exact to round-off like the reference's LU",
+        solve_info = {"kind": ("direct: sine transforms along y and z (FP64 matrix products) x tridiagonal solve per mode along x, "
+                               "point electrodes by the capacitance-matrix method; exact to round-off like the reference's LU")
+                      if three_d else
+                      ("direct: sine transform along z (FP64 matrix product) x tridiagonal solve per mode along x "
+                       "(the grid has no internal electrodes); exact to round-off like the reference's LU"),
                       "ms_per_step": tm["solve"] / args.steps, "vcycles_per_step": 0,
                       "max_resid_over_timed_steps": monitored_resid,
                       "resid_def": "max|r_k/a_kk| / max|u| (largest Jacobi update relative to the potential)"}
@@ -283,19 +296,19 @@ def bench_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (device-side Philox loaders, seed 1234)",
             "config": {"workload": WORKLOADS[wl], "particles_per_gpu": n, "live_particles": n_live_all,
-                       "grid": [int(sim.param["x_sampl"]), int(sim.param["z_sampl"])],
+                       "grid": list(sim.shape),
                        "species": d["species"], "sort_interval": sort_interval, "species_sort_interval": species_sort,
                        "l2": "inputs larger than L2 (%.1f GB of particle state per GPU)" % (n * 40 / 1e9)
                        if n * 40 > 200e6 else "particle state fits L2: flush not applied, see roofline note",
                        "parallelism": "particle shards, %d rank(s), NCCL all-reduce of the int64 charge grid" % world,
-                       "poisson": ("direct (sine transform x tridiagonal)" if direct else "multigrid, %d V-cycles/step" % abs(args.cycles))
+                       "poisson": (("direct (2 sine transforms x tridiagonal + capacitance matrix)" if three_d else "direct (sine transform x tridiagonal)") if direct else "multigrid, %d V-cycles/step" % abs(args.cycles))
                        if selfconsistent else "none (vacuum field solved once)"},
             "gpu_launches": int(launches),
             "clocks": clock_info,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic(wl, n_now / n_push_launches),
                          "algorithmic_bytes_per_launch": BYTES[wl] * n_now / n_push_launches,
-                         "kernel": "k_push_boris (fused gather+push+MCC+boundary+deposit), %d launches/step" % n_push_launches,
+                         "kernel": "%s (fused gather+push+MCC+boundary+deposit), %d launches/step" % ("k_push3d" if three_d else "k_push_boris", n_push_launches),
                          "algorithmic_bytes_per_particle_step": BYTES[wl], "push_ms_per_step": push_ms,
                          "peak_source": peak_src},
             "phases_ms_per_step": {k: v / args.steps for k, v in tm.items()},
@@ -318,13 +331,14 @@ def bench_e2e(sim, part_species, args, torch, stream, world, dist, dev):
     h2d = d2h = 0
     for s in part_species:
         n_slots = sim.count(s)[1]
-        host = {k: torch.empty(n_slots, dtype=torch.float64).pin_memory() for k in ("x", "z", "vx", "vy", "vz")}
-        alive = np.empty(1, dtype=np.uint8)
+        comps = ("x", "y", "z", "vx", "vy", "vz") if sim.is3d else ("x", "z", "vx", "vy", "vz")
+        host = {k: torch.empty(n_slots, dtype=torch.float64).pin_memory() for k in comps}
         bufs[s] = (n_slots, host)
-        h2d += 5 * 8 * n_slots
-        d2h += 5 * 8 * n_slots
-    rho_host = torch.empty(sim.M * sim.N, dtype=torch.float64).pin_memory()
-    d2h += 8 * sim.M * sim.N
+        h2d += len(comps) * 8 * n_slots
+        d2h += len(comps) * 8 * n_slots
+    n_nodes = int(np.prod(sim.shape))
+    rho_host = torch.empty(n_nodes, dtype=torch.float64).pin_memory()
+    d2h += 8 * n_nodes
     dp = C.POINTER(C.c_double)
 
     def ptr(t):
@@ -333,13 +347,13 @@ def bench_e2e(sim, part_species, args, torch, stream, world, dist, dev):
     def download(s):
         n_slots, host = bufs[s]
         ns = C.c_int64()
-        sim._chk(sim.L.mag2d_particles_download_soa(sim.h, s, n_slots, ptr(host["x"]), None, ptr(host["z"]), ptr(host["vx"]),
+        sim._chk(sim.L.mag2d_particles_download_soa(sim.h, s, n_slots, ptr(host["x"]), ptr(host["y"]) if sim.is3d else None, ptr(host["z"]), ptr(host["vx"]),
                                                     ptr(host["vy"]), ptr(host["vz"]), None, None, C.byref(ns)))
 
     def upload(s):
         n_slots, host = bufs[s]
         sim._chk(sim.L.mag2d_particles_clear(sim.h, s))
-        sim._chk(sim.L.mag2d_particles_upload_soa(sim.h, s, n_slots, ptr(host["x"]), None, ptr(host["z"]), ptr(host["vx"]),
+        sim._chk(sim.L.mag2d_particles_upload_soa(sim.h, s, n_slots, ptr(host["x"]), ptr(host["y"]) if sim.is3d else None, ptr(host["z"]), ptr(host["vx"]),
                                                   ptr(host["vy"]), ptr(host["vz"]), None))
     for s in part_species:
         download(s)          # the host-side particle arrays the caller owns
@@ -441,7 +455,51 @@ def _reference_run(workload, d, n_cpu, steps, u=None, variant="fast"):
     raise RuntimeError("oracle/_ref is not built on this machine")
 
 
+def port3d_run(d, n_cpu, steps, u=None):
+    """CPU arm of the 3-D workload: the reference's 3-D step does not compile (species3d.cpp is dead code), so the
+    restatement oracle/mag3d_oracle.c (pinned to the reference's Field3D / Geometry) is what runs: kind = port"""
+    import numpy as np
+
+    from mag2d_b200 import config as cfg
+    from oracle import Oracle3, Orc3Grid
+    p = cfg.read_config(d["config"])
+    sp, _ = cfg.read_species(d["species_conf"])
+    s = [q for q in sp if q["name"] == "ELECTRON"][0]
+    g = Orc3Grid.make((int(p["x_sampl"]), int(p["y_sampl"]), int(p["z_sampl"])), p["idx"], p["idy"], p["idz"], p["x_max"], p["y_max"],
+                      p["z_max"], int(p["boundary"]), p["macroparticle_factor"])
+    orc = Oracle3()
+    mask, _ = orc.geometry(g)
+    rng = np.random.default_rng(1234)
+    vth = np.sqrt(1.380662e-23 * s["temperature"] / s["mass"])
+    soa = {k: np.ascontiguousarray(rng.uniform(0, hi, n_cpu)) for k, hi in (("x", p["x_max"]), ("y", p["y_max"]), ("z", p["z_max"]))}
+    key = (np.floor(soa["x"] * p["idx"]).astype(np.int64) * int(p["y_sampl"]) + np.floor(soa["y"] * p["idy"]).astype(np.int64)) * int(p["z_sampl"]) \
+        + np.floor(soa["z"] * p["idz"]).astype(np.int64)
+    order = np.argsort(key, kind="stable")         # cell-sorted like the GPU store
+    for k in ("x", "y", "z"):
+        soa[k] = np.ascontiguousarray(soa[k][order])
+    for k in ("vx", "vy", "vz"):
+        soa[k] = np.ascontiguousarray(rng.normal(size=n_cpu) * vth)
+    alive = np.ones(n_cpu, dtype=np.uint8)
+    if u is None:
+        u = np.zeros(g.shape)
+    fixed = np.zeros(g.shape, dtype=np.int64)
+    orc.advance(g, u, mask, s["charge"], s["mass"], s["dt"], (0, 0, 0), soa, alive, None, fixed)     # warm the caches
+    n0 = int(alive.sum())
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.advance(g, u, mask, s["charge"], s["mass"], s["dt"], (0, 0, 0), soa, alive, None, fixed)
+    wall = time.perf_counter() - t0
+    n1 = int(alive.sum())
+    return {"value": 0.5 * (n0 + n1) * steps / wall, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+            "sample": "%d particles x %d steps of the same deck, oracle/mag3d_oracle.c (gcc -O2; the reference's 3-D step "
+                      "species3d.cpp does not compile) gather + Boris + boundary + 8-node deposit, collisions and the field solve "
+                      "excluded, single thread; wall %.2f s" % (n0, steps, wall),
+            "seconds": wall}
+
+
 def cpu_baseline(workload, d, sim, part_species, args):
+    if workload == "c5":
+        return port3d_run(d, 2_000_000, 40, sim.get_field("u"))
     u = sim.get_field("u") if sim.param["selfconsistent"] else None
     n_cpu = {"c1": 40000}.get(workload, 4_000_000)      # about 10 s of single-thread work
     steps = {"c1": 25}.get(workload, 100)
@@ -459,9 +517,12 @@ def bench_reference(args):
     d = make_deck(wl, n, 1, tmp)
     n_cpu = {"c1": 20000}.get(wl, 4_000_000)
     try:
-        for _ in range(max(0, min(args.warmup, 1))):
-            reference_run(wl, d, n_cpu, 2)
-        r = reference_run(wl, d, n_cpu, args.steps)
+        if wl == "c5":
+            r = port3d_run(d, 1_000_000, args.steps)
+        else:
+            for _ in range(max(0, min(args.warmup, 1))):
+                reference_run(wl, d, n_cpu, 2)
+            r = reference_run(wl, d, n_cpu, args.steps)
     except Exception as ex:
         print(json.dumps({"impl": "reference", "unavailable": repr(ex)[:200]}))
         return

@@ -15,6 +15,9 @@
  *     on the context's stream and is asynchronous unless stated (download / sync / solve block);
  *   - 2-D naming follows the reference: position (x, z), velocity (vx, vz) in plane, vy out of plane
  *     (azimuthal in cylindrical coordinates); grids are row-major a[i*N + j], i along x/r;
+ *   - coord = MAG2D_CARTESIAN3D runs the reference's 3-D path (src/species3d.cpp, src/fields3d.cpp, src/Field3D.hpp)
+ *     through the same entry points: grids are then a[(i*K + j)*N + k] with i along x (M nodes), j along y (K nodes),
+ *     k along z (N nodes), particles carry y, and (Br, Bt, Bz) are the constant (Bx, By, Bz);
  *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
  */
 #ifndef MAG2D_B200_H
@@ -25,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAG2D_ABI_VERSION 1
+#define MAG2D_ABI_VERSION 2
 #define MAG2D_MAX_SPECIES 16
 
 typedef struct mag2d_ctx mag2d_ctx;
@@ -121,6 +124,8 @@ int mag2d_solver_is_direct(mag2d_ctx* ctx);
 int mag2d_solver_stats(mag2d_ctx* ctx, int* last_cycles, double* last_resid);
 /* Fields::u_smooth, src/fields.cpp:28-113 */
 int mag2d_u_smooth(mag2d_ctx* ctx, int symmetry, double radius);
+/* ElMag3D::E at n points, src/fields3d.hpp:95-101 (CARTESIAN3D; diagnostics / parity checks) */
+int mag2d_field_E3(mag2d_ctx* ctx, int n, const double* x, const double* y, const double* z, double* Ex, double* Ey, double* Ez);
 /* Fields::E at n points, src/fields.hpp:124-150 (diagnostics / parity checks) */
 int mag2d_field_E(mag2d_ctx* ctx, int n, const double* x, const double* z, double time, double* Ex, double* Ez);
 

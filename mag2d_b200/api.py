@@ -85,6 +85,7 @@ def lib():
     L.mag2d_solver_stats.argtypes = [vp, C.POINTER(C.c_int), dp]
     L.mag2d_u_smooth.argtypes = [vp, C.c_int, C.c_double]
     L.mag2d_field_E.argtypes = [vp, C.c_int, dp, dp, C.c_double, dp, dp]
+    L.mag2d_field_E3.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp]
     L.mag2d_set_species.argtypes = [vp, C.c_int, C.POINTER(SpeciesDesc), C.c_int, C.POINTER(InteractionDesc), dp, dp, C.c_int]
     L.mag2d_species_get.argtypes = [vp, C.c_int, C.c_int, dp]
     L.mag2d_species_rates.argtypes = [vp, C.c_int, dp]
@@ -155,6 +156,8 @@ class Sim:
         self.names = [s["name"] for s in self.species]
         p = self.param
         self.M, self.N = int(p["x_sampl"]), int(p["z_sampl"])
+        self.is3d = int(p["coord"]) == 2
+        self.shape = (self.M, int(p["y_sampl"]), self.N) if self.is3d else (self.M, self.N)
         self.grid = grid_desc_from_param(p)
         h = C.c_void_p()
         # stream: a cudaStream_t handle (int); None -> the context owns a private non-blocking stream.  The
@@ -168,7 +171,11 @@ class Sim:
         self.solver_tol = solver_tol
         self._chk(self.L.mag2d_set_solver(self.h, 0, solver_tol, 100))
         self.solve_info = {}
-        if presolve and not p["electric_field_from_file"]:
+        if self.is3d:
+            # plasma3d.cpp:44-46: the vacuum field of the electrodes is solved once at start-up
+            if presolve:
+                self.solve_info["u"] = self.solve(rf=False)
+        elif presolve and not p["electric_field_from_file"]:
             # Pic ctor: boundary_solve_rf(); if(!selfconsistent){ boundary_solve(); reset(); }  (pic.cpp:180-187)
             self.solve_info["uRF"] = self.solve(rf=True)
             if not p["selfconsistent"]:
@@ -347,7 +354,7 @@ class Sim:
             return self.mask.copy()
         if which == "voltage":
             return self.voltage.copy()
-        out = np.zeros((self.M, self.N))
+        out = np.zeros(self.shape)
         if which in ("u", "uRF"):
             self._chk(self.L.mag2d_get_potential(self.h, 0 if which == "u" else 1, _d(out)))
         elif which == "rho":
@@ -361,7 +368,7 @@ class Sim:
         self._chk(self.L.mag2d_set_potential(self.h, 0 if which == "u" else 1, _d(a)))
 
     def rho_fixed(self, i):
-        out = np.zeros((self.M, self.N), dtype=np.int64)
+        out = np.zeros(self.shape, dtype=np.int64)
         self._chk(self.L.mag2d_rho_fixed_download(self.h, i, out.ctypes.data_as(i64p)))
         return out
 
@@ -371,6 +378,14 @@ class Sim:
 
     def u_smooth(self, symmetry=False, radius=-1.0):
         self._chk(self.L.mag2d_u_smooth(self.h, 1 if symmetry else 0, radius))
+
+    def field_E3(self, x, y, z):
+        """ElMag3D::E at points (CARTESIAN3D) -> array [n, 3]"""
+        x, y, z = (np.ascontiguousarray(v, dtype=np.float64) for v in (x, y, z))
+        n = len(x)
+        ex, ey, ez = np.zeros(n), np.zeros(n), np.zeros(n)
+        self._chk(self.L.mag2d_field_E3(self.h, n, _d(x), _d(y), _d(z), _d(ex), _d(ey), _d(ez)))
+        return np.stack([ex, ey, ez], axis=1)
 
     def field_E(self, x, z, time=0.0):
         x = np.ascontiguousarray(x, dtype=np.float64)

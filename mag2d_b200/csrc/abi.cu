@@ -24,7 +24,7 @@ void mag2d_set_error(const std::string& msg) { g_last_error = msg; }
 
 namespace {
 
-size_t grid_n(const mag2d_ctx* c) { return (size_t)c->g.M * c->g.N; }
+size_t grid_n(const mag2d_ctx* c) { return grid_nodes(c); }
 
 __global__ void k_count_alive(const double* __restrict__ x, long long n, unsigned long long* __restrict__ out2)
 {
@@ -178,7 +178,7 @@ int effective_sort_interval(const mag2d_ctx* c, const SpeciesStore& S)
     if (c->sort_interval >= 0) return c->sort_interval;
     if (!(S.desc.mass > 0) || !(S.desc.dt > 0)) return 64;
     const double vth = sqrt(1.380662e-23 * std::max(S.desc.temperature, 0.0) / S.desc.mass);
-    const double h = std::min(c->g.dx, c->g.dz);
+    const double h = is3d(c) ? std::min(std::min(c->g.dx, c->g.dz), c->g.dy) : std::min(c->g.dx, c->g.dz);
     const double per_step = vth * S.desc.dt / h;
     if (!(per_step > 0)) return 64;
     const double k = 0.35 / per_step;
@@ -189,7 +189,7 @@ int effective_sort_interval(const mag2d_ctx* c, const SpeciesStore& S)
 // With an interval of K pushes the sequence is PERMUTE, K-2 plain pushes, COUNT, PERMUTE, ... (K = 1: both every push)
 int fused_sort_mode(const mag2d_ctx* c, const SpeciesStore& S)
 {
-    if (!c->fused_sort || c->g.mover == MAG2D_ADVANCE_MULTICOLL || S.n_slots == 0) return 0;
+    if (!c->fused_sort || c->g.mover == MAG2D_ADVANCE_MULTICOLL || is3d(c) || S.n_slots == 0) return 0;
     const int K = effective_sort_interval(c, S);
     if (K <= 0) return 0;
     int mode = S.tickets_valid ? 1 : 0;
@@ -201,6 +201,7 @@ int fused_sort_mode(const mag2d_ctx* c, const SpeciesStore& S)
 int advance_one(mag2d_ctx* c, int s, bool in_step)
 {
     if (refresh_pools(c, s)) return 1;
+    if (is3d(c)) return launch_species_advance3d(c, s, false);
     return launch_species_advance(c, s, in_step ? fused_sort_mode(c, c->sp[s]) : 0);
 }
 
@@ -226,12 +227,17 @@ const char* mag2d_last_error(void) { return g_last_error.c_str(); }
 int mag2d_create(int device, const mag2d_grid_desc* grid, void* stream, mag2d_ctx** out)
 {
     if (!grid || !out) { mag2d_set_error("mag2d_create: null argument"); return 1; }
-    if (grid->coord != MAG2D_CARTESIAN && grid->coord != MAG2D_CYLINDRICAL)
+    if (grid->coord != MAG2D_CARTESIAN && grid->coord != MAG2D_CYLINDRICAL && grid->coord != MAG2D_CARTESIAN3D)
     {
-        mag2d_set_error("mag2d_create: coord must be CARTESIAN or CYLINDRICAL (CARTESIAN3D: use mag3d_*)");
+        mag2d_set_error("mag2d_create: coord must be CARTESIAN, CYLINDRICAL or CARTESIAN3D");
         return 1;
     }
     if (grid->M < 2 || grid->N < 2) { mag2d_set_error("mag2d_create: grid must be at least 2x2"); return 1; }
+    if (grid->coord == MAG2D_CARTESIAN3D)
+    {
+        if (grid->K < 3 || grid->M < 3 || grid->N < 3) { mag2d_set_error("mag2d_create: a 3-D grid must be at least 3x3x3"); return 1; }
+        if (grid->rf || grid->mover != MAG2D_ADVANCE_BORIS) { mag2d_set_error("mag2d_create: CARTESIAN3D supports the Boris mover without RF only"); return 1; }
+    }
     // Param's own validation (param.cpp:60-64, 91-95)
     if (grid->selfconsistent && grid->rf) { mag2d_set_error("Param: selfconsistent rf trap not implemented\n"); return 1; }
     if (grid->selfconsistent && grid->electric_field_from_file)
@@ -266,10 +272,17 @@ int mag2d_create(int device, const mag2d_grid_desc* grid, void* stream, mag2d_ct
     CUDA_OK(cudaMalloc(&c->d_mask, n));
     CUDA_OK(cudaMalloc(&c->d_voltage, sizeof(double) * n));
     CUDA_OK(cudaMalloc(&c->d_u, sizeof(double) * n));
-    CUDA_OK(cudaMalloc(&c->d_uRF, sizeof(double) * n));
-    CUDA_OK(cudaMalloc(&c->d_ueff, sizeof(double) * n));
+    const bool three_d = grid->coord == MAG2D_CARTESIAN3D;
+    // uRF / the scratch copy are 2-D features; a 3-D grid only gets one-node stand-ins (the potential alone is 134 MB at 256^3)
+    CUDA_OK(cudaMalloc(&c->d_uRF, sizeof(double) * (three_d ? 1 : n)));
+    CUDA_OK(cudaMalloc(&c->d_ueff, sizeof(double) * (three_d ? 1 : n)));
     CUDA_OK(cudaMalloc(&c->d_gx, sizeof(double) * n));
     CUDA_OK(cudaMalloc(&c->d_gz, sizeof(double) * n));
+    if (three_d)
+    {
+        CUDA_OK(cudaMalloc(&c->d_gy, sizeof(double) * n));
+        CUDA_OK(cudaMemsetAsync(c->d_gy, 0, sizeof(double) * n, c->stream));
+    }
     CUDA_OK(cudaMalloc(&c->d_cfree, n));
     CUDA_OK(cudaMemsetAsync(c->d_cfree, 1, n, c->stream));
     CUDA_OK(cudaMemsetAsync(c->d_gx, 0, sizeof(double) * n, c->stream));
@@ -278,8 +291,8 @@ int mag2d_create(int device, const mag2d_grid_desc* grid, void* stream, mag2d_ct
     CUDA_OK(cudaMalloc(&c->d_scratch, sizeof(double) * 64));
     CUDA_OK(cudaMemsetAsync(c->d_scratch, 0, sizeof(double) * 64, c->stream));
     CUDA_OK(cudaMemsetAsync(c->d_u, 0, sizeof(double) * n, c->stream));
-    CUDA_OK(cudaMemsetAsync(c->d_uRF, 0, sizeof(double) * n, c->stream));
-    CUDA_OK(cudaMemsetAsync(c->d_ueff, 0, sizeof(double) * n, c->stream));
+    CUDA_OK(cudaMemsetAsync(c->d_uRF, 0, sizeof(double) * (three_d ? 1 : n), c->stream));
+    CUDA_OK(cudaMemsetAsync(c->d_ueff, 0, sizeof(double) * (three_d ? 1 : n), c->stream));
     CUDA_OK(cudaMemsetAsync(c->d_voltage, 0, sizeof(double) * n, c->stream));
     CUDA_OK(cudaMemsetAsync(c->d_mask, MAG2D_FREE, n, c->stream));
     for (int q = 0; q < 8; q++) CUDA_OK(cudaEventCreate(&c->ev[q]));
@@ -295,7 +308,9 @@ int mag2d_destroy(mag2d_ctx* c)
     mag2d_comm_destroy(c);
     mg_free(c);
     direct_free(c);
+    direct3d_free(c);
     for (auto& S : c->sp) free_store(S);
+    cudaFree(c->d_gy);
     cudaFree(c->d_mask);
     cudaFree(c->d_voltage);
     cudaFree(c->d_u);
@@ -347,6 +362,25 @@ int mag2d_set_grid(mag2d_ctx* c, const uint8_t* mask, const double* voltage)
     // t_grid::is_free per cell (fields.hpp:94-101): a particle survives when any corner of its cell is FREE
     std::vector<unsigned char> cfree(n, 0);
     const int M = c->g.M, N = c->g.N;
+    if (is3d(c))
+    {
+        // Geometry::is_free, fields3d.hpp:48-57: eight corners
+        const int K = c->g.K;
+        const size_t sj = N, si = (size_t)K * N;
+        for (int i = 0; i + 1 < M; i++)
+            for (int j = 0; j + 1 < K; j++)
+                for (int k = 0; k + 1 < N; k++)
+                {
+                    const size_t m = ((size_t)i * K + j) * N + k;
+                    bool f = false;
+                    for (int q = 0; q < 8; q++) f = f || mask[m + (q & 1 ? si : 0) + (q & 2 ? sj : 0) + (q >> 2)] == MAG2D_FREE;
+                    cfree[m] = f;
+                }
+        CUDA_OK(cudaMemcpyAsync(c->d_cfree, cfree.data(), n, cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        c->grid_set = true;
+        return direct3d_setup(c);
+    }
     for (int i = 0; i + 1 < M; i++)
         for (int j = 0; j + 1 < N; j++)
         {
@@ -363,6 +397,7 @@ int mag2d_set_grid(mag2d_ctx* c, const uint8_t* mask, const double* voltage)
 int mag2d_set_potential(mag2d_ctx* c, int which, const double* values)
 {
     CHECK_CTX(c);
+    if (is3d(c) && which != 0) { mag2d_set_error("CARTESIAN3D has no RF potential"); return 1; }
     double* dst = which == 0 ? c->d_u : c->d_uRF;
     CUDA_OK(cudaMemcpyAsync(dst, values, sizeof(double) * grid_n(c), cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -372,6 +407,7 @@ int mag2d_set_potential(mag2d_ctx* c, int which, const double* values)
 int mag2d_get_potential(mag2d_ctx* c, int which, double* values)
 {
     CHECK_CTX(c);
+    if (is3d(c) && which != 0) { mag2d_set_error("CARTESIAN3D has no RF potential"); return 1; }
     const double* src = which == 0 ? c->d_u : c->d_uRF;
     CUDA_OK(cudaMemcpyAsync(values, src, sizeof(double) * grid_n(c), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -386,6 +422,17 @@ int mag2d_solve(mag2d_ctx* c, int rf, double tol, int max_cycles, int* cycles_ou
         // no species yet (the Pic constructor pre-solves the vacuum fields, pic.cpp:180-187): zero charge
         CUDA_OK(cudaMalloc(&c->d_rho, sizeof(unsigned long long) * grid_n(c)));
         CUDA_OK(cudaMemsetAsync(c->d_rho, 0, sizeof(unsigned long long) * grid_n(c), c->stream));
+    }
+    if (is3d(c))
+    {
+        if (rf) { mag2d_set_error("CARTESIAN3D has no RF potential"); return 1; }
+        if (cycles_out) *cycles_out = 0;
+        double r = 0.0;
+        if (solve3d(c, &r)) return 1;
+        if (resid_out) *resid_out = r;
+        c->last_cycles = 0;
+        c->last_resid = r;
+        return 0;
     }
     return mg_solve(c, rf, tol, max_cycles, 0, cycles_out, resid_out);
 }
@@ -410,6 +457,11 @@ int mag2d_set_solver_kind(mag2d_ctx* c, int kind)
         mag2d_set_error("mag2d_set_solver_kind: unknown solver kind");
         return 1;
     }
+    if (is3d(c))
+    {
+        if (kind == MAG2D_SOLVER_MULTIGRID) { mag2d_set_error("mag2d_set_solver_kind: CARTESIAN3D has the direct solver only"); return 1; }
+        return 0;
+    }
     if (kind == MAG2D_SOLVER_DIRECT && !c->direct.ok)
     {
         mag2d_set_error("mag2d_set_solver_kind: the grid does not separate (electrodes inside free rows); use the multigrid solver");
@@ -423,6 +475,7 @@ int mag2d_set_solver_kind(mag2d_ctx* c, int kind)
 int mag2d_solver_is_direct(mag2d_ctx* c)
 {
     if (!c) return 0;
+    if (is3d(c)) return c->direct3.ok;
     return c->direct.ok && c->solver_kind != MAG2D_SOLVER_MULTIGRID;
 }
 
@@ -450,9 +503,17 @@ int mag2d_u_smooth(mag2d_ctx* c, int symmetry, double radius)
     return launch_u_smooth(c, symmetry, radius);
 }
 
+int mag2d_field_E3(mag2d_ctx* c, int n, const double* x, const double* y, const double* z, double* Ex, double* Ey, double* Ez)
+{
+    CHECK_CTX(c);
+    if (!is3d(c)) { mag2d_set_error("mag2d_field_E3: CARTESIAN3D only"); return 1; }
+    return launch_field_E3d(c, n, x, y, z, Ex, Ey, Ez);
+}
+
 int mag2d_field_E(mag2d_ctx* c, int n, const double* x, const double* z, double time, double* Ex, double* Ez)
 {
     CHECK_CTX(c);
+    if (is3d(c)) { mag2d_set_error("mag2d_field_E: use mag2d_field_E3 for CARTESIAN3D"); return 1; }
     return launch_field_E(c, n, x, z, time, Ex, Ez);
 }
 
@@ -751,6 +812,7 @@ int mag2d_particles_generate(mag2d_ctx* c, int s, int kind, int64_t n, double a,
     if (kind < 0 || kind > 2) { mag2d_set_error("mag2d_particles_generate: unknown loader"); return 1; }
     if (kind == 2 && c->g.coord != MAG2D_CYLINDRICAL) { mag2d_set_error("mag2d_particles_generate: loader 2 is cylindrical only"); return 1; }
     if (kind == 2 && (b < 0 || b > c->g.z_max)) return 0;   // particles.cpp:489
+    if (is3d(c) && kind != 0) { mag2d_set_error("mag2d_particles_generate: CARTESIAN3D has the uniform loader (kind 0) only"); return 1; }
     SpeciesStore& S = c->sp[s];
     if (ensure_capacity(c, S, S.n_slots + n)) return 1;
     return launch_generate(c, s, kind, n, a, b, cc, d);
@@ -823,6 +885,7 @@ int mag2d_species_accumulate(mag2d_ctx* c, int s)
 {
     CHECK_CTX(c);
     CHECK_SPECIES(c, s);
+    if (is3d(c)) return launch_species_advance3d(c, s, true);
     return launch_species_accumulate(c, s);
 }
 
@@ -861,6 +924,18 @@ int mag2d_rho_download(mag2d_ctx* c, double* rho)
 int mag2d_advance_init(mag2d_ctx* c)
 {
     CHECK_CTX(c);
+    if (is3d(c))
+    {
+        // the reference's 3-D species has no half-step-back; only the first charge deposit and field solve apply
+        if (c->g.selfconsistent)
+        {
+            if (mag2d_rho_reset(c, -1)) return 1;
+            for (size_t s = 0; s < c->sp.size(); s++)
+                if (launch_species_advance3d(c, (int)s, true)) return 1;
+            if (comm_allreduce_rho(c)) return 1;
+        }
+        return solve3d(c, nullptr);
+    }
     if (c->g.selfconsistent)
     {
         if (mag2d_rho_reset(c, -1)) return 1;
@@ -884,7 +959,15 @@ int mag2d_step(mag2d_ctx* c, int nsteps)
     for (int it = 0; it < nsteps; it++)
     {
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
-        if (c->g.selfconsistent)
+        if (is3d(c))
+        {
+            if (c->g.selfconsistent)
+            {
+                if (solve3d(c, nullptr)) return 1;
+                if (mag2d_rho_reset(c, -1)) return 1;
+            }
+        }
+        else if (c->g.selfconsistent)
         {
             // the direct solver needs no convergence test: never synchronise with the host inside the step
             const bool direct = c->direct.ok && c->solver_kind != MAG2D_SOLVER_MULTIGRID;
@@ -899,7 +982,7 @@ int mag2d_step(mag2d_ctx* c, int nsteps)
         if (c->g.selfconsistent && comm_allreduce_rho(c)) return 1;
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
         // stand-alone sort: the multi-collision mover, or the fused sort switched off
-        if (!c->fused_sort || c->g.mover == MAG2D_ADVANCE_MULTICOLL)
+        if (!c->fused_sort || c->g.mover == MAG2D_ADVANCE_MULTICOLL || is3d(c))
             for (size_t s = 0; s < c->sp.size(); s++)
             {
                 const int K = effective_sort_interval(c, c->sp[s]);

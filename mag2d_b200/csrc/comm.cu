@@ -115,7 +115,7 @@ extern "C" int mag2d_comm_destroy(mag2d_ctx* c)
 int comm_allreduce_rho(mag2d_ctx* c)
 {
     if (!c->nccl_comm || c->nranks <= 1) return 0;
-    const size_t count = (size_t)c->sp.size() * c->g.M * c->g.N;
+    const size_t count = (size_t)c->sp.size() * grid_nodes(c);
     const int ncclInt64 = 4, ncclSum = 0;
     const int rc = g_nccl.AllReduce(c->d_rho, c->d_rho, count, ncclInt64, ncclSum, (NcclComm)c->nccl_comm, c->stream);
     if (rc) return nccl_fail("ncclAllReduce", rc);

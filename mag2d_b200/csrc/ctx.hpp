@@ -73,6 +73,26 @@ struct DirectSolver
     double* k2 = nullptr;
 };
 
+// direct solver of the 3-D box (poisson3d.cu)
+struct Direct3D
+{
+    bool ok = false;
+    int n_i = 0, n_j = 0, n_k = 0;   // interior unknowns along x, y, z
+    int ldj = 0, ldk = 0;            // n_j, n_k rounded up to multiples of 32
+    int ne = 0;                      // electrode nodes inside the box (capacitance-matrix method)
+    double* Sy = nullptr;            // [ldj][ldj], [ldk][ldk] sine matrices
+    double* Sz = nullptr;
+    double* inv = nullptr;           // [n_i][ldj][ldk] Thomas factors
+    double* R = nullptr;             // [n_i][ldj][ldk] work arrays
+    double* T = nullptr;
+    unsigned char* interior_fixed = nullptr;
+    int* e_nodes = nullptr;
+    double* e_volts = nullptr;
+    double* cinv = nullptr;
+    double* alpha = nullptr;
+    double* green = nullptr;         // [ne][M*K*N] Green's functions of the electrode nodes
+};
+
 struct mag2d_ctx
 {
     int device = 0;
@@ -90,6 +110,7 @@ struct mag2d_ctx
     double* d_ueff = nullptr;   // grid-sized scratch (u_smooth)
     double* d_gx = nullptr;     // edge-centred field differences of the current step (push.cu: k_edge_fields)
     double* d_gz = nullptr;
+    double* d_gy = nullptr;     // CARTESIAN3D only
     unsigned char* d_cfree = nullptr;   // per-cell "has a FREE corner" flag (t_grid::is_free)
     double* d_b = nullptr;      // RHS in the reference's scaling (for the residual check)
     double* d_rowscale = nullptr;  // symmetrising row scale s_i of the cylindrical operator, [M]
@@ -102,6 +123,7 @@ struct mag2d_ctx
     std::vector<MgLevel> mg;
     double* d_mg_inv = nullptr;   // dense inverse of the coarsest-level operator
     DirectSolver direct;
+    Direct3D direct3;
     int solver_kind = MAG2D_SOLVER_AUTO;
     unsigned long long direct_calls = 0;
     int cycles_per_step = 0;
@@ -183,5 +205,14 @@ int direct_setup(mag2d_ctx* c);
 void direct_free(mag2d_ctx* c);
 int direct_solve(mag2d_ctx* c, double* u);
 int launch_rho_total(mag2d_ctx* c, double* d_out);
+// push3d.cu / poisson3d.cu (coord == MAG2D_CARTESIAN3D)
+int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only);
+int launch_field_E3d(mag2d_ctx* c, int n, const double* x, const double* y, const double* z, double* Ex, double* Ey, double* Ez);
+int update_edge_fields3d(mag2d_ctx* c);
+int direct3d_setup(mag2d_ctx* c);
+void direct3d_free(mag2d_ctx* c);
+int solve3d(mag2d_ctx* c, double* resid_out);
+inline bool is3d(const mag2d_ctx* c) { return c->g.coord == MAG2D_CARTESIAN3D; }
+inline size_t grid_nodes(const mag2d_ctx* c) { return (size_t)c->g.M * c->g.N * (is3d(c) ? (size_t)c->g.K : 1); }
 // comm.cu
 int comm_allreduce_rho(mag2d_ctx* c);

@@ -79,7 +79,7 @@ __device__ __forceinline__ void deflect(double angle, uint32_t w0, uint32_t w1, 
 // One null-collision event for the particle (vx, vy, vz).  Returns the process index inside
 // interactions_by_species[target] or -1 for a null collision; target receives the species index.
 // Consumes up to three Philox blocks.
-__device__ __noinline__ int mcc_scatter(const MccBlob* __restrict__ B, Rng& rng, double& pvx, double& pvy, double& pvz,
+static __device__ __noinline__ int mcc_scatter(const MccBlob* __restrict__ B, Rng& rng, double& pvx, double& pvy, double& pvz,
                                         int& target)
 {
     const uint4 ra = rng.block();

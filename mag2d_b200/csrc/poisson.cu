@@ -985,7 +985,7 @@ int mg_solve(mag2d_ctx* c, int rf, double tol, int max_cycles, int fixed_cycles,
 
 int launch_rho_total(mag2d_ctx* c, double* d_out)
 {
-    const size_t n = (size_t)c->g.M * c->g.N;
+    const size_t n = grid_nodes(c);
     k_rho_total<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_rho, c->d_charges, (int)c->sp.size(), n, d_out);
     c->launches++;
     CUDA_OK(cudaGetLastError());

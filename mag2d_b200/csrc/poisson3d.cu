@@ -1,0 +1,526 @@
+// poisson3d.cu — Poisson solve of the 3-D path.
+//
+// The reference factorises the seven-point operator of Solver::matrix_init (src/fields3d.cpp:39-73: unit stencil
+// [1,1,1,-6,1,1,1], identity rows on Dirichlet nodes, neighbours addressed by FLAT index) with UMFPACK and solves
+// A^T x = b every step (Solver::solve, src/fields3d.cpp:83-95; right-hand side rho * (-macroparticle_factor/eps_0)).
+// Its only geometry (Geometry::Geometry, src/fields3d.cpp:13-37) is a zero-Dirichlet box frame plus point
+// electrodes, for which the operator is a constant-coefficient Laplacian on a box: it is diagonalised by sine
+// transforms along y and z and tridiagonal (Toeplitz) along x.  The solve is
+//     R^  = S_y (R S_z)            two FP64 matrix products with the symmetric sine matrices
+//     T u^ = R^                    one Thomas solve along x per (y,z) mode, factors precomputed at set_grid
+//     U   = S_y (U^ S_z) * 4/((n_y+1)(n_z+1))
+// and interior electrode nodes are imposed exactly afterwards by the capacitance-matrix method (Green's functions
+// of the electrode nodes are precomputed with the same solver).  Exact to round-off like the reference's LU.
+// Geometries with extended internal electrodes need a 3-D multigrid (not built yet): set_grid refuses them.
+#include <cmath>
+#include <vector>
+
+#include "ctx.hpp"
+
+namespace {
+
+// ---- batched FP64 matrix product C_b = A_b x B_b (row major), tile 64 x 32, 4 x 4 per thread, cp.async ring -----
+constexpr int G3_TM = 64, G3_TN = 32, G3_KC = 32, G3_THREADS = 128, G3_STAGES = 3;
+constexpr int G3_LDA = G3_KC + 2;
+constexpr int G3_STAGE_DOUBLES = G3_TM * G3_LDA + G3_KC * G3_TN;
+constexpr int G3_SMEM = G3_STAGES * G3_STAGE_DOUBLES * (int)sizeof(double);
+
+struct Gemm3Args
+{
+    const double* A; long long strideA; int lda;     // [rows][Kdim]
+    const double* B; long long strideB; int ldb;     // [Kdim][cols]
+    double* C; long long strideC; int ldc;
+    int rows, cols, Kdim;                            // cols and Kdim are multiples of 32
+    double scale;
+    // SCATTER epilogue: row r = il*ldj + jl of the interior block goes to node (il+1, jl+1, 1..) of the potential
+    int ldj, n_j, n_k, K, N;
+};
+
+__device__ __forceinline__ void cp16(void* smem, const void* gmem)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int W>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(W) : "memory"); }
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(G3_THREADS) k_gemm3(const __grid_constant__ Gemm3Args G)
+{
+    extern __shared__ __align__(16) double g3_smem[];
+    const int t = threadIdx.x;
+    const int r0 = blockIdx.y * G3_TM, c0 = blockIdx.x * G3_TN;
+    const double* A = G.A + (long long)blockIdx.z * G.strideA;
+    const double* B = G.B + (long long)blockIdx.z * G.strideB;
+    double* C = G.C + (long long)blockIdx.z * G.strideC;
+    const int tr = (t / 8) * 4, tc = (t % 8) * 4;
+    const int nk = G.Kdim / G3_KC;
+    auto issue = [&](int kb) {
+        double* sa = g3_smem + (kb % G3_STAGES) * G3_STAGE_DOUBLES;
+        double* sb = sa + G3_TM * G3_LDA;
+        const int k0 = kb * G3_KC;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+        {
+            const int e = t + q * G3_THREADS, r = e >> 4, c2 = (e & 15) * 2;
+            const int row = min(r0 + r, G.rows - 1);
+            cp16(sa + r * G3_LDA + c2, A + (size_t)row * G.lda + k0 + c2);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            const int e = t + q * G3_THREADS, r = e >> 4, c2 = (e & 15) * 2;
+            cp16(sb + r * G3_TN + c2, B + (size_t)(k0 + r) * G.ldb + c0 + c2);
+        }
+    };
+    double acc[4][4] = {};
+    for (int s = 0; s < G3_STAGES - 1; s++)
+    {
+        if (s < nk) issue(s);
+        cp_commit();
+    }
+    for (int kb = 0; kb < nk; kb++)
+    {
+        cp_wait<G3_STAGES - 2>();
+        __syncthreads();
+        if (kb + G3_STAGES - 1 < nk) issue(kb + G3_STAGES - 1);
+        cp_commit();
+        const double* sa = g3_smem + (kb % G3_STAGES) * G3_STAGE_DOUBLES;
+        const double* sb = sa + G3_TM * G3_LDA;
+#pragma unroll 8
+        for (int k = 0; k < G3_KC; k++)
+        {
+            double a[4], b[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++) a[p] = sa[(tr + p) * G3_LDA + k];
+            const double2 b01 = *reinterpret_cast<const double2*>(sb + k * G3_TN + tc);
+            const double2 b23 = *reinterpret_cast<const double2*>(sb + k * G3_TN + tc + 2);
+            b[0] = b01.x; b[1] = b01.y; b[2] = b23.x; b[3] = b23.y;
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc[p][q] = fma(a[p], b[q], acc[p][q]);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+    {
+        const int r = r0 + tr + p;
+        if (r >= G.rows) continue;
+        if (SCATTER)
+        {
+            const int il = r / G.ldj, jl = r % G.ldj;
+            if (jl >= G.n_j) continue;
+            double* out = C + ((size_t)(il + 1) * G.K + (jl + 1)) * G.N + 1;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const int k = c0 + tc + q;
+                if (k < G.n_k) out[k] = acc[p][q] * G.scale;
+            }
+        }
+        else
+        {
+            double* out = C + (size_t)r * G.ldc + c0 + tc;
+            *reinterpret_cast<double2*>(out) = make_double2(acc[p][0] * G.scale, acc[p][1] * G.scale);
+            *reinterpret_cast<double2*>(out + 2) = make_double2(acc[p][2] * G.scale, acc[p][3] * G.scale);
+        }
+    }
+}
+
+struct Rhs3Args
+{
+    int M, K, N, n_i, n_j, n_k, ldj, ldk, n_species;
+    double factor;                       // -macroparticle_factor / eps_0
+    const unsigned char* mask;           // MAG2D_FREE or Dirichlet (anything else)
+    const unsigned char* interior_fixed; // 1 on electrode nodes inside the box (capacitance method)
+    const double* voltage;
+    const unsigned long long* rho;       // [n_species][M*K*N] Q32 counts
+    const double* charges;
+    double* b;                           // reference right-hand side (diagnostics, residual)
+    double* u;                           // Dirichlet nodes receive their voltage
+    double* R;                           // [n_i][ldj][ldk] interior right-hand side with the frame values moved over
+};
+
+// Solver::solve's right-hand side + the reduction to the interior block
+__global__ void k_rhs3d(const __grid_constant__ Rhs3Args A)
+{
+    const size_t n = (size_t)A.M * A.K * A.N;
+    const long long sj = A.N, si = (long long)A.K * A.N;
+    for (size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x; m < n; m += (size_t)gridDim.x * blockDim.x)
+    {
+        const int k = (int)(m % A.N), j = (int)((m / A.N) % A.K), i = (int)(m / si);
+        const bool fixed = A.mask[m] != MAG2D_FREE;
+        double b;
+        if (fixed) b = A.voltage[m];
+        else
+        {
+            double q = 0.0;
+            for (int s = 0; s < A.n_species; s++)
+            {
+                const double c = A.charges[s];
+                if (c != 0.0) q += c * ((double)(long long)A.rho[(size_t)s * n + m] * 2.3283064365386963e-10);
+            }
+            b = q * A.factor;
+        }
+        A.b[m] = b;
+        if (fixed) A.u[m] = b;
+        const int il = i - 1, jl = j - 1, kl = k - 1;
+        if (il < 0 || il >= A.n_i || jl < 0 || jl >= A.n_j || kl < 0 || kl >= A.n_k) continue;
+        double r = 0.0;
+        if (!A.interior_fixed[m])
+        {
+            r = b;
+            // neighbours by flat index, exactly as the reference's matrix rows address them (fields3d.cpp:61-67);
+            // Dirichlet neighbours on the frame contribute their value to the right-hand side
+            const long long nb[6] = {(long long)m - si, (long long)m - sj, (long long)m - 1, (long long)m + 1, (long long)m + sj, (long long)m + si};
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+                if (A.mask[nb[q]] != MAG2D_FREE && !A.interior_fixed[nb[q]]) r -= A.voltage[nb[q]];
+        }
+        A.R[((size_t)il * A.ldj + jl) * A.ldk + kl] = r;
+    }
+}
+
+// Thomas factors of the Toeplitz systems [1, d, 1], d = -6 + lam_j + lam_k: inv[i][mode] = 1 / (d - inv[i-1][mode])
+__global__ void k_thomas_setup(int n_i, int n_j, int n_k, int ldj, int ldk, double* __restrict__ inv)
+{
+    const int mode = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mode >= ldj * ldk) return;
+    const int jl = mode / ldk, kl = mode % ldk;
+    double d = -6.0;
+    if (jl < n_j && kl < n_k) d += 2.0 * cospi((double)(jl + 1) / (double)(n_j + 1)) + 2.0 * cospi((double)(kl + 1) / (double)(n_k + 1));
+    double c = 0.0;
+    for (int i = 0; i < n_i; i++)
+    {
+        c = 1.0 / (d - c);
+        inv[(size_t)i * ldj * ldk + mode] = c;
+    }
+}
+
+// y_i = (r_i - y_(i-1)) inv_i ; x_i = y_i - inv_i x_(i+1); one thread per (y,z) mode, coalesced across modes.
+// The 65k independent modes of a 256^3 grid hide the latency of the recurrence by themselves.
+__global__ void k_thomas_solve(int n_i, int plane, const double* __restrict__ inv, double* __restrict__ v, double scale)
+{
+    const int mode = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mode >= plane) return;
+    double y = 0.0;
+    for (int i = 0; i < n_i; i++)
+    {
+        const size_t e = (size_t)i * plane + mode;
+        y = (v[e] - y) * inv[e];
+        v[e] = y;
+    }
+    double x = 0.0;
+    for (int i = n_i - 1; i >= 0; i--)
+    {
+        const size_t e = (size_t)i * plane + mode;
+        x = v[e] - inv[e] * x;
+        v[e] = x;
+    }
+    // the two inverse transforms carry the factor 4 / ((n_j+1)(n_k+1)); fold it in here
+    for (int i = 0; i < n_i; i++) v[(size_t)i * plane + mode] *= scale;
+}
+
+// alpha = Cinv (V_E - u0[E]);  one block
+__global__ void k_capacitance(int ne, const int* __restrict__ nodes, const double* __restrict__ volts, const double* __restrict__ cinv,
+                              const double* __restrict__ u, double* __restrict__ alpha)
+{
+    __shared__ double d[64];
+    const int t = threadIdx.x;
+    if (t < ne) d[t] = volts[t] - u[nodes[t]];
+    __syncthreads();
+    if (t < ne)
+    {
+        double a = 0.0;
+        for (int q = 0; q < ne; q++) a += cinv[t * ne + q] * d[q];
+        alpha[t] = a;
+    }
+}
+
+__global__ void k_add_green(size_t n, int ne, const double* __restrict__ alpha, const double* __restrict__ green, double* __restrict__ u)
+{
+    for (size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x; m < n; m += (size_t)gridDim.x * blockDim.x)
+    {
+        double s = u[m];
+        for (int e = 0; e < ne; e++) s += alpha[e] * green[(size_t)e * n + m];
+        u[m] = s;
+    }
+}
+
+__global__ void k_residual3d(int M, int K, int N, const unsigned char* __restrict__ mask, const double* __restrict__ u,
+                             const double* __restrict__ b, double* __restrict__ out)
+{
+    const size_t n = (size_t)M * K * N;
+    const long long sj = N, si = (long long)K * N;
+    double r = 0.0, um = 0.0;
+    for (size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x; m < n; m += (size_t)gridDim.x * blockDim.x)
+    {
+        const double c = u[m];
+        um = fmax(um, fabs(c));
+        if (mask[m] != MAG2D_FREE) { r = fmax(r, fabs(c - b[m])); continue; }
+        const double res = b[m] - (u[m - si] + u[m - sj] + u[m - 1] - 6.0 * c + u[m + 1] + u[m + sj] + u[m + si]);
+        r = fmax(r, fabs(res) / 6.0);
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+        um = fmax(um, __shfl_xor_sync(0xffffffffu, um, o));
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(r));
+        atomicMax(reinterpret_cast<unsigned long long*>(out + 1), (unsigned long long)__double_as_longlong(um));
+    }
+}
+
+int gemm3(mag2d_ctx* c, const Gemm3Args& G, int batch, bool scatter)
+{
+    const dim3 grid(G.cols / G3_TN, (G.rows + G3_TM - 1) / G3_TM, batch);
+    if (scatter) k_gemm3<true><<<grid, G3_THREADS, G3_SMEM, c->stream>>>(G);
+    else k_gemm3<false><<<grid, G3_THREADS, G3_SMEM, c->stream>>>(G);
+    c->launches++;
+    return 0;
+}
+
+// interior block R (in D.R) -> potential on the interior nodes of u (frame untouched)
+int solve_interior(mag2d_ctx* c, double* u)
+{
+    Direct3D& D = c->direct3;
+    const int plane = D.ldj * D.ldk;
+    Gemm3Args G;
+    memset(&G, 0, sizeof(G));
+    G.scale = 1.0;
+    // along z: T = R S_z, rows = n_i * ldj
+    G.A = D.R; G.lda = D.ldk; G.strideA = 0;
+    G.B = D.Sz; G.ldb = D.ldk; G.strideB = 0;
+    G.C = D.T; G.ldc = D.ldk; G.strideC = 0;
+    G.rows = D.n_i * D.ldj; G.cols = D.ldk; G.Kdim = D.ldk;
+    gemm3(c, G, 1, false);
+    // along y: R_i = S_y T_i for every x plane
+    G.A = D.Sy; G.lda = D.ldj; G.strideA = 0;
+    G.B = D.T; G.ldb = D.ldk; G.strideB = plane;
+    G.C = D.R; G.ldc = D.ldk; G.strideC = plane;
+    G.rows = D.ldj; G.cols = D.ldk; G.Kdim = D.ldj;
+    gemm3(c, G, D.n_i, false);
+    k_thomas_solve<<<(plane + 127) / 128, 128, 0, c->stream>>>(D.n_i, plane, D.inv, D.R, 4.0 / ((double)(D.n_j + 1) * (double)(D.n_k + 1)));
+    c->launches++;
+    // back: T_i = S_y R_i, then U = T S_z scattered into the potential
+    G.A = D.Sy; G.lda = D.ldj; G.strideA = 0;
+    G.B = D.R; G.ldb = D.ldk; G.strideB = plane;
+    G.C = D.T; G.ldc = D.ldk; G.strideC = plane;
+    G.rows = D.ldj; G.cols = D.ldk; G.Kdim = D.ldj;
+    gemm3(c, G, D.n_i, false);
+    G.A = D.T; G.lda = D.ldk; G.strideA = 0;
+    G.B = D.Sz; G.ldb = D.ldk; G.strideB = 0;
+    G.C = u; G.strideC = 0;
+    G.rows = D.n_i * D.ldj; G.cols = D.ldk; G.Kdim = D.ldk;
+    G.ldj = D.ldj; G.n_j = D.n_j; G.n_k = D.n_k; G.K = c->g.K; G.N = c->g.N;
+    gemm3(c, G, 1, true);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+std::vector<double> sine_matrix(int n, int ld)
+{
+    std::vector<double> S((size_t)ld * ld, 0.0);
+    for (int j = 0; j < n; j++)
+        for (int k = j; k < n; k++)
+        {
+            const long long p = (long long)(j + 1) * (k + 1) % (2LL * (n + 1));
+            const double s = (double)sinl(M_PIl * (long double)p / (long double)(n + 1));
+            S[(size_t)j * ld + k] = S[(size_t)k * ld + j] = s;
+        }
+    return S;
+}
+
+}  // namespace
+
+void direct3d_free(mag2d_ctx* c)
+{
+    Direct3D& D = c->direct3;
+    cudaFree(D.Sy); cudaFree(D.Sz); cudaFree(D.inv); cudaFree(D.R); cudaFree(D.T); cudaFree(D.interior_fixed);
+    cudaFree(D.e_nodes); cudaFree(D.e_volts); cudaFree(D.cinv); cudaFree(D.alpha); cudaFree(D.green);
+    D = Direct3D();
+}
+
+int direct3d_setup(mag2d_ctx* c)
+{
+    direct3d_free(c);
+    Direct3D& D = c->direct3;
+    const int M = c->g.M, K = c->g.K, N = c->g.N;
+    const size_t n = (size_t)M * K * N;
+    const unsigned char* mask = c->h_mask.data();
+    auto fixed = [&](int i, int j, int k) { return mask[((size_t)i * K + j) * N + k] != MAG2D_FREE; };
+    // the five faces the reference fixes must be Dirichlet; the k = N-1 face is either Dirichlet or (the reference's
+    // off-by-one, fields3d.cpp:28) free, in which case its free nodes couple to the k = 0 node of the next row
+    bool top_fixed = true, top_free = true;
+    for (int i = 0; i < M; i++)
+        for (int j = 0; j < K; j++)
+        {
+            if (!fixed(i, j, 0)) { mag2d_set_error("3-D solver: the k = 0 face must be Dirichlet"); return 1; }
+            const bool frame_ij = i == 0 || i == M - 1 || j == 0 || j == K - 1;
+            if (frame_ij) continue;
+            if (fixed(i, j, N - 1)) top_free = false;
+            else top_fixed = false;
+        }
+    for (int j = 0; j < K; j++)
+        for (int k = 0; k < N; k++)
+            if (!fixed(0, j, k) || !fixed(M - 1, j, k)) { mag2d_set_error("3-D solver: the x faces must be Dirichlet"); return 1; }
+    for (int i = 0; i < M; i++)
+        for (int k = 0; k < N; k++)
+            if (!fixed(i, 0, k) || !fixed(i, K - 1, k)) { mag2d_set_error("3-D solver: the y faces must be Dirichlet"); return 1; }
+    if (!top_fixed && !top_free) { mag2d_set_error("3-D solver: the k = N-1 face must be entirely Dirichlet or entirely free"); return 1; }
+    D.n_i = M - 2;
+    D.n_j = K - 2;
+    D.n_k = top_fixed ? N - 2 : N - 1;
+    if (D.n_i < 1 || D.n_j < 1 || D.n_k < 1) { mag2d_set_error("3-D solver: grid too small"); return 1; }
+    if (!top_fixed)
+        // the wrapped neighbour (i, j+1, 0) of a free top node must carry zero volts for the sine transform to apply
+        for (int i = 1; i < M - 1; i++)
+            for (int j = 1; j < K; j++)
+                if (c->h_voltage[((size_t)i * K + j) * N] != 0.0)
+                {
+                    mag2d_set_error("3-D solver: a free k = N-1 face needs zero volts on the k = 0 face");
+                    return 1;
+                }
+    D.ldj = (D.n_j + 31) / 32 * 32;
+    D.ldk = (D.n_k + 31) / 32 * 32;
+    // electrode nodes inside the box
+    std::vector<unsigned char> interior_fixed(n, 0);
+    std::vector<int> e_nodes;
+    std::vector<double> e_volts;
+    for (int i = 1; i <= D.n_i; i++)
+        for (int j = 1; j <= D.n_j; j++)
+            for (int k = 1; k <= D.n_k; k++)
+                if (fixed(i, j, k))
+                {
+                    const size_t m = ((size_t)i * K + j) * N + k;
+                    interior_fixed[m] = 1;
+                    e_nodes.push_back((int)m);
+                    e_volts.push_back(c->h_voltage[m]);
+                }
+    D.ne = (int)e_nodes.size();
+    if (D.ne > 64)
+    {
+        mag2d_set_error("3-D solver: more than 64 electrode nodes inside the box (extended electrodes need the 3-D multigrid, not built yet)");
+        return 1;
+    }
+    const size_t block = (size_t)D.n_i * D.ldj * D.ldk;
+    const std::vector<double> Sy = sine_matrix(D.n_j, D.ldj), Sz = sine_matrix(D.n_k, D.ldk);
+    CUDA_OK(cudaMalloc(&D.Sy, sizeof(double) * Sy.size()));
+    CUDA_OK(cudaMalloc(&D.Sz, sizeof(double) * Sz.size()));
+    CUDA_OK(cudaMalloc(&D.inv, sizeof(double) * block));
+    CUDA_OK(cudaMalloc(&D.R, sizeof(double) * block));
+    CUDA_OK(cudaMalloc(&D.T, sizeof(double) * block));
+    CUDA_OK(cudaMalloc(&D.interior_fixed, n));
+    CUDA_OK(cudaMemcpyAsync(D.Sy, Sy.data(), sizeof(double) * Sy.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(D.Sz, Sz.data(), sizeof(double) * Sz.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(D.interior_fixed, interior_fixed.data(), n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemsetAsync(D.R, 0, sizeof(double) * block, c->stream));
+    CUDA_OK(cudaMemsetAsync(D.T, 0, sizeof(double) * block, c->stream));
+    CUDA_OK(cudaFuncSetAttribute(k_gemm3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
+    CUDA_OK(cudaFuncSetAttribute(k_gemm3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
+    const int plane = D.ldj * D.ldk;
+    k_thomas_setup<<<(plane + 127) / 128, 128, 0, c->stream>>>(D.n_i, D.n_j, D.n_k, D.ldj, D.ldk, D.inv);
+    c->launches++;
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    D.ok = true;
+    if (D.ne > 0)
+    {
+        // Green's functions of the electrode nodes: unit source at node e, zero frame
+        CUDA_OK(cudaMalloc(&D.green, sizeof(double) * n * D.ne));
+        CUDA_OK(cudaMemsetAsync(D.green, 0, sizeof(double) * n * D.ne, c->stream));
+        std::vector<double> cmat((size_t)D.ne * D.ne);
+        for (int e = 0; e < D.ne; e++)
+        {
+            const int m = e_nodes[e];
+            const int k = m % N, j = (m / N) % K, i = m / (K * N);
+            CUDA_OK(cudaMemsetAsync(D.R, 0, sizeof(double) * block, c->stream));
+            const double one = 1.0;
+            CUDA_OK(cudaMemcpyAsync(D.R + ((size_t)(i - 1) * D.ldj + (j - 1)) * D.ldk + (k - 1), &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            if (solve_interior(c, D.green + (size_t)e * n)) return 1;
+            for (int q = 0; q < D.ne; q++)
+                CUDA_OK(cudaMemcpyAsync(&cmat[(size_t)q * D.ne + e], D.green + (size_t)e * n + e_nodes[q], sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_OK(cudaStreamSynchronize(c->stream));
+        }
+        // invert the capacitance matrix (Gauss-Jordan, partial pivoting)
+        const int ne = D.ne;
+        std::vector<double> a = cmat, inv((size_t)ne * ne, 0.0);
+        for (int q = 0; q < ne; q++) inv[(size_t)q * ne + q] = 1.0;
+        for (int col = 0; col < ne; col++)
+        {
+            int piv = col;
+            for (int r = col + 1; r < ne; r++)
+                if (std::fabs(a[(size_t)r * ne + col]) > std::fabs(a[(size_t)piv * ne + col])) piv = r;
+            if (std::fabs(a[(size_t)piv * ne + col]) < 1e-300) { mag2d_set_error("3-D solver: singular capacitance matrix"); return 1; }
+            for (int q = 0; q < ne; q++)
+            {
+                std::swap(a[(size_t)piv * ne + q], a[(size_t)col * ne + q]);
+                std::swap(inv[(size_t)piv * ne + q], inv[(size_t)col * ne + q]);
+            }
+            const double d = 1.0 / a[(size_t)col * ne + col];
+            for (int q = 0; q < ne; q++) { a[(size_t)col * ne + q] *= d; inv[(size_t)col * ne + q] *= d; }
+            for (int r = 0; r < ne; r++)
+            {
+                if (r == col) continue;
+                const double f = a[(size_t)r * ne + col];
+                if (f == 0.0) continue;
+                for (int q = 0; q < ne; q++) { a[(size_t)r * ne + q] -= f * a[(size_t)col * ne + q]; inv[(size_t)r * ne + q] -= f * inv[(size_t)col * ne + q]; }
+            }
+        }
+        CUDA_OK(cudaMalloc(&D.e_nodes, sizeof(int) * ne));
+        CUDA_OK(cudaMalloc(&D.e_volts, sizeof(double) * ne));
+        CUDA_OK(cudaMalloc(&D.cinv, sizeof(double) * ne * ne));
+        CUDA_OK(cudaMalloc(&D.alpha, sizeof(double) * ne));
+        CUDA_OK(cudaMemcpyAsync(D.e_nodes, e_nodes.data(), sizeof(int) * ne, cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(cudaMemcpyAsync(D.e_volts, e_volts.data(), sizeof(double) * ne, cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(cudaMemcpyAsync(D.cinv, inv.data(), sizeof(double) * ne * ne, cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+// ElMag3D::solve / Solver::solve (src/fields3d.cpp:83-95, 170-181): rho of every species -> b -> u
+int solve3d(mag2d_ctx* c, double* resid_out)
+{
+    Direct3D& D = c->direct3;
+    if (!D.ok) { mag2d_set_error("mag2d_solve: mag2d_set_grid has not been called (3-D)"); return 1; }
+    const int M = c->g.M, K = c->g.K, N = c->g.N;
+    const size_t n = (size_t)M * K * N;
+    Rhs3Args A;
+    A.M = M; A.K = K; A.N = N;
+    A.n_i = D.n_i; A.n_j = D.n_j; A.n_k = D.n_k; A.ldj = D.ldj; A.ldk = D.ldk;
+    A.n_species = (int)c->sp.size();
+    A.factor = -c->g.macroparticle_factor / MAG2D_EPS0;
+    A.mask = c->d_mask;
+    A.interior_fixed = D.interior_fixed;
+    A.voltage = c->d_voltage;
+    A.rho = c->d_rho;
+    A.charges = c->d_charges;
+    A.b = c->d_b;
+    A.u = c->d_u;
+    A.R = D.R;
+    k_rhs3d<<<148 * 8, 256, 0, c->stream>>>(A);
+    c->launches++;
+    if (solve_interior(c, c->d_u)) return 1;
+    if (D.ne > 0)
+    {
+        k_capacitance<<<1, 64, 0, c->stream>>>(D.ne, D.e_nodes, D.e_volts, D.cinv, c->d_u, D.alpha);
+        k_add_green<<<148 * 8, 256, 0, c->stream>>>(n, D.ne, D.alpha, D.green, c->d_u);
+        c->launches += 2;
+    }
+    CUDA_OK(cudaGetLastError());
+    if (resid_out)
+    {
+        CUDA_OK(cudaMemsetAsync(c->d_scratch, 0, 2 * sizeof(double), c->stream));
+        k_residual3d<<<148 * 8, 256, 0, c->stream>>>(M, K, N, c->d_mask, c->d_u, c->d_b, c->d_scratch);
+        c->launches++;
+        double h[2];
+        CUDA_OK(cudaMemcpyAsync(h, c->d_scratch, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        *resid_out = h[1] > 0 ? h[0] / h[1] : h[0];
+    }
+    return 0;
+}

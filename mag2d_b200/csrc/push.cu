@@ -874,7 +874,7 @@ struct GenArgs
     long long first, n;
     int kind;
     double a, b, c, d;
-    double x_max, z_max;
+    double x_max, z_max, y_max;
     double vth;        // v_max / sqrt(2)
     double lifetime;
     double vmono;      // veV(energy)
@@ -889,12 +889,13 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_generate(const __grid_constant
     if (q >= G.n) return;
     const long long k = G.first + q;
     Rng rng = make_rng(G.seed ^ 0xA5A5A5A55A5A5A5AULL, G.species, 0xFFFFFFFF00000000ULL + (unsigned long long)G.kind, (unsigned long long)k);
-    double x, z, vx, vy, vz;
+    double x, z, vx, vy, vz, y = 0.0;
     if (G.kind == 0)
     {
         const uint4 r = rng.block();
         x = G.x_max * u01(r.x);
         z = G.z_max * u01(r.z);
+        y = G.y_max * u01(r.y);      // stored for CARTESIAN3D only
     }
     else
     {
@@ -939,6 +940,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_generate(const __grid_constant
     G.p.vx[k] = vx;
     G.p.vy[k] = vy;
     G.p.vz[k] = vz;
+    if (G.p.y) G.p.y[k] = y;
     if (G.has_ttd)
     {
         const uint4 r = rng.block();
@@ -1391,6 +1393,7 @@ int launch_generate(mag2d_ctx* c, int s, int kind, long long n, double a, double
     G.d = d;
     G.x_max = c->g.x_max;
     G.z_max = c->g.z_max;
+    G.y_max = c->g.y_max;
     G.vth = S.v_max / M_SQRT2;
     G.lifetime = std::isfinite(S.lifetime) ? S.lifetime : 0.0;
     G.vmono = sqrt(a * MAG2D_QE / S.desc.mass * 2.0);

@@ -1,0 +1,479 @@
+// push3d.cu — the 3-D Cartesian (3D3V) step: field gather + Boris push + null-collision MCC + box boundary /
+// electrode absorption + fixed-point CIC deposit on eight nodes, one kernel per species and step.
+//
+// Reference code replaced (dead code there — species3d.cpp does not compile — restated in oracle/mag3d_oracle.c):
+//   Species<CARTESIAN3D>::advance              src/species3d.cpp:3-93
+//   ElMag3D::E / Field3D::grad, grad_component  src/fields3d.hpp:95-101, src/Field3D.hpp:110-163
+//   Geometry::is_free                           src/fields3d.hpp:48-57
+//   Field3D::accumulate                         src/Field3D.hpp:40-65
+// Grids use the reference's Array3D layout a[(i*K + j)*N + k] (i along x, j along y, k along z; M, K, N nodes).
+// 96 B per particle-step (six fp64 components read and written once).
+#include <cstring>
+
+#include "ctx.hpp"
+#include "mcc.cuh"
+
+namespace {
+
+constexpr int P3_THREADS = 256;
+
+struct Grid3Dev
+{
+    int M, K, N;                    // nodes along x, y, z
+    int boundary, check_mask, deposit;
+    double x_max, y_max, z_max;
+    double idx, idy, idz;
+    double hiX, hiY, hiZ;           // ((M-1)/idx)*idx ...: the upper clamp of Field3D::grad_component in index units
+    const double* gx;               // edge differences u[m] - u[m - stride] along x / y / z
+    const double* gy;
+    const double* gz;
+    const unsigned char* cfree;     // per cell (indexed by its lowest node): any corner FREE
+    unsigned long long* rho;        // this species' fixed-point charge grid
+};
+
+struct Push3Args
+{
+    Grid3Dev g;
+    SpeciesDev s;
+    ParticlesDev p;
+    const MccBlob* mcc;
+    unsigned long long* counts;
+    unsigned long long* removed;
+    unsigned long long seed;
+    unsigned* coll_list;
+    unsigned* coll_count;
+};
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+__device__ __forceinline__ unsigned long long q32_rn3(double w)
+{
+    const double magic = 6755399441055744.0;   // 1.5 * 2^52
+    const double t = __dadd_rn(__dmul_rn(w, 4294967296.0), magic);
+    return (unsigned long long)(__double_as_longlong(t) - __double_as_longlong(magic));
+}
+
+// one component of -grad u at (X, Y, Z) in index units; DIR selects the differenced axis (0 x, 1 y, 2 z)
+template <int DIR>
+__device__ __forceinline__ double grad_component(const Grid3Dev& g, double X, double Y, double Z)
+{
+    const double hx = DIR == 0 ? 0.5 : 0.0, hy = DIR == 1 ? 0.5 : 0.0, hz = DIR == 2 ? 0.5 : 0.0;
+    const double xc = clampd(X, hx, g.hiX - hx) + hx, yc = clampd(Y, hy, g.hiY - hy) + hy, zc = clampd(Z, hz, g.hiZ - hz) + hz;
+    // at the upper clamp the reference reads plane i+1 = M with weight exactly 0: use planes M-2, M-1 with weight 1
+    const int i = min((int)xc, g.M - 2), j = min((int)yc, g.K - 2), k = min((int)zc, g.N - 2);
+    const double u = xc - i, v = yc - j, w = zc - k;
+    const double* f = (DIR == 0 ? g.gx : DIR == 1 ? g.gy : g.gz) + ((size_t)i * g.K + j) * g.N + k;
+    const size_t sj = g.N, si = (size_t)g.K * g.N;
+    const double g0 = __ldg(f), g1 = __ldg(f + si), g2 = __ldg(f + sj), g3 = __ldg(f + si + sj);
+    const double g4 = __ldg(f + 1), g5 = __ldg(f + si + 1), g6 = __ldg(f + sj + 1), g7 = __ldg(f + si + sj + 1);
+    const double cu = 1 - u, cv = 1 - v, cw = 1 - w;
+    const double r = cu * cv * cw * g0 + u * cv * cw * g1 + cu * v * cw * g2 + u * v * cw * g3 + cu * cv * w * g4 + u * cv * w * g5 +
+                     cu * v * w * g6 + u * v * w * g7;
+    return r * (DIR == 0 ? g.idx : DIR == 1 ? g.idy : g.idz);
+}
+
+// box boundary, electrode absorption and the eight Q32 weights (Field3D.hpp:56-64 order)
+template <bool DEPOSIT>
+__device__ __forceinline__ bool boundary_weights3(const Grid3Dev& g, double& x, double& y, double& z, unsigned& node, unsigned long long (&w)[8])
+{
+    node = 0;
+    if (!(x >= 0.0 && x <= g.x_max && y >= 0.0 && y <= g.y_max && z >= 0.0 && z <= g.z_max))
+    {
+        if (g.boundary == MAG2D_BOUNDARY_FREE || !(x == x && y == y && z == z)) return false;
+        x = fmod(x, g.x_max); if (x < 0) x += g.x_max;
+        y = fmod(y, g.y_max); if (y < 0) y += g.y_max;
+        z = fmod(z, g.z_max); if (z < 0) z += g.z_max;
+    }
+    const double X = __dmul_rn(x, g.idx), Y = __dmul_rn(y, g.idy), Z = __dmul_rn(z, g.idz);
+    const int i = max(min((int)X, g.M - 2), 0), j = max(min((int)Y, g.K - 2), 0), k = max(min((int)Z, g.N - 2), 0);
+    const size_t m = ((size_t)i * g.K + j) * g.N + k;
+    node = (unsigned)m;
+    if (g.check_mask && !g.cfree[m]) return false;
+    if (DEPOSIT)
+    {
+        const double u = __dsub_rn(X, (double)i), v = __dsub_rn(Y, (double)j), t = __dsub_rn(Z, (double)k);
+        const double cu = __dsub_rn(1.0, u), cv = __dsub_rn(1.0, v), ct = __dsub_rn(1.0, t);
+        const double a00 = __dmul_rn(cu, cv), a10 = __dmul_rn(u, cv), a01 = __dmul_rn(cu, v), a11 = __dmul_rn(u, v);
+        w[0] = q32_rn3(__dmul_rn(a00, ct));
+        w[1] = q32_rn3(__dmul_rn(a10, ct));
+        w[2] = q32_rn3(__dmul_rn(a01, ct));
+        w[3] = q32_rn3(__dmul_rn(a11, ct));
+        w[4] = q32_rn3(__dmul_rn(a00, t));
+        w[5] = q32_rn3(__dmul_rn(a10, t));
+        w[6] = q32_rn3(__dmul_rn(a01, t));
+        w[7] = q32_rn3(__dmul_rn(a11, t));
+    }
+    return true;
+}
+
+// warp-aggregated scatter: lanes that share a cell are summed with REDUX (two 16/17-bit pieces per weight), lanes
+// 0..7 issue one RED.ADD.64 each; after MAX_RUNS distinct cells the remaining lanes scatter on their own
+template <int MAX_RUNS>
+__device__ __forceinline__ void warp_deposit3(const Grid3Dev& g, bool valid, unsigned node, const unsigned long long (&w)[8])
+{
+    const unsigned lane = lane_id();
+    unsigned remaining = __ballot_sync(MAG2D_FULL_MASK, valid);
+    if (remaining == 0) return;
+    const unsigned sj = (unsigned)g.N, si = (unsigned)(g.K * g.N);
+#pragma unroll 1
+    for (int it = 0; remaining && it < MAX_RUNS; it++)
+    {
+        const int src = __ffs(remaining) - 1;
+        const unsigned k0 = __shfl_sync(MAG2D_FULL_MASK, node, src);
+        const bool mine = valid && node == k0;
+        const unsigned m = __ballot_sync(MAG2D_FULL_MASK, mine);
+        unsigned long long mysum = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+        {
+            const unsigned lo = __reduce_add_sync(MAG2D_FULL_MASK, mine ? (unsigned)(w[q] & 0xFFFFu) : 0u);
+            const unsigned hi = __reduce_add_sync(MAG2D_FULL_MASK, mine ? (unsigned)(w[q] >> 16) : 0u);
+            if ((int)lane == q) mysum = ((unsigned long long)hi << 16) + lo;
+        }
+        if (lane < 8) atomicAdd(g.rho + k0 + (lane & 1 ? si : 0u) + (lane & 2 ? sj : 0u) + (lane >> 2), mysum);
+        remaining &= ~m;
+    }
+    if (valid && ((remaining >> lane) & 1u))
+    {
+        unsigned long long* r = g.rho + node;
+        atomicAdd(r, w[0]);
+        atomicAdd(r + si, w[1]);
+        atomicAdd(r + sj, w[2]);
+        atomicAdd(r + si + sj, w[3]);
+        atomicAdd(r + 1, w[4]);
+        atomicAdd(r + si + 1, w[5]);
+        atomicAdd(r + sj + 1, w[6]);
+        atomicAdd(r + si + sj + 1, w[7]);
+    }
+}
+
+// ---- the fused 3-D step -------------------------------------------------------------------------------------------
+// Each thread owns two neighbouring slots (128-bit loads and stores, a warp moves 512 B per instruction).  PUSH =
+// false is the deposit-only pass of Pic::advance_init.
+template <bool PUSH, bool GATHER, bool HASB, bool MCC, bool DEPOSIT>
+__global__ void __launch_bounds__(P3_THREADS) k_push3d(const __grid_constant__ Push3Args A)
+{
+    const unsigned lane = lane_id();
+    const long long k = 2 * ((long long)blockIdx.x * P3_THREADS + threadIdx.x);
+    const long long n = A.p.n;
+    if ((k & ~63LL) >= n) return;       // warp-uniform: the slabs are allocated in multiples of 256 slots
+    double x[2], y[2], z[2], vx[2], vy[2], vz[2];
+    {
+        const double2 a = *reinterpret_cast<const double2*>(A.p.x + k);
+        const double2 b = *reinterpret_cast<const double2*>(A.p.y + k);
+        const double2 c = *reinterpret_cast<const double2*>(A.p.z + k);
+        x[0] = a.x; x[1] = a.y; y[0] = b.x; y[1] = b.y; z[0] = c.x; z[1] = c.y;
+        if (PUSH)
+        {
+            const double2 d = *reinterpret_cast<const double2*>(A.p.vx + k);
+            const double2 e = *reinterpret_cast<const double2*>(A.p.vy + k);
+            const double2 f = *reinterpret_cast<const double2*>(A.p.vz + k);
+            vx[0] = d.x; vx[1] = d.y; vy[0] = e.x; vy[1] = e.y; vz[0] = f.x; vz[1] = f.y;
+        }
+    }
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    if (MCC)
+    {
+        Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)k);
+        rnd = rng.block();
+    }
+    const double dt = A.s.dt;
+    bool keep[2];
+    unsigned node[2], removed = 0, hit_mask = 0;
+    unsigned long long w[2][8];
+#pragma unroll
+    for (int e = 0; e < 2; e++)
+    {
+        const bool live = (k + e < n) && particle_alive(x[e]);
+        if (PUSH)
+        {
+            double Ex = 0.0, Ey = 0.0, Ez = 0.0;
+            if (GATHER)
+            {
+                const double X = x[e] * A.g.idx, Y = y[e] * A.g.idy, Z = z[e] * A.g.idz;
+                Ex = -grad_component<0>(A.g, X, Y, Z);
+                Ey = -grad_component<1>(A.g, X, Y, Z);
+                Ez = -grad_component<2>(A.g, X, Y, Z);
+            }
+            // half acceleration, rotation (species3d.cpp:39-50, its own sign convention), half acceleration
+            vx[e] += Ex * A.s.hq;
+            vy[e] += Ey * A.s.hq;
+            vz[e] += Ez * A.s.hq;
+            if (HASB)
+            {
+                const double px = vx[e] - vy[e] * A.s.tz + vz[e] * A.s.ty;
+                const double py = vy[e] - vz[e] * A.s.tx + vx[e] * A.s.tz;
+                const double pz = vz[e] - vx[e] * A.s.ty + vy[e] * A.s.tx;
+                const double ox = vx[e], oy = vy[e], oz = vz[e];
+                vx[e] = ox - py * A.s.sz + pz * A.s.sy;
+                vy[e] = oy - pz * A.s.sx + px * A.s.sz;
+                vz[e] = oz - px * A.s.sy + py * A.s.sx;
+            }
+            vx[e] += Ex * A.s.hq;
+            vy[e] += Ey * A.s.hq;
+            vz[e] += Ez * A.s.hq;
+            x[e] += vx[e] * dt;
+            y[e] += vy[e] * dt;
+            z[e] += vz[e] * dt;
+        }
+        const bool inside = boundary_weights3<DEPOSIT>(A.g, x[e], y[e], z[e], node[e], w[e]);
+        keep[e] = live && inside;
+        removed += (live && !inside) ? 1u : 0u;
+        if (!keep[e]) x[e] = dead_marker();
+        if (MCC)
+        {
+            const unsigned word = e == 0 ? rnd.x : rnd.y;
+            if (keep[e] && u01(word) < A.s.prob) hit_mask |= 1u << e;
+        }
+    }
+    if (PUSH)
+    {
+        *reinterpret_cast<double2*>(A.p.x + k) = make_double2(x[0], x[1]);
+        *reinterpret_cast<double2*>(A.p.y + k) = make_double2(y[0], y[1]);
+        *reinterpret_cast<double2*>(A.p.z + k) = make_double2(z[0], z[1]);
+        *reinterpret_cast<double2*>(A.p.vx + k) = make_double2(vx[0], vx[1]);
+        *reinterpret_cast<double2*>(A.p.vy + k) = make_double2(vy[0], vy[1]);
+        *reinterpret_cast<double2*>(A.p.vz + k) = make_double2(vz[0], vz[1]);
+    }
+    if (DEPOSIT)
+    {
+        if (keep[0] && keep[1] && node[0] == node[1])
+        {
+#pragma unroll
+            for (int c = 0; c < 8; c++) w[0][c] += w[1][c];
+            keep[1] = false;
+        }
+        warp_deposit3<3>(A.g, keep[0], node[0], w[0]);
+        warp_deposit3<3>(A.g, keep[1], node[1], w[1]);
+    }
+    if (MCC)
+    {
+        const unsigned cnt = __popc(hit_mask);
+        if (__any_sync(MAG2D_FULL_MASK, cnt != 0))
+        {
+            unsigned incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const unsigned t = __shfl_up_sync(MAG2D_FULL_MASK, incl, o);
+                if (lane >= (unsigned)o) incl += t;
+            }
+            const unsigned total = __shfl_sync(MAG2D_FULL_MASK, incl, 31);
+            unsigned start = 0;
+            if (lane == 31) start = atomicAdd(A.coll_count, total);
+            start = __shfl_sync(MAG2D_FULL_MASK, start, 31) + incl - cnt;
+            if (hit_mask & 1u) A.coll_list[start++] = (unsigned)k;
+            if (hit_mask & 2u) A.coll_list[start++] = (unsigned)(k + 1);
+        }
+    }
+    if (PUSH && __any_sync(MAG2D_FULL_MASK, removed != 0))
+    {
+        unsigned rsum = removed;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(MAG2D_FULL_MASK, rsum, o);
+        if (lane == 0) atomicAdd(A.removed, (unsigned long long)rsum);
+    }
+}
+
+// BaseSpecies::scatter for the slots whose Bernoulli test fired (velocity space only: shared with the 2-D movers)
+__global__ void __launch_bounds__(128) k_mcc_collide3d(const __grid_constant__ Push3Args A)
+{
+    const unsigned n = *A.coll_count;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
+    {
+        const long long k = A.coll_list[q];
+        double vx = A.p.vx[k], vy = A.p.vy[k], vz = A.p.vz[k];
+        Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)k);
+        rng.draw = 1;
+        int target;
+        const int proc = mcc_scatter(A.mcc, rng, vx, vy, vz, target);
+        mcc_count(A.counts, A.mcc->n_targets, target, proc);
+        if (proc >= 0)
+        {
+            A.p.vx[k] = vx;
+            A.p.vy[k] = vy;
+            A.p.vz[k] = vz;
+        }
+    }
+}
+
+// gx[m] = u[m] - u[m - stride_x] (i >= 1), likewise gy, gz: the eight differences Field3D::grad_component forms per
+// particle become eight loads.  Planes i = 0 (j = 0, k = 0) are never addressed by the clamped stencil.
+__global__ void k_edge_fields3d(const double* __restrict__ u, int M, int K, int N, double* __restrict__ gx, double* __restrict__ gy,
+                                double* __restrict__ gz)
+{
+    const size_t n = (size_t)M * K * N;
+    const size_t sj = N, si = (size_t)K * N;
+    for (size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x; m < n; m += (size_t)gridDim.x * blockDim.x)
+    {
+        const int k = (int)(m % N), j = (int)((m / N) % K), i = (int)(m / si);
+        const double c = u[m];
+        gx[m] = i > 0 ? c - u[m - si] : 0.0;
+        gy[m] = j > 0 ? c - u[m - sj] : 0.0;
+        gz[m] = k > 0 ? c - u[m - 1] : 0.0;
+    }
+}
+
+__global__ void k_field_E3d(Grid3Dev g, int n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                            double* __restrict__ Ex, double* __restrict__ Ey, double* __restrict__ Ez)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const double X = x[p] * g.idx, Y = y[p] * g.idy, Z = z[p] * g.idz;
+    Ex[p] = -grad_component<0>(g, X, Y, Z);
+    Ey[p] = -grad_component<1>(g, X, Y, Z);
+    Ez[p] = -grad_component<2>(g, X, Y, Z);
+}
+
+Grid3Dev grid3_view(const mag2d_ctx* c, int s)
+{
+    Grid3Dev g;
+    memset(&g, 0, sizeof(g));
+    const mag2d_grid_desc& d = c->g;
+    g.M = d.M; g.K = d.K; g.N = d.N;
+    g.boundary = d.boundary;
+    g.check_mask = 1;
+    g.deposit = d.selfconsistent;
+    g.x_max = d.x_max; g.y_max = d.y_max; g.z_max = d.z_max;
+    g.idx = d.idx; g.idy = d.idy; g.idz = d.idz;
+    // xmax = (imax-1)/idx, then xmax*idx, as Field3D::grad_component evaluates it
+    g.hiX = ((d.M - 1) / d.idx) * d.idx;
+    g.hiY = ((d.K - 1) / d.idy) * d.idy;
+    g.hiZ = ((d.N - 1) / d.idz) * d.idz;
+    g.gx = c->d_gx; g.gy = c->d_gy; g.gz = c->d_gz;
+    g.cfree = c->d_cfree;
+    g.rho = s >= 0 && c->d_rho ? c->d_rho + (size_t)s * d.M * d.K * d.N : nullptr;
+    return g;
+}
+
+SpeciesDev species3_view(const mag2d_ctx* c, int s)
+{
+    const SpeciesStore& S = c->sp[s];
+    const mag2d_grid_desc& d = c->g;
+    SpeciesDev v;
+    memset(&v, 0, sizeof(v));
+    const double charge = S.desc.charge, mass = S.desc.mass, dt = S.desc.dt;
+    v.dt = dt;
+    v.hq = charge / mass * dt / 2.0;
+    // (Bx, By, Bz) = (Br, Bt, Bz) of the grid descriptor; the reference hard-wires zero (species3d.cpp:18)
+    double tmp = charge * dt / (2.0 * mass);
+    v.tx = d.Br * tmp;
+    v.ty = d.Bt * tmp;
+    v.tz = d.Bz * tmp;
+    tmp = 2.0 / (1 + v.tx * v.tx + v.ty * v.ty + v.tz * v.tz);
+    v.sx = v.tx * tmp;
+    v.sy = v.ty * tmp;
+    v.sz = v.tz * tmp;
+    v.has_B = (d.Br != 0.0 || d.Bt != 0.0 || d.Bz != 0.0);
+    v.species = s;
+    v.prob = 1.0 - exp(-dt / S.lifetime);
+    v.lifetime = S.lifetime;
+    v.qm = charge / mass;
+    v.step = S.niter;
+    return v;
+}
+
+ParticlesDev particles3_view(const SpeciesStore& S)
+{
+    ParticlesDev p;
+    double* const* a = S.arr[S.cur];
+    p.x = a[ARR_X]; p.z = a[ARR_Z]; p.vx = a[ARR_VX]; p.vy = a[ARR_VY]; p.vz = a[ARR_VZ]; p.y = a[ARR_Y]; p.ttd = a[ARR_TTD];
+    p.n = S.n_slots;
+    return p;
+}
+
+}  // namespace
+
+int update_edge_fields3d(mag2d_ctx* c)
+{
+    k_edge_fields3d<<<148 * 8, 256, 0, c->stream>>>(c->d_u, c->g.M, c->g.K, c->g.N, c->d_gx, c->d_gy, c->d_gz);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Species<CARTESIAN3D>::advance (deposit_only: the accumulate pass of Pic::advance_init)
+int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only)
+{
+    SpeciesStore& S = c->sp[s];
+    const mag2d_grid_desc& d = c->g;
+    if (S.n_slots > 0)
+    {
+        Push3Args A;
+        A.g = grid3_view(c, s);
+        A.s = species3_view(c, s);
+        A.p = particles3_view(S);
+        A.mcc = S.d_blob;
+        A.counts = c->count_collisions ? S.d_counts : nullptr;
+        A.removed = S.d_removed;
+        A.seed = c->seed;
+        A.coll_list = nullptr;
+        A.coll_count = nullptr;
+        const unsigned blocks = (unsigned)((S.n_slots + 2 * P3_THREADS - 1) / (2 * P3_THREADS));
+        const bool mcc = !deposit_only && S.h_blob && S.h_blob->has_collisions && std::isfinite(S.lifetime);
+        const bool deposit = d.selfconsistent != 0;
+        if (deposit_only)
+        {
+            if (deposit) k_push3d<false, false, false, false, true><<<blocks, P3_THREADS, 0, c->stream>>>(A);
+        }
+        else
+        {
+            if (update_edge_fields3d(c)) return 1;
+            if (mcc)
+            {
+                if (ensure_particle_scratch(c, S.capacity)) return 1;
+                A.coll_list = c->d_key;
+                A.coll_count = c->d_coll_count;
+                CUDA_OK(cudaMemsetAsync(c->d_coll_count, 0, sizeof(unsigned), c->stream));
+            }
+            const int code = (A.s.has_B ? 4 : 0) | (mcc ? 2 : 0) | (deposit ? 1 : 0);
+#define L3(B, Mc, D) k_push3d<true, true, B, Mc, D><<<blocks, P3_THREADS, 0, c->stream>>>(A)
+            switch (code)
+            {
+                case 0: L3(false, false, false); break;
+                case 1: L3(false, false, true); break;
+                case 2: L3(false, true, false); break;
+                case 3: L3(false, true, true); break;
+                case 4: L3(true, false, false); break;
+                case 5: L3(true, false, true); break;
+                case 6: L3(true, true, false); break;
+                default: L3(true, true, true); break;
+            }
+#undef L3
+            if (mcc)
+            {
+                k_mcc_collide3d<<<148 * 8, 128, 0, c->stream>>>(A);
+                c->launches++;
+            }
+        }
+        c->launches++;
+        CUDA_OK(cudaGetLastError());
+    }
+    if (!deposit_only)
+    {
+        S.niter++;
+        S.t += S.desc.dt;
+        S.steps_since_sort++;
+    }
+    return 0;
+}
+
+int launch_field_E3d(mag2d_ctx* c, int n, const double* x, const double* y, const double* z, double* Ex, double* Ey, double* Ez)
+{
+    if (n <= 0) return 0;
+    if (update_edge_fields3d(c)) return 1;
+    double* d;
+    CUDA_OK(cudaMalloc(&d, sizeof(double) * 6 * (size_t)n));
+    CUDA_OK(cudaMemcpyAsync(d, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d + n, y, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d + 2 * (size_t)n, z, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    k_field_E3d<<<(n + 255) / 256, 256, 0, c->stream>>>(grid3_view(c, -1), n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, d + 4 * (size_t)n,
+                                                         d + 5 * (size_t)n);
+    c->launches++;
+    CUDA_OK(cudaMemcpyAsync(Ex, d + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(Ey, d + 4 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(Ez, d + 5 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaFree(d));
+    return 0;
+}

@@ -17,7 +17,8 @@ constexpr int SCAN_ITEMS = 4;   // per thread
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 __global__ void k_sort_count(const double* __restrict__ x, const double* __restrict__ z, long long n, double idx, double idz,
-                             int M, int N, unsigned* __restrict__ count, unsigned* __restrict__ key, unsigned* __restrict__ rank)
+                             int M, int N, unsigned* __restrict__ count, unsigned* __restrict__ key, unsigned* __restrict__ rank,
+                             const double* __restrict__ y, double idy, int K)
 {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const double px = k < n ? x[k] : dead_marker();
@@ -29,6 +30,13 @@ __global__ void k_sort_count(const double* __restrict__ x, const double* __restr
         i = max(min(i, M - 2), 0);
         j = max(min(j, N - 2), 0);
         ky = (unsigned)i * (unsigned)(N - 1) + (unsigned)j;
+        if (y)
+        {
+            // CARTESIAN3D: cell (i, jy, k) in the Array3D order, x slowest
+            int jy = (int)(y[k] * idy);
+            jy = max(min(jy, K - 2), 0);
+            ky = ((unsigned)i * (unsigned)(K - 1) + (unsigned)jy) * (unsigned)(N - 1) + (unsigned)j;
+        }
     }
     // warp-aggregated ticket: the store is already almost sorted, so the lanes of a warp share a few cells;
     // one atomic per (warp, cell) instead of one per particle, ranks handed out in lane order
@@ -196,7 +204,8 @@ int launch_sort(mag2d_ctx* c, int s, bool trim)
     S.tickets_valid = false;
     if (n == 0) return 0;
     const int M = c->g.M, N = c->g.N;
-    const int ncells = (M - 1) * (N - 1);
+    const bool three_d = is3d(c);
+    const int ncells = (M - 1) * (N - 1) * (three_d ? c->g.K - 1 : 1);
     if (!c->d_cell_count)
     {
         const int ntiles = (ncells + SCAN_TILE - 1) / SCAN_TILE;
@@ -211,7 +220,8 @@ int launch_sort(mag2d_ctx* c, int s, bool trim)
     double* const* oth = S.arr[S.cur ^ 1];
     CUDA_OK(cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned) * (size_t)ncells, c->stream));
     const unsigned pblocks = (unsigned)((n + 255) / 256);
-    k_sort_count<<<pblocks, 256, 0, c->stream>>>(cur[ARR_X], cur[ARR_Z], n, c->g.idx, c->g.idz, M, N, c->d_cell_count, c->d_key, c->d_rank);
+    k_sort_count<<<pblocks, 256, 0, c->stream>>>(cur[ARR_X], cur[ARR_Z], n, c->g.idx, c->g.idz, M, N, c->d_cell_count, c->d_key, c->d_rank,
+                                                 three_d ? cur[ARR_Y] : nullptr, c->g.idy, c->g.K);
     k_scan_tiles<<<ntiles, SCAN_THREADS, 0, c->stream>>>(c->d_cell_count, c->d_cell_offset, c->d_block_sums, ncells);
     k_scan_sums<<<1, 1024, 0, c->stream>>>(c->d_block_sums, ntiles, d_total);
     k_scan_add<<<ntiles, SCAN_THREADS, 0, c->stream>>>(c->d_cell_offset, c->d_block_sums, ncells);

@@ -53,8 +53,27 @@ def _multipole(mask, volt, dx, dz, npoles, r_ring, r_rod):
         _circle(mask, volt, dx, dz, x, y, r_rod, -1 if i % 2 == 0 else 1, FIXED_RF)
 
 
+def build_geometry3d(p, electrode=True):
+    """Geometry::Geometry of the reference's 3-D code (src/fields3d.cpp:13-37): zero-Dirichlet box frame — the test
+    `k == z_sampl` of :28 never fires, so the k = z_sampl-1 face stays FREE — plus the one-node Quadrupole electrode
+    (id -1, 1 V; fields3d.hpp:26-36) at the centre node.  -> (mask uint8 [M,K,N] with the electrode id stored as 255,
+    voltage float64 [M,K,N]); any mask value other than FREE is a Dirichlet node."""
+    M, K, N = int(p["x_sampl"]), int(p["y_sampl"]), int(p["z_sampl"])
+    mask = np.full((M, K, N), FREE, dtype=np.uint8)
+    mask[0, :, :] = mask[M - 1, :, :] = FIXED
+    mask[:, 0, :] = mask[:, K - 1, :] = FIXED
+    mask[:, :, 0] = FIXED
+    volt = np.zeros((M, K, N))
+    if electrode:
+        mask[M // 2, K // 2, N // 2] = 255
+        volt[M // 2, K // 2, N // 2] = 1.0
+    return mask, volt
+
+
 def build_geometry(p):
     """p: Param dict from config.read_config -> (mask uint8 [M,N], voltage float64 [M,N])"""
+    if int(p["coord"]) == 2:
+        return build_geometry3d(p)
     M, N = int(p["x_sampl"]), int(p["z_sampl"])
     dx, dz = p["dx"], p["dz"]
     geo = int(p["geometry"])

@@ -1,0 +1,174 @@
+"""GPU parity of the 3-D path (coord = CARTESIAN3D) against oracle/mag3d_oracle.c, which is
+itself pinned to the reference's Field3D / Geometry / Solver (tests/test_oracle3d_vs_reference.py).
+
+Tolerances: trajectories (collisions off) 1e-12 relative after 1 step, 1e-10 after 50; deposit bit-exact against the
+fixed-point restatement; Poisson solve 1e-8 against the direct solve of the reference's matrix."""
+import numpy as np
+import pytest
+
+from mag2d_b200 import decks
+from oracle import Oracle3, Orc3Grid
+
+pytestmark = pytest.mark.gpu
+QE, ME = 1.602189e-19, 9.11e-31
+
+
+def _sim(*a, **k):
+    from mag2d_b200.api import Sim
+    return Sim(*a, **k)
+
+
+def grid3(p):
+    return Orc3Grid.make((int(p["x_sampl"]), int(p["y_sampl"]), int(p["z_sampl"])), p["idx"], p["idy"], p["idz"], p["x_max"],
+                         p["y_max"], p["z_max"], int(p["boundary"]), p["macroparticle_factor"])
+
+
+def box_particles(rng, n, g, vth, margin=0.0):
+    a = np.zeros((n, 7))
+    a[:, 0] = rng.uniform(margin, g.x_max - margin, n)
+    a[:, 1] = rng.uniform(margin, g.y_max - margin, n)
+    a[:, 2] = rng.uniform(margin, g.z_max - margin, n)
+    a[:, 3:6] = rng.normal(size=(n, 3)) * vth
+    return a
+
+
+def soa_of(aos):
+    return {k: np.ascontiguousarray(aos[:, c]) for c, k in enumerate(("x", "y", "z", "vx", "vy", "vz"))}
+
+
+def small_deck(deckdir, **kw):
+    args = dict(n_particles=1000, collisions=False, x_sampl=17, y_sampl=15, z_sampl=13)
+    args.update(kw)
+    return decks.deck("c5", deckdir, **args)
+
+
+def test_geometry_and_vacuum_solve(deckdir):
+    orc = Oracle3()
+    d = small_deck(deckdir)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        g = grid3(sim.param)
+        assert sim.param["dy"] == pytest.approx(1e-4, rel=1e-12)
+        mask, volt = orc.geometry(g)
+        assert np.array_equal(sim.mask.astype(np.int8), mask) and np.array_equal(sim.voltage, volt)
+        u_ref = orc.solve_direct(g, mask, orc.rhs(g, mask, volt, np.zeros(g.shape)))
+        u = sim.get_field("u")
+        assert np.abs(u - u_ref).max() <= 1e-9 * np.abs(u_ref).max(), sim.solve_info
+        assert u[8, 7, 6] == pytest.approx(1.0, abs=1e-12)
+        assert sim.solve_info["u"]["resid"] < 1e-12
+
+
+def test_solve_with_charge_and_gather(deckdir):
+    orc = Oracle3()
+    d = small_deck(deckdir, x_sampl=20, y_sampl=17, z_sampl=23)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        g = grid3(sim.param)
+        mask, volt = orc.geometry(g)
+        rng = np.random.default_rng(7)
+        e = sim.species_index("ELECTRON")
+        aos = box_particles(rng, 20000, g, 1e5, margin=2e-4)
+        sim.set_particles(e, aos)
+        sim.species_accumulate(e)
+        fixed, bad = orc.deposit_fixed(g, aos[:, 0], aos[:, 1], aos[:, 2])
+        assert bad == 0 and np.array_equal(sim.rho_fixed(e), fixed)
+        rho = sim.get_field("rho")
+        assert np.abs(rho - fixed * 2.0 ** -32 * -QE).max() <= 1e-12 * np.abs(rho).max()
+        info = sim.solve()
+        u_ref = orc.solve_direct(g, mask, orc.rhs(g, mask, volt, rho))
+        u = sim.get_field("u")
+        assert np.abs(u - u_ref).max() <= 1e-9 * np.abs(u_ref).max(), info
+        n = 3000
+        x = rng.uniform(0, g.x_max, n)
+        y = rng.uniform(0, g.y_max, n)
+        z = rng.uniform(0, g.z_max, n)
+        got = sim.field_E3(x, y, z)
+        want = -orc.grad(g, u, x, y, z)
+        assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("B", [(0.0, 0.0, 0.0), (0.01, -0.02, 0.03)])
+def test_trajectories_vs_oracle(deckdir, B):
+    orc = Oracle3()
+    d = small_deck(deckdir, selfconsistent=0, Br=B[0], Bt=B[1], Bz=B[2])
+    with _sim(d["config"], d["species_conf"]) as sim:
+        g = grid3(sim.param)
+        mask, _ = orc.geometry(g)
+        # a stronger field than the 1 V point electrode gives: scale the vacuum solution
+        u = sim.get_field("u") * 50.0
+        sim.set_field("u", u)
+        rng = np.random.default_rng(9)
+        e = sim.species_index("ELECTRON")
+        aos = box_particles(rng, 5000, g, 3e5)
+        sim.set_particles(e, aos)
+        soa = soa_of(aos)
+        alive = np.ones(len(aos), dtype=np.uint8)
+        dt = sim.species[e]["dt"]
+        for steps, tol in ((1, 1e-12), (49, 1e-10)):
+            for _ in range(steps):
+                sim.species_advance(e)
+                orc.advance(g, u, mask, -QE, ME, dt, B, soa, alive)
+            out = sim.get_particles(e)
+            assert np.array_equal(out[:, 7] > 0, alive > 0)
+            live = alive > 0
+            for c, k in enumerate(("x", "y", "z", "vx", "vy", "vz")):
+                scale = np.abs(soa[k][live]).max()
+                assert np.abs(out[live, c] - soa[k][live]).max() <= tol * scale, (steps, k)
+        assert 0 < (alive == 0).sum() < len(alive)
+
+
+def test_selfconsistent_loop_deposit_bit_exact(deckdir):
+    orc = Oracle3()
+    d = small_deck(deckdir, x_sampl=14, y_sampl=12, z_sampl=13, macroparticle_factor=2e6)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        g = grid3(sim.param)
+        mask, volt = orc.geometry(g)
+        rng = np.random.default_rng(11)
+        e = sim.species_index("ELECTRON")
+        aos = box_particles(rng, 8000, g, 2e5)
+        sim.set_particles(e, aos)
+        soa = soa_of(aos)
+        alive = np.ones(len(aos), dtype=np.uint8)
+        dt = sim.species[e]["dt"]
+        sim.advance_init()
+        fixed, _ = orc.deposit_fixed(g, soa["x"], soa["y"], soa["z"])
+        for step in range(4):
+            sim.advance(1)
+            # Pic::advance order: solve with the charge of the previous step, then push + deposit
+            u_ref = orc.solve_direct(g, mask, orc.rhs(g, mask, volt, fixed * 2.0 ** -32 * -QE))
+            fixed = np.zeros(g.shape, dtype=np.int64)
+            orc.advance(g, u_ref, mask, -QE, ME, dt, (0, 0, 0), soa, alive, None, fixed)
+            assert np.abs(sim.get_field("u") - u_ref).max() <= 1e-9 * np.abs(u_ref).max()
+            out = sim.get_particles(e)
+            assert np.array_equal(out[:, 7] > 0, alive > 0)
+            live = alive > 0
+            for c, k in enumerate(("x", "y", "z", "vx", "vy", "vz")):
+                assert np.abs(out[live, c] - soa[k][live]).max() <= 1e-9 * np.abs(soa[k][live]).max(), (step, k)
+            # the deposit is an integer sum: bit-exact against the restatement fed the GPU's own positions
+            gfix, _ = orc.deposit_fixed(g, out[live, 0], out[live, 1], out[live, 2])
+            assert np.array_equal(sim.rho_fixed(e), gfix)
+
+
+def test_sort_and_loader_3d(deckdir):
+    d = small_deck(deckdir, x_sampl=17, y_sampl=17, z_sampl=17, collisions=True)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        g = grid3(sim.param)
+        e = sim.species_index("ELECTRON")
+        sim.generate(e, "everywhere", 50000)
+        p = sim.get_particles(e)
+        assert p.shape[0] == 50000 and (p[:, 7] > 0).all()
+        for c, hi in ((0, g.x_max), (1, g.y_max), (2, g.z_max)):
+            assert 0 <= p[:, c].min() and p[:, c].max() <= hi
+            assert abs(p[:, c].mean() / hi - 0.5) < 0.01
+        before = p[np.lexsort(p[:, :6].T[::-1])]
+        sim.sort(e)
+        q = sim.get_particles(e)
+        assert np.array_equal(q[np.lexsort(q[:, :6].T[::-1])][:, :6], before[:, :6])
+        key = (np.floor(q[:, 0] * g.idx).astype(np.int64) * (g.jmax - 1) + np.floor(q[:, 1] * g.idy).astype(np.int64)) * (g.kmax - 1) \
+            + np.floor(q[:, 2] * g.idz).astype(np.int64)
+        assert (np.diff(key) >= 0).all()
+        # a few self-consistent steps with collisions on: particles are conserved or absorbed, never created
+        sim.set_sort_interval(2)
+        sim.advance_init()
+        sim.advance(5)
+        alive, slots = sim.count(e)
+        assert 0 < alive <= 50000
+        assert np.isfinite(sim.get_field("u")).all()
