@@ -563,10 +563,17 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    # the contract is ONE JSON line on stdout: anything native code prints there (NCCL's version banner, the
+    # reference's progress echoes) is sent to stderr; only the final print goes to the real stdout
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w")
     if args.impl == "reference":
         bench_reference(args)
     else:
         bench_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
