@@ -164,6 +164,14 @@ int mag2d_count(mag2d_ctx* ctx, int species, int64_t* n_alive, int64_t* n_slots)
 int mag2d_particles_generate(mag2d_ctx* ctx, int species, int kind, int64_t n, double a, double b, double c, double d);
 /* cell sort + compaction of removed particles (replaces the free list, src/particles.hpp:223-247) */
 int mag2d_sort(mag2d_ctx* ctx, int species);
+/* Pic<D>::advance (src/pic.cpp:330-358) for a caller that keeps its particles in HOST memory, as the reference does
+ * (BaseSpecies::particles, src/particles.hpp:113): species[q] has n_slots[q] slots in the host SoA arrays x[q], z[q],
+ * vx[q], vy[q], vz[q] (pinned memory recommended).  The arrays stream through device staging buffers in chunks of
+ * chunk_slots (0 = 4 Mi slots): upload, fused push / MCC / deposit and download of successive chunks overlap, the
+ * field solve and the charge all-reduce run as in mag2d_step.  Blocks until the host arrays hold the new state;
+ * removed particles come back with x = NaN.  2-D Boris movers. */
+int mag2d_step_streamed(mag2d_ctx* ctx, int n_species, const int32_t* species, const int64_t* n_slots, double* const* x,
+                        double* const* z, double* const* vx, double* const* vy, double* const* vz, int64_t chunk_slots);
 int mag2d_set_sort_interval(mag2d_ctx* ctx, int steps); /* 0 = never sort inside mag2d_step; -1 = per species from its thermal drift (v_th dt K ~ 0.35 cell, 2..64) */
 /* per-species override (-1 = use the context-wide interval): slow species (ions) need far fewer sorts than fast
  * ones.  With the Boris movers the sort is carried by the push kernels themselves (a COUNT step hands out cell

@@ -311,6 +311,12 @@ int mag2d_destroy(mag2d_ctx* c)
     direct3d_free(c);
     for (auto& S : c->sp) free_store(S);
     cudaFree(c->d_gy);
+    for (int b = 0; b < 3; b++)
+    {
+        for (int a = 0; a < 5; a++) cudaFree(c->d_chunk[b][a]);
+        if (c->ev_h2d[b]) { cudaEventDestroy(c->ev_h2d[b]); cudaEventDestroy(c->ev_comp[b]); cudaEventDestroy(c->ev_d2h[b]); }
+    }
+    if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h); }
     cudaFree(c->d_mask);
     cudaFree(c->d_voltage);
     cudaFree(c->d_u);
@@ -1001,6 +1007,91 @@ int mag2d_step(mag2d_ctx* c, int nsteps)
             CUDA_OK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->timers[4] += ms;
         }
     }
+    return 0;
+}
+
+// Pic<D>::advance for a caller that keeps the particle arrays in HOST memory (the reference's own layout): every
+// species' SoA arrays stream through a three-deep ring of device staging buffers, chunk by chunk — H2D copy of chunk
+// i+1, the fused push/deposit kernel on chunk i and the D2H copy of chunk i-1 run concurrently on three streams, so
+// the step costs max(upload, compute, download) instead of their sum, and the particle set is not limited by HBM.
+// Blocks until the host arrays hold the pushed particles.  Removed particles come back with x = NaN.
+int mag2d_step_streamed(mag2d_ctx* c, int n_sp, const int32_t* species, const int64_t* n_slots, double* const* x, double* const* z,
+                        double* const* vx, double* const* vy, double* const* vz, int64_t chunk_slots)
+{
+    CHECK_CTX(c);
+    if (is3d(c) || c->g.mover != MAG2D_ADVANCE_BORIS) { mag2d_set_error("mag2d_step_streamed: 2-D Boris movers only"); return 1; }
+    if (chunk_slots <= 0) chunk_slots = 1 << 22;
+    chunk_slots = (chunk_slots + 1023) / 1024 * 1024;
+    if (!c->s_h2d)
+    {
+        CUDA_OK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+        for (int b = 0; b < 3; b++)
+        {
+            CUDA_OK(cudaEventCreateWithFlags(&c->ev_h2d[b], cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&c->ev_comp[b], cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&c->ev_d2h[b], cudaEventDisableTiming));
+        }
+    }
+    if (c->chunk_capacity < chunk_slots)
+    {
+        CUDA_OK(cudaStreamSynchronize(c->s_d2h));
+        for (int b = 0; b < 3; b++)
+            for (int a = 0; a < 5; a++)
+            {
+                cudaFree(c->d_chunk[b][a]);
+                CUDA_OK(cudaMalloc(&c->d_chunk[b][a], sizeof(double) * (size_t)chunk_slots));
+            }
+        c->chunk_capacity = chunk_slots;
+    }
+    if (c->g.selfconsistent)
+    {
+        const bool direct = c->direct.ok && c->solver_kind != MAG2D_SOLVER_MULTIGRID;
+        if (mg_solve(c, 0, c->solve_tol, c->max_cycles, direct && !c->cycles_per_step ? 1 : c->cycles_per_step, nullptr, nullptr)) return 1;
+        if (c->g.u_smooth && launch_u_smooth(c, 0, -1.0)) return 1;
+        if (mag2d_rho_reset(c, -1)) return 1;
+    }
+    long long ring = 0;
+    int rc = 0;
+    for (int q = 0; q < n_sp && !rc; q++)
+    {
+        const int s = species[q];
+        CHECK_SPECIES(c, s);
+        SpeciesStore& S = c->sp[s];
+        if (refresh_pools(c, s)) return 1;
+        double* const host[5] = {x[q], z[q], vx[q], vy[q], vz[q]};
+        for (long long off = 0; off < n_slots[q] && !rc; off += chunk_slots, ring++)
+        {
+            const int b = (int)(ring % 3);
+            const long long cnt = std::min<long long>(chunk_slots, n_slots[q] - off);
+            CUDA_OK(cudaStreamWaitEvent(c->s_h2d, c->ev_d2h[b], 0));       // the buffer's previous tenant has left
+            for (int a = 0; a < 5; a++)
+                CUDA_OK(cudaMemcpyAsync(c->d_chunk[b][a], host[a] + off, sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, c->s_h2d));
+            CUDA_OK(cudaEventRecord(c->ev_h2d[b], c->s_h2d));
+            CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
+            ParticlesDev view;
+            memset(&view, 0, sizeof(view));
+            view.x = c->d_chunk[b][0]; view.z = c->d_chunk[b][1]; view.vx = c->d_chunk[b][2]; view.vy = c->d_chunk[b][3]; view.vz = c->d_chunk[b][4];
+            view.n = cnt;
+            c->chunk_view = &view;
+            c->chunk_slot0 = off;
+            rc = launch_species_advance(c, s, 0);
+            c->chunk_view = nullptr;
+            if (rc) break;
+            CUDA_OK(cudaEventRecord(c->ev_comp[b], c->stream));
+            CUDA_OK(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[b], 0));
+            for (int a = 0; a < 5; a++)
+                CUDA_OK(cudaMemcpyAsync(host[a] + off, c->d_chunk[b][a], sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, c->s_d2h));
+            CUDA_OK(cudaEventRecord(c->ev_d2h[b], c->s_d2h));
+        }
+        // Species<D>::advance: niter++, t += dt — once per step, not per chunk
+        S.niter++;
+        S.t += S.desc.dt;
+    }
+    if (rc) return rc;
+    if (c->g.selfconsistent && comm_allreduce_rho(c)) return 1;
+    CUDA_OK(cudaStreamSynchronize(c->s_d2h));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

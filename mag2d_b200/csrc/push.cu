@@ -35,6 +35,7 @@ struct PushArgs
     unsigned long long seed;
     unsigned* coll_list;           // slots whose Bernoulli test fired this step (processed by k_mcc_collide)
     unsigned* coll_count;
+    long long slot0;               // global slot of p.x[0]: the arrays may be one chunk of a host-resident store (streamed step)
     // cell sort fused into the step (SORTING kernels; sort.cu describes the pipeline)
     int permute;                   // write every array to its sorted slot of the other slab (keys of an earlier COUNT step)
     int count;                     // hand every surviving particle a ticket of its new cell for the next permuting step
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, MAG2D_PUSH_MIN_BLOCKS) k_push_bo
     uint4 rnd = make_uint4(0, 0, 0, 0);
     if (MCC)
     {
-        Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)base);
+        Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)(A.slot0 + base));
         rnd = rng.block();
     }
     const double dt = A.s.dt;
@@ -564,7 +565,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, MAG2D_TMA_CTAS_PER_SM) k_push_bo
         uint4 rnd = make_uint4(0, 0, 0, 0);
         if (MCC)
         {
-            Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)base);
+            Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)(A.slot0 + base));
             rnd = rng.block();
         }
         unsigned hit_mask = 0;
@@ -702,7 +703,7 @@ __global__ void __launch_bounds__(128) k_mcc_collide(const __grid_constant__ Pus
     {
         const long long k = A.coll_list[q];
         double vx = A.p.vx[k], vy = A.p.vy[k], vz = A.p.vz[k];
-        Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)k);
+        Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)(A.slot0 + k));
         rng.draw = 1;     // block 0 was consumed by the Bernoulli test
         int target;
         const int proc = mcc_scatter(A.mcc, rng, vx, vy, vz, target);
@@ -1184,7 +1185,10 @@ int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
 {
     SpeciesStore& S = c->sp[s];
     const mag2d_grid_desc& d = c->g;
-    if (S.n_slots > 0)
+    // streamed step (abi.cu): the particle arrays are one chunk of a host-resident store staged in device buffers
+    const bool chunked = c->chunk_view != nullptr;
+    const long long n_active = chunked ? c->chunk_view->n : S.n_slots;
+    if (n_active > 0)
     {
         if (!d.magnetic_field_const)
         {
@@ -1194,7 +1198,8 @@ int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
         PushArgs A;
         A.g = grid_view(c, s);
         A.s = species_view(c, s, false);
-        A.p = particles_view(S);
+        A.p = chunked ? *c->chunk_view : particles_view(S);
+        A.slot0 = chunked ? c->chunk_slot0 : 0;
         A.mcc = S.d_blob;
         A.counts = c->count_collisions ? S.d_counts : nullptr;
         A.removed = S.d_removed;
@@ -1205,9 +1210,14 @@ int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
         A.key_in = A.rank_in = A.offset_in = nullptr;
         A.key_out = A.rank_out = A.count_out = nullptr;
         memset(&A.dst, 0, sizeof(A.dst));
-        const unsigned blocks = (unsigned)((S.n_slots + PUSH_THREADS - 1) / PUSH_THREADS);
-        const unsigned tile_blocks = (unsigned)((S.n_slots + PUSH_THREADS * PPT - 1) / (PUSH_THREADS * PPT));
+        const unsigned blocks = (unsigned)((n_active + PUSH_THREADS - 1) / PUSH_THREADS);
+        const unsigned tile_blocks = (unsigned)((n_active + PUSH_THREADS * PPT - 1) / (PUSH_THREADS * PPT));
         const bool mcc = S.h_blob && S.h_blob->has_collisions && std::isfinite(S.lifetime);
+        if (chunked && d.mover == MAG2D_ADVANCE_MULTICOLL)
+        {
+            mag2d_set_error("mag2d_step_streamed: Boris movers only");
+            return 1;
+        }
         if (d.mover == MAG2D_ADVANCE_MULTICOLL)
         {
             if (d.coord != MAG2D_CARTESIAN)
@@ -1242,7 +1252,7 @@ int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
                 if (update_ueff(c, d.rf ? rf_phase(c, S) : 0.0, d.rf != 0)) return 1;
             if (mcc)
             {
-                if (ensure_particle_scratch(c, S.capacity)) return 1;
+                if (ensure_particle_scratch(c, chunked ? std::max(n_active, S.capacity) : S.capacity)) return 1;
                 A.coll_list = c->d_key;          // the stand-alone sort's key buffer is idle during a push
                 A.coll_count = c->d_coll_count;
                 CUDA_OK(cudaMemsetAsync(c->d_coll_count, 0, sizeof(unsigned), c->stream));
@@ -1290,6 +1300,7 @@ int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
         }
         CUDA_OK(cudaGetLastError());
     }
+    if (chunked) return 0;        // mag2d_step_streamed advances the species clock once per step
     // Species<D>::advance: niter++, t += dt; advance_multicoll advances the clock a second time
     // (particles.cpp:857-858) — kept so that <name>.dat columns match the reference
     S.niter++;

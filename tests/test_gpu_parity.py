@@ -407,6 +407,48 @@ def test_fused_cell_sort_keeps_the_particle_set_and_the_charge(orc, deckdir, int
         assert (np.diff(key) < 0).mean() < 0.35      # an unsorted store has ~0.5
 
 
+def test_streamed_step_with_host_resident_particles_equals_the_resident_step(orc, deckdir):
+    """mag2d_step_streamed pushes host SoA arrays through device staging buffers chunk by chunk; with collisions off
+    it must leave exactly the particles, charge grids and potential of mag2d_step on a device-resident store"""
+    d = decks.deck("c4", deckdir, n_particles=30000, collisions=False, x_sampl=33, z_sampl=49, r_max=3.2e-3, z_max=4.8e-3)
+    rng = np.random.default_rng(31)
+    init = {}
+    for name, vth in (("ARGON_POS", 4e5), ("ELECTRON", 8e5)):
+        a = np.zeros((7000, 7))
+        a[:, 0] = rng.uniform(1e-7, 3.2e-3 - 1e-7, 7000)
+        a[:, 2] = rng.uniform(1e-7, 4.8e-3 - 1e-7, 7000)
+        a[:, 3:6] = rng.normal(size=(7000, 3)) * vth
+        init[name] = a
+    with _sim(d["config"], d["species_conf"]) as ref, _sim(d["config"], d["species_conf"]) as sim:
+        idx = [sim.species_index(n) for n in ("ARGON_POS", "ELECTRON")]
+        for s_, name in zip(idx, ("ARGON_POS", "ELECTRON")):
+            ref.set_particles(s_, init[name])
+            sim.set_particles(s_, init[name])
+        ref.set_sort_interval(0)
+        ref.advance_init()
+        sim.advance_init()
+        host = {}
+        for s_ in idx:
+            p = sim.get_particles(s_)
+            cols = [np.ascontiguousarray(p[:, c]) for c in (0, 2, 3, 4, 5)]
+            cols[0][p[:, 7] == 0] = np.nan
+            host[s_] = cols
+            sim._chk(sim.L.mag2d_particles_clear(sim.h, s_))
+        for _ in range(4):
+            ref.advance(1)
+            # 2048-slot chunks: 4 chunks per species, so the staging ring wraps
+            sim.step_streamed(idx, [7000, 7000], [[c.ctypes.data for c in host[s_]] for s_ in idx], chunk_slots=2048)
+        for s_ in idx:
+            want = ref.get_particles(s_)
+            alive = want[:, 7] > 0
+            assert np.array_equal(~np.isnan(host[s_][0]), alive)
+            assert 0 < alive.sum() < 7000
+            for c, col in zip((0, 2, 3, 4, 5), host[s_]):
+                assert np.array_equal(col[alive], want[alive, c])
+            assert np.array_equal(sim.rho_fixed(s_), ref.rho_fixed(s_))
+        assert np.array_equal(sim.get_field("u"), ref.get_field("u"))
+
+
 @pytest.mark.skipif(not needs_ref, reason="oracle/_ref not present on this machine")
 def test_live_reference_rf_trap_100_steps(deckdir):
     from oracle import RefHarness
