@@ -35,7 +35,6 @@ struct PushArgs
     unsigned long long seed;
     unsigned* coll_list;           // slots whose Bernoulli test fired this step (processed by k_mcc_collide)
     unsigned* coll_count;
-    long long slot0;               // global slot of p.x[0]: the arrays may be one chunk of a host-resident store (streamed step)
     // cell sort fused into the step (SORTING kernels; sort.cu describes the pipeline)
     int permute;                   // write every array to its sorted slot of the other slab (keys of an earlier COUNT step)
     int count;                     // hand every surviving particle a ticket of its new cell for the next permuting step
@@ -281,8 +280,11 @@ constexpr int TILE = 32 * PPT;               // slots per warp
 #endif
 constexpr int DEPOSIT_RUNS = MAG2D_DEPOSIT_RUNS;   // cells per warp call that get the REDUX treatment
 
+#ifndef MAG2D_SORT_MIN_BLOCKS
+#define MAG2D_SORT_MIN_BLOCKS MAG2D_PUSH_MIN_BLOCKS
+#endif
 template <int COORD, bool GATHER, bool HASB, bool MCC, bool DEPOSIT, bool SORTING>
-__global__ void __launch_bounds__(PUSH_THREADS, MAG2D_PUSH_MIN_BLOCKS) k_push_boris(const __grid_constant__ PushArgs A)
+__global__ void __launch_bounds__(PUSH_THREADS, SORTING ? MAG2D_SORT_MIN_BLOCKS : MAG2D_PUSH_MIN_BLOCKS) k_push_boris(const __grid_constant__ PushArgs A)
 {
     const unsigned lane = lane_id();
     const long long warp_id = ((long long)blockIdx.x * PUSH_THREADS + threadIdx.x) >> 5;
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, MAG2D_PUSH_MIN_BLOCKS) k_push_bo
     uint4 rnd = make_uint4(0, 0, 0, 0);
     if (MCC)
     {
-        Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)(A.slot0 + base));
+        Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)base);
         rnd = rng.block();
     }
     const double dt = A.s.dt;
@@ -565,7 +567,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, MAG2D_TMA_CTAS_PER_SM) k_push_bo
         uint4 rnd = make_uint4(0, 0, 0, 0);
         if (MCC)
         {
-            Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)(A.slot0 + base));
+            Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)base);
             rnd = rng.block();
         }
         unsigned hit_mask = 0;
@@ -703,7 +705,7 @@ __global__ void __launch_bounds__(128) k_mcc_collide(const __grid_constant__ Pus
     {
         const long long k = A.coll_list[q];
         double vx = A.p.vx[k], vy = A.p.vy[k], vz = A.p.vz[k];
-        Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)(A.slot0 + k));
+        Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)k);
         rng.draw = 1;     // block 0 was consumed by the Bernoulli test
         int target;
         const int proc = mcc_scatter(A.mcc, rng, vx, vy, vz, target);
@@ -1199,11 +1201,19 @@ int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
         A.g = grid_view(c, s);
         A.s = species_view(c, s, false);
         A.p = chunked ? *c->chunk_view : particles_view(S);
-        A.slot0 = chunked ? c->chunk_slot0 : 0;
         A.mcc = S.d_blob;
         A.counts = c->count_collisions ? S.d_counts : nullptr;
         A.removed = S.d_removed;
         A.seed = c->seed;
+        if (chunked)
+        {
+            // every chunk of a streamed step draws from its own Philox key (splitmix64 of its first global slot);
+            // folding the offset into the key costs the kernels nothing, an extra 64-bit add per thread cost 6 %
+            unsigned long long zz = (unsigned long long)c->chunk_slot0 + 0x9E3779B97F4A7C15ULL;
+            zz = (zz ^ (zz >> 30)) * 0xBF58476D1CE4E5B9ULL;
+            zz = (zz ^ (zz >> 27)) * 0x94D049BB133111EBULL;
+            A.seed ^= c->chunk_slot0 ? (zz ^ (zz >> 31)) : 0ULL;
+        }
         A.coll_list = nullptr;
         A.coll_count = nullptr;
         A.permute = A.count = A.cell_cols = 0;
