@@ -85,6 +85,29 @@ def test_solve_with_charge_and_gather(deckdir):
         assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max()
 
 
+def test_dense_deposit_uses_the_warp_merge_and_stays_bit_exact(deckdir):
+    """>= 32 particles per cell switches the REDUX merge on (push3d.cu: warp_deposit3); sorted and unsorted stores,
+    one and many particles per warp call must all give the oracle's integer grid"""
+    orc = Oracle3()
+    d = small_deck(deckdir, x_sampl=7, y_sampl=6, z_sampl=8)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        g = grid3(sim.param)
+        rng = np.random.default_rng(5)
+        e = sim.species_index("ELECTRON")
+        n = 30001                                   # ragged: not a multiple of the 512-slot CTA tile
+        aos = box_particles(rng, n, g, 1e5)
+        assert n / ((g.imax - 1) * (g.jmax - 1) * (g.kmax - 1)) > 32
+        sim.set_particles(e, aos)
+        for sort_first in (False, True):
+            if sort_first:
+                sim.sort(e)
+            sim.rho_reset()
+            sim.species_accumulate(e)
+            fixed, bad = orc.deposit_fixed(g, aos[:, 0], aos[:, 1], aos[:, 2])
+            assert bad == 0 and np.array_equal(sim.rho_fixed(e), fixed)
+        assert fixed.sum() == pytest.approx(n * 2.0 ** 32, abs=8 * n)
+
+
 @pytest.mark.parametrize("B", [(0.0, 0.0, 0.0), (0.01, -0.02, 0.03)])
 def test_trajectories_vs_oracle(deckdir, B):
     orc = Oracle3()
