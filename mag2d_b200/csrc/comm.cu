@@ -115,9 +115,20 @@ extern "C" int mag2d_comm_destroy(mag2d_ctx* c)
 int comm_allreduce_rho(mag2d_ctx* c)
 {
     if (!c->nccl_comm || c->nranks <= 1) return 0;
-    const size_t count = (size_t)c->sp.size() * grid_nodes(c);
+    // neutral species never deposit: reduce the contiguous range of charged species only
+    int first = -1, last = -1;
+    for (int s = 0; s < (int)c->sp.size(); s++)
+        if (c->sp[s].desc.charge != 0.0)
+        {
+            if (first < 0) first = s;
+            last = s;
+        }
+    if (first < 0) return 0;
+    const size_t n = grid_nodes(c);
+    const size_t count = (size_t)(last - first + 1) * n;
     const int ncclInt64 = 4, ncclSum = 0;
-    const int rc = g_nccl.AllReduce(c->d_rho, c->d_rho, count, ncclInt64, ncclSum, (NcclComm)c->nccl_comm, c->stream);
+    unsigned long long* buf = c->d_rho + (size_t)first * n;
+    const int rc = g_nccl.AllReduce(buf, buf, count, ncclInt64, ncclSum, (NcclComm)c->nccl_comm, c->stream);
     if (rc) return nccl_fail("ncclAllReduce", rc);
     return 0;
 }
