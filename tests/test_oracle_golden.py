@@ -169,3 +169,26 @@ def test_fixed_point_deposit_properties(orc):
     assert abs(int(a.sum()) - n * 2 ** 32) <= 2 * n
     f, _ = orc.deposit_fp64(g, 1.0, x, z)
     assert np.abs(a * 2.0 ** -32 - f).max() <= n * 2.0 ** -33
+
+
+def test_3d_field_code_golden():
+    """oracle/mag3d_oracle.c against the fixture recorded from the reference's Field3D / Geometry / Solver
+    (tests/golden/make_golden3d.py): deposit, interpolation and gradient bit-exact, geometry identical, solve 1e-11"""
+    from oracle import Oracle3, Orc3Grid
+    G3 = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference3d_v1.npz"))
+    idx, idy, idz, x_max, y_max, z_max, mpf = G3["grid"]
+    g = Orc3Grid.make(tuple(int(v) for v in G3["dims"]), idx, idy, idz, x_max, y_max, z_max, 0, mpf)
+    orc3 = Oracle3()
+    mask, volt = orc3.geometry(g)
+    assert np.array_equal(mask, G3["mask"]) and np.array_equal(volt, G3["voltage"])
+    x, y, z = (np.ascontiguousarray(G3["pos"][:, c]) for c in range(3))
+    assert np.array_equal(orc3.is_free(g, mask, x, y, z), G3["is_free"])
+    rho, bad = orc3.accumulate(g, -1.6e-19, x, y, z)
+    assert bad == 0 and np.array_equal(rho, G3["rho"])
+    assert np.array_equal(orc3.interpolate(g, G3["u_random"], x, y, z), G3["interp"])
+    gx, gy, gz = (np.ascontiguousarray(G3["grad_pos"][:, c]) for c in range(3))
+    assert np.array_equal(orc3.grad(g, G3["u_random"], gx, gy, gz), G3["grad"])
+    b = orc3.rhs(g, mask, volt, rho)
+    assert np.array_equal(b, G3["rhs"])
+    u = orc3.solve_direct(g, mask, b)
+    assert np.abs(u - G3["u_solved"]).max() <= 1e-11 * np.abs(G3["u_solved"]).max()
