@@ -189,7 +189,7 @@ int effective_sort_interval(const mag2d_ctx* c, const SpeciesStore& S)
 // With an interval of K pushes the sequence is PERMUTE, K-2 plain pushes, COUNT, PERMUTE, ... (K = 1: both every push)
 int fused_sort_mode(const mag2d_ctx* c, const SpeciesStore& S)
 {
-    if (!c->fused_sort || c->g.mover == MAG2D_ADVANCE_MULTICOLL || is3d(c) || S.n_slots == 0) return 0;
+    if (!c->fused_sort || c->g.mover == MAG2D_ADVANCE_MULTICOLL || S.n_slots == 0) return 0;
     const int K = effective_sort_interval(c, S);
     if (K <= 0) return 0;
     int mode = S.tickets_valid ? 1 : 0;
@@ -201,7 +201,7 @@ int fused_sort_mode(const mag2d_ctx* c, const SpeciesStore& S)
 int advance_one(mag2d_ctx* c, int s, bool in_step)
 {
     if (refresh_pools(c, s)) return 1;
-    if (is3d(c)) return launch_species_advance3d(c, s, false);
+    if (is3d(c)) return launch_species_advance3d(c, s, false, in_step ? fused_sort_mode(c, c->sp[s]) : 0);
     return launch_species_advance(c, s, in_step ? fused_sort_mode(c, c->sp[s]) : 0);
 }
 
@@ -988,7 +988,7 @@ int mag2d_step(mag2d_ctx* c, int nsteps)
         if (c->g.selfconsistent && comm_allreduce_rho(c)) return 1;
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
         // stand-alone sort: the multi-collision mover, or the fused sort switched off
-        if (!c->fused_sort || c->g.mover == MAG2D_ADVANCE_MULTICOLL || is3d(c))
+        if (!c->fused_sort || c->g.mover == MAG2D_ADVANCE_MULTICOLL)
             for (size_t s = 0; s < c->sp.size(); s++)
             {
                 const int K = effective_sort_interval(c, c->sp[s]);

@@ -214,7 +214,7 @@ void direct_free(mag2d_ctx* c);
 int direct_solve(mag2d_ctx* c, double* u);
 int launch_rho_total(mag2d_ctx* c, double* d_out);
 // push3d.cu / poisson3d.cu (coord == MAG2D_CARTESIAN3D)
-int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only);
+int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only, int sort_mode = 0);
 int launch_field_E3d(mag2d_ctx* c, int n, const double* x, const double* y, const double* z, double* Ex, double* Ey, double* Ez);
 int update_edge_fields3d(mag2d_ctx* c);
 int direct3d_setup(mag2d_ctx* c);

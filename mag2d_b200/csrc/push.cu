@@ -48,23 +48,6 @@ struct PushArgs
     unsigned* count_out;           // [cell]
 };
 
-constexpr unsigned SORT_INVALID_KEY = 0xFFFFFFFFu;
-
-// warp-aggregated ticket: one atomic per (warp, cell), ranks handed out in lane order.  MATCH.ANY finds the lanes
-// that share a cell in one instruction, so all group leaders issue their atomics together: one memory round trip
-// per call, not one per distinct cell (the returning atomic is the long pole of a COUNT step).
-__device__ __forceinline__ unsigned warp_ticket(unsigned* __restrict__ count, bool valid, unsigned key)
-{
-    const unsigned lane = lane_id();
-    // invalid lanes get distinct pseudo-keys so that they never join a group of live particles
-    const unsigned group = __match_any_sync(MAG2D_FULL_MASK, valid ? key : (0xFFFFFFE0u | lane));
-    const int leader = __ffs(group) - 1;
-    unsigned base = 0;
-    if (valid && (int)lane == leader) base = atomicAdd(&count[key], (unsigned)__popc(group));
-    base = __shfl_sync(MAG2D_FULL_MASK, base, leader);
-    return base + __popc(group & ((1u << lane) - 1u));
-}
-
 // ---- gather: E = -grad(ue), the staggered-difference bilinear form of Field2D::grad ----------------
 // The reference differences the potential around every particle; here the differences live in the
 // precomputed edge fields gx/gz (same operations, same rounding) and the particle only interpolates:

@@ -46,6 +46,15 @@ struct Push3Args
     unsigned* coll_list;
     unsigned* coll_count;
     int deposit_runs;   // distinct cells per warp call that get the REDUX merge (0: every lane scatters on its own)
+    // cell sort fused into the step (sort.cu): COUNT hands out tickets, the next PERMUTE step stores sorted
+    int permute, count;
+    const unsigned* key_in;
+    const unsigned* rank_in;
+    const unsigned* offset_in;
+    ParticlesDev dst;
+    unsigned* key_out;
+    unsigned* rank_out;
+    unsigned* count_out;
 };
 
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
@@ -78,7 +87,8 @@ __device__ __forceinline__ double grad_component(const Grid3Dev& g, double X, do
 
 // box boundary, electrode absorption and the eight Q32 weights (Field3D.hpp:56-64 order)
 template <bool DEPOSIT>
-__device__ __forceinline__ bool boundary_weights3(const Grid3Dev& g, double& x, double& y, double& z, unsigned& node, unsigned long long (&w)[8])
+__device__ __forceinline__ bool boundary_weights3(const Grid3Dev& g, double& x, double& y, double& z, unsigned& node, unsigned long long (&w)[8],
+                                                  unsigned* cell = nullptr)
 {
     node = 0;
     if (!(x >= 0.0 && x <= g.x_max && y >= 0.0 && y <= g.y_max && z >= 0.0 && z <= g.z_max))
@@ -92,6 +102,7 @@ __device__ __forceinline__ bool boundary_weights3(const Grid3Dev& g, double& x, 
     const int i = max(min((int)X, g.M - 2), 0), j = max(min((int)Y, g.K - 2), 0), k = max(min((int)Z, g.N - 2), 0);
     const size_t m = ((size_t)i * g.K + j) * g.N + k;
     node = (unsigned)m;
+    if (cell) *cell = ((unsigned)i * (unsigned)(g.K - 1) + (unsigned)j) * (unsigned)(g.N - 1) + (unsigned)k;
     if (g.check_mask && !g.cfree[m]) return false;
     if (DEPOSIT)
     {
@@ -155,9 +166,10 @@ __device__ __forceinline__ void warp_deposit3(const Grid3Dev& g, bool valid, uns
 // ---- the fused 3-D step -------------------------------------------------------------------------------------------
 // Each thread owns two neighbouring slots (128-bit loads and stores, a warp moves 512 B per instruction).  PUSH =
 // false is the deposit-only pass of Pic::advance_init.
-template <bool PUSH, bool GATHER, bool HASB, bool MCC, bool DEPOSIT>
+template <bool PUSH, bool GATHER, bool HASB, bool MCC, bool DEPOSIT, bool SORTING>
 __global__ void __launch_bounds__(P3_THREADS, MAG3D_MIN_BLOCKS) k_push3d(const __grid_constant__ Push3Args A)
 {
+    const bool permute = SORTING && A.permute, count = SORTING && A.count;
     const unsigned lane = lane_id();
     const long long k = 2 * ((long long)blockIdx.x * P3_THREADS + threadIdx.x);
     const long long n = A.p.n;
@@ -182,9 +194,17 @@ __global__ void __launch_bounds__(P3_THREADS, MAG3D_MIN_BLOCKS) k_push3d(const _
         Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)k);
         rnd = rng.block();
     }
+    long long dest[2] = {k, k + 1};
+    if (permute)
+    {
+        const uint2 ky = *reinterpret_cast<const uint2*>(A.key_in + k);
+        const uint2 rk = *reinterpret_cast<const uint2*>(A.rank_in + k);
+        dest[0] = (k < n && ky.x != SORT_INVALID_KEY) ? (long long)__ldg(A.offset_in + ky.x) + rk.x : -1;
+        dest[1] = (k + 1 < n && ky.y != SORT_INVALID_KEY) ? (long long)__ldg(A.offset_in + ky.y) + rk.y : -1;
+    }
     const double dt = A.s.dt;
     bool keep[2];
-    unsigned node[2], removed = 0, hit_mask = 0;
+    unsigned node[2], cell[2] = {0, 0}, removed = 0, hit_mask = 0;
     unsigned long long w[2][8];
 #pragma unroll
     for (int e = 0; e < 2; e++)
@@ -221,7 +241,7 @@ __global__ void __launch_bounds__(P3_THREADS, MAG3D_MIN_BLOCKS) k_push3d(const _
             y[e] += vy[e] * dt;
             z[e] += vz[e] * dt;
         }
-        const bool inside = boundary_weights3<DEPOSIT>(A.g, x[e], y[e], z[e], node[e], w[e]);
+        const bool inside = boundary_weights3<DEPOSIT>(A.g, x[e], y[e], z[e], node[e], w[e], SORTING ? &cell[e] : nullptr);
         keep[e] = live && inside;
         removed += (live && !inside) ? 1u : 0u;
         if (!keep[e]) x[e] = dead_marker();
@@ -231,7 +251,18 @@ __global__ void __launch_bounds__(P3_THREADS, MAG3D_MIN_BLOCKS) k_push3d(const _
             if (keep[e] && u01(word) < A.s.prob) hit_mask |= 1u << e;
         }
     }
-    if (PUSH)
+    if (PUSH && permute)
+    {
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+        {
+            const long long d = dest[e];
+            if (d < 0) continue;
+            A.dst.x[d] = x[e]; A.dst.y[d] = y[e]; A.dst.z[d] = z[e];
+            A.dst.vx[d] = vx[e]; A.dst.vy[d] = vy[e]; A.dst.vz[d] = vz[e];
+        }
+    }
+    else if (PUSH)
     {
         *reinterpret_cast<double2*>(A.p.x + k) = make_double2(x[0], x[1]);
         *reinterpret_cast<double2*>(A.p.y + k) = make_double2(y[0], y[1]);
@@ -239,6 +270,21 @@ __global__ void __launch_bounds__(P3_THREADS, MAG3D_MIN_BLOCKS) k_push3d(const _
         *reinterpret_cast<double2*>(A.p.vx + k) = make_double2(vx[0], vx[1]);
         *reinterpret_cast<double2*>(A.p.vy + k) = make_double2(vy[0], vy[1]);
         *reinterpret_cast<double2*>(A.p.vz + k) = make_double2(vz[0], vz[1]);
+    }
+    if (count)
+    {
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+        {
+            const unsigned key = keep[e] ? cell[e] : SORT_INVALID_KEY;
+            const unsigned rk = warp_ticket(A.count_out, keep[e], key);
+            const long long d = dest[e];
+            if (d >= 0 && (permute || k + e < n))
+            {
+                A.key_out[d] = key;
+                A.rank_out[d] = rk;
+            }
+        }
     }
     if (DEPOSIT)
     {
@@ -267,8 +313,8 @@ __global__ void __launch_bounds__(P3_THREADS, MAG3D_MIN_BLOCKS) k_push3d(const _
             unsigned start = 0;
             if (lane == 31) start = atomicAdd(A.coll_count, total);
             start = __shfl_sync(MAG2D_FULL_MASK, start, 31) + incl - cnt;
-            if (hit_mask & 1u) A.coll_list[start++] = (unsigned)k;
-            if (hit_mask & 2u) A.coll_list[start++] = (unsigned)(k + 1);
+            if (hit_mask & 1u) A.coll_list[start++] = (unsigned)dest[0];
+            if (hit_mask & 2u) A.coll_list[start++] = (unsigned)dest[1];
         }
     }
     if (PUSH && __any_sync(MAG2D_FULL_MASK, removed != 0))
@@ -397,8 +443,8 @@ int update_edge_fields3d(mag2d_ctx* c)
     return 0;
 }
 
-// Species<CARTESIAN3D>::advance (deposit_only: the accumulate pass of Pic::advance_init)
-int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only)
+// Species<CARTESIAN3D>::advance (deposit_only: the accumulate pass of Pic::advance_init); sort_mode as in 2-D
+int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only, int sort_mode)
 {
     SpeciesStore& S = c->sp[s];
     const mag2d_grid_desc& d = c->g;
@@ -414,6 +460,10 @@ int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only)
         A.seed = c->seed;
         A.coll_list = nullptr;
         A.coll_count = nullptr;
+        A.permute = A.count = 0;
+        A.key_in = A.rank_in = A.offset_in = nullptr;
+        A.key_out = A.rank_out = A.count_out = nullptr;
+        memset(&A.dst, 0, sizeof(A.dst));
         const double per_cell = (double)S.n_slots / ((double)(d.M - 1) * (d.K - 1) * (d.N - 1));
         A.deposit_runs = per_cell >= 32.0 ? 3 : 0;
         const unsigned blocks = (unsigned)((S.n_slots + 2 * P3_THREADS - 1) / (2 * P3_THREADS));
@@ -421,7 +471,7 @@ int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only)
         const bool deposit = d.selfconsistent != 0;
         if (deposit_only)
         {
-            if (deposit) k_push3d<false, false, false, false, true><<<blocks, P3_THREADS, 0, c->stream>>>(A);
+            if (deposit) k_push3d<false, false, false, false, true, false><<<blocks, P3_THREADS, 0, c->stream>>>(A);
         }
         else
         {
@@ -433,20 +483,54 @@ int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only)
                 A.coll_count = c->d_coll_count;
                 CUDA_OK(cudaMemsetAsync(c->d_coll_count, 0, sizeof(unsigned), c->stream));
             }
-            const int code = (A.s.has_B ? 4 : 0) | (mcc ? 2 : 0) | (deposit ? 1 : 0);
-#define L3(B, Mc, D) k_push3d<true, true, B, Mc, D><<<blocks, P3_THREADS, 0, c->stream>>>(A)
+            const bool permute = (sort_mode & 1) != 0, count = (sort_mode & 2) != 0;
+            const bool sorting = permute || count;
+            if (sorting)
+            {
+                if (sort_fused_begin(c, s, permute, count)) return 1;
+                A.permute = permute;
+                A.count = count;
+                A.key_in = S.d_key[S.kr];
+                A.rank_in = S.d_rank[S.kr];
+                A.offset_in = S.d_cell_offset;
+                A.key_out = S.d_key[permute ? S.kr ^ 1 : S.kr];
+                A.rank_out = S.d_rank[permute ? S.kr ^ 1 : S.kr];
+                A.count_out = S.d_cell_count;
+                if (permute)
+                {
+                    double* const* o = S.arr[S.cur ^ 1];
+                    A.dst.x = o[ARR_X]; A.dst.y = o[ARR_Y]; A.dst.z = o[ARR_Z];
+                    A.dst.vx = o[ARR_VX]; A.dst.vy = o[ARR_VY]; A.dst.vz = o[ARR_VZ];
+                    A.dst.n = S.n_slots;
+                }
+            }
+            const int code = (sorting ? 8 : 0) | (A.s.has_B ? 4 : 0) | (mcc ? 2 : 0) | (deposit ? 1 : 0);
+#define L3(B, Mc, D, So) k_push3d<true, true, B, Mc, D, So><<<blocks, P3_THREADS, 0, c->stream>>>(A)
             switch (code)
             {
-                case 0: L3(false, false, false); break;
-                case 1: L3(false, false, true); break;
-                case 2: L3(false, true, false); break;
-                case 3: L3(false, true, true); break;
-                case 4: L3(true, false, false); break;
-                case 5: L3(true, false, true); break;
-                case 6: L3(true, true, false); break;
-                default: L3(true, true, true); break;
+                case 0: L3(false, false, false, false); break;
+                case 1: L3(false, false, true, false); break;
+                case 2: L3(false, true, false, false); break;
+                case 3: L3(false, true, true, false); break;
+                case 4: L3(true, false, false, false); break;
+                case 5: L3(true, false, true, false); break;
+                case 6: L3(true, true, false, false); break;
+                case 7: L3(true, true, true, false); break;
+                case 8: L3(false, false, false, true); break;
+                case 9: L3(false, false, true, true); break;
+                case 10: L3(false, true, false, true); break;
+                case 11: L3(false, true, true, true); break;
+                case 12: L3(true, false, false, true); break;
+                case 13: L3(true, false, true, true); break;
+                case 14: L3(true, true, false, true); break;
+                default: L3(true, true, true, true); break;
             }
 #undef L3
+            if (sorting)
+            {
+                if (sort_fused_end(c, s, permute, count)) return 1;
+                if (permute) A.p = particles3_view(S);
+            }
             if (mcc)
             {
                 k_mcc_collide3d<<<148 * 8, 128, 0, c->stream>>>(A);
@@ -461,6 +545,7 @@ int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only)
         S.niter++;
         S.t += S.desc.dt;
         S.steps_since_sort++;
+        if (S.pushes_since_permute < (1 << 20)) S.pushes_since_permute++;
     }
     return 0;
 }

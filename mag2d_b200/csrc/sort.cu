@@ -280,7 +280,7 @@ void sort_fused_free(SpeciesStore& S)
 int sort_fused_begin(mag2d_ctx* c, int s, bool permute, bool count)
 {
     SpeciesStore& S = c->sp[s];
-    const int ncells = (c->g.M - 1) * (c->g.N - 1);
+    const int ncells = (c->g.M - 1) * (c->g.N - 1) * (is3d(c) ? c->g.K - 1 : 1);
     const int ntiles = (ncells + SCAN_TILE - 1) / SCAN_TILE;
     if (!S.d_cell_count)
     {
@@ -317,7 +317,7 @@ int sort_fused_begin(mag2d_ctx* c, int s, bool permute, bool count)
 int sort_fused_end(mag2d_ctx* c, int s, bool permute, bool count)
 {
     SpeciesStore& S = c->sp[s];
-    const int ncells = (c->g.M - 1) * (c->g.N - 1);
+    const int ncells = (c->g.M - 1) * (c->g.N - 1) * (is3d(c) ? c->g.K - 1 : 1);
     const int ntiles = (ncells + SCAN_TILE - 1) / SCAN_TILE;
     unsigned long long* d_total = reinterpret_cast<unsigned long long*>(S.d_sort_sums + ((ntiles + 1) / 2 * 2 + 2));
     if (permute)

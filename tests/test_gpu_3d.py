@@ -170,6 +170,36 @@ def test_selfconsistent_loop_deposit_bit_exact(deckdir):
             assert np.array_equal(sim.rho_fixed(e), gfix)
 
 
+@pytest.mark.parametrize("interval", [1, 3])
+def test_fused_cell_sort_3d_keeps_the_particle_set_and_the_charge(deckdir, interval):
+    """the 3-D push carries the cell sort like the 2-D one: with collisions off the multiset of particles, the
+    integer charge grid and the potential must equal those of a run that never sorts"""
+    d = small_deck(deckdir, x_sampl=12, y_sampl=11, z_sampl=13, macroparticle_factor=2e6)
+    rng = np.random.default_rng(41)
+    results = []
+    aos = None
+    for k in (0, interval):
+        with _sim(d["config"], d["species_conf"]) as sim:
+            g = grid3(sim.param)
+            e = sim.species_index("ELECTRON")
+            if aos is None:
+                aos = box_particles(rng, 9001, g, 4e5)
+            sim.set_particles(e, aos)
+            sim.set_sort_interval(k)
+            sim.advance_init()
+            sim.advance(7)
+            p = sim.get_particles(e)
+            live = p[p[:, 7] > 0][:, :6]
+            results.append((live[np.lexsort(live.T[::-1])], sim.rho_fixed(e), sim.get_field("u"), p[:, 7]))
+    a, b = results
+    assert 0 < len(a[0]) < 9001 and len(a[0]) == len(b[0])
+    assert np.array_equal(a[0], b[0])
+    assert np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2], b[2])
+    n_alive = int(b[3].sum())
+    assert (b[3][:n_alive] == 0).sum() < 0.6 * (9001 - n_alive)      # dead slots were compacted away
+
+
 def test_sort_and_loader_3d(deckdir):
     d = small_deck(deckdir, x_sampl=17, y_sampl=17, z_sampl=17, collisions=True)
     with _sim(d["config"], d["species_conf"]) as sim:
