@@ -13,6 +13,8 @@
 // of the electrode nodes are precomputed with the same solver).  Exact to round-off like the reference's LU.
 // Geometries with extended internal electrodes need a 3-D multigrid (not built yet): set_grid refuses them.
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "ctx.hpp"
@@ -125,6 +127,108 @@ __global__ void __launch_bounds__(G3_THREADS) k_gemm3(const __grid_constant__ Ge
             double* out = C + (size_t)r * G.ldc + c0 + tc;
             *reinterpret_cast<double2*>(out) = make_double2(acc[p][0] * G.scale, acc[p][1] * G.scale);
             *reinterpret_cast<double2*>(out + 2) = make_double2(acc[p][2] * G.scale, acc[p][3] * G.scale);
+        }
+    }
+}
+
+// ---- the same product on the FP64 tensor cores: mma.sync m8n8k4 (DMMA) ---------------------------------------------
+// CTA tile 128 x 32 (four warps stacked along the rows, 32 x 32 per warp = 4 x 4 DMMA tiles), K in chunks of 16 through a
+// 3-stage cp.async ring.  Per k4-step a warp loads 4 A and 4 B fragments (one double per lane each) for 16 DMMAs:
+// 16 FMAs per shared-memory double instead of 2 with the 4 x 4 register tile of k_gemm3, and 8x fewer issue slots.
+// Row strides of 20 / 36 doubles make both fragment loads bank-conflict free (lane/4 -> row * 8 banks, lane%4 -> 2 banks).
+constexpr int M3_TM = 128, M3_TN = 32, M3_KC = 16, M3_THREADS = 128, M3_STAGES = 3;
+constexpr int M3_LDA = M3_KC + 4, M3_LDB = M3_TN + 4;
+constexpr int M3_STAGE_DOUBLES = M3_TM * M3_LDA + M3_KC * M3_LDB;
+constexpr int M3_SMEM = M3_STAGES * M3_STAGE_DOUBLES * (int)sizeof(double);
+
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(M3_THREADS) k_gemm3_mma(const __grid_constant__ Gemm3Args G)
+{
+    extern __shared__ __align__(16) double m3_smem[];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int r0 = blockIdx.y * M3_TM, c0 = blockIdx.x * M3_TN;
+    const double* A = G.A + (long long)blockIdx.z * G.strideA;
+    const double* B = G.B + (long long)blockIdx.z * G.strideB;
+    double* C = G.C + (long long)blockIdx.z * G.strideC;
+    const int nk = G.Kdim / M3_KC;
+    auto issue = [&](int kb) {
+        double* sa = m3_smem + (kb % M3_STAGES) * M3_STAGE_DOUBLES;
+        double* sb = sa + M3_TM * M3_LDA;
+        const int k0 = kb * M3_KC;
+        // A tile: 128 rows x 16 doubles = 1024 16-byte pieces (8 per row), 8 per thread
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+        {
+            const int e = t + q * M3_THREADS, r = e >> 3, c2 = (e & 7) * 2;
+            const int row = min(r0 + r, G.rows - 1);
+            cp16(sa + r * M3_LDA + c2, A + (size_t)row * G.lda + k0 + c2);
+        }
+        // B tile: 16 k x 32 columns = 256 pieces, 2 per thread
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+        {
+            const int e = t + q * M3_THREADS, r = e >> 4, c2 = (e & 15) * 2;
+            cp16(sb + r * M3_LDB + c2, B + (size_t)(k0 + r) * G.ldb + c0 + c2);
+        }
+    };
+    double acc[4][4][2] = {};
+    for (int s = 0; s < M3_STAGES - 1; s++)
+    {
+        if (s < nk) issue(s);
+        cp_commit();
+    }
+    const int fr = lane >> 2, fc = lane & 3;     // fragment row / column of this lane
+    for (int kb = 0; kb < nk; kb++)
+    {
+        cp_wait<M3_STAGES - 2>();
+        __syncthreads();
+        if (kb + M3_STAGES - 1 < nk) issue(kb + M3_STAGES - 1);
+        cp_commit();
+        const double* sa = m3_smem + (kb % M3_STAGES) * M3_STAGE_DOUBLES + (warp * 32 + fr) * M3_LDA + fc;
+        const double* sb = m3_smem + (kb % M3_STAGES) * M3_STAGE_DOUBLES + M3_TM * M3_LDA + fc * M3_LDB + fr;
+#pragma unroll
+        for (int k4 = 0; k4 < M3_KC / 4; k4++)
+        {
+            double a[4], b[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++) a[p] = sa[p * 8 * M3_LDA + k4 * 4];            // A[rb*8 + fr][k4*4 + fc]
+#pragma unroll
+            for (int q = 0; q < 4; q++) b[q] = sb[k4 * 4 * M3_LDB + q * 8];            // B[k4*4 + fc][cb*8 + fr]
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) dmma884(acc[p][q], a[p], b[q]);
+        }
+    }
+    // D fragment: row fr, columns 2*fc, 2*fc+1 of every 8 x 8 block
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+    {
+        const int r = r0 + warp * 32 + p * 8 + fr;
+        if (r >= G.rows) continue;
+        if (SCATTER)
+        {
+            const int il = r / G.ldj, jl = r % G.ldj;
+            if (jl >= G.n_j) continue;
+            double* out = C + ((size_t)(il + 1) * G.K + (jl + 1)) * G.N + 1;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const int k = c0 + q * 8 + 2 * fc;
+                if (k < G.n_k) out[k] = acc[p][q][0] * G.scale;
+                if (k + 1 < G.n_k) out[k + 1] = acc[p][q][1] * G.scale;
+            }
+        }
+        else
+        {
+            double* out = C + (size_t)r * G.ldc + c0 + 2 * fc;
+#pragma unroll
+            for (int q = 0; q < 4; q++) *reinterpret_cast<double2*>(out + q * 8) = make_double2(acc[p][q][0] * G.scale, acc[p][q][1] * G.scale);
         }
     }
 }
@@ -277,9 +381,19 @@ __global__ void k_residual3d(int M, int K, int N, const unsigned char* __restric
 
 int gemm3(mag2d_ctx* c, const Gemm3Args& G, int batch, bool scatter)
 {
-    const dim3 grid(G.cols / G3_TN, (G.rows + G3_TM - 1) / G3_TM, batch);
-    if (scatter) k_gemm3<true><<<grid, G3_THREADS, G3_SMEM, c->stream>>>(G);
-    else k_gemm3<false><<<grid, G3_THREADS, G3_SMEM, c->stream>>>(G);
+    static const bool use_fma = getenv("MAG2D_GEMM") && !strcmp(getenv("MAG2D_GEMM"), "fma");
+    if (use_fma)
+    {
+        const dim3 grid(G.cols / G3_TN, (G.rows + G3_TM - 1) / G3_TM, batch);
+        if (scatter) k_gemm3<true><<<grid, G3_THREADS, G3_SMEM, c->stream>>>(G);
+        else k_gemm3<false><<<grid, G3_THREADS, G3_SMEM, c->stream>>>(G);
+    }
+    else
+    {
+        const dim3 grid(G.cols / M3_TN, (G.rows + M3_TM - 1) / M3_TM, batch);
+        if (scatter) k_gemm3_mma<true><<<grid, M3_THREADS, M3_SMEM, c->stream>>>(G);
+        else k_gemm3_mma<false><<<grid, M3_THREADS, M3_SMEM, c->stream>>>(G);
+    }
     c->launches++;
     return 0;
 }
@@ -422,6 +536,8 @@ int direct3d_setup(mag2d_ctx* c)
     CUDA_OK(cudaMemsetAsync(D.T, 0, sizeof(double) * block, c->stream));
     CUDA_OK(cudaFuncSetAttribute(k_gemm3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
     CUDA_OK(cudaFuncSetAttribute(k_gemm3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
+    CUDA_OK(cudaFuncSetAttribute(k_gemm3_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM));
+    CUDA_OK(cudaFuncSetAttribute(k_gemm3_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM));
     const int plane = D.ldj * D.ldk;
     k_thomas_setup<<<(plane + 127) / 128, 128, 0, c->stream>>>(D.n_i, D.n_j, D.n_k, D.ldj, D.ldk, D.inv);
     c->launches++;
