@@ -127,3 +127,38 @@ def test_test_mcc_driver_runs_c1(host_bins, tmp_path):
     assert "ms / iteration" in log
     e = np.loadtxt(os.path.join(out, "ELECTRON_energy_dist.dat"))
     assert e.shape[1] >= 2 and e[:, 1].sum() > 0
+
+
+@pytest.mark.gpu
+def test_plasma3d_driver_field_and_trajectory(host_bins, tmp_path):
+    """plasma3d_b200 (the reference's 3-D test driver, which does not build there): vacuum field of the point electrode
+    and one electron trajectory, against the 3-D oracle"""
+    from oracle import Oracle3, Orc3Grid
+    d = decks.deck("c5", str(tmp_path), n_particles=10, collisions=False, x_sampl=17, y_sampl=15, z_sampl=13, niter=40, dt_elon=2e-10)
+    out = str(tmp_path / "out3d")
+    r = subprocess.run([os.path.join(host_bins, "plasma3d_b200"), "config=" + d["config"], "output_dir=" + out],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    p = cfg.read_config(d["config"])
+    g = Orc3Grid.make((17, 15, 13), p["idx"], p["idy"], p["idz"], p["x_max"], p["y_max"], p["z_max"], 0, p["macroparticle_factor"])
+    orc = Oracle3()
+    mask, volt = orc.geometry(g)
+    u_ref = orc.solve_direct(g, mask, orc.rhs(g, mask, volt, np.zeros(g.shape)))
+    table = np.loadtxt(os.path.join(out, "field3d.dat"))
+    assert table.shape == (17 * 15 * 13, 4)
+    assert np.abs(table[:, 3].reshape(g.shape) - u_ref).max() <= 1e-5 * np.abs(u_ref).max()      # 6 printed digits
+    vtk = open(os.path.join(out, "field3d.vtk")).read().splitlines()
+    assert vtk[0] == "# vtk DataFile Version 2.0" and vtk[4] == "DIMENSIONS 17 15 13" and len(vtk) == 10 + 17 * 15 * 13
+    volt_table = np.loadtxt(os.path.join(out, "voltage.dat"))
+    assert volt_table[:, 3].sum() == 1.0
+    traj = np.loadtxt(os.path.join(out, "traj1.dat"))
+    vel = np.loadtxt(os.path.join(out, "vel1.dat"))
+    assert traj.shape == (40, 3) and vel.shape == (40, 3)
+    mass, charge = 9.109534e-31, -1.6e-19
+    soa = {k: np.array([v]) for k, v in dict(x=p["x_max"] * 0.5, y=p["y_max"] * 0.5, z=p["z_max"] * 0.7,
+                                             vx=np.sqrt(0.03 * 1.602189e-19 / mass * 2.0), vy=0.0, vz=0.0).items()}
+    alive = np.ones(1, dtype=np.uint8)
+    for step in range(40):
+        assert traj[step] == pytest.approx([soa["x"][0], soa["y"][0], soa["z"][0]], rel=2e-5)
+        assert vel[step] == pytest.approx([soa["vx"][0], soa["vy"][0], soa["vz"][0]], rel=2e-5, abs=1e-3)
+        orc.advance(g, u_ref, mask, charge, mass, 2e-10, (0, 0, 0), soa, alive)
