@@ -50,12 +50,22 @@ struct SpeciesDev
     int has_B;
     int species;          // index, part of the RNG key
     double prob;          // 1 - exp(-dt/lifetime)
+    unsigned long long prob_u32;   // the same test on the raw Philox word: u01(w) < prob  <=>  w < prob_u32 (bernoulli_threshold)
     double lifetime;
     double qm;            // charge/mass (multi-collision mover)
     unsigned long long step;   // species step counter (niter), part of the RNG counter
 };
 
 // SoA particle arrays of one species (device pointers, capacity elements each)
+// u01(w) = (w + 0.5) 2^-32 < prob  <=>  w < ceil(prob 2^32 - 0.5): the Bernoulli test of the null-collision method as one
+// integer compare instead of an I2F.F64 + DFMA + DSETP chain per particle
+inline unsigned long long bernoulli_threshold(double prob)
+{
+    if (!(prob > 0.0)) return 0ULL;
+    const double t = ceil(prob * 4294967296.0 - 0.5);
+    return t >= 4294967296.0 ? 4294967296ULL : (t <= 0.0 ? 0ULL : (unsigned long long)t);
+}
+
 struct ParticlesDev
 {
     double* __restrict__ x;

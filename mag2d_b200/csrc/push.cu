@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, SORTING ? MAG2D_SORT_MIN_BLOCKS 
             {
                 const int q = 2 * p + e;
                 const unsigned word = q == 0 ? rnd.x : q == 1 ? rnd.y : q == 2 ? rnd.z : rnd.w;
-                if (keep[e] && u01(word) < A.s.prob) hit_mask |= 1u << q;
+                if (keep[e] && (unsigned long long)word < A.s.prob_u32) hit_mask |= 1u << q;
             }
         }
         if (permute)
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, MAG2D_TMA_CTAS_PER_SM) k_push_bo
                 {
                     const int q = 2 * p + e;
                     const unsigned word = q == 0 ? rnd.x : q == 1 ? rnd.y : q == 2 ? rnd.z : rnd.w;
-                    if (keep[e] && u01(word) < A.s.prob) hit_mask |= 1u << q;
+                    if (keep[e] && (unsigned long long)word < A.s.prob_u32) hit_mask |= 1u << q;
                 }
             }
             *reinterpret_cast<double2*>(sx + slot) = make_double2(x[0], x[1]);
@@ -1095,6 +1095,7 @@ SpeciesDev species_view(const mag2d_ctx* c, int s, bool init)
     v.has_B = (Bx != 0.0 || By != 0.0 || Bz != 0.0);
     v.species = s;
     v.prob = 1.0 - exp(-dt / S.lifetime);
+    v.prob_u32 = bernoulli_threshold(v.prob);
     v.lifetime = S.lifetime;
     v.qm = charge / mass;
     v.step = S.niter;

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(P3_THREADS, MAG3D_MIN_BLOCKS) k_push3d(const _
         if (MCC)
         {
             const unsigned word = e == 0 ? rnd.x : rnd.y;
-            if (keep[e] && u01(word) < A.s.prob) hit_mask |= 1u << e;
+            if (keep[e] && (unsigned long long)word < A.s.prob_u32) hit_mask |= 1u << e;
         }
     }
     if (PUSH && permute)
@@ -418,6 +418,7 @@ SpeciesDev species3_view(const mag2d_ctx* c, int s)
     v.has_B = (d.Br != 0.0 || d.Bt != 0.0 || d.Bz != 0.0);
     v.species = s;
     v.prob = 1.0 - exp(-dt / S.lifetime);
+    v.prob_u32 = bernoulli_threshold(v.prob);
     v.lifetime = S.lifetime;
     v.qm = charge / mass;
     v.step = S.niter;
