@@ -276,8 +276,10 @@ int mag2d_create(int device, const mag2d_grid_desc* grid, void* stream, mag2d_ct
     // uRF / the scratch copy are 2-D features; a 3-D grid only gets one-node stand-ins (the potential alone is 134 MB at 256^3)
     CUDA_OK(cudaMalloc(&c->d_uRF, sizeof(double) * (three_d ? 1 : n)));
     CUDA_OK(cudaMalloc(&c->d_ueff, sizeof(double) * (three_d ? 1 : n)));
-    CUDA_OK(cudaMalloc(&c->d_gx, sizeof(double) * n));
-    CUDA_OK(cudaMalloc(&c->d_gz, sizeof(double) * n));
+    // 2-D edge fields carry a ghost row and column (push.cu: gather_E); 3-D ones are node-sized
+    const size_t n_edge = three_d ? n : (size_t)(grid->M + 1) * (grid->N + 1);
+    CUDA_OK(cudaMalloc(&c->d_gx, sizeof(double) * n_edge));
+    CUDA_OK(cudaMalloc(&c->d_gz, sizeof(double) * n_edge));
     if (three_d)
     {
         CUDA_OK(cudaMalloc(&c->d_gy, sizeof(double) * n));
@@ -285,8 +287,8 @@ int mag2d_create(int device, const mag2d_grid_desc* grid, void* stream, mag2d_ct
     }
     CUDA_OK(cudaMalloc(&c->d_cfree, n));
     CUDA_OK(cudaMemsetAsync(c->d_cfree, 1, n, c->stream));
-    CUDA_OK(cudaMemsetAsync(c->d_gx, 0, sizeof(double) * n, c->stream));
-    CUDA_OK(cudaMemsetAsync(c->d_gz, 0, sizeof(double) * n, c->stream));
+    CUDA_OK(cudaMemsetAsync(c->d_gx, 0, sizeof(double) * n_edge, c->stream));
+    CUDA_OK(cudaMemsetAsync(c->d_gz, 0, sizeof(double) * n_edge, c->stream));
     CUDA_OK(cudaMalloc(&c->d_b, sizeof(double) * n));
     CUDA_OK(cudaMalloc(&c->d_scratch, sizeof(double) * 64));
     CUDA_OK(cudaMemsetAsync(c->d_scratch, 0, sizeof(double) * 64, c->stream));
@@ -395,6 +397,11 @@ int mag2d_set_grid(mag2d_ctx* c, const uint8_t* mask, const double* voltage)
         }
     CUDA_OK(cudaMemcpyAsync(c->d_cfree, cfree.data(), n, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    // no electrode blocks a whole cell (geometry EMPTY): the push kernels can skip the per-particle flag load
+    c->all_cells_free = true;
+    for (int i = 0; i + 1 < M && c->all_cells_free; i++)
+        for (int j = 0; j + 1 < N; j++)
+            if (!cfree[(size_t)i * N + j]) { c->all_cells_free = false; break; }
     c->grid_set = true;
     if (mg_setup(c)) return 1;
     return direct_setup(c);

@@ -117,6 +117,7 @@ struct mag2d_ctx
     unsigned long long* d_rho = nullptr;   // [n_species][M*N] fixed-point charge grids
     double* d_scratch = nullptr;           // reductions
     bool grid_set = false;
+    bool all_cells_free = false;  // every cell has a FREE corner: t_grid::is_free is true everywhere inside the box
     std::vector<unsigned char> h_mask;
     std::vector<double> h_voltage;
 

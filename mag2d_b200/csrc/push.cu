@@ -58,44 +58,36 @@ struct PushArgs
 // lies within one ulp below a half-integer, where both stencils interpolate the same edge value.
 __device__ __forceinline__ void gather_E(const GridDev& g, double x, double z, double& Ex, double& Ez)
 {
+    // gx / gz carry one ghost row and column on every side that the stencil can reach ([M+1][N+1], k_edge_fields):
+    // the copies of the first / last difference make the reference's one-sided edge rules (i == 0, i == jmax-1,
+    // j == 0, j == lmax-1 of Field2D::grad) fall out of the general formula, so no per-particle edge tests remain.
+    // (Tests of a clamped integer against its bound are also what ptxas 12.9 miscompiled on sm_100a, see DESIGN.md.)
     const int M = g.M, N = g.N;
+    const unsigned ld = (unsigned)N + 1u;
     const double X = x * g.idx, Y = z * g.idz;
     int ix = (int)X, jy = (int)Y;
     ix = max(min(ix, M - 1), 0);
     jy = max(min(jy, N - 1), 0);
     const double dix = (double)ix, djy = (double)jy;
-    const bool upx = X - dix >= 0.5, upy = Y - djy >= 0.5;
-    // NB edge tests on the double, not on the clamped integer: ptxas 12.9 fuses "min(i, M-1) ... i == M-1"
-    // into a VIMNMX.RELU predicate that came out always-true on sm_100a
-    const double Xs = X + 0.5, Ys = Y + 0.5;
-    const bool xlo = Xs < 1.0, xhi = Xs >= g.dM1, zlo = Ys < 1.0, zhi = Ys >= g.dN1;
+    const double fxc = X - dix, fyc = Y - djy;
+    const bool upx = fxc >= 0.5, upy = fyc >= 0.5;
     {
-        // x component: i = (int)(X + 0.5), j = min((int)Y, N-2)
+        // x component: rows (int)(X + 0.5) and the next one, columns (int)Y and the next one
         const int i = min(ix + (upx ? 1 : 0), M - 1);
-        const int j = min(jy, N - 2);
-        double fx = X - (upx ? dix + 1.0 : dix) + .5;
-        const double fy = Y - fmin(djy, g.dN2);
-        fx = xlo ? 1.0 : fx;
-        fx = xhi ? 0.0 : fx;
-        const double* r1 = g.gx + ((unsigned)i * (unsigned)N + (unsigned)j);
-        const double* r2 = r1 + (xhi ? 0 : N);
-        const double g1 = __ldg(r1), g2 = __ldg(r1 + 1), g4 = __ldg(r2), g3 = __ldg(r2 + 1);
-        const double cx = 1 - fx, cy = 1 - fy;
-        Ex = -(g1 * cx * cy + g2 * cx * fy + g3 * fx * fy + g4 * fx * cy);
+        const double fx = X - (upx ? dix + 1.0 : dix) + .5;
+        const double* r1 = g.gx + ((unsigned)i * ld + (unsigned)jy);
+        const double g1 = __ldg(r1), g2 = __ldg(r1 + 1), g4 = __ldg(r1 + ld), g3 = __ldg(r1 + ld + 1);
+        const double cx = 1 - fx, cy = 1 - fyc;
+        Ex = -(g1 * cx * cy + g2 * cx * fyc + g3 * fx * fyc + g4 * fx * cy);
     }
     {
-        // z component: i = min((int)X, M-2), j = (int)(Y + 0.5)
-        const int i = min(ix, M - 2);
+        // z component: rows (int)X and the next one, columns (int)(Y + 0.5) and the next one
         const int j = min(jy + (upy ? 1 : 0), N - 1);
-        const double fx = X - fmin(dix, g.dM2);
-        double fy = Y - (upy ? djy + 1.0 : djy) + 0.5;
-        fy = zlo ? 1.0 : fy;
-        fy = zhi ? 0.0 : fy;
-        const double* r0 = g.gz + ((unsigned)i * (unsigned)N + (unsigned)j);
-        const int jo = zhi ? 0 : 1;
-        const double g1 = __ldg(r0), g4 = __ldg(r0 + jo), g2 = __ldg(r0 + N), g3 = __ldg(r0 + N + jo);
-        const double cx = 1 - fx, cy = 1 - fy;
-        Ez = -(g1 * cx * cy + g2 * cy * fx + g3 * fx * fy + g4 * fy * cx);
+        const double fy = Y - (upy ? djy + 1.0 : djy) + 0.5;
+        const double* r0 = g.gz + ((unsigned)ix * ld + (unsigned)j);
+        const double g1 = __ldg(r0), g4 = __ldg(r0 + 1), g2 = __ldg(r0 + ld), g3 = __ldg(r0 + ld + 1);
+        const double cx = 1 - fxc, cy = 1 - fy;
+        Ez = -(g1 * cx * cy + g2 * cy * fxc + g3 * fxc * fy + g4 * fy * cx);
     }
 }
 
@@ -164,8 +156,8 @@ __device__ __forceinline__ bool boundary_weights(const GridDev& g, double& x, do
     // the reference indexes one node past the grid for x == x_max exactly (fields.hpp:96-100); clamp
     i = max(min(i, g.M - 2), 0);
     j = max(min(j, g.N - 2), 0);
-    const size_t k = (size_t)i * g.N + j;
-    node = (unsigned)k;
+    const unsigned k = (unsigned)i * (unsigned)g.N + (unsigned)j;      // grids stay far below 2^32 nodes
+    node = k;
     if (row) *row = (unsigned)i;
     if (g.check_mask && !g.cfree[k]) return false;
     if (DEPOSIT)
@@ -831,14 +823,16 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_accumulate(const __grid_consta
 __global__ void k_edge_fields(const double* __restrict__ u, const double* __restrict__ urf, double phase, int rf, int M, int N,
                               double idx, double idz, double* __restrict__ gx, double* __restrict__ gz)
 {
+    // [M+1][N+1] with ghosts: gx row 0 repeats row 1 and row M repeats row M-1 (the one-sided differences the
+    // reference uses next to the walls); gz likewise along j; the ghost column of gx / ghost row of gz is zero
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= M || j >= N) return;
-    const size_t k = (size_t)i * N + j;
-    auto ue = [&](size_t q) { return rf ? u[q] + urf[q] * phase : u[q]; };
-    const double c = ue(k);
-    gx[k] = i > 0 ? (c - ue(k - N)) * idx : 0.0;
-    gz[k] = j > 0 ? (c - ue(k - 1)) * idz : 0.0;
+    if (i > M || j > N) return;
+    auto ue = [&](int a, int b) { const size_t q = (size_t)a * N + b; return rf ? u[q] + urf[q] * phase : u[q]; };
+    const size_t k = (size_t)i * (N + 1) + j;
+    const int ii = max(min(i, M - 1), 1), jj = max(min(j, N - 1), 1);
+    gx[k] = j < N ? (ue(ii, j) - ue(ii - 1, j)) * idx : 0.0;
+    gz[k] = i < M ? (ue(i, jj) - ue(i, jj - 1)) * idz : 0.0;
 }
 
 // Fields::E at arbitrary points (diagnostics, parity tests)
@@ -1051,7 +1045,7 @@ GridDev grid_view(const mag2d_ctx* c, int s)
     g.idx = d.idx;
     g.idz = d.idz;
     g.const_E = d.geometry_empty && !d.selfconsistent;
-    g.check_mask = !d.electric_field_from_file;
+    g.check_mask = !d.electric_field_from_file && !c->all_cells_free;
     g.deposit = d.selfconsistent;
     g.extern_field = d.extern_field;
     g.dM1 = (double)(d.M - 1);
@@ -1150,7 +1144,7 @@ int ensure_particle_scratch(mag2d_ctx* c, long long capacity)
 int update_ueff(mag2d_ctx* c, double phase, bool rf)
 {
     const int M = c->g.M, N = c->g.N;
-    const dim3 block(32, 8), grid((N + 31) / 32, (M + 7) / 8);
+    const dim3 block(32, 8), grid((N + 1 + 31) / 32, (M + 1 + 7) / 8);
     k_edge_fields<<<grid, block, 0, c->stream>>>(c->d_u, c->d_uRF, phase, rf ? 1 : 0, M, N, c->g.idx, c->g.idz, c->d_gx, c->d_gz);
     c->launches++;
     CUDA_OK(cudaGetLastError());
