@@ -23,6 +23,9 @@
 namespace {
 
 constexpr int PUSH_THREADS = 256;
+#ifndef MAG2D_DEPOSIT_SMALL
+#define MAG2D_DEPOSIT_SMALL 2   // measured on C4: 1.91 ms (2) vs 1.97 ms (off), 1.92 ms (3)
+#endif
 
 struct PushArgs
 {
@@ -183,6 +186,22 @@ __device__ __forceinline__ void warp_deposit(unsigned long long* __restrict__ rh
                                              const unsigned long long (&w)[4])
 {
     const unsigned lane = lane_id();
+#if MAG2D_DEPOSIT_SMALL > 0
+    if (!__any_sync(MAG2D_FULL_MASK, valid)) return;
+    // MATCH.ANY groups the lanes by cell in one instruction: cells that only one or two lanes sit in (particles that
+    // drifted out of the warp's home cell) are scattered directly; the REDUX merge is kept for the crowded cells
+    const unsigned group = __match_any_sync(MAG2D_FULL_MASK, valid ? node : (0xFFFFFFE0u | lane));
+    const bool small = valid && __popc(group) <= MAG2D_DEPOSIT_SMALL;
+    if (small)
+    {
+        unsigned long long* r = rho + node;
+        atomicAdd(r, w[0]);
+        atomicAdd(r + N, w[1]);
+        atomicAdd(r + 1, w[2]);
+        atomicAdd(r + N + 1, w[3]);
+    }
+    valid = valid && !small;
+#endif
     unsigned remaining = __ballot_sync(MAG2D_FULL_MASK, valid);
     if (remaining == 0) return;
     // 32-bit pieces once per entry: hi = w >> 16 (<= 2^16), lo = w & 0xffff
