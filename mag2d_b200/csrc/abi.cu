@@ -276,14 +276,14 @@ int mag2d_create(int device, const mag2d_grid_desc* grid, void* stream, mag2d_ct
     // uRF / the scratch copy are 2-D features; a 3-D grid only gets one-node stand-ins (the potential alone is 134 MB at 256^3)
     CUDA_OK(cudaMalloc(&c->d_uRF, sizeof(double) * (three_d ? 1 : n)));
     CUDA_OK(cudaMalloc(&c->d_ueff, sizeof(double) * (three_d ? 1 : n)));
-    // 2-D edge fields carry a ghost row and column (push.cu: gather_E); 3-D ones are node-sized
-    const size_t n_edge = three_d ? n : (size_t)(grid->M + 1) * (grid->N + 1);
+    // the edge fields carry one ghost plane per axis (push.cu: gather_E, push3d.cu: grad_component)
+    const size_t n_edge = (size_t)(grid->M + 1) * (grid->N + 1) * (three_d ? (size_t)(grid->K + 1) : 1);
     CUDA_OK(cudaMalloc(&c->d_gx, sizeof(double) * n_edge));
     CUDA_OK(cudaMalloc(&c->d_gz, sizeof(double) * n_edge));
     if (three_d)
     {
-        CUDA_OK(cudaMalloc(&c->d_gy, sizeof(double) * n));
-        CUDA_OK(cudaMemsetAsync(c->d_gy, 0, sizeof(double) * n, c->stream));
+        CUDA_OK(cudaMalloc(&c->d_gy, sizeof(double) * n_edge));
+        CUDA_OK(cudaMemsetAsync(c->d_gy, 0, sizeof(double) * n_edge, c->stream));
     }
     CUDA_OK(cudaMalloc(&c->d_cfree, n));
     CUDA_OK(cudaMemsetAsync(c->d_cfree, 1, n, c->stream));

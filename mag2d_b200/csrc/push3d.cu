@@ -26,7 +26,6 @@ struct Grid3Dev
     int boundary, check_mask, deposit;
     double x_max, y_max, z_max;
     double idx, idy, idz;
-    double hiX, hiY, hiZ;           // ((M-1)/idx)*idx ...: the upper clamp of Field3D::grad_component in index units
     const double* gx;               // edge differences u[m] - u[m - stride] along x / y / z
     const double* gy;
     const double* gz;
@@ -57,8 +56,6 @@ struct Push3Args
     unsigned* count_out;
 };
 
-__device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
-
 __device__ __forceinline__ unsigned long long q32_rn3(double w)
 {
     const double magic = 6755399441055744.0;   // 1.5 * 2^52
@@ -66,17 +63,19 @@ __device__ __forceinline__ unsigned long long q32_rn3(double w)
     return (unsigned long long)(__double_as_longlong(t) - __double_as_longlong(magic));
 }
 
-// one component of -grad u at (X, Y, Z) in index units; DIR selects the differenced axis (0 x, 1 y, 2 z)
+// one component of grad u at (X, Y, Z) in index units; DIR selects the differenced axis (0 x, 1 y, 2 z).
+// The edge-difference arrays carry ghost planes ([M+1][K+1][N+1], k_edge_fields3d): along the differenced axis plane 0
+// repeats plane 1 and plane M repeats plane M-1, which is exactly what Field3D::grad_component's clamp of the
+// coordinate to [0.5, xmax*idx - 0.5] produces; along the other axes the plane past the end repeats the last one.
+// No floating-point clamps remain in the particle loop (nine per particle before), only integer ones.
 template <int DIR>
 __device__ __forceinline__ double grad_component(const Grid3Dev& g, double X, double Y, double Z)
 {
-    const double hx = DIR == 0 ? 0.5 : 0.0, hy = DIR == 1 ? 0.5 : 0.0, hz = DIR == 2 ? 0.5 : 0.0;
-    const double xc = clampd(X, hx, g.hiX - hx) + hx, yc = clampd(Y, hy, g.hiY - hy) + hy, zc = clampd(Z, hz, g.hiZ - hz) + hz;
-    // at the upper clamp the reference reads plane i+1 = M with weight exactly 0: use planes M-2, M-1 with weight 1
-    const int i = min((int)xc, g.M - 2), j = min((int)yc, g.K - 2), k = min((int)zc, g.N - 2);
-    const double u = xc - i, v = yc - j, w = zc - k;
-    const double* f = (DIR == 0 ? g.gx : DIR == 1 ? g.gy : g.gz) + ((size_t)i * g.K + j) * g.N + k;
-    const size_t sj = g.N, si = (size_t)g.K * g.N;
+    const double xs = DIR == 0 ? X + 0.5 : X, ys = DIR == 1 ? Y + 0.5 : Y, zs = DIR == 2 ? Z + 0.5 : Z;
+    const int i = max(min((int)xs, g.M - 1), 0), j = max(min((int)ys, g.K - 1), 0), k = max(min((int)zs, g.N - 1), 0);
+    const double u = xs - i, v = ys - j, w = zs - k;
+    const unsigned sj = (unsigned)g.N + 1u, si = ((unsigned)g.K + 1u) * sj;
+    const double* f = (DIR == 0 ? g.gx : DIR == 1 ? g.gy : g.gz) + ((unsigned)i * si + (unsigned)j * sj + (unsigned)k);
     const double g0 = __ldg(f), g1 = __ldg(f + si), g2 = __ldg(f + sj), g3 = __ldg(f + si + sj);
     const double g4 = __ldg(f + 1), g5 = __ldg(f + si + 1), g6 = __ldg(f + sj + 1), g7 = __ldg(f + si + sj + 1);
     const double cu = 1 - u, cv = 1 - v, cw = 1 - w;
@@ -348,20 +347,22 @@ __global__ void __launch_bounds__(128) k_mcc_collide3d(const __grid_constant__ P
     }
 }
 
-// gx[m] = u[m] - u[m - stride_x] (i >= 1), likewise gy, gz: the eight differences Field3D::grad_component forms per
-// particle become eight loads.  Planes i = 0 (j = 0, k = 0) are never addressed by the clamped stencil.
+// gx'[i][j][k] = u[ic][jc][kc] - u[ic-1][jc][kc] with ic = clamp(i, 1, M-1), jc = min(j, K-1), kc = min(k, N-1) on the
+// ghost-extended index range [0..M][0..K][0..N]; gy', gz' likewise along their own axes.  The eight differences that
+// Field3D::grad_component forms per particle become eight loads.
 __global__ void k_edge_fields3d(const double* __restrict__ u, int M, int K, int N, double* __restrict__ gx, double* __restrict__ gy,
                                 double* __restrict__ gz)
 {
-    const size_t n = (size_t)M * K * N;
-    const size_t sj = N, si = (size_t)K * N;
+    const size_t sj = (size_t)N + 1, si = ((size_t)K + 1) * sj, n = ((size_t)M + 1) * si;
+    const size_t uj = N, ui = (size_t)K * N;
     for (size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x; m < n; m += (size_t)gridDim.x * blockDim.x)
     {
-        const int k = (int)(m % N), j = (int)((m / N) % K), i = (int)(m / si);
-        const double c = u[m];
-        gx[m] = i > 0 ? c - u[m - si] : 0.0;
-        gy[m] = j > 0 ? c - u[m - sj] : 0.0;
-        gz[m] = k > 0 ? c - u[m - 1] : 0.0;
+        const int k = (int)(m % sj), j = (int)((m / sj) % (K + 1)), i = (int)(m / si);
+        const int i0 = min(i, M - 1), j0 = min(j, K - 1), k0 = min(k, N - 1);
+        const int i1 = max(i0, 1), j1 = max(j0, 1), k1 = max(k0, 1);
+        gx[m] = u[i1 * ui + j0 * uj + k0] - u[(i1 - 1) * ui + j0 * uj + k0];
+        gy[m] = u[i0 * ui + j1 * uj + k0] - u[i0 * ui + (j1 - 1) * uj + k0];
+        gz[m] = u[i0 * ui + j0 * uj + k1] - u[i0 * ui + j0 * uj + k1 - 1];
     }
 }
 
@@ -387,10 +388,6 @@ Grid3Dev grid3_view(const mag2d_ctx* c, int s)
     g.deposit = d.selfconsistent;
     g.x_max = d.x_max; g.y_max = d.y_max; g.z_max = d.z_max;
     g.idx = d.idx; g.idy = d.idy; g.idz = d.idz;
-    // xmax = (imax-1)/idx, then xmax*idx, as Field3D::grad_component evaluates it
-    g.hiX = ((d.M - 1) / d.idx) * d.idx;
-    g.hiY = ((d.K - 1) / d.idy) * d.idy;
-    g.hiZ = ((d.N - 1) / d.idz) * d.idz;
     g.gx = c->d_gx; g.gy = c->d_gy; g.gz = c->d_gz;
     g.cfree = c->d_cfree;
     g.rho = s >= 0 && c->d_rho ? c->d_rho + (size_t)s * d.M * d.K * d.N : nullptr;
