@@ -47,11 +47,39 @@ def main():
     lo, hi = shard_range(n, rank, world)
     ri, re, u = run(sim, lo, hi, 4)
     sim.close()
+    # the same for the 3-D path (coord = CARTESIAN3D): one species, fused cell sort on, all-reduce of the [M][K][N] grid
+    d3 = decks.deck("c5", tmp, n_particles=n, collisions=False, x_sampl=14, y_sampl=12, z_sampl=13, macroparticle_factor=2e6)
+    a3 = np.zeros((n, 7))
+    a3[:, 0] = rng.uniform(0, 1.3e-3, n)
+    a3[:, 1] = rng.uniform(0, 1.1e-3, n)
+    a3[:, 2] = rng.uniform(0, 1.2e-3, n)
+    a3[:, 3:6] = rng.normal(size=(n, 3)) * 3e5
+
+    def run3(sim3, lo, hi, steps):
+        e = sim3.species_index("ELECTRON")
+        sim3.set_particles(e, a3[lo:hi])
+        sim3.set_sort_interval(2)
+        sim3.advance_init()
+        sim3.advance(steps)
+        return sim3.rho_fixed(e), sim3.get_field("u")
+    sim3 = Sim(d3["config"], d3["species_conf"], device=local)
+    uid3 = torch.zeros(128, dtype=torch.uint8, device=dev)      # every communicator needs its own id
+    if rank == 0:
+        uid3.copy_(torch.frombuffer(bytearray(Sim.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid3, 0)
+    sim3.comm_init(rank, world, bytes(uid3.cpu().numpy().tobytes()))
+    r3, u3 = run3(sim3, lo, hi, 4)
+    sim3.close()
     ok = True
     if rank == 0:
         with Sim(d["config"], d["species_conf"], device=local) as solo:
             si, se, su = run(solo, 0, n, 4)
         ok = np.array_equal(ri, si) and np.array_equal(re, se) and np.array_equal(u, su)
+        with Sim(d3["config"], d3["species_conf"], device=local) as solo3:
+            s3, su3 = run3(solo3, 0, n, 4)
+        ok3 = np.array_equal(r3, s3) and np.array_equal(u3, su3)
+        print("MGPU_RESULT_3D", "ok" if ok3 else "mismatch", "max|du|", float(np.abs(u3 - su3).max()))
+        ok = ok and ok3
         print("MGPU_RESULT", "ok" if ok else "mismatch", "world", world, "max|du|", float(np.abs(u - su).max()))
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
