@@ -107,6 +107,7 @@ bool needs_array(const mag2d_ctx* c, int a)
 int ensure_capacity(mag2d_ctx* c, SpeciesStore& S, long long need)
 {
     S.tickets_valid = false;      // every append goes through here: pending sort tickets do not cover the new slots
+    S.append_epoch++;
     if (need <= S.capacity) return 0;
     long long cap = std::max<long long>(need, (long long)(S.capacity * 1.5) + 1024);
     cap = (cap + 255) / 256 * 256;
@@ -793,6 +794,7 @@ int mag2d_particles_clear(mag2d_ctx* c, int s)
     CHECK_SPECIES(c, s);
     c->sp[s].n_slots = 0;
     c->sp[s].tickets_valid = false;
+    c->sp[s].append_epoch++;
     CUDA_OK(cudaMemsetAsync(c->sp[s].d_removed, 0, sizeof(unsigned long long), c->stream));
     return 0;
 }

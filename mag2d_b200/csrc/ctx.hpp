@@ -44,6 +44,12 @@ struct SpeciesStore
     bool tickets_valid = false;       // a COUNT step has run and nothing has disturbed the slots since
     int sort_interval = -1;           // pushes between permuting steps (-1: the context-wide setting)
     int pushes_since_permute = 1 << 20;
+    // n_slots is only an upper bound after a fused permute (the live count stays on the device); every permute also
+    // sends it to a pinned host word, and a later step adopts it once the copy has landed — no synchronisation
+    unsigned long long* h_total = nullptr;   // pinned
+    cudaEvent_t ev_total = nullptr;
+    bool total_pending = false;
+    long long append_epoch = 0, total_epoch = -1;
 };
 
 // one level of the Galerkin multigrid hierarchy (poisson.cu)

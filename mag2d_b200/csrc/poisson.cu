@@ -237,21 +237,6 @@ __device__ __forceinline__ double offdiag_sum(const LevelDev& L, int i, int j, d
     return s;
 }
 
-// one colour of the 4-colour Gauss-Seidel sweep: colour = (i&1)*2 + (j&1)
-__global__ void k_mg_smooth(const __grid_constant__ LevelDev L, int colour)
-{
-    const int ci = colour >> 1, cj = colour & 1;
-    const int tj = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ti = blockIdx.y * blockDim.y + threadIdx.y;
-    const int i = 2 * ti + ci, j = 2 * tj + cj;
-    if (i >= L.M || j >= L.N) return;
-    const size_t k = (size_t)i * L.N + j;
-    if (!L.freem[k]) return;
-    double diag;
-    const double s = offdiag_sum(L, i, j, diag);
-    L.u[k] = (L.b[k] - s) / diag;
-}
-
 __device__ __forceinline__ double residual_at(const LevelDev& L, int i, int j)
 {
     const size_t k = (size_t)i * L.N + j;

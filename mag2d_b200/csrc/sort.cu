@@ -272,6 +272,11 @@ void sort_fused_free(SpeciesStore& S)
     cudaFree(S.d_cell_count);
     cudaFree(S.d_cell_offset);
     cudaFree(S.d_sort_sums);
+    if (S.h_total) cudaFreeHost(S.h_total);
+    if (S.ev_total) cudaEventDestroy(S.ev_total);
+    S.h_total = nullptr;
+    S.ev_total = nullptr;
+    S.total_pending = false;
     S.d_cell_count = S.d_cell_offset = S.d_sort_sums = nullptr;
     S.key_capacity = 0;
     S.tickets_valid = false;
@@ -305,6 +310,17 @@ int sort_fused_begin(mag2d_ctx* c, int s, bool permute, bool count)
         S.key_capacity = S.capacity;
     }
     if (count) CUDA_OK(cudaMemsetAsync(S.d_cell_count, 0, sizeof(unsigned) * (size_t)ncells, c->stream));
+    // a live count sent home by an earlier permute has landed and nothing was appended since: everything behind it
+    // is dead in the current slab, so the slot range shrinks to it (rounded up to the 256-slot allocation unit)
+    if (S.total_pending && cudaEventQuery(S.ev_total) == cudaSuccess)
+    {
+        S.total_pending = false;
+        if (S.total_epoch == S.append_epoch)
+        {
+            const long long live = (long long)*S.h_total;
+            if (live < S.n_slots) S.n_slots = live;
+        }
+    }
     if (permute)
     {
         if (!S.arr[S.cur ^ 1][ARR_X] && store_alloc_slab(c, S, S.cur ^ 1, S.capacity)) return 1;
@@ -325,6 +341,18 @@ int sort_fused_end(mag2d_ctx* c, int s, bool permute, bool count)
         // d_total still holds the number of particles the consumed tickets covered: everything behind is dead
         k_fill_dead_keys<<<148 * 4, 256, 0, c->stream>>>(S.arr[S.cur ^ 1][ARR_X], count ? S.d_key[S.kr ^ 1] : nullptr, d_total, S.n_slots);
         c->launches++;
+        if (!S.total_pending)
+        {
+            if (!S.h_total)
+            {
+                CUDA_OK(cudaMallocHost(&S.h_total, sizeof(unsigned long long)));
+                CUDA_OK(cudaEventCreateWithFlags(&S.ev_total, cudaEventDisableTiming));
+            }
+            CUDA_OK(cudaMemcpyAsync(S.h_total, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_OK(cudaEventRecord(S.ev_total, c->stream));
+            S.total_pending = true;
+            S.total_epoch = S.append_epoch;
+        }
         S.cur ^= 1;
         if (count) S.kr ^= 1;
         S.pushes_since_permute = 0;
