@@ -126,6 +126,16 @@ int mag2d_solver_stats(mag2d_ctx* ctx, int* last_cycles, double* last_resid);
 int mag2d_u_smooth(mag2d_ctx* ctx, int symmetry, double radius);
 /* ElMag3D::E at n points, src/fields3d.hpp:95-101 (CARTESIAN3D; diagnostics / parity checks) */
 int mag2d_field_E3(mag2d_ctx* ctx, int n, const double* x, const double* y, const double* z, double* Ex, double* Ey, double* Ez);
+/* Fields::Br / Fields::Bz as filled by Fields::load_magnetic_field (src/fields.cpp:870-959) when
+ * magnetic_field_const = 0: two tables on their own r_sampl x z_sampl grid (row-major, r slowest, spacing dr / dz,
+ * origin r_min / z_min), interpolated bilinearly at every particle by the Boris movers (Fields::B,
+ * src/fields.hpp:172-175; B_theta = 0).  The reference throws "Field2D::interpolate() outside of range" when a
+ * particle leaves the table; here the table must cover the simulation box [0, x_max] x [0, z_max] and the call
+ * fails with that message otherwise.  Br = Bz = NULL returns to the constant field of the grid descriptor. */
+int mag2d_set_magnetic_field(mag2d_ctx* ctx, int r_sampl, int z_sampl, double dr, double dz, double r_min, double z_min,
+                             const double* Br, const double* Bz);
+/* Fields::B at n points, src/fields.hpp:152-177 (diagnostics / parity checks) */
+int mag2d_field_B(mag2d_ctx* ctx, int n, const double* x, const double* z, double* Br, double* Bz, double* Bt);
 /* Fields::E at n points, src/fields.hpp:124-150 (diagnostics / parity checks) */
 int mag2d_field_E(mag2d_ctx* ctx, int n, const double* x, const double* z, double time, double* Ex, double* Ez);
 

@@ -92,6 +92,8 @@ def lib():
     L.mag2d_collision_counts.argtypes = [vp, C.c_int, i64p, C.c_int]
     L.mag2d_set_collision_counting.argtypes = [vp, C.c_int]
     L.mag2d_reserve.argtypes = [vp, C.c_int, C.c_int64]
+    L.mag2d_set_magnetic_field.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp]
+    L.mag2d_field_B.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp]
     L.mag2d_particles_upload.argtypes = [vp, C.c_int, vp, C.c_int64]
     L.mag2d_particles_upload_soa.argtypes = [vp, C.c_int, C.c_int64, dp, dp, dp, dp, dp, dp, dp]
     L.mag2d_particles_download.argtypes = [vp, C.c_int, vp, C.c_int64, i64p]
@@ -169,6 +171,10 @@ class Sim:
         self.mask, self.voltage = geometry.build_geometry(p)
         self._chk(self.L.mag2d_set_grid(self.h, self.mask.ctypes.data_as(u8p), _d(self.voltage)))
         self._set_species()
+        self.btable = None
+        if not self.is3d and not p["magnetic_field_const"]:
+            # Pic ctor: if(!param.magnetic_field_const) field.load_magnetic_field(...)  (pic.cpp:148-149)
+            self.set_magnetic_field(cfg.load_magnetic_field(p["magnetic_field_file"]))
         self.solver_tol = solver_tol
         self._chk(self.L.mag2d_set_solver(self.h, 0, solver_tol, 100))
         self.solve_info = {}
@@ -225,6 +231,25 @@ class Sim:
         tEa = np.ascontiguousarray(tE if tE else [0.0], dtype=np.float64)
         tSa = np.ascontiguousarray(tS if tS else [0.0], dtype=np.float64)
         self._chk(self.L.mag2d_set_species(self.h, ns, sd, ni, idesc, _d(tEa), _d(tSa), len(tE)))
+
+    def set_magnetic_field(self, table):
+        """table: what config.load_magnetic_field returns; None goes back to the constant (Br, Bz, Bt) of config.txt"""
+        if table is None:
+            self._chk(self.L.mag2d_set_magnetic_field(self.h, 0, 0, 0.0, 0.0, 0.0, 0.0, None, None))
+        else:
+            br = np.ascontiguousarray(table["Br"], dtype=np.float64)
+            bz = np.ascontiguousarray(table["Bz"], dtype=np.float64)
+            self._chk(self.L.mag2d_set_magnetic_field(self.h, table["r_sampl"], table["z_sampl"], table["dr"], table["dz"],
+                                                      table["r_min"], table["z_min"], _d(br), _d(bz)))
+        self.btable = table
+
+    def field_B(self, x, z):
+        """Fields::B at points (fields.hpp:152-177) -> array [3][n]: Br, Bz, Bt"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        out = np.zeros((3, x.size))
+        self._chk(self.L.mag2d_field_B(self.h, x.size, _d(x), _d(z), _d(out[0]), _d(out[1]), _d(out[2])))
+        return out
 
     # ---- configuration queries
     def species_index(self, name):

@@ -11,6 +11,8 @@ These only describe a run; all computation happens behind the C ABI (include/mag
 """
 import math
 
+import numpy as np
+
 EPS0 = 8.854187817e-12   # reference src/param.cpp:8-10 (old CODATA values kept for parity)
 KB = 1.380662e-23
 QE = 1.602189e-19
@@ -243,3 +245,58 @@ def read_initscript(path):
                 raise ConfigError("Pic::run_initscript: wrong number of parameters (%d) to %s\n" % (len(t), t[0]))
             out.append((t[0], t[1], [float(v) for v in t[2:]]))
     return out
+
+
+def _double2int(x, eps=1e-2):
+    """util.cpp:22-28"""
+    res = int(x + 0.5)
+    if abs(res - x) > eps:
+        raise RuntimeError("double2int() %r is not integer\n" % x)
+    return res
+
+
+def load_magnetic_field(fname):
+    """Fields::load_magnetic_field (reference src/fields.cpp:870-959): rows "r z Br Bz" (anything else is skipped),
+    r and z on a regular grid in either order -> dict(r_sampl, z_sampl, dr, dz, r_min, z_min, Br[r_sampl][z_sampl], Bz),
+    what mag2d_set_magnetic_field takes.  Same error texts as the reference."""
+    try:
+        f = open(fname)
+    except OSError:
+        raise RuntimeError("Fields::load_magnetic_field(): failed opening file\n")
+    rows = []
+    with f:
+        for line in f:
+            t = line.split()
+            try:
+                rows.append((float(t[0]), float(t[1]), float(t[2]), float(t[3])))
+            except (ValueError, IndexError):
+                continue
+    a = np.array(rows, dtype=np.float64).reshape(-1, 4)
+    n = a.shape[0]
+    if n < 2:
+        raise RuntimeError("Fields::load_magnetic_field() wrong size of input vector")
+    rv, zv = a[:, 0], a[:, 1]
+
+    def axis(v):
+        lo, hi = v[0], v[-1]
+        nz = np.nonzero(np.diff(v) != 0.0)[0]
+        if nz.size == 0:
+            raise RuntimeError("Fields::load_magnetic_field() wrong size of input vector")
+        d = v[nz[0] + 1] - v[nz[0]]
+        if d < 0:
+            d, lo, hi = -d, v[-1], v[0]
+        return d, lo, _double2int((hi - lo) / d + 1)
+
+    dr, r_min, r_sampl = axis(rv)
+    dz, z_min, z_sampl = axis(zv)
+    if r_sampl * z_sampl != n:
+        raise RuntimeError("Fields::load_magnetic_field() wrong size of input vector")
+    Br = np.full((r_sampl, z_sampl), np.nan)
+    Bz = np.full((r_sampl, z_sampl), np.nan)
+    for k in range(n):
+        ri, zi = _double2int((rv[k] - r_min) / dr), _double2int((zv[k] - z_min) / dz)
+        Br[ri, zi] = a[k, 2]
+        Bz[ri, zi] = a[k, 3]
+    if np.isnan(Br).any() or np.isnan(Bz).any():
+        raise RuntimeError("Fields::load_magnetic_field() garbage loaded")
+    return dict(r_sampl=r_sampl, z_sampl=z_sampl, dr=float(dr), dz=float(dz), r_min=float(r_min), z_min=float(z_min), Br=Br, Bz=Bz)

@@ -327,6 +327,8 @@ int mag2d_destroy(mag2d_ctx* c)
     cudaFree(c->d_uRF);
     cudaFree(c->d_ueff);
     cudaFree(c->d_gx);
+    cudaFree(c->d_btab_r);
+    cudaFree(c->d_btab_z);
     cudaFree(c->d_gz);
     cudaFree(c->d_cfree);
     cudaFree(c->d_b);
@@ -419,6 +421,52 @@ int mag2d_set_potential(mag2d_ctx* c, int which, const double* values)
     CUDA_OK(cudaMemcpyAsync(dst, values, sizeof(double) * grid_n(c), cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+int mag2d_set_magnetic_field(mag2d_ctx* c, int r_sampl, int z_sampl, double dr, double dz, double r_min, double z_min, const double* Br,
+                             const double* Bz)
+{
+    CHECK_CTX(c);
+    if (is3d(c)) { mag2d_set_error("mag2d_set_magnetic_field: CARTESIAN3D uses the constant field of the grid descriptor"); return 1; }
+    if (c->d_btab_r) { cudaFree(c->d_btab_r); c->d_btab_r = nullptr; }
+    if (c->d_btab_z) { cudaFree(c->d_btab_z); c->d_btab_z = nullptr; }
+    c->btab_M = c->btab_N = 0;
+    if (!Br && !Bz) return 0;
+    if (!Br || !Bz || r_sampl < 2 || z_sampl < 2 || !(dr > 0) || !(dz > 0))
+    {
+        mag2d_set_error("Fields::load_magnetic_field() wrong size of input vector");
+        return 1;
+    }
+    // Field2D::interpolate accepts (int)((x - xmin)*idx) in [0, jmax-1] (Field2D.hpp:74): the box has to lie inside
+    const double r_top = r_min + (r_sampl - 1) * dr, z_top = z_min + (z_sampl - 1) * dz;
+    const double er = 1e-9 * dr, ez = 1e-9 * dz;
+    if (r_min > er || z_min > ez || r_top < c->g.x_max - er || z_top < c->g.z_max - ez)
+    {
+        mag2d_set_error("Field2D::interpolate() outside of range");
+        return 1;
+    }
+    const size_t n = (size_t)r_sampl * z_sampl;
+    for (size_t k = 0; k < n; k++)
+        if (std::isnan(Br[k]) || std::isnan(Bz[k])) { mag2d_set_error("Fields::load_magnetic_field() garbage loaded"); return 1; }
+    CUDA_OK(cudaMalloc(&c->d_btab_r, sizeof(double) * n));
+    CUDA_OK(cudaMalloc(&c->d_btab_z, sizeof(double) * n));
+    CUDA_OK(cudaMemcpyAsync(c->d_btab_r, Br, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->d_btab_z, Bz, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->btab_M = r_sampl;
+    c->btab_N = z_sampl;
+    c->btab_idx = 1.0 / dr;      // Field2D::resize: idx = 1.0/dx (Field2D.hpp)
+    c->btab_idz = 1.0 / dz;
+    c->btab_xmin = r_min;
+    c->btab_zmin = z_min;
+    return 0;
+}
+
+int mag2d_field_B(mag2d_ctx* c, int n, const double* x, const double* z, double* Br, double* Bz, double* Bt)
+{
+    CHECK_CTX(c);
+    if (is3d(c)) { mag2d_set_error("mag2d_field_B: 2-D grids only"); return 1; }
+    return launch_field_B(c, n, x, z, Br, Bz, Bt);
 }
 
 int mag2d_get_potential(mag2d_ctx* c, int which, double* values)

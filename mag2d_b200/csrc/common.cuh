@@ -37,6 +37,12 @@ struct GridDev
     // cfree[i*N+j] = 1 when any corner of cell (i,j) is a FREE node: t_grid::is_free (fields.hpp:94-101)
     const unsigned char* __restrict__ cfree;
     unsigned long long* __restrict__ rho;      // fixed-point charge grid of this species, [M*N]
+    // magnetic field table of Fields::load_magnetic_field (fields.cpp:870-959), nullptr while magnetic_field_const:
+    // Br, Bz on their own bM x bN grid, row-major like Field2D; bilinear Field2D::interpolate per particle (fields.hpp:172-175)
+    const double* __restrict__ b_r;
+    const double* __restrict__ b_z;
+    int bM, bN;
+    double bidx, bidz, bxmin, bzmin;
 };
 
 // Species constants of one step, precomputed on the host with the reference's own expression
@@ -47,6 +53,7 @@ struct SpeciesDev
     double hq;            // (charge/mass*dt)/2  — exact halving of qmdt
     double tx, ty, tz;    // Boris t = B * charge*dt/(2 mass)   (x, out-of-plane y, z)
     double sx, sy, sz;    // s = t * 2/(1+|t|^2)
+    double tb;            // charge*dt/(2 mass): t = B * tb per particle when B comes from the table
     int has_B;
     int species;          // index, part of the RNG key
     double prob;          // 1 - exp(-dt/lifetime)

@@ -117,6 +117,11 @@ struct mag2d_ctx
     double* d_gx = nullptr;     // edge-centred field differences of the current step (push.cu: k_edge_fields)
     double* d_gz = nullptr;
     double* d_gy = nullptr;     // CARTESIAN3D only
+    // magnetic field table (mag2d_set_magnetic_field; Fields::load_magnetic_field, fields.cpp:870-959)
+    double* d_btab_r = nullptr;
+    double* d_btab_z = nullptr;
+    int btab_M = 0, btab_N = 0;
+    double btab_idx = 0, btab_idz = 0, btab_xmin = 0, btab_zmin = 0;
     unsigned char* d_cfree = nullptr;   // per-cell "has a FREE corner" flag (t_grid::is_free)
     double* d_b = nullptr;      // RHS in the reference's scaling (for the residual check)
     double* d_rowscale = nullptr;  // symmetrising row scale s_i of the cylindrical operator, [M]
@@ -198,6 +203,7 @@ int launch_species_accumulate(mag2d_ctx* c, int s);
 int launch_generate(mag2d_ctx* c, int s, int kind, long long n, double a, double b, double cc, double d);
 int launch_energy_hist(mag2d_ctx* c, int s, int nbins, double emax, double* hist, double* stats);
 int launch_field_E(mag2d_ctx* c, int n, const double* x, const double* z, double time, double* Ex, double* Ez);
+int launch_field_B(mag2d_ctx* c, int n, const double* x, const double* z, double* Br, double* Bz, double* Bt);
 int launch_aos_to_soa(mag2d_ctx* c, int s, const mag2d_particle* d_aos, long long n_in, long long* n_added);
 int launch_soa_to_aos(mag2d_ctx* c, int s, mag2d_particle* d_aos);
 int update_ueff(mag2d_ctx* c, double phase, bool rf);

@@ -211,11 +211,61 @@ class Fields
         if (p_param->geometry == Param::EMPTY && !p_param->selfconsistent) { ex = 0.; ez = p_param->extern_field; return; }
         gpu_check(mag2d_field_E(gpu, 1, &x, &y, time, &ex, &ez));
     }
-    void B(double, double, double& br, double& bz, double& bt) const
+    // fields.hpp:152-177: the constants of config.txt or the interpolated table (host diagnostics; the movers read the
+    // device copy of the table)
+    void B(double x, double y, double& br, double& bz, double& bt) const
     {
-        if (!p_param->magnetic_field_const) throw std::runtime_error("Fields::B: magnetic field from file is not implemented");
-        br = p_param->Br; bz = p_param->Bz; bt = p_param->Bt;
+        if (p_param->magnetic_field_const) { br = p_param->Br; bz = p_param->Bz; bt = p_param->Bt; return; }
+        br = Br.interpolate(x, y);
+        bz = Bz.interpolate(x, y);
+        bt = 0.00;
     }
+    // fields.cpp:870-959: four-column file "r z Br Bz" on a regular grid, either row order; fills Br / Bz and hands the
+    // table to the GPU context
+    void load_magnetic_field(const char* fname)
+    {
+        std::ifstream fr(fname);
+        if (fr.fail()) throw std::runtime_error("Fields::load_magnetic_field(): failed opening file\n");
+        std::vector<double> rvec, zvec, brvec, bzvec;
+        for (std::string line; std::getline(fr, line);)
+        {
+            std::istringstream row(line);
+            double a, b, c, d;
+            if (row >> a >> b >> c >> d) { rvec.push_back(a); zvec.push_back(b); brvec.push_back(c); bzvec.push_back(d); }
+        }
+        if (rvec.size() < 2) throw std::runtime_error("Fields::load_magnetic_field() wrong size of input vector");
+        auto to_int = [](double x) {       // double2int, util.cpp:22-28
+            const int res = (int)(x + 0.5);
+            if (std::fabs(res - x) > 1e-2) throw std::runtime_error("double2int() " + std::to_string(x) + " is not integer\n");
+            return res;
+        };
+        auto axis = [&](const std::vector<double>& v, double& lo, double& step) {
+            lo = v.front();
+            double hi = v.back();
+            size_t k = 1;
+            while (k < v.size() && v[k] - v[k - 1] == 0.0) k++;
+            if (k >= v.size()) throw std::runtime_error("Fields::load_magnetic_field() wrong size of input vector");
+            step = v[k] - v[k - 1];
+            if (step < 0) { step = -step; lo = v.back(); hi = v.front(); }
+            return (unsigned)to_int((hi - lo) / step + 1);
+        };
+        double rmin, zmin, dr, dz;
+        const unsigned rsampl = axis(rvec, rmin, dr), zsampl = axis(zvec, zmin, dz);
+        if ((size_t)rsampl * zsampl != rvec.size()) throw std::runtime_error("Fields::load_magnetic_field() wrong size of input vector");
+        Br.resize(rsampl, zsampl, dr, dz, rmin, zmin);
+        Bz.resize(rsampl, zsampl, dr, dz, rmin, zmin);
+        for (unsigned i = 0; i < rsampl; i++)
+            for (unsigned j = 0; j < zsampl; j++) Br[i][j] = Bz[i][j] = std::numeric_limits<double>::quiet_NaN();
+        for (size_t k = 0; k < rvec.size(); k++)
+        {
+            const int ri = to_int((rvec[k] - rmin) / dr), zi = to_int((zvec[k] - zmin) / dz);
+            Br[ri][zi] = brvec[k];
+            Bz[ri][zi] = bzvec[k];
+        }
+        if (Br.hasnan() || Bz.hasnan()) throw std::runtime_error("Fields::load_magnetic_field() garbage loaded");
+        gpu_check(mag2d_set_magnetic_field(gpu, (int)rsampl, (int)zsampl, dr, dz, rmin, zmin, Br[0], Bz[0]));
+    }
+    Field2D Br, Bz;     // private in the reference (fields.hpp:78); public here for the dump tool
     void u_sample() { download(); uAvg.add(u); nsampl++; }
     void u_reset() { uAvg.reset(); nsampl = 0; }
     void u_print(const char* fname) { uAvg.print(fname, 1.0 / nsampl); }

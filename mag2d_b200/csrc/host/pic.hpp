@@ -100,7 +100,7 @@ class Pic
         for (size_t i = 0; i < speclist.size(); i++) string2speciestype[speclist[i]->name] = (SpeciesType)i;
         if (param.particle_reload)
             for (size_t i = 0; i < speclist.size(); i++) speclist[i]->load(param.particle_reload_dir + "/particles_" + speclist[i]->name + ".dat");
-        if (!param.magnetic_field_const) throw std::runtime_error("Fields::load_magnetic_field(): not implemented in this build");
+        if (!param.magnetic_field_const) field.load_magnetic_field(param.magnetic_field_file.c_str());     // pic.cpp:148-149
         dist_reset();
         if (param.electric_field_from_file)
         {

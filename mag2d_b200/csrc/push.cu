@@ -95,34 +95,69 @@ __device__ __forceinline__ void gather_E(const GridDev& g, double x, double z, d
 }
 
 // ---- Boris rotation + half accelerations (velocity part of the movers) ---------------------------
-template <int COORD, bool HASB>
-__device__ __forceinline__ void boris_velocity(const SpeciesDev& s, double Ex, double Ez, double& vx, double& vy, double& vz)
+// BMODE: 0 no magnetic field, 1 constant B (t and s precomputed per species), 2 B interpolated per particle from the
+// table of Fields::load_magnetic_field (t and s formed per particle with the reference's expression order)
+constexpr int B_NONE = 0, B_CONST = 1, B_TABLE = 2;
+
+// Field2D::interpolate (Field2D.hpp:64-78) on the magnetic field table.  The reference throws outside the table;
+// mag2d_set_magnetic_field only accepts tables that cover the whole box, so the index clamp never changes a result
+// (it only keeps x == table edge from reading one row past the end, which the reference does with weight zero).
+__device__ __forceinline__ double table_interpolate(const GridDev& g, const double* __restrict__ data, double x, double z)
+{
+    x -= g.bxmin;
+    z -= g.bzmin;
+    const int i = max(min((int)(x * g.bidx), g.bM - 2), 0), j = max(min((int)(z * g.bidz), g.bN - 2), 0);
+    const double u = x * g.bidx - i, v = z * g.bidz - j;
+    const double* r = data + (unsigned)i * (unsigned)g.bN + (unsigned)j;
+    return (1 - u) * (1 - v) * __ldg(r) + u * (1 - v) * __ldg(r + g.bN) + (1 - u) * v * __ldg(r + 1) + u * v * __ldg(r + g.bN + 1);
+}
+
+template <int COORD>
+__device__ __forceinline__ void boris_rotate(double tx, double ty, double tz, double sx, double sy, double sz, double& vx, double& vy,
+                                             double& vz)
+{
+    if (COORD == MAG2D_CYLINDRICAL)
+    {
+        // textbook orientation in (r, theta, z), particles.cpp:581-592
+        const double pr = vx + vy * tz - vz * ty;
+        const double pt = vy + vz * tx - vx * tz;
+        const double pz = vz + vx * ty - vy * tx;
+        vx = vx + pt * sz - pz * sy;
+        vy = vy + pz * sx - pr * sz;
+        vz = vz + pr * sy - pt * sx;
+    }
+    else
+    {
+        // right-handed (x, z, y) triad: opposite signs, particles.cpp:964-979
+        const double pr = vx - vy * tz + vz * ty;
+        const double pz = vz - vx * ty + vy * tx;
+        const double pt = vy - vz * tx + vx * tz;
+        vx = vx - pt * sz + pz * sy;
+        vy = vy - pz * sx + pr * sz;
+        vz = vz - pr * sy + pt * sx;
+    }
+}
+
+// rotation about the table's B at (x, z): Fields::B gives (Br, Bz, 0) (fields.hpp:172-175)
+template <int COORD>
+__device__ __forceinline__ void boris_rotate_table(const GridDev& g, const SpeciesDev& s, double x, double z, double& vx, double& vy,
+                                                   double& vz)
+{
+    const double tx = table_interpolate(g, g.b_r, x, z) * s.tb;
+    const double ty = 0.0 * s.tb;
+    const double tz = table_interpolate(g, g.b_z, x, z) * s.tb;
+    const double tmp = 2.0 / (1 + tx * tx + ty * ty + tz * tz);
+    boris_rotate<COORD>(tx, ty, tz, tx * tmp, ty * tmp, tz * tmp, vx, vy, vz);
+}
+
+template <int COORD, int BMODE>
+__device__ __forceinline__ void boris_velocity(const GridDev& g, const SpeciesDev& s, double x, double z, double Ex, double Ez, double& vx,
+                                               double& vy, double& vz)
 {
     vx += Ex * s.hq;
     vz += Ez * s.hq;
-    if (HASB)
-    {
-        if (COORD == MAG2D_CYLINDRICAL)
-        {
-            // textbook orientation in (r, theta, z), particles.cpp:581-592
-            const double pr = vx + vy * s.tz - vz * s.ty;
-            const double pt = vy + vz * s.tx - vx * s.tz;
-            const double pz = vz + vx * s.ty - vy * s.tx;
-            vx = vx + pt * s.sz - pz * s.sy;
-            vy = vy + pz * s.sx - pr * s.sz;
-            vz = vz + pr * s.sy - pt * s.sx;
-        }
-        else
-        {
-            // right-handed (x, z, y) triad: opposite signs, particles.cpp:964-979
-            const double pr = vx - vy * s.tz + vz * s.ty;
-            const double pz = vz - vx * s.ty + vy * s.tx;
-            const double pt = vy - vz * s.tx + vx * s.tz;
-            vx = vx - pt * s.sz + pz * s.sy;
-            vy = vy - pz * s.sx + pr * s.sz;
-            vz = vz - pr * s.sy + pt * s.sx;
-        }
-    }
+    if (BMODE == B_CONST) boris_rotate<COORD>(s.tx, s.ty, s.tz, s.sx, s.sy, s.sz, vx, vy, vz);
+    if (BMODE == B_TABLE) boris_rotate_table<COORD>(g, s, x, z, vx, vy, vz);
     vx += Ex * s.hq;
     vz += Ez * s.hq;
 }
@@ -277,7 +312,7 @@ constexpr int DEPOSIT_RUNS = MAG2D_DEPOSIT_RUNS;   // cells per warp call that g
 #ifndef MAG2D_SORT_MIN_BLOCKS
 #define MAG2D_SORT_MIN_BLOCKS MAG2D_PUSH_MIN_BLOCKS
 #endif
-template <int COORD, bool GATHER, bool HASB, bool MCC, bool DEPOSIT, bool SORTING>
+template <int COORD, bool GATHER, int BMODE, bool MCC, bool DEPOSIT, bool SORTING>
 __global__ void __launch_bounds__(PUSH_THREADS, SORTING ? MAG2D_SORT_MIN_BLOCKS : MAG2D_PUSH_MIN_BLOCKS) k_push_boris(const __grid_constant__ PushArgs A)
 {
     const unsigned lane = lane_id();
@@ -286,7 +321,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, SORTING ? MAG2D_SORT_MIN_BLOCKS 
     const long long n = A.p.n;
     if (tile0 >= n) return;                   // warp-uniform; arrays are allocated in multiples of 256 slots
     const long long base = tile0 + 2 * lane;  // slot of this thread's first pair
-    constexpr bool need_vy = HASB || COORD == MAG2D_CYLINDRICAL;
+    constexpr bool need_vy = BMODE != B_NONE || COORD == MAG2D_CYLINDRICAL;
     const bool permute = SORTING && A.permute, count = SORTING && A.count;
     uint4 rnd = make_uint4(0, 0, 0, 0);
     if (MCC)
@@ -338,7 +373,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, SORTING ? MAG2D_SORT_MIN_BLOCKS 
             const bool live = (k + e < n) && particle_alive(x[e]);
             double Ex = 0.0, Ez = A.g.extern_field;
             if (GATHER) gather_E(A.g, x[e], z[e], Ex, Ez);
-            boris_velocity<COORD, HASB>(A.s, Ex, Ez, vx[e], vy[e], vz[e]);
+            boris_velocity<COORD, BMODE>(A.g, A.s, x[e], z[e], Ex, Ez, vx[e], vy[e], vz[e]);
             if (COORD == MAG2D_CYLINDRICAL)
             {
                 // Birdsall & Langdon p.338: drift in the local Cartesian frame, rotate back (particles.cpp:599-614)
@@ -594,7 +629,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, MAG2D_TMA_CTAS_PER_SM) k_push_bo
                 const bool live = (k + e < n) && particle_alive(x[e]);
                 double Ex = 0.0, Ez = A.g.extern_field;
                 if (GATHER) gather_E(A.g, x[e], z[e], Ex, Ez);
-                boris_velocity<COORD, HASB>(A.s, Ex, Ez, vx[e], vy[e], vz[e]);
+                boris_velocity<COORD, HASB ? B_CONST : B_NONE>(A.g, A.s, x[e], z[e], Ex, Ez, vx[e], vy[e], vz[e]);
                 if (COORD == MAG2D_CYLINDRICAL)
                 {
                     const double x2 = x[e] + vx[e] * dt;
@@ -727,24 +762,8 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push_boris_init(const __grid_c
     if (GATHER) gather_E(A.g, x, z, Ex, Ez);
     // A.s holds the init constants: t = B*(-0.5*q*dt/(2m)), hq = (-q/m*dt)/2  (particles.cpp:1010,1028)
     const SpeciesDev& s = A.s;
-    if (COORD == MAG2D_CYLINDRICAL)
-    {
-        const double pr = vx + vy * s.tz - vz * s.ty;
-        const double pt = vy + vz * s.tx - vx * s.tz;
-        const double pz = vz + vx * s.ty - vy * s.tx;
-        vx = vx + pt * s.sz - pz * s.sy;
-        vy = vy + pz * s.sx - pr * s.sz;
-        vz = vz + pr * s.sy - pt * s.sx;
-    }
-    else
-    {
-        const double pr = vx - vy * s.tz + vz * s.ty;
-        const double pz = vz - vx * s.ty + vy * s.tx;
-        const double pt = vy - vz * s.tx + vx * s.tz;
-        vx = vx - pt * s.sz + pz * s.sy;
-        vy = vy - pz * s.sx + pr * s.sz;
-        vz = vz - pr * s.sy + pt * s.sx;
-    }
+    if (A.g.b_r) boris_rotate_table<COORD>(A.g, s, x, z, vx, vy, vz);
+    else boris_rotate<COORD>(s.tx, s.ty, s.tz, s.sx, s.sy, s.sz, vx, vy, vz);
     vx += Ex * s.hq;
     vz += Ez * s.hq;
     A.p.vx[k] = vx;
@@ -864,6 +883,17 @@ __global__ void k_field_E(const __grid_constant__ GridDev g, int n, const double
     if (!g.const_E) gather_E(g, x[k], z[k], ex, ez);
     Ex[k] = ex;
     Ez[k] = ez;
+}
+
+// Fields::B at n points (fields.hpp:152-177): the constants of the grid descriptor or the interpolated table
+__global__ void k_field_B(const __grid_constant__ GridDev g, double Br0, double Bz0, double Bt0, int n, const double* __restrict__ x,
+                          const double* __restrict__ z, double* __restrict__ Br, double* __restrict__ Bz, double* __restrict__ Bt)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Br[k] = g.b_r ? table_interpolate(g, g.b_r, x[k], z[k]) : Br0;
+    Bz[k] = g.b_r ? table_interpolate(g, g.b_z, x[k], z[k]) : Bz0;
+    Bt[k] = g.b_r ? 0.0 : Bt0;
 }
 
 // ---- device-side loaders (Philox), src/particles.cpp:685-749, 485-510 -----------------------------
@@ -1075,6 +1105,15 @@ GridDev grid_view(const mag2d_ctx* c, int s)
     g.gz = c->d_gz;
     g.cfree = c->d_cfree;
     g.rho = s >= 0 ? c->d_rho + (size_t)s * d.M * d.N : nullptr;
+    // Fields::B reads the table only when magnetic_field_const = 0 (fields.hpp:154)
+    g.b_r = c->g.magnetic_field_const ? nullptr : c->d_btab_r;
+    g.b_z = c->g.magnetic_field_const ? nullptr : c->d_btab_z;
+    g.bM = c->btab_M;
+    g.bN = c->btab_N;
+    g.bidx = c->btab_idx;
+    g.bidz = c->btab_idz;
+    g.bxmin = c->btab_xmin;
+    g.bzmin = c->btab_zmin;
     return g;
 }
 
@@ -1097,6 +1136,7 @@ SpeciesDev species_view(const mag2d_ctx* c, int s, bool init)
     const double qmdt = init ? -charge / mass * dt : charge / mass * dt;
     v.hq = qmdt / 2.0;
     double tmp = init ? -0.5 * charge * dt / (2.0 * mass) : charge * dt / (2.0 * mass);
+    v.tb = tmp;
     const double Bx = d.Br, By = d.Bt, Bz = d.Bz;
     v.tx = Bx * tmp;
     v.ty = By * tmp;
@@ -1115,31 +1155,27 @@ SpeciesDev species_view(const mag2d_ctx* c, int s, bool init)
     return v;
 }
 
-template <int COORD, bool SORTING>
-int launch_boris_variant(mag2d_ctx* c, const PushArgs& A, bool gather, bool hasb, bool mcc, bool deposit, unsigned blocks)
+template <int COORD, bool SORTING, bool G, int B>
+void launch_boris_gb(mag2d_ctx* c, const PushArgs& A, bool mcc, bool deposit, unsigned blocks)
 {
-#define LAUNCH(G, B, Mc, D) k_push_boris<COORD, G, B, Mc, D, SORTING><<<blocks, PUSH_THREADS, 0, c->stream>>>(A)
-    const int code = (gather ? 8 : 0) | (hasb ? 4 : 0) | (mcc ? 2 : 0) | (deposit ? 1 : 0);
-    switch (code)
-    {
-        case 0: LAUNCH(false, false, false, false); break;
-        case 1: LAUNCH(false, false, false, true); break;
-        case 2: LAUNCH(false, false, true, false); break;
-        case 3: LAUNCH(false, false, true, true); break;
-        case 4: LAUNCH(false, true, false, false); break;
-        case 5: LAUNCH(false, true, false, true); break;
-        case 6: LAUNCH(false, true, true, false); break;
-        case 7: LAUNCH(false, true, true, true); break;
-        case 8: LAUNCH(true, false, false, false); break;
-        case 9: LAUNCH(true, false, false, true); break;
-        case 10: LAUNCH(true, false, true, false); break;
-        case 11: LAUNCH(true, false, true, true); break;
-        case 12: LAUNCH(true, true, false, false); break;
-        case 13: LAUNCH(true, true, false, true); break;
-        case 14: LAUNCH(true, true, true, false); break;
-        default: LAUNCH(true, true, true, true); break;
-    }
+#define LAUNCH(Mc, D) k_push_boris<COORD, G, B, Mc, D, SORTING><<<blocks, PUSH_THREADS, 0, c->stream>>>(A)
+    if (mcc) { if (deposit) LAUNCH(true, true); else LAUNCH(true, false); }
+    else { if (deposit) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
+}
+
+template <int COORD, bool SORTING>
+int launch_boris_variant(mag2d_ctx* c, const PushArgs& A, bool gather, int bmode, bool mcc, bool deposit, unsigned blocks)
+{
+    switch ((gather ? 3 : 0) + bmode)
+    {
+        case 0: launch_boris_gb<COORD, SORTING, false, B_NONE>(c, A, mcc, deposit, blocks); break;
+        case 1: launch_boris_gb<COORD, SORTING, false, B_CONST>(c, A, mcc, deposit, blocks); break;
+        case 2: launch_boris_gb<COORD, SORTING, false, B_TABLE>(c, A, mcc, deposit, blocks); break;
+        case 3: launch_boris_gb<COORD, SORTING, true, B_NONE>(c, A, mcc, deposit, blocks); break;
+        case 4: launch_boris_gb<COORD, SORTING, true, B_CONST>(c, A, mcc, deposit, blocks); break;
+        default: launch_boris_gb<COORD, SORTING, true, B_TABLE>(c, A, mcc, deposit, blocks); break;
+    }
     c->launches++;
     return 0;
 }
@@ -1189,9 +1225,9 @@ int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
     const long long n_active = chunked ? c->chunk_view->n : S.n_slots;
     if (n_active > 0)
     {
-        if (!d.magnetic_field_const)
+        if (!d.magnetic_field_const && !c->d_btab_r)
         {
-            mag2d_set_error("magnetic field from file is not implemented (magnetic_field_const = 0)");
+            mag2d_set_error("magnetic_field_const = 0 but no table was loaded (mag2d_set_magnetic_field)");
             return 1;
         }
         PushArgs A;
@@ -1255,6 +1291,7 @@ int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
         else
         {
             const bool gather = !A.g.const_E;
+            const int bmode = A.g.b_r ? B_TABLE : A.s.has_B ? B_CONST : B_NONE;
             if (gather)
                 if (update_ueff(c, d.rf ? rf_phase(c, S) : 0.0, d.rf != 0)) return 1;
             if (mcc)
@@ -1289,16 +1326,16 @@ int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
                     A.dst.n = S.n_slots;
                 }
                 if (d.coord == MAG2D_CYLINDRICAL)
-                    launch_boris_variant<MAG2D_CYLINDRICAL, true>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, tile_blocks);
+                    launch_boris_variant<MAG2D_CYLINDRICAL, true>(c, A, gather, bmode, mcc, d.selfconsistent != 0, tile_blocks);
                 else
-                    launch_boris_variant<MAG2D_CARTESIAN, true>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, tile_blocks);
+                    launch_boris_variant<MAG2D_CARTESIAN, true>(c, A, gather, bmode, mcc, d.selfconsistent != 0, tile_blocks);
                 if (sort_fused_end(c, s, permute, count)) return 1;
                 if (permute) A.p = particles_view(S);      // the collision pass works on the new slab
             }
             else if (d.coord == MAG2D_CYLINDRICAL)
-                launch_boris_variant<MAG2D_CYLINDRICAL, false>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, tile_blocks);
+                launch_boris_variant<MAG2D_CYLINDRICAL, false>(c, A, gather, bmode, mcc, d.selfconsistent != 0, tile_blocks);
             else
-                launch_boris_variant<MAG2D_CARTESIAN, false>(c, A, gather, A.s.has_B, mcc, d.selfconsistent != 0, tile_blocks);
+                launch_boris_variant<MAG2D_CARTESIAN, false>(c, A, gather, bmode, mcc, d.selfconsistent != 0, tile_blocks);
             if (mcc)
             {
                 k_mcc_collide<<<148 * 8, 128, 0, c->stream>>>(A);
@@ -1392,6 +1429,25 @@ int launch_field_E(mag2d_ctx* c, int n, const double* x, const double* z, double
     CUDA_OK(cudaMemcpyAsync(Ez, dez, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     CUDA_OK(cudaFree(dx));
+    return 0;
+}
+
+int launch_field_B(mag2d_ctx* c, int n, const double* x, const double* z, double* Br, double* Bz, double* Bt)
+{
+    if (n <= 0) return 0;
+    double* d;
+    CUDA_OK(cudaMalloc(&d, sizeof(double) * 5 * (size_t)n));
+    CUDA_OK(cudaMemcpyAsync(d, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d + n, z, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    k_field_B<<<(n + 255) / 256, 256, 0, c->stream>>>(grid_view(c, -1), c->g.Br, c->g.Bz, c->g.Bt, n, d, d + n, d + 2 * (size_t)n,
+                                                      d + 3 * (size_t)n, d + 4 * (size_t)n);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(Br, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(Bz, d + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(Bt, d + 4 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaFree(d));
     return 0;
 }
 

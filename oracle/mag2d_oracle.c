@@ -773,22 +773,114 @@ static void count_coll(int64_t* counts, int target, int intid, int ns)
     else if (intid < 16) counts[target * 16 + intid]++;
 }
 
-void orc_advance_boris(const orc_grid* g, const double* u, const double* uRF, const orc_model* m, int sp,
-                       orc_particles* p, unsigned long niter, orc_rng* rng, int64_t* coll_counts)
+/* util.cpp:22-28 with the default eps = 1e-2 used by fields.cpp:911,927,948-949 */
+static int double2int_ref(double x, int* bad)
+{
+    int res = (int)(x + 0.5);
+    if (fabs(res - x) > 1e-2) *bad = 1;
+    return res;
+}
+
+/* fields.cpp:898-959 (the file has been read into the four vectors, :882-896) */
+int orc_btable_build(int n, const double* rvec, const double* zvec, const double* brvec, const double* bzvec, orc_btable* out)
+{
+    int bad = 0;
+    memset(out, 0, sizeof(*out));
+    if (n < 2) return 1;
+    double dx = 0, rmin = rvec[0], rmax = rvec[n - 1];
+    int i = 1;
+    while (i < n && rvec[i] - rvec[i - 1] == 0.0) i++;
+    if (i >= n) return 1;
+    dx = rvec[i] - rvec[i - 1];
+    if (dx < 0)
+    {
+        dx = -dx;
+        rmin = rvec[n - 1];
+        rmax = rvec[0];
+    }
+    const int rsampl = double2int_ref((rmax - rmin) / dx + 1, &bad);
+    double dz = 0, zmin = zvec[0], zmax = zvec[n - 1];
+    i = 1;
+    while (i < n && zvec[i] - zvec[i - 1] == 0.0) i++;
+    if (i >= n) return 1;
+    dz = zvec[i] - zvec[i - 1];
+    if (dz < 0)
+    {
+        dz = -dz;
+        zmin = zvec[n - 1];
+        zmax = zvec[0];
+    }
+    const int zsampl = double2int_ref((zmax - zmin) / dz + 1, &bad);
+    if (bad) return 3;
+    if ((long long)rsampl * zsampl != n) return 1;
+    out->jmax = rsampl;
+    out->lmax = zsampl;
+    out->dx = dx;
+    out->dy = dz;
+    out->xmin = rmin;
+    out->ymin = zmin;
+    out->Br = (double*)malloc(sizeof(double) * (size_t)n);
+    out->Bz = (double*)malloc(sizeof(double) * (size_t)n);
+    for (int k = 0; k < n; k++) out->Br[k] = out->Bz[k] = NAN;
+    for (int k = 0; k < n; k++)
+    {
+        const int ri = double2int_ref((rvec[k] - rmin) / dx, &bad);
+        const int zi = double2int_ref((zvec[k] - zmin) / dz, &bad);
+        if (bad || ri < 0 || ri >= rsampl || zi < 0 || zi >= zsampl)
+        {
+            orc_btable_free(out);
+            return 3;
+        }
+        out->Br[(size_t)ri * zsampl + zi] = brvec[k];
+        out->Bz[(size_t)ri * zsampl + zi] = bzvec[k];
+    }
+    for (int k = 0; k < n; k++)
+        if (isnan(out->Br[k]) || isnan(out->Bz[k]))
+        {
+            orc_btable_free(out);
+            return 2;
+        }
+    return 0;
+}
+
+void orc_btable_free(orc_btable* t)
+{
+    free(t->Br);
+    free(t->Bz);
+    t->Br = t->Bz = NULL;
+}
+
+void orc_field_B(const orc_grid* g, const orc_btable* t, double x, double y, double* Br, double* Bz, double* Bt)
+{
+    if (!t)
+    {
+        *Br = g->Br;
+        *Bz = g->Bz;
+        *Bt = g->Bt;
+        return;
+    }
+    /* Field2D::resize sets idx = 1.0/dx (Field2D.cpp:11) */
+    *Br = orc_interpolate(t->Br, t->jmax, t->lmax, 1.0 / t->dx, 1.0 / t->dy, t->xmin, t->ymin, x, y);
+    *Bz = orc_interpolate(t->Bz, t->jmax, t->lmax, 1.0 / t->dx, 1.0 / t->dy, t->xmin, t->ymin, x, y);
+    *Bt = 0.00;
+}
+
+void orc_advance_boris_B(const orc_grid* g, const orc_btable* t, const double* u, const double* uRF, const orc_model* m, int sp,
+                         orc_particles* p, unsigned long niter, orc_rng* rng, int64_t* coll_counts)
 {
     const orc_spec* s = &m->s[sp];
     double fx = 0, fz = g->extern_field;
+    double Bx = g->Br, Bz = g->Bz, By = g->Bt;
     const double prob = 1.0 - exp(-s->dt / s->lifetime);
     for (int k = 0; k < p->n; k++)
     {
         if (!p->alive[k]) continue;
         orc_field_E(g, u, uRF, p->x[k], p->z[k], niter * s->dt, &fx, &fz);
+        orc_field_B(g, t, p->x[k], p->z[k], &Bx, &Bz, &By);
         if (g->coord == ORC_CYLINDRICAL)
-            orc_boris_cyl(s->charge, s->mass, s->dt, fx, fz, g->Br, g->Bz, g->Bt, &p->x[k], &p->z[k], &p->vx[k],
-                          &p->vy[k], &p->vz[k]);
+            orc_boris_cyl(s->charge, s->mass, s->dt, fx, fz, Bx, Bz, By, &p->x[k], &p->z[k], &p->vx[k], &p->vy[k], &p->vz[k]);
         else
-            orc_boris_cart(s->charge, s->mass, s->dt, fx, fz, g->Br, g->Bz, g->Bt, &p->x[k], &p->z[k], &p->vx[k],
-                           &p->vy[k], &p->vz[k]);
+            orc_boris_cart(s->charge, s->mass, s->dt, fx, fz, Bx, Bz, By, &p->x[k], &p->z[k], &p->vx[k], &p->vy[k], &p->vz[k]);
         if (rng && orc_rng_uni(rng) < prob)
         {
             int target;
@@ -798,20 +890,34 @@ void orc_advance_boris(const orc_grid* g, const double* u, const double* uRF, co
     }
 }
 
-void orc_advance_boris_init(const orc_grid* g, const double* u, const double* uRF, const orc_model* m,
-                            int sp, orc_particles* p, unsigned long niter)
+void orc_advance_boris(const orc_grid* g, const double* u, const double* uRF, const orc_model* m, int sp,
+                       orc_particles* p, unsigned long niter, orc_rng* rng, int64_t* coll_counts)
+{
+    orc_advance_boris_B(g, NULL, u, uRF, m, sp, p, niter, rng, coll_counts);
+}
+
+void orc_advance_boris_init_B(const orc_grid* g, const orc_btable* t, const double* u, const double* uRF, const orc_model* m,
+                              int sp, orc_particles* p, unsigned long niter)
 {
     const orc_spec* s = &m->s[sp];
     double fx = 0, fz = g->extern_field;
+    double Bx = g->Br, Bz = g->Bz, By = g->Bt;
     for (int k = 0; k < p->n; k++)
     {
         if (!p->alive[k]) continue;
         orc_field_E(g, u, uRF, p->x[k], p->z[k], niter * s->dt, &fx, &fz);
+        orc_field_B(g, t, p->x[k], p->z[k], &Bx, &Bz, &By);
         if (g->coord == ORC_CYLINDRICAL)
-            orc_boris_cyl_init(s->charge, s->mass, s->dt, fx, fz, g->Br, g->Bz, g->Bt, &p->vx[k], &p->vy[k], &p->vz[k]);
+            orc_boris_cyl_init(s->charge, s->mass, s->dt, fx, fz, Bx, Bz, By, &p->vx[k], &p->vy[k], &p->vz[k]);
         else
-            orc_boris_cart_init(s->charge, s->mass, s->dt, fx, fz, g->Br, g->Bz, g->Bt, &p->vx[k], &p->vy[k], &p->vz[k]);
+            orc_boris_cart_init(s->charge, s->mass, s->dt, fx, fz, Bx, Bz, By, &p->vx[k], &p->vy[k], &p->vz[k]);
     }
+}
+
+void orc_advance_boris_init(const orc_grid* g, const double* u, const double* uRF, const orc_model* m,
+                            int sp, orc_particles* p, unsigned long niter)
+{
+    orc_advance_boris_init_B(g, NULL, u, uRF, m, sp, p, niter);
 }
 
 void orc_advance_multicoll(double fx, double fz, const orc_model* m, int sp, orc_particles* p, orc_rng* rng,

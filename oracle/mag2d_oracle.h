@@ -58,6 +58,21 @@ double orc_interpolate(const double* data, int jmax, int lmax, double idx, doubl
 void orc_field_E(const orc_grid* g, const double* u, const double* uRF, double x, double y, double time,
                  double* Ex, double* Ez);
 
+/* ---- magnetic field table (magnetic_field_const = 0) ---- */
+/* Fields::Br / Fields::Bz: two Field2D on their own grid (src/fields.hpp:64) */
+typedef struct
+{
+    int jmax, lmax;           /* rsampl, zsampl */
+    double dx, dy, xmin, ymin;
+    double *Br, *Bz;          /* [jmax*lmax], row-major like Array2D */
+} orc_btable;
+/* Fields::load_magnetic_field, src/fields.cpp:870-959, from the n parsed rows (r, z, Br, Bz) of the file.
+ * Returns 0, or 1 "wrong size of input vector", 2 "garbage loaded", 3 double2int "is not integer" (src/util.cpp:22-28) */
+int orc_btable_build(int n, const double* r, const double* z, const double* br, const double* bz, orc_btable* out);
+void orc_btable_free(orc_btable* t);
+/* Fields::B, src/fields.hpp:152-177; t == NULL: magnetic_field_const */
+void orc_field_B(const orc_grid* g, const orc_btable* t, double x, double y, double* Br, double* Bz, double* Bt);
+
 /* ---- movers (collisions handled separately), src/particles.cpp ---- */
 /* one particle, Species<CARTESIAN>::advance_boris body :947-987 */
 void orc_boris_cart(double charge, double mass, double dt, double fx, double fz, double Bx, double Bz,
@@ -144,6 +159,11 @@ void orc_advance_boris(const orc_grid* g, const double* u, const double* uRF, co
                        orc_particles* p, unsigned long niter, orc_rng* rng, int64_t* coll_counts);
 void orc_advance_boris_init(const orc_grid* g, const double* u, const double* uRF, const orc_model* m,
                             int sp, orc_particles* p, unsigned long niter);
+/* the same two with field->B(I->x, I->z, Bx, Bz, By) read from a table (src/particles.cpp:563, 648, 948, 1022) */
+void orc_advance_boris_B(const orc_grid* g, const orc_btable* t, const double* u, const double* uRF, const orc_model* m, int sp,
+                         orc_particles* p, unsigned long niter, orc_rng* rng, int64_t* coll_counts);
+void orc_advance_boris_init_B(const orc_grid* g, const orc_btable* t, const double* u, const double* uRF, const orc_model* m,
+                              int sp, orc_particles* p, unsigned long niter);
 /* Species<CARTESIAN>::advance_multicoll, src/particles.cpp:813-859 (constant field fx,fz) */
 void orc_advance_multicoll(double fx, double fz, const orc_model* m, int sp, orc_particles* p, orc_rng* rng,
                            int64_t* coll_counts);

@@ -54,6 +54,11 @@ class OrcParticles(C.Structure):
     _fields_ = [("n", C.c_int)] + [(k, dp) for k in ("x", "y", "z", "vx", "vy", "vz", "ttd")] + [("alive", u8p)]
 
 
+class OrcBTable(C.Structure):
+    _fields_ = [("jmax", C.c_int), ("lmax", C.c_int), ("dx", C.c_double), ("dy", C.c_double),
+                ("xmin", C.c_double), ("ymin", C.c_double), ("Br", dp), ("Bz", dp)]
+
+
 class OrcRng(C.Structure):
     _fields_ = [
         ("jz", C.c_uint32), ("jsr", C.c_uint32), ("hz", C.c_int32), ("iz", C.c_uint32),
@@ -206,6 +211,13 @@ class Oracle:
         lib.orc_scatter.argtypes = [C.c_void_p, C.c_int, R, dp, dp, dp, C.POINTER(C.c_int)]
         lib.orc_advance_boris.argtypes = [G, dp, dp, C.c_void_p, C.c_int, P, C.c_ulong, R, i64p]
         lib.orc_advance_boris_init.argtypes = [G, dp, dp, C.c_void_p, C.c_int, P, C.c_ulong]
+        BT = C.POINTER(OrcBTable)
+        lib.orc_btable_build.argtypes = [C.c_int, dp, dp, dp, dp, BT]
+        lib.orc_btable_build.restype = C.c_int
+        lib.orc_btable_free.argtypes = [BT]
+        lib.orc_field_B.argtypes = [G, BT, C.c_double, C.c_double, dp, dp, dp]
+        lib.orc_advance_boris_B.argtypes = [G, BT, dp, dp, C.c_void_p, C.c_int, P, C.c_ulong, R, i64p]
+        lib.orc_advance_boris_init_B.argtypes = [G, BT, dp, dp, C.c_void_p, C.c_int, P, C.c_ulong]
         lib.orc_advance_multicoll.argtypes = [C.c_double, C.c_double, C.c_void_p, C.c_int, P, R, i64p]
         lib.orc_advance_boundary.argtypes = [G, u8p, C.c_double, P, dp, i64p]
         lib.orc_deposit_fp64.argtypes = [G, C.c_double, C.c_int, dp, dp, u8p, dp]
@@ -275,15 +287,48 @@ class Oracle:
             out[k] = (vx.value, vy.value, vz.value)
         return out, proc, targ
 
-    def advance_boris(self, g, u, uRF, model, sp, particles, niter=0, rng=None, counts=None):
+    def advance_boris(self, g, u, uRF, model, sp, particles, niter=0, rng=None, counts=None, btable=None):
         v = particles.cview()
-        self.lib.orc_advance_boris(C.byref(g), _d(u), _d(uRF), model.h, sp, C.byref(v), niter,
-                                   C.byref(rng) if rng is not None else None,
-                                   counts.ctypes.data_as(i64p) if counts is not None else None)
+        self.lib.orc_advance_boris_B(C.byref(g), C.byref(btable) if btable is not None else None, _d(u), _d(uRF), model.h, sp,
+                                     C.byref(v), niter, C.byref(rng) if rng is not None else None,
+                                     counts.ctypes.data_as(i64p) if counts is not None else None)
 
-    def advance_boris_init(self, g, u, uRF, model, sp, particles, niter=0):
+    def advance_boris_init(self, g, u, uRF, model, sp, particles, niter=0, btable=None):
         v = particles.cview()
-        self.lib.orc_advance_boris_init(C.byref(g), _d(u), _d(uRF), model.h, sp, C.byref(v), niter)
+        self.lib.orc_advance_boris_init_B(C.byref(g), C.byref(btable) if btable is not None else None, _d(u), _d(uRF), model.h, sp,
+                                          C.byref(v), niter)
+
+    # ---- magnetic field table (Fields::load_magnetic_field, fields.cpp:870-959)
+    def load_magnetic_field(self, fname):
+        """the file loop of fields.cpp:882-896 (rows with four numbers; everything else is skipped) + orc_btable_build"""
+        rows = []
+        with open(fname) as f:
+            for line in f:
+                t = line.split()
+                try:
+                    rows.append([float(t[0]), float(t[1]), float(t[2]), float(t[3])])
+                except (ValueError, IndexError):
+                    continue
+        a = np.ascontiguousarray(np.array(rows, dtype=np.float64).T)
+        bt = OrcBTable()
+        rc = self.lib.orc_btable_build(a.shape[1], _d(a[0]), _d(a[1]), _d(a[2]), _d(a[3]), C.byref(bt))
+        if rc:
+            raise RuntimeError({1: "Fields::load_magnetic_field() wrong size of input vector",
+                                2: "Fields::load_magnetic_field() garbage loaded", 3: "double2int() is not integer"}[rc])
+        return bt
+
+    def btable_arrays(self, bt):
+        n = bt.jmax * bt.lmax
+        return (np.ctypeslib.as_array(bt.Br, shape=(n,)).reshape(bt.jmax, bt.lmax).copy(),
+                np.ctypeslib.as_array(bt.Bz, shape=(n,)).reshape(bt.jmax, bt.lmax).copy())
+
+    def field_B(self, g, bt, x, z):
+        out = np.zeros((3, len(x)))
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        for k in range(len(x)):
+            self.lib.orc_field_B(C.byref(g), C.byref(bt) if bt is not None else None, float(x[k]), float(z[k]), C.byref(a), C.byref(b), C.byref(c))
+            out[:, k] = a.value, b.value, c.value
+        return out
 
     def advance_multicoll(self, fx, fz, model, sp, particles, rng, counts=None):
         v = particles.cview()

@@ -72,6 +72,9 @@ def _lib(variant):
     lib.ref_set_field.argtypes = [C.c_void_p, C.c_char_p, dp]
     lib.ref_field_op.argtypes = [C.c_void_p, C.c_char_p]
     lib.ref_field_E.argtypes = [C.c_void_p, C.c_int, dp, dp, C.c_double, dp, dp]
+    lib.ref_field_B.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, dp, dp]
+    lib.ref_btable_info.argtypes = [C.c_void_p, dp]
+    lib.ref_btable_get.argtypes = [C.c_void_p, C.c_int, dp]
     lib.ref_field_accumulate.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_int, dp, dp]
     lib.ref_is_free.argtypes = [C.c_void_p, C.c_int, dp, dp, C.POINTER(C.c_int)]
     lib.ref_scatter.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
@@ -231,6 +234,23 @@ class RefHarness:
         ez = np.zeros_like(x)
         self._chk(self.lib.ref_field_E(self.h, x.size, _dp(x), _dp(z), float(time), _dp(ex), _dp(ez)))
         return ex, ez
+
+    def field_B(self, x, z):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        out = np.zeros((3, len(x)))
+        self._chk(self.lib.ref_field_B(self.h, len(x), _dp(x), _dp(z), _dp(out[0]), _dp(out[1]), _dp(out[2])))
+        return out
+
+    def btable(self):
+        """(info dict, Br, Bz) of the table loaded by Fields::load_magnetic_field"""
+        o = np.zeros(6)
+        self._chk(self.lib.ref_btable_info(self.h, _dp(o)))
+        M, N = int(o[0]), int(o[1])
+        br, bz = np.zeros((M, N)), np.zeros((M, N))
+        self._chk(self.lib.ref_btable_get(self.h, 0, _dp(br)))
+        self._chk(self.lib.ref_btable_get(self.h, 1, _dp(bz)))
+        return dict(jmax=M, lmax=N, dx=o[2], dy=o[3], xmin=o[4], ymin=o[5]), br, bz
 
     def field_accumulate(self, which, charge, x, z):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -404,6 +404,30 @@ int ref_field_E(void* hv, int n, const double* x, const double* z, double time, 
     Handle* h = (Handle*)hv;
     return guarded(h, [&] { for (int k = 0; k < n; k++) h->field()->E(x[k], z[k], Ex[k], Ez[k], time); });
 }
+/* Fields::B (fields.hpp:152-177): the constants or the table read by Fields::load_magnetic_field in the Pic constructor */
+int ref_field_B(void* hv, int n, const double* x, const double* z, double* Br, double* Bz, double* Bt)
+{
+    Handle* h = (Handle*)hv;
+    return guarded(h, [&] { for (int k = 0; k < n; k++) h->field()->B(x[k], z[k], Br[k], Bz[k], Bt[k]); });
+}
+/* the loaded tables themselves: dims (rsampl, zsampl, dx, dz, rmin, zmin), then the data with which = "Br" / "Bz" */
+int ref_btable_info(void* hv, double* o)
+{
+    Handle* h = (Handle*)hv;
+    return guarded(h, [&] {
+        Field2D& f = h->field()->Br;
+        o[0] = f.jmax; o[1] = f.lmax; o[2] = f.GetDx(); o[3] = f.GetDy(); o[4] = f.GetXMin(); o[5] = f.GetYMin();
+    });
+}
+int ref_btable_get(void* hv, int which, double* out)
+{
+    Handle* h = (Handle*)hv;
+    return guarded(h, [&] {
+        Field2D& f = which == 0 ? h->field()->Br : h->field()->Bz;
+        for (int i = 0; i < f.jmax; i++)
+            for (int j = 0; j < f.lmax; j++) out[(size_t)i * f.lmax + j] = f[i][j];
+    });
+}
 int ref_field_accumulate(void* hv, const char* which, double charge, int n, const double* x, const double* z)
 {
     Handle* h = (Handle*)hv;

@@ -41,3 +41,21 @@ def disk_particles(rng, n, cx, cz, radius, vth, ttd=0.0):
     aos[:, 3:6] = rng.normal(size=(n, 3)) * vth
     aos[:, 6] = ttd
     return aos
+
+
+def write_btable(path, nr, nz, r_max, z_max, descending=False, header=True):
+    """a magnetic field table in the four-column format Fields::load_magnetic_field reads (fields.cpp:882-896):
+    r z Br Bz per row, r slowest; a mirror-like field Bz = B0 (1 + a z'^2 - a r^2 / 2), Br = -a B0 r z'"""
+    r = np.linspace(0.0, r_max, nr)
+    z = np.linspace(0.0, z_max, nz)
+    if descending:
+        r, z = r[::-1], z[::-1]
+    B0, a = 0.03, 400.0
+    with open(path, "w") as f:
+        if header:
+            f.write("# r z Br Bz\n")
+        for ri in r:
+            for zj in z:
+                zp = zj - 0.5 * z_max
+                f.write("%.17g %.17g %.17g %.17g\n" % (ri, zj, -a * B0 * ri * zp, B0 * (1 + a * zp * zp - 0.5 * a * ri * ri)))
+    return path

@@ -516,3 +516,102 @@ def test_device_loaders_fill_the_domain_statistically(deckdir):
             assert abs(p[:, 0].mean() / 6.4e-3 - 0.5) < 0.01 and abs(p[:, 2].mean() / 6.4e-3 - 0.5) < 0.01
             vth = np.sqrt(1.380662e-23 * T / m)              # each component: rnor * v_max / sqrt(2)
             assert abs(p[:, 3:6].std() / vth - 1.0) < 0.01
+
+
+# --------------------------------------------------------------------- magnetic field from file (f-row 3)
+GB = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_v2_btable.npz"))
+
+
+def test_magnetic_field_table_cylindrical_vs_golden_reference(orc, deckdir):
+    """magnetic_field_const = 0: the table travels through config.load_magnetic_field -> mag2d_set_magnetic_field,
+    Fields::B and the cylindrical Boris mover (init + 20 steps) against the reference's recorded outputs"""
+    from common import write_btable
+    bfile = write_btable(os.path.join(deckdir, "btable_gpu.txt"), 25, 31, 1.2e-2, 7.5e-2)
+    d = decks.deck("c3", deckdir + "_bt", n_particles=10, collisions=False, x_sampl=41, z_sampl=61, magnetic_field_const=0,
+                   magnetic_field_file=bfile, selfconsistent=0, geometry="PENNING_SIMPLE")
+    with _sim(d["config"], d["species_conf"], presolve=False) as sim:
+        assert sim.btable["r_sampl"] == 25 and sim.btable["z_sampl"] == 31
+        B = sim.field_B(GB["bt_x"], GB["bt_z"])
+        assert np.abs(B - GB["bt_B"]).max() <= 1e-15 * np.abs(GB["bt_B"]).max() * 4
+        e = sim.species_index("ELECTRON")
+        sim.set_field("u", GB["bt_u"])
+        sim.set_field("uRF", GB["bt_uRF"])
+        for _ in range(3):
+            sim.species_advance(e)          # the golden run started at niter = 3
+        sim.set_particles(e, GB["bt_in"])
+        sim.species_advance_init(e)
+        out = sim.get_particles(e)
+        assert relerr(out[:, 3:6], GB["bt_init"][:, 3:6]) <= 1e-12
+        sim.species_advance(e)
+        for _ in range(19):
+            sim.species_advance(e)
+        out = sim.get_particles(e)
+        ref = GB["bt_out"]
+        both = out[:, 7] > 0
+        assert both.sum() >= 0.9 * len(ref)
+        assert relerr(out[both][:, [0, 2, 3, 4, 5]], ref[both][:, [0, 2, 3, 4, 5]]) <= 1e-10
+
+
+@pytest.mark.parametrize("coord", ["CARTESIAN", "CYLINDRICAL"])
+def test_magnetic_field_table_vs_oracle_with_deposit_and_sort(orc, deckdir, coord):
+    """the table mode of the fused kernel in the self-consistent configuration (deposit + fused sort variants):
+    trajectories against the oracle, charge grid bit-exact for the final particle set"""
+    from common import write_btable
+    r_max, z_max = (1.2e-2, 7.5e-2) if coord == "CYLINDRICAL" else (6.4e-3, 6.4e-3)
+    bfile = write_btable(os.path.join(deckdir, "btable_gpu_%s.txt" % coord), 33, 21, r_max, z_max, descending=True)
+    if coord == "CYLINDRICAL":
+        d = decks.deck("c3", deckdir + "_bts", n_particles=10, collisions=False, x_sampl=41, z_sampl=61, magnetic_field_const=0,
+                       magnetic_field_file=bfile, macroparticle_factor=1e-3)     # light macro-particles: negligible space charge
+        name = "ELECTRON"
+    else:
+        d = decks.deck("c4", deckdir + "_bts", n_particles=10, collisions=False, x_sampl=65, z_sampl=65, r_max=r_max, z_max=z_max,
+                       magnetic_field_const=0, magnetic_field_file=bfile, density_total=1e6)
+        name = "ELECTRON"
+    with _sim(d["config"], d["species_conf"]) as sim:
+        g = grid_from_param(sim.param)
+        bt = orc.load_magnetic_field(bfile)
+        m, names = model_from(orc, d["species_conf"])
+        e = names.index(name)
+        rng = np.random.default_rng(12)
+        aos = disk_particles(rng, 6000, 0.5 * r_max, 0.5 * z_max, 0.3 * r_max, 4e5)
+        sim.set_particles(e, aos)
+        P = Particles.from_aos7(aos)
+        u = np.zeros((sim.M, sim.N))
+        sim.set_field("u", u)          # field-free: the same array drives both sides
+        for step in range(9):
+            if step == 8:
+                sim.rho_reset(e)       # the grid then holds the deposit of the last step alone
+            sim.species_advance(e)
+            orc.advance_boris(g, u, u, m, e, P, niter=step, rng=None, btable=bt)
+            orc.advance_boundary(g, sim.mask, m.get(e, "charge"), P)
+        out = sim.get_particles(e)
+        both = (out[:, 7] > 0) & (P.alive > 0)
+        assert np.sum((out[:, 7] > 0) != (P.alive > 0)) <= 2 and both.sum() > 3000
+        assert relerr(out[both][:, [0, 2, 3, 4, 5]], P.aos7()[both][:, [0, 2, 3, 4, 5]]) <= 1e-11
+        fixed, _ = orc.deposit_fixed(g, out[:, 0].copy(), out[:, 2].copy(), out[:, 7].astype(np.uint8))
+        assert np.array_equal(sim.rho_fixed(e), fixed)
+        # the full step (solve + push with the cell sort fused in: the SORTING instantiations of the table mode)
+        n0 = int((out[:, 7] > 0).sum())
+        sim.set_sort_interval(2)
+        sim.advance_init()
+        sim.advance(6)
+        out2 = sim.get_particles(e)
+        live = out2[:, 7] > 0
+        assert 0.9 * n0 <= live.sum() <= n0 and np.isfinite(out2[live][:, [0, 2, 3, 4, 5]]).all()
+        fixed2, _ = orc.deposit_fixed(g, out2[:, 0].copy(), out2[:, 2].copy(), out2[:, 7].astype(np.uint8))
+        assert np.array_equal(sim.rho_fixed(e), fixed2)
+
+
+def test_magnetic_field_table_must_cover_the_box(deckdir):
+    """the reference throws "Field2D::interpolate() outside of range" when a particle leaves the table; the ABI refuses
+    such a table up front, with the same text"""
+    from common import write_btable
+    from mag2d_b200.api import Mag2dError
+    bfile = write_btable(os.path.join(deckdir, "btable_small.txt"), 9, 9, 0.6e-2, 7.5e-2)
+    d = decks.deck("c3", deckdir + "_btx", n_particles=10, x_sampl=41, z_sampl=61, magnetic_field_const=0, magnetic_field_file=bfile)
+    with pytest.raises(Mag2dError, match="outside of range"):
+        _sim(d["config"], d["species_conf"], presolve=False)
+    d = decks.deck("c3", deckdir + "_bty", n_particles=10, x_sampl=41, z_sampl=61, magnetic_field_const=0,
+                   magnetic_field_file=os.path.join(deckdir, "no_such_file.txt"))
+    with pytest.raises(RuntimeError, match="failed opening file"):
+        _sim(d["config"], d["species_conf"], presolve=False)

@@ -162,3 +162,25 @@ def test_plasma3d_driver_field_and_trajectory(host_bins, tmp_path):
         assert traj[step] == pytest.approx([soa["x"][0], soa["y"][0], soa["z"][0]], rel=2e-5)
         assert vel[step] == pytest.approx([soa["vx"][0], soa["vy"][0], soa["vz"][0]], rel=2e-5, abs=1e-3)
         orc.advance(g, u_ref, mask, charge, mass, 2e-10, (0, 0, 0), soa, alive)
+
+
+@pytest.mark.gpu
+def test_plasma2d_driver_loads_a_magnetic_field_table(host_bins, tmp_path):
+    """magnetic_field_const = 0 through the C++ host layer: Pic ctor -> Fields::load_magnetic_field (pic.cpp:148-149) ->
+    mag2d_set_magnetic_field; a table that does not cover the box is refused with the reference's interpolate() message"""
+    from common import write_btable
+    L = 6.4e-3
+    bfile = write_btable(str(tmp_path / "btable.txt"), 17, 17, L, L)
+    d = decks.deck("c4", str(tmp_path), n_particles=4000, x_sampl=33, z_sampl=33, r_max=L, z_max=L, niter=10, t_print=5, t_print_dist=0,
+                   magnetic_field_const=0, magnetic_field_file=bfile)
+    out = str(tmp_path / "out_bt")
+    log = run_driver(host_bins, "plasma2d_b200", d, out)
+    assert "plot 10" in log
+    rows = np.loadtxt(os.path.join(out, "out.dat"))
+    assert np.isfinite(rows).all()
+    small = write_btable(str(tmp_path / "btable_small.txt"), 9, 9, 0.5 * L, L)
+    d = decks.deck("c4", str(tmp_path / "bad"), n_particles=4000, x_sampl=33, z_sampl=33, r_max=L, z_max=L, niter=10, t_print=5,
+                   t_print_dist=0, magnetic_field_const=0, magnetic_field_file=small)
+    r = subprocess.run([os.path.join(host_bins, "plasma2d_b200"), "config=" + d["config"], "species_conf=" + d["species_conf"],
+                        "initscript=" + d["initscript"], "output_dir=" + str(tmp_path / "out_bad")], capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "outside of range" in (r.stdout + r.stderr)

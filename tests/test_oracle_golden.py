@@ -192,3 +192,29 @@ def test_3d_field_code_golden():
     assert np.array_equal(b, G3["rhs"])
     u = orc3.solve_direct(g, mask, b)
     assert np.abs(u - G3["u_solved"]).max() <= 1e-11 * np.abs(G3["u_solved"]).max()
+
+
+def test_magnetic_field_table_golden(orc, deckdir):
+    """magnetic_field_const = 0: table build, Fields::B and the cylindrical Boris mover against the reference's
+    outputs in reference_v2_btable.npz (make_golden_btable.py)"""
+    from common import write_btable
+    GB = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_v2_btable.npz"))
+    r_max, z_max = 1.2e-2, 7.5e-2
+    bfile = write_btable(os.path.join(deckdir, "btable_golden.txt"), 25, 31, r_max, z_max)
+    d = decks.deck("c3", deckdir, n_particles=10, x_sampl=41, z_sampl=61, magnetic_field_const=0, magnetic_field_file=bfile,
+                   selfconsistent=0, geometry="PENNING_SIMPLE")
+    p = cfg.read_config(d["config"])
+    g = grid_from_param(p)
+    bt = orc.load_magnetic_field(bfile)
+    assert np.array_equal(np.array([bt.jmax, bt.lmax, bt.dx, bt.dy, bt.xmin, bt.ymin], dtype=np.float64), GB["bt_info"])
+    br, bz = orc.btable_arrays(bt)
+    assert np.array_equal(br, GB["bt_Br"]) and np.array_equal(bz, GB["bt_Bz"])
+    assert np.array_equal(orc.field_B(g, bt, GB["bt_x"], GB["bt_z"]), GB["bt_B"])
+    m, names = model_from(orc, d["species_conf"])
+    e = names.index("ELECTRON")
+    P = Particles.from_aos7(GB["bt_in"])
+    orc.advance_boris_init(g, GB["bt_u"], GB["bt_uRF"], m, e, P, niter=3, btable=bt)
+    assert np.array_equal(GB["bt_init"][:, :7], P.aos7())
+    for step in range(20):
+        orc.advance_boris(g, GB["bt_u"], GB["bt_uRF"], m, e, P, niter=3 + step, rng=None, btable=bt)
+    assert np.array_equal(GB["bt_out"][:, :7], P.aos7())
