@@ -920,6 +920,133 @@ void orc_advance_boris_init(const orc_grid* g, const double* u, const double* uR
     orc_advance_boris_init_B(g, NULL, u, uRF, m, sp, p, niter);
 }
 
+void orc_advance_boris_extern(const orc_grid* g, const orc_model* m, int sp, orc_particles* p, orc_rng* rng,
+                              int64_t* coll_counts, int init)
+{
+    const orc_spec* s = &m->s[sp];
+    const double fx = 0, fz = g->extern_field;
+    const double prob = 1.0 - exp(-s->dt / s->lifetime);
+    for (int k = 0; k < p->n; k++)
+    {
+        if (!p->alive[k]) continue;
+        if (init)
+        {
+            orc_boris_cart_init(s->charge, s->mass, s->dt, fx, fz, g->Br, g->Bz, g->Bt, &p->vx[k], &p->vy[k], &p->vz[k]);
+            continue;
+        }
+        orc_boris_cart(s->charge, s->mass, s->dt, fx, fz, g->Br, g->Bz, g->Bt, &p->x[k], &p->z[k], &p->vx[k], &p->vy[k], &p->vz[k]);
+        if (rng && orc_rng_uni(rng) < prob)
+        {
+            int target;
+            int intid = orc_scatter(m, sp, rng, &p->vx[k], &p->vy[k], &p->vz[k], &target);
+            count_coll(coll_counts, target, intid, m->ns);
+        }
+    }
+}
+
+unsigned orc_source_size(const orc_model* m, int sp, double V, unsigned factor)
+{
+    double N = m->s[sp].density * V;
+    unsigned int n_particles = N / factor;
+    return n_particles;
+}
+
+void orc_source_refresh(const orc_grid* g, const orc_model* m, int sp, unsigned factor, orc_rng* rng, orc_particles* src)
+{
+    const orc_spec* s = &m->s[sp];
+    double K = 1.0 / factor;
+    for (int i = 0; i < src->n; i++)
+    {
+        src->alive[i] = 1;
+        src->x[i] = K * g->x_max * orc_rng_uni(rng);
+        src->z[i] = K * g->z_max * orc_rng_uni(rng);
+        src->vx[i] = orc_rng_rnor(rng) * s->v_max / (M_SQRT2);
+        src->vz[i] = orc_rng_rnor(rng) * s->v_max / (M_SQRT2);
+        src->vy[i] = orc_rng_rnor(rng) * s->v_max / (M_SQRT2);
+        src->ttd[i] = orc_rng_rexp(rng) * s->lifetime;
+    }
+    orc_advance_boris_extern(g, m, sp, src, NULL, NULL, 1);
+}
+
+/* one "j = insert(); particles[j] = *I; shift; inside ? accumulate : remove(j)" block of source() */
+static int source_inject(const orc_grid* g, double charge, const orc_particles* src, int k, double x, double z,
+                         orc_particles* dst, int* n_dst, int dst_cap, double* rho, int64_t* rho_fixed)
+{
+    if (!(z < g->z_max && z > 0 && x < g->x_max && x > 0)) return 0;      /* inserted and removed again */
+    if (*n_dst >= dst_cap) return -1;
+    const int j = (*n_dst)++;
+    dst->x[j] = x;
+    dst->z[j] = z;
+    if (dst->y) dst->y[j] = src->y ? src->y[k] : 0.0;
+    dst->vx[j] = src->vx[k];
+    dst->vy[j] = src->vy[k];
+    dst->vz[j] = src->vz[k];
+    if (dst->ttd) dst->ttd[j] = src->ttd ? src->ttd[k] : 0.0;
+    dst->alive[j] = 1;
+    unsigned char one = 1;
+    if (rho) orc_deposit_fp64(g, charge, 1, &x, &z, &one, rho);
+    if (rho_fixed) orc_deposit_fixed(g, 1, &x, &z, &one, rho_fixed);
+    return 1;
+}
+
+int orc_source(const orc_grid* g, const orc_model* m, int sp, unsigned factor, orc_particles* src, orc_rng* rng,
+               int64_t* coll_counts, orc_particles* dst, int* n_dst, int dst_cap, double* rho, int64_t* rho_fixed,
+               int (*irand)(void))
+{
+    const orc_spec* s = &m->s[sp];
+    double K = 1.0 / factor;
+    double src_z_max = K * g->z_max;
+    double src_x_max = K * g->x_max;
+    int injected = 0, r;
+    orc_advance_boris_extern(g, m, sp, src, rng, coll_counts, 0);
+#define INJECT(X, Z)                                                                                  \
+    do {                                                                                              \
+        r = source_inject(g, s->charge, src, k, (X), (Z), dst, n_dst, dst_cap, rho, rho_fixed);          \
+        if (r < 0) return -1;                                                                         \
+        injected += r;                                                                                \
+    } while (0)
+    for (int k = 0; k < src->n; k++)
+    {
+        /* the reference does not skip empty reservoir slots; the reservoir never has any */
+        if (src->x[k] > src_x_max)
+            while (src->x[k] > src_x_max)
+            {
+                src->x[k] -= src_x_max;
+                double pz = src->z[k];
+                pz += irand() % factor * src_z_max;
+                INJECT(src->x[k], pz);
+            }
+        else if (src->x[k] < 0)
+            while (src->x[k] < 0)
+            {
+                double pz = src->z[k], px = src->x[k];
+                pz += irand() % factor * src_z_max;
+                px += g->x_max;
+                src->x[k] += src_x_max;
+                INJECT(px, pz);
+            }
+        if (src->z[k] > src_z_max)
+            while (src->z[k] > src_z_max)
+            {
+                src->z[k] -= src_z_max;
+                double px = src->x[k];
+                px += irand() % factor * src_x_max;
+                INJECT(px, src->z[k]);
+            }
+        else if (src->z[k] < 0)
+            while (src->z[k] < 0)
+            {
+                double px = src->x[k], pz = src->z[k];
+                px += irand() % factor * src_x_max;
+                pz += g->z_max;
+                src->z[k] += src_z_max;
+                INJECT(px, pz);
+            }
+    }
+#undef INJECT
+    return injected;
+}
+
 void orc_advance_multicoll(double fx, double fz, const orc_model* m, int sp, orc_particles* p, orc_rng* rng,
                            int64_t* coll_counts)
 {

@@ -172,6 +172,26 @@ void orc_advance_multicoll(double fx, double fz, const orc_model* m, int sp, orc
 int orc_advance_boundary(const orc_grid* g, const unsigned char* mask, double charge, orc_particles* p,
                          double* rho, int64_t* rho_fixed);
 
+/* ---- particle source (use_source = 1), Cartesian only: Species<CYLINDRICAL>::source is never defined ---- */
+/* advance_boris(what, extern_fields = true) / advance_boris_init(what, true), src/particles.cpp:925-995, 997-1050:
+ * fx = 0, fz = extern_field, B = the constants of config.txt; neither field is looked up (:944-949).  init != 0 selects the
+ * half step back (no collisions there) */
+void orc_advance_boris_extern(const orc_grid* g, const orc_model* m, int sp, orc_particles* p, orc_rng* rng,
+                              int64_t* coll_counts, int init);
+/* reservoir size of Species<CARTESIAN>::source5_refresh, src/particles.cpp:1057-1060: (unsigned)(density*V/factor) */
+unsigned orc_source_size(const orc_model* m, int sp, double V, unsigned factor);
+/* Species<CARTESIAN>::source5_refresh, src/particles.cpp:1053-1080: src->n reservoir particles in the box
+ * [0, x_max/factor] x [0, z_max/factor] with Maxwellian velocities, then the half step back */
+void orc_source_refresh(const orc_grid* g, const orc_model* m, int sp, unsigned factor, orc_rng* rng, orc_particles* src);
+/* Species<CARTESIAN>::source, src/particles.cpp:1158-1226: push the reservoir with the external fields, wrap what left it and
+ * inject a copy per crossing at the opposite edge of the main box, shifted by rand() % factor reservoir widths along the
+ * other axis.  Copies land in dst from slot *n_dst on (the reference's insert() recycles freed slots instead; the particle
+ * SET is the same), dst_cap slots available.  rho (fp64, Field2D::accumulate order) and rho_fixed may be NULL.  irand
+ * stands for libc rand().  Returns the number of injected particles, -1 when dst is full. */
+int orc_source(const orc_grid* g, const orc_model* m, int sp, unsigned factor, orc_particles* src, orc_rng* rng,
+               int64_t* coll_counts, orc_particles* dst, int* n_dst, int dst_cap, double* rho, int64_t* rho_fixed,
+               int (*irand)(void));
+
 /* ---- deposition ---- */
 /* Field2D::accumulate, src/Field2D.hpp:45-62, sequential fp64 in particle order */
 int orc_deposit_fp64(const orc_grid* g, double charge, int n, const double* x, const double* z,

@@ -211,6 +211,12 @@ class Oracle:
         lib.orc_scatter.argtypes = [C.c_void_p, C.c_int, R, dp, dp, dp, C.POINTER(C.c_int)]
         lib.orc_advance_boris.argtypes = [G, dp, dp, C.c_void_p, C.c_int, P, C.c_ulong, R, i64p]
         lib.orc_advance_boris_init.argtypes = [G, dp, dp, C.c_void_p, C.c_int, P, C.c_ulong]
+        lib.orc_advance_boris_extern.argtypes = [G, C.c_void_p, C.c_int, P, R, i64p, C.c_int]
+        lib.orc_source_size.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_uint]
+        lib.orc_source_size.restype = C.c_uint
+        lib.orc_source_refresh.argtypes = [G, C.c_void_p, C.c_int, C.c_uint, R, P]
+        lib.orc_source.argtypes = [G, C.c_void_p, C.c_int, C.c_uint, P, R, i64p, P, C.POINTER(C.c_int), C.c_int, dp, i64p, C.c_void_p]
+        lib.orc_source.restype = C.c_int
         BT = C.POINTER(OrcBTable)
         lib.orc_btable_build.argtypes = [C.c_int, dp, dp, dp, dp, BT]
         lib.orc_btable_build.restype = C.c_int
@@ -297,6 +303,36 @@ class Oracle:
         v = particles.cview()
         self.lib.orc_advance_boris_init_B(C.byref(g), C.byref(btable) if btable is not None else None, _d(u), _d(uRF), model.h, sp,
                                           C.byref(v), niter)
+
+    # ---- particle source (use_source; particles.cpp:1053-1080, 1158-1226)
+    def advance_boris_extern(self, g, model, sp, particles, rng=None, counts=None, init=False):
+        v = particles.cview()
+        self.lib.orc_advance_boris_extern(C.byref(g), model.h, sp, C.byref(v), C.byref(rng) if rng is not None else None,
+                                          counts.ctypes.data_as(i64p) if counts is not None else None, int(init))
+
+    def source_refresh(self, g, model, sp, factor, V, rng):
+        n = self.lib.orc_source_size(model.h, sp, float(V), int(factor))
+        src = Particles(n)
+        v = src.cview()
+        self.lib.orc_source_refresh(C.byref(g), model.h, sp, int(factor), C.byref(rng), C.byref(v))
+        return src
+
+    def source(self, g, model, sp, factor, src, dst, n_dst, rng=None, counts=None, rho=None, rho_fixed=None, libc_seed=None):
+        """-> (injected, new n_dst).  dst: Particles with spare slots from n_dst on.  The lateral shifts come from libc
+        rand(), as in the reference (srand(libc_seed) first when given)"""
+        libc = C.CDLL(None)
+        if libc_seed is not None:
+            libc.srand(int(libc_seed))
+        irand = C.cast(libc.rand, C.c_void_p)
+        vs, vd = src.cview(), dst.cview()
+        nd = C.c_int(int(n_dst))
+        r = self.lib.orc_source(C.byref(g), model.h, sp, int(factor), C.byref(vs), C.byref(rng) if rng is not None else None,
+                                counts.ctypes.data_as(i64p) if counts is not None else None, C.byref(vd), C.byref(nd), dst.n,
+                                _d(rho) if rho is not None else None,
+                                rho_fixed.ctypes.data_as(i64p) if rho_fixed is not None else None, irand)
+        if r < 0:
+            raise RuntimeError("orc_source: destination store is full")
+        return r, nd.value
 
     # ---- magnetic field table (Fields::load_magnetic_field, fields.cpp:870-959)
     def load_magnetic_field(self, fname):

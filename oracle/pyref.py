@@ -72,6 +72,11 @@ def _lib(variant):
     lib.ref_set_field.argtypes = [C.c_void_p, C.c_char_p, dp]
     lib.ref_field_op.argtypes = [C.c_void_p, C.c_char_p]
     lib.ref_field_E.argtypes = [C.c_void_p, C.c_int, dp, dp, C.c_double, dp, dp]
+    lib.ref_source_refresh.argtypes = [C.c_void_p, C.c_int, C.c_uint]
+    lib.ref_source.argtypes = [C.c_void_p, C.c_int]
+    lib.ref_source_n.argtypes = [C.c_void_p, C.c_int]
+    lib.ref_source_get.argtypes = [C.c_void_p, C.c_int, dp, C.c_int]
+    lib.ref_srand.argtypes = [C.c_uint]
     lib.ref_field_B.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, dp, dp]
     lib.ref_btable_info.argtypes = [C.c_void_p, dp]
     lib.ref_btable_get.argtypes = [C.c_void_p, C.c_int, dp]
@@ -251,6 +256,22 @@ class RefHarness:
         self._chk(self.lib.ref_btable_get(self.h, 0, _dp(br)))
         self._chk(self.lib.ref_btable_get(self.h, 1, _dp(bz)))
         return dict(jmax=M, lmax=N, dx=o[2], dy=o[3], xmin=o[4], ymin=o[5]), br, bz
+
+    # ---- particle source (use_source)
+    def source_refresh(self, i, factor):
+        self._chk(self.lib.ref_source_refresh(self.h, i, int(factor)))
+
+    def source(self, i):
+        self._chk(self.lib.ref_source(self.h, i))
+
+    def source_particles(self, i):
+        n = self.lib.ref_source_n(self.h, i)
+        out = np.zeros((max(n, 1), 8))
+        n = self.lib.ref_source_get(self.h, i, _dp(out), n)
+        return out[:n]
+
+    def srand(self, seed):
+        self.lib.ref_srand(int(seed))
 
     def field_accumulate(self, which, charge, x, z):
         x = np.ascontiguousarray(x, dtype=np.float64)

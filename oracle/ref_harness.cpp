@@ -338,6 +338,38 @@ int ref_species_accumulate(void* hv, int i)
         else h->cyl->speclist[(size_t)i]->accumulate();
     });
 }
+// ---- particle source (use_source), Cartesian only: Species<CARTESIAN>::source5_refresh / source (particles.cpp:1053-1080, 1158-1226)
+int ref_source_refresh(void* hv, int i, unsigned factor)
+{
+    Handle* h = (Handle*)hv;
+    return guarded(h, [&] {
+        if (!h->cart) throw std::runtime_error("ref_source_refresh: Cartesian only");
+        h->cart->speclist[(size_t)i]->source5_refresh(factor);
+    });
+}
+int ref_source(void* hv, int i)
+{
+    Handle* h = (Handle*)hv;
+    return guarded(h, [&] {
+        if (!h->cart) throw std::runtime_error("ref_source: Cartesian only");
+        h->cart->speclist[(size_t)i]->source();
+    });
+}
+int ref_source_n(void* hv, int i) { return (int)((Handle*)hv)->species(i)->source2_particles.size(); }
+int ref_source_get(void* hv, int i, double* out, int max_slots)
+{
+    BaseSpecies* s = ((Handle*)hv)->species(i);
+    int n = (int)std::min((size_t)max_slots, s->source2_particles.size());
+    for (int k = 0; k < n; k++)
+    {
+        const t_particle& p = s->source2_particles[(size_t)k];
+        double* a = out + 8 * (size_t)k;
+        a[0] = p.x; a[1] = p.y; a[2] = p.z; a[3] = p.vx; a[4] = p.vy; a[5] = p.vz;
+        a[6] = p.time_to_death; a[7] = p.empty ? 0.0 : 1.0;
+    }
+    return n;
+}
+void ref_srand(unsigned seed) { srand(seed); }     // source() draws its lateral shifts from libc rand() (particles.cpp:1177)
 // seconds for nsteps of the chosen phase, measured with the reference's own t_timer (timer.hpp:15-27):
 // returns wall-clock seconds, *cpu_seconds gets the getrusage user time test_MCC.cpp:86 reports
 double ref_time_advance(void* hv, int nsteps, int particles_only, double* cpu_seconds)

@@ -347,3 +347,63 @@ def test_magnetic_field_table_and_boris_bit_exact(orc, deckdir, coord, descendin
         assert np.array_equal(ref.get_particles(h)[:, :7], P.aos7())
         # the rotation really depends on the position: the same run with the table's centre value differs
         assert np.abs(P.aos7()[:, 3:6] - aos[:, 3:6]).max() > 1.0
+
+
+def _sorted_rows(a):
+    a = np.asarray(a)
+    return a[np.lexsort(a.T[::-1])]
+
+
+@pytest.mark.parametrize("factor,collisions", [(4, True), (1, False), (3, True)])
+def test_particle_source_bit_exact(orc, deckdir, factor, collisions):
+    """use_source (f-row 4): Species<CARTESIAN>::source5_refresh and ::source against the compiled reference under the same
+    SHR3 seed and the same libc rand() sequence: reservoir, injected particle set and the fp64 charge they deposit"""
+    L = 6.4e-3
+    d = decks.deck("c4", deckdir, n_particles=10, collisions=collisions, x_sampl=33, z_sampl=33, r_max=L, z_max=L, use_source=1,
+                   src_fact=factor, n_particles_total=40, density_total=1e13, Bz=0.02, extern_field=200.0)
+    with RefHarness(d["config"], d["species_conf"], seed=5) as ref:
+        p = ref.param()
+        g = grid_from_param(p)
+        m, names = model_from(orc, d["species_conf"])
+        e = names.index("ELECTRON")
+        sp = cfg.read_species(d["species_conf"])[0][e]
+        aos = disk_particles(np.random.default_rng(3), 50, 0.5 * L, 0.5 * L, 0.2 * L, 4e5)
+        ref.set_particles(e, aos)
+        ref.rng_seed(21)
+        ref.source_refresh(e, factor)
+        R = ref.source_particles(e)
+        r = orc.rng(21)
+        V = cfg.read_config(d["config"])["V"]
+        src = orc.source_refresh(g, m, e, factor, V, r)
+        assert src.n == R.shape[0] > 200
+        assert np.array_equal(R[:, [0, 2, 3, 4, 5, 6]], src.aos7()[:, [0, 2, 3, 4, 5, 6]])
+        # the reference first: both sides draw from the one libc rand() state
+        nsteps = 12
+        ref.rng_seed(33)
+        ref.srand(7)
+        rho0 = ref.get_field("rho:%d" % e).copy()
+        assert not rho0.any()
+        for _ in range(nsteps):
+            ref.source(e)
+        out_ref = ref.get_particles(e)
+        rho_ref = ref.get_field("rho:%d" % e)
+        src_ref = ref.source_particles(e)
+        orc.rng_seed(r, 33)
+        dst = Particles(50 + 4000)
+        dst.alive[:] = 0
+        for c, k in enumerate(("x", "y", "z", "vx", "vy", "vz", "ttd")):
+            getattr(dst, k)[:50] = aos[:, c]
+        dst.alive[:50] = 1
+        n_dst, total = 50, 0
+        rho = np.zeros((g.M, g.N))
+        for step in range(nsteps):
+            inj, n_dst = orc.source(g, m, e, factor, src, dst, n_dst, rng=r, rho=rho, libc_seed=7 if step == 0 else None)
+            total += inj
+        assert total > 20 and n_dst == 50 + total
+        assert np.array_equal(src_ref[:, [0, 2, 3, 4, 5, 6]], src.aos7()[:, [0, 2, 3, 4, 5, 6]])
+        live_ref = out_ref[out_ref[:, 7] > 0][:, [0, 2, 3, 4, 5, 6]]
+        live_orc = dst.aos7()[dst.alive > 0][:, [0, 2, 3, 4, 5, 6]]
+        assert live_ref.shape == live_orc.shape
+        assert np.array_equal(_sorted_rows(live_ref), _sorted_rows(live_orc))
+        assert np.array_equal(rho_ref, rho)
+        assert np.array_equal(ref.rng_draw("iuni", 3), orc.rng_draw(r, "iuni", 3))      # SHR3 streams stayed in step
