@@ -172,6 +172,24 @@ int mag2d_count(mag2d_ctx* ctx, int species, int64_t* n_alive, int64_t* n_slots)
  * kind 0 add_particles_everywhere(n), 1 add_particles_on_disk(n, a=cx, b=cz, c=radius),
  * 2 add_monoenergetic_particles_on_cylinder_cylindrical(n, a=energy eV, b=centre z, c=radius, d=height) */
 int mag2d_particles_generate(mag2d_ctx* ctx, int species, int kind, int64_t n, double a, double b, double c, double d);
+/* ---- particle source (use_source = 1; CARTESIAN + ADVANCE_BORIS, as far as the reference's own code goes) ----- */
+/* Param::use_source: mag2d_step then runs Species::source() after every species advance (src/pic.cpp:346-347) and
+ * sorts with the stand-alone pass, which also trims the slot range */
+int mag2d_set_use_source(mag2d_ctx* ctx, int on);
+/* Species<CARTESIAN>::source5_refresh(factor) (src/particles.cpp:1053-1080): (unsigned)(density*V/factor) reservoir
+ * particles, uniform in [0, x_max/factor] x [0, z_max/factor], Maxwellian at the species temperature, then the half
+ * step back with the external fields.  V is Param::V (n_particles_total / density_total).  A species without particles
+ * keeps an empty reservoir (:1063).  Device-side Philox generation. */
+int mag2d_source_refresh(mag2d_ctx* ctx, int species, uint32_t factor, double V);
+/* BaseSpecies::source2_particles (src/particles.hpp:114) as the save/load files carry it (src/particles.cpp:115-138) */
+int mag2d_source_upload(mag2d_ctx* ctx, int species, uint32_t factor, const mag2d_particle* aos, int64_t n);
+int mag2d_source_download(mag2d_ctx* ctx, int species, mag2d_particle* aos, int64_t capacity, int64_t* n_out);
+/* Species<CARTESIAN>::source() (src/particles.cpp:1158-1226): push the reservoir with the external fields (collisions
+ * included), wrap it, and for every crossing of a reservoir edge insert a copy at the opposite edge of the simulation box,
+ * shifted by a random whole number of reservoir widths along the other axis; copies deposit their charge when the run is
+ * self-consistent.  injected (may be NULL) receives the number of particles added.  Blocks (the slot count comes back). */
+int mag2d_species_source(mag2d_ctx* ctx, int species, int64_t* injected);
+
 /* cell sort + compaction of removed particles (replaces the free list, src/particles.hpp:223-247) */
 int mag2d_sort(mag2d_ctx* ctx, int species);
 /* Pic<D>::advance (src/pic.cpp:330-358) for a caller that keeps its particles in HOST memory, as the reference does

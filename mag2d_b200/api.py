@@ -92,6 +92,11 @@ def lib():
     L.mag2d_collision_counts.argtypes = [vp, C.c_int, i64p, C.c_int]
     L.mag2d_set_collision_counting.argtypes = [vp, C.c_int]
     L.mag2d_reserve.argtypes = [vp, C.c_int, C.c_int64]
+    L.mag2d_set_use_source.argtypes = [vp, C.c_int]
+    L.mag2d_source_refresh.argtypes = [vp, C.c_int, C.c_uint32, C.c_double]
+    L.mag2d_source_upload.argtypes = [vp, C.c_int, C.c_uint32, vp, C.c_int64]
+    L.mag2d_source_download.argtypes = [vp, C.c_int, vp, C.c_int64, i64p]
+    L.mag2d_species_source.argtypes = [vp, C.c_int, i64p]
     L.mag2d_set_magnetic_field.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp]
     L.mag2d_field_B.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp]
     L.mag2d_particles_upload.argtypes = [vp, C.c_int, vp, C.c_int64]
@@ -171,6 +176,7 @@ class Sim:
         self.mask, self.voltage = geometry.build_geometry(p)
         self._chk(self.L.mag2d_set_grid(self.h, self.mask.ctypes.data_as(u8p), _d(self.voltage)))
         self._set_species()
+        self._chk(self.L.mag2d_set_use_source(self.h, int(bool(p.get("use_source", 0)))))
         self.btable = None
         if not self.is3d and not p["magnetic_field_const"]:
             # Pic ctor: if(!param.magnetic_field_const) field.load_magnetic_field(...)  (pic.cpp:148-149)
@@ -334,6 +340,38 @@ class Sim:
     # ---- stepping
     def advance_init(self):
         self._chk(self.L.mag2d_advance_init(self.h))
+
+    # ---- particle source (use_source; Species<CARTESIAN>::source5_refresh / source)
+    def source_refresh(self, i=None, factor=None):
+        """what the driver does after advance_init (test.cpp:56-59): one reservoir per particle species"""
+        factor = int(self.param["src_fact"] if factor is None else factor)
+        for k in (range(len(self.species)) if i is None else [i]):
+            if self.species[k]["type"] != 0:          # speclist[i]->particle: everything but NEUTRAL
+                self._chk(self.L.mag2d_source_refresh(self.h, k, factor, float(self.param["V"])))
+
+    def set_source_particles(self, i, factor, aos7):
+        a = np.ascontiguousarray(aos7, dtype=np.float64).reshape(-1, 7)
+        rec = np.zeros(a.shape[0], dtype=PARTICLE_DTYPE)
+        for c, k in enumerate(("x", "y", "z", "vx", "vy", "vz", "time_to_death")):
+            rec[k] = a[:, c]
+        self._chk(self.L.mag2d_source_upload(self.h, i, int(factor), rec.ctypes.data_as(C.c_void_p), rec.shape[0]))
+
+    def get_source_particles(self, i):
+        n = C.c_int64()
+        self._chk(self.L.mag2d_source_download(self.h, i, None, 0, C.byref(n)))
+        rec = np.zeros(max(n.value, 1), dtype=PARTICLE_DTYPE)
+        self._chk(self.L.mag2d_source_download(self.h, i, rec.ctypes.data_as(C.c_void_p), rec.shape[0], C.byref(n)))
+        rec = rec[:n.value]
+        out = np.zeros((rec.shape[0], 8))
+        for c, k in enumerate(("x", "y", "z", "vx", "vy", "vz", "time_to_death")):
+            out[:, c] = rec[k]
+        out[:, 7] = 1 - rec["empty"]
+        return out
+
+    def species_source(self, i):
+        n = C.c_int64()
+        self._chk(self.L.mag2d_species_source(self.h, i, C.byref(n)))
+        return n.value
 
     def advance(self, nsteps=1):
         self._chk(self.L.mag2d_step(self.h, nsteps))

@@ -93,6 +93,7 @@ int free_store(SpeciesStore& S)
     if (S.d_blob) cudaFree(S.d_blob);
     delete S.h_blob;
     sort_fused_free(S);
+    source_free(S);
     S = SpeciesStore();
     return 0;
 }
@@ -205,6 +206,23 @@ int advance_one(mag2d_ctx* c, int s, bool in_step)
     if (refresh_pools(c, s)) return 1;
     if (is3d(c)) return launch_species_advance3d(c, s, false, in_step ? fused_sort_mode(c, c->sp[s]) : 0);
     return launch_species_advance(c, s, in_step ? fused_sort_mode(c, c->sp[s]) : 0);
+}
+
+// Species<CARTESIAN>::source() of species s (particles.cpp:1158-1226)
+int species_source(mag2d_ctx* c, int s, long long* injected)
+{
+    SpeciesStore& S = c->sp[s];
+    if (injected) *injected = 0;
+    if (S.src_n == 0) return 0;
+    if (c->g.coord != MAG2D_CARTESIAN || c->g.mover != MAG2D_ADVANCE_BORIS)
+    {
+        // Species<CYLINDRICAL>::source is declared but never defined in the reference (it does not link)
+        mag2d_set_error("mag2d_species_source: CARTESIAN coordinates with the ADVANCE_BORIS mover only");
+        return 1;
+    }
+    if (ensure_capacity(c, S, S.n_slots + 2 * S.src_n + 256)) return 1;
+    if (refresh_pools(c, s)) return 1;        // the arrays may have moved
+    return launch_species_source(c, s, injected);
 }
 
 }  // namespace
@@ -897,6 +915,85 @@ static int sort_species(mag2d_ctx* c, int s, bool trim)
     return launch_sort(c, s, trim);
 }
 
+int mag2d_set_use_source(mag2d_ctx* c, int on)
+{
+    CHECK_CTX(c);
+    c->use_source = on != 0;
+    return 0;
+}
+
+int mag2d_source_refresh(mag2d_ctx* c, int s, uint32_t factor, double V)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    if (factor == 0) { mag2d_set_error("mag2d_source_refresh: factor must be positive"); return 1; }
+    if (c->g.coord != MAG2D_CARTESIAN) { mag2d_set_error("mag2d_source_refresh: CARTESIAN coordinates only"); return 1; }
+    SpeciesStore& S = c->sp[s];
+    // particles.cpp:1057-1064: N = density*V, n = (unsigned)(N/factor); species without particles keep an empty reservoir
+    const double N = S.desc.density * V;
+    const unsigned n = (unsigned)(N / factor);
+    if (S.n_slots == 0) return 0;
+    return launch_source_generate(c, s, factor, (long long)n);
+}
+
+int mag2d_source_upload(mag2d_ctx* c, int s, uint32_t factor, const mag2d_particle* aos, int64_t n)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    if (factor == 0 || n < 0) { mag2d_set_error("mag2d_source_upload: bad arguments"); return 1; }
+    SpeciesStore& S = c->sp[s];
+    if (source_alloc(c, S, n)) return 1;
+    S.src_factor = factor;
+    std::vector<double> col((size_t)std::max<int64_t>(n, 1));
+    for (int a = 0; a < 6; a++)
+    {
+        for (int64_t k = 0; k < n; k++)
+        {
+            const mag2d_particle& p = aos[k];
+            col[(size_t)k] = a == 0 ? p.x : a == 1 ? p.z : a == 2 ? p.vx : a == 3 ? p.vy : a == 4 ? p.vz : p.time_to_death;
+        }
+        if (n > 0) CUDA_OK(cudaMemcpy(S.src[a], col.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int mag2d_source_download(mag2d_ctx* c, int s, mag2d_particle* aos, int64_t capacity, int64_t* n_out)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    SpeciesStore& S = c->sp[s];
+    if (n_out) *n_out = S.src_n;
+    if (S.src_n == 0 || !aos) return 0;
+    if (capacity < S.src_n) { mag2d_set_error("mag2d_source_download: buffer too small"); return 1; }
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    std::vector<double> col((size_t)S.src_n);
+    for (long long k = 0; k < S.src_n; k++)
+    {
+        memset(&aos[k], 0, sizeof(mag2d_particle));
+        aos[k].empty = 0;
+    }
+    for (int a = 0; a < 6; a++)
+    {
+        CUDA_OK(cudaMemcpy(col.data(), S.src[a], sizeof(double) * (size_t)S.src_n, cudaMemcpyDeviceToHost));
+        for (long long k = 0; k < S.src_n; k++)
+        {
+            mag2d_particle& p = aos[k];
+            (a == 0 ? p.x : a == 1 ? p.z : a == 2 ? p.vx : a == 3 ? p.vy : a == 4 ? p.vz : p.time_to_death) = col[(size_t)k];
+        }
+    }
+    return 0;
+}
+
+int mag2d_species_source(mag2d_ctx* c, int s, int64_t* injected)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    long long n = 0;
+    const int rc = species_source(c, s, &n);
+    if (injected) *injected = n;
+    return rc;
+}
+
 int mag2d_sort(mag2d_ctx* c, int s)
 {
     CHECK_CTX(c);
@@ -1043,17 +1140,22 @@ int mag2d_step(mag2d_ctx* c, int nsteps)
         }
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
         for (size_t s = 0; s < c->sp.size(); s++)
-            if (advance_one(c, (int)s, true)) return 1;
+        {
+            // the source appends to the store after every push: pending sort tickets would never survive, so these runs
+            // use the stand-alone sort below (which also trims the slot range: the influx balances the wall losses)
+            if (advance_one(c, (int)s, !c->use_source)) return 1;
+            if (c->use_source && species_source(c, (int)s, nullptr)) return 1;      // pic.cpp:346-347
+        }
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
         if (c->g.selfconsistent && comm_allreduce_rho(c)) return 1;
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
         // stand-alone sort: the multi-collision mover, or the fused sort switched off
-        if (!c->fused_sort || c->g.mover == MAG2D_ADVANCE_MULTICOLL)
+        if (!c->fused_sort || c->g.mover == MAG2D_ADVANCE_MULTICOLL || c->use_source)
             for (size_t s = 0; s < c->sp.size(); s++)
             {
                 const int K = effective_sort_interval(c, c->sp[s]);
                 if (K > 0 && c->sp[s].n_slots > 0 && c->sp[s].steps_since_sort >= K)
-                    if (sort_species(c, (int)s, false)) return 1;
+                    if (sort_species(c, (int)s, c->use_source)) return 1;
             }
         if (c->timing)
         {

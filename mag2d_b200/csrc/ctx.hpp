@@ -50,6 +50,13 @@ struct SpeciesStore
     cudaEvent_t ev_total = nullptr;
     bool total_pending = false;
     long long append_epoch = 0, total_epoch = -1;
+    // particle source (use_source): the reservoir BaseSpecies::source2_particles (particles.hpp:114), filled by
+    // mag2d_source_refresh / mag2d_source_upload and pushed + sampled by mag2d_species_source.  x, z, vx, vy, vz, ttd
+    double* src[6] = {};
+    long long src_n = 0, src_capacity = 0;
+    unsigned src_factor = 0;              // source5_factor
+    unsigned* d_src_count = nullptr;      // particles injected by the current call
+    unsigned long long src_calls = 0;     // part of the reservoir's RNG counter
 };
 
 // one level of the Galerkin multigrid hierarchy (poisson.cu)
@@ -151,6 +158,7 @@ struct mag2d_ctx
     std::vector<SpeciesStore> sp;
     double* d_charges = nullptr;  // [n_species]
     int sort_interval = 0;
+    bool use_source = false;      // Param::use_source: mag2d_step calls Species::source() after every advance (pic.cpp:346-347)
     bool fused_sort = true;       // cell sort carried by the Boris push itself (MAG2D_FUSED_SORT=0: stand-alone passes)
     bool count_collisions = false;
 
@@ -203,6 +211,11 @@ int launch_species_accumulate(mag2d_ctx* c, int s);
 int launch_generate(mag2d_ctx* c, int s, int kind, long long n, double a, double b, double cc, double d);
 int launch_energy_hist(mag2d_ctx* c, int s, int nbins, double emax, double* hist, double* stats);
 int launch_field_E(mag2d_ctx* c, int n, const double* x, const double* z, double time, double* Ex, double* Ez);
+int source_alloc(mag2d_ctx* c, SpeciesStore& S, long long n);
+void source_free(SpeciesStore& S);
+int launch_source_generate(mag2d_ctx* c, int s, unsigned factor, long long n);
+int launch_source_init(mag2d_ctx* c, int s);
+int launch_species_source(mag2d_ctx* c, int s, long long* injected);
 int launch_field_B(mag2d_ctx* c, int n, const double* x, const double* z, double* Br, double* Bz, double* Bt);
 int launch_aos_to_soa(mag2d_ctx* c, int s, const mag2d_particle* d_aos, long long n_in, long long* n_added);
 int launch_soa_to_aos(mag2d_ctx* c, int s, mag2d_particle* d_aos);

@@ -184,6 +184,7 @@ class Fields
         g.magnetic_field_const = param.magnetic_field_const; g.u_smooth = param.u_smooth;
         g.Br = param.Br; g.Bz = param.Bz; g.Bt = param.Bt; g.dV = param.dV; g.macroparticle_factor = param.macroparticle_factor;
         gpu_check(mag2d_create(0, &g, nullptr, &gpu));
+        gpu_check(mag2d_set_use_source(gpu, param.use_source));
         gpu_check(mag2d_set_grid(gpu, reinterpret_cast<const uint8_t*>(grid.mask[0]), grid.voltage[0]));
     }
     ~Fields() { mag2d_destroy(gpu); }

@@ -15,6 +15,9 @@ static int run(Param& param, const std::string& initscript)
     pic.check_params();
     pic.run_initscript(initscript);
     pic.advance_init();
+    if (param.use_source)      // test.cpp:56-59
+        for (size_t i = 0; i < pic.speclist.size(); i++)
+            if (pic.speclist[i]->particle) pic.speclist[i]->source5_refresh(param.src_fact);
     std::ofstream fw((param.output_dir + "/out.dat").c_str());
     for (unsigned long i = 1; i < param.niter + 1; ++i)
     {

@@ -177,6 +177,15 @@ class Species : public BaseSpecies
     void advance() { gpu_check(mag2d_species_advance(gpu, id)); }
     void advance_init() { gpu_check(mag2d_species_advance_init(gpu, id)); }
     void accumulate() { gpu_check(mag2d_species_accumulate(gpu, id)); }
+    // particle source (use_source; src/particles.cpp:1053-1080, 1158-1226): the reservoir lives on the device
+    void source5_refresh(unsigned int factor)
+    {
+        gpu_check(mag2d_source_refresh(gpu, id, factor, p_param->V));
+        int64_t n = 0;
+        gpu_check(mag2d_source_download(gpu, id, nullptr, 0, &n));
+        std::cout << name << " source initialized:  " << n << " particles  @  " << density << " particle/m3" << std::endl;
+    }
+    void source() { gpu_check(mag2d_species_source(gpu, id, nullptr)); }
 
     // loaders of the initscript language (src/particles.cpp:685-749); the uniform ones run on the device
     void add_particles_everywhere(int n) { gpu_check(mag2d_particles_generate(gpu, id, 0, n, 0, 0, 0, 0)); }

@@ -885,6 +885,147 @@ __global__ void k_field_E(const __grid_constant__ GridDev g, int n, const double
     Ez[k] = ez;
 }
 
+// ---- particle source: Species<CARTESIAN>::source5_refresh / source (particles.cpp:1053-1080, 1158-1226) ------------
+// A reservoir of density*V/factor particles lives in the periodic box [0, x_max/factor] x [0, z_max/factor] outside the
+// simulated plasma.  Every step it is pushed with the external fields only; whatever leaves it is wrapped back and a copy
+// enters the main box through the opposite edge, shifted by a random number of reservoir widths along the other axis —
+// a thermal influx without simulating the surrounding plasma.  One thread per reservoir particle; copies take the next
+// free tail slot of the species' store (atomic counter) and deposit their charge.
+struct SourceArgs
+{
+    GridDev g;                     // check_mask = 0: source() tests the box only (particles.cpp:1178-1179)
+    SpeciesDev s;
+    double *x, *z, *vx, *vy, *vz, *ttd;   // reservoir
+    long long n;
+    ParticlesDev dst;              // the species' store
+    long long dst_base, dst_cap;
+    unsigned* inject_count;
+    const MccBlob* mcc;            // nullptr: no collisions
+    unsigned long long* counts;
+    unsigned long long seed;
+    unsigned factor;
+    double src_x_max, src_z_max, v_scale;
+};
+
+__device__ __forceinline__ void source_inject(const SourceArgs& A, double x, double z, double vx, double vy, double vz, double ttd)
+{
+    if (!(z < A.g.z_max && z > 0 && x < A.g.x_max && x > 0)) return;        // the reference inserts and removes again
+    const long long d = A.dst_base + atomicAdd(A.inject_count, 1u);
+    if (d >= A.dst_cap) return;                                             // the host reads the count and reports it
+    A.dst.x[d] = x;
+    A.dst.z[d] = z;
+    A.dst.vx[d] = vx;
+    A.dst.vy[d] = vy;
+    A.dst.vz[d] = vz;
+    if (A.dst.ttd) A.dst.ttd[d] = ttd;
+    if (A.g.deposit)
+    {
+        unsigned node;
+        unsigned long long w[4];
+        boundary_weights<true>(A.g, x, z, node, w);
+        unsigned long long* r = A.g.rho + node;
+        atomicAdd(r, w[0]);
+        atomicAdd(r + A.g.N, w[1]);
+        atomicAdd(r + 1, w[2]);
+        atomicAdd(r + A.g.N + 1, w[3]);
+    }
+}
+
+// INIT: the half step back of source5_refresh (advance_position_init(source2_particles, true), particles.cpp:1077)
+template <bool INIT>
+__global__ void __launch_bounds__(128) k_source(const __grid_constant__ SourceArgs A)
+{
+    const long long k = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (k >= A.n) return;
+    double x = A.x[k], z = A.z[k], vx = A.vx[k], vy = A.vy[k], vz = A.vz[k];
+    // advance_boris(what, extern_fields = true): E = (0, extern_field), B = the constants, nothing is looked up
+    const double Ex = 0.0, Ez = A.g.extern_field;
+    if (INIT)
+    {
+        if (A.s.has_B) boris_rotate<MAG2D_CARTESIAN>(A.s.tx, A.s.ty, A.s.tz, A.s.sx, A.s.sy, A.s.sz, vx, vy, vz);
+        vx += Ex * A.s.hq;
+        vz += Ez * A.s.hq;
+        A.vx[k] = vx;
+        A.vy[k] = vy;
+        A.vz[k] = vz;
+        return;
+    }
+    if (A.s.has_B) boris_velocity<MAG2D_CARTESIAN, B_CONST>(A.g, A.s, x, z, Ex, Ez, vx, vy, vz);
+    else boris_velocity<MAG2D_CARTESIAN, B_NONE>(A.g, A.s, x, z, Ex, Ez, vx, vy, vz);
+    x += vx * A.s.dt;
+    z += vz * A.s.dt;
+    Rng rng = make_rng(A.seed ^ 0x9D2C5680A5A5F00DULL, A.s.species, A.s.step, (unsigned long long)k);
+    const uint4 r0 = rng.block();
+    if (A.mcc && (unsigned long long)r0.x < A.s.prob_u32)
+    {
+        int target;
+        const int proc = mcc_scatter(A.mcc, rng, vx, vy, vz, target);
+        mcc_count(A.counts, A.mcc->n_targets, target, proc);
+    }
+    const double ttd = A.ttd ? A.ttd[k] : 0.0;
+    // lateral shifts: rand() % source5_factor of the reference; three words of the first block, then further blocks
+    uint4 sh = r0;
+    int used = 1;
+    auto shift = [&]() -> double {
+        if (used == 4)
+        {
+            sh = rng.block();
+            used = 0;
+        }
+        const unsigned w = used == 0 ? sh.x : used == 1 ? sh.y : used == 2 ? sh.z : sh.w;
+        used++;
+        return (double)__umulhi(w, A.factor);
+    };
+    if (x > A.src_x_max)
+        while (x > A.src_x_max)
+        {
+            x -= A.src_x_max;
+            source_inject(A, x, z + shift() * A.src_z_max, vx, vy, vz, ttd);
+        }
+    else if (x < 0)
+        while (x < 0)
+        {
+            source_inject(A, x + A.g.x_max, z + shift() * A.src_z_max, vx, vy, vz, ttd);
+            x += A.src_x_max;
+        }
+    if (z > A.src_z_max)
+        while (z > A.src_z_max)
+        {
+            z -= A.src_z_max;
+            source_inject(A, x + shift() * A.src_x_max, z, vx, vy, vz, ttd);
+        }
+    else if (z < 0)
+        while (z < 0)
+        {
+            source_inject(A, x + shift() * A.src_x_max, z + A.g.z_max, vx, vy, vz, ttd);
+            z += A.src_z_max;
+        }
+    A.x[k] = x;
+    A.z[k] = z;
+    A.vx[k] = vx;
+    A.vy[k] = vy;
+    A.vz[k] = vz;
+}
+
+// the random part of source5_refresh (particles.cpp:1066-1075): uniform positions in the reservoir box, Maxwellian
+// velocities rnor()*v_max/sqrt(2), time_to_death = rexp()*lifetime
+__global__ void __launch_bounds__(128) k_source_generate(const __grid_constant__ SourceArgs A)
+{
+    const long long k = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (k >= A.n) return;
+    Rng rng = make_rng(A.seed ^ 0x3C6EF372FE94F82BULL, A.s.species, A.s.step, (unsigned long long)k);
+    const uint4 a = rng.block(), b = rng.block();
+    A.x[k] = A.src_x_max * u01(a.x);
+    A.z[k] = A.src_z_max * u01(a.y);
+    float n0, n1, n2, n3;
+    normal2(a.z, a.w, n0, n1);
+    normal2(b.x, b.y, n2, n3);
+    A.vx[k] = n0 * A.v_scale;
+    A.vz[k] = n1 * A.v_scale;
+    A.vy[k] = n2 * A.v_scale;
+    A.ttd[k] = rexp1(b.z) * A.s.lifetime;
+}
+
 // Fields::B at n points (fields.hpp:152-177): the constants of the grid descriptor or the interpolated table
 __global__ void k_field_B(const __grid_constant__ GridDev g, double Br0, double Bz0, double Bt0, int n, const double* __restrict__ x,
                           const double* __restrict__ z, double* __restrict__ Br, double* __restrict__ Bz, double* __restrict__ Bt)
@@ -1429,6 +1570,116 @@ int launch_field_E(mag2d_ctx* c, int n, const double* x, const double* z, double
     CUDA_OK(cudaMemcpyAsync(Ez, dez, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     CUDA_OK(cudaFree(dx));
+    return 0;
+}
+
+int source_alloc(mag2d_ctx* c, SpeciesStore& S, long long n)
+{
+    (void)c;
+    if (!S.d_src_count) CUDA_OK(cudaMalloc(&S.d_src_count, sizeof(unsigned)));
+    if (n > S.src_capacity)
+    {
+        for (int a = 0; a < 6; a++)
+        {
+            if (S.src[a]) cudaFree(S.src[a]);
+            S.src[a] = nullptr;
+            CUDA_OK(cudaMalloc(&S.src[a], sizeof(double) * (size_t)n));
+        }
+        S.src_capacity = n;
+    }
+    S.src_n = n;
+    return 0;
+}
+
+void source_free(SpeciesStore& S)
+{
+    for (int a = 0; a < 6; a++)
+    {
+        if (S.src[a]) cudaFree(S.src[a]);
+        S.src[a] = nullptr;
+    }
+    if (S.d_src_count) cudaFree(S.d_src_count);
+    S.d_src_count = nullptr;
+    S.src_n = S.src_capacity = 0;
+}
+
+static SourceArgs source_args(mag2d_ctx* c, int s, bool init)
+{
+    SpeciesStore& S = c->sp[s];
+    SourceArgs A;
+    memset(&A, 0, sizeof(A));
+    A.g = grid_view(c, s);
+    A.g.check_mask = 0;
+    A.s = species_view(c, s, init);
+    A.s.step = S.src_calls;
+    A.x = S.src[0]; A.z = S.src[1]; A.vx = S.src[2]; A.vy = S.src[3]; A.vz = S.src[4]; A.ttd = S.src[5];
+    A.n = S.src_n;
+    A.seed = c->seed;
+    A.factor = S.src_factor;
+    const double K = 1.0 / S.src_factor;
+    A.src_x_max = K * c->g.x_max;
+    A.src_z_max = K * c->g.z_max;
+    A.v_scale = S.v_max / M_SQRT2;
+    return A;
+}
+
+int launch_source_generate(mag2d_ctx* c, int s, unsigned factor, long long n)
+{
+    SpeciesStore& S = c->sp[s];
+    if (source_alloc(c, S, n)) return 1;
+    S.src_factor = factor;
+    if (n == 0) return 0;
+    SourceArgs A = source_args(c, s, true);
+    k_source_generate<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(A);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    S.src_calls++;
+    return launch_source_init(c, s);
+}
+
+int launch_source_init(mag2d_ctx* c, int s)
+{
+    SpeciesStore& S = c->sp[s];
+    if (S.src_n == 0) return 0;
+    SourceArgs A = source_args(c, s, true);
+    k_source<true><<<(unsigned)((S.src_n + 127) / 128), 128, 0, c->stream>>>(A);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Species<CARTESIAN>::source (particles.cpp:1158-1226).  One host synchronisation: the new slot count comes back.
+int launch_species_source(mag2d_ctx* c, int s, long long* injected)
+{
+    SpeciesStore& S = c->sp[s];
+    if (injected) *injected = 0;
+    if (S.src_n == 0) return 0;
+    // the caller (abi.cu: species_source) has reserved room for two copies per reservoir particle — a corner crossing;
+    // more would need v*dt beyond a reservoir width
+    SourceArgs A = source_args(c, s, false);
+    A.dst = particles_view(S);
+    A.dst_base = S.n_slots;
+    A.dst_cap = S.capacity;
+    A.inject_count = S.d_src_count;
+    const bool mcc = S.h_blob && S.h_blob->has_collisions && std::isfinite(S.lifetime);
+    A.mcc = mcc ? S.d_blob : nullptr;
+    A.counts = c->count_collisions ? S.d_counts : nullptr;
+    CUDA_OK(cudaMemsetAsync(S.d_src_count, 0, sizeof(unsigned), c->stream));
+    k_source<false><<<(unsigned)((S.src_n + 127) / 128), 128, 0, c->stream>>>(A);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    unsigned count = 0;
+    CUDA_OK(cudaMemcpyAsync(&count, S.d_src_count, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    S.src_calls++;
+    if ((long long)count > S.capacity - S.n_slots)
+    {
+        S.n_slots = S.capacity;
+        mag2d_set_error("mag2d_species_source: more than two copies per reservoir particle in one step (dt too long for the reservoir)");
+        return 1;
+    }
+    S.n_slots += count;
+    if (injected) *injected = count;
     return 0;
 }
 

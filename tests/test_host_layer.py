@@ -184,3 +184,17 @@ def test_plasma2d_driver_loads_a_magnetic_field_table(host_bins, tmp_path):
     r = subprocess.run([os.path.join(host_bins, "plasma2d_b200"), "config=" + d["config"], "species_conf=" + d["species_conf"],
                         "initscript=" + d["initscript"], "output_dir=" + str(tmp_path / "out_bad")], capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "outside of range" in (r.stdout + r.stderr)
+
+
+@pytest.mark.gpu
+def test_plasma2d_driver_with_particle_source(host_bins, tmp_path):
+    """use_source = 1 through the C++ host layer: the driver refreshes one reservoir per particle species after
+    advance_init (test.cpp:56-59) and Pic::advance runs Species::source() after every push (pic.cpp:346-347)"""
+    Lx = 6.4e-3
+    d = decks.deck("c4", str(tmp_path), n_particles=4000, x_sampl=33, z_sampl=33, r_max=Lx, z_max=Lx, niter=20, t_print=10, t_print_dist=0,
+                   use_source=1, src_fact=4, density_total=1e13)
+    out = str(tmp_path / "out_src")
+    log = run_driver(host_bins, "plasma2d_b200", d, out)
+    assert "ELECTRON source initialized:" in log and "ARGON_POS source initialized:" in log and "plot 20" in log
+    rows = np.loadtxt(os.path.join(out, "out.dat"))
+    assert np.isfinite(rows).all()
