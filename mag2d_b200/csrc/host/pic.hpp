@@ -99,7 +99,12 @@ class Pic
     {
         for (size_t i = 0; i < speclist.size(); i++) string2speciestype[speclist[i]->name] = (SpeciesType)i;
         if (param.particle_reload)
-            for (size_t i = 0; i < speclist.size(); i++) speclist[i]->load(param.particle_reload_dir + "/particles_" + speclist[i]->name + ".dat");
+            for (size_t i = 0; i < speclist.size(); i++)
+                if (speclist[i]->particle)          // pic.cpp:136-145
+                {
+                    speclist[i]->load(param.particle_reload_dir + "/particles_" + speclist[i]->name + ".dat");
+                    speclist[i]->source5_load(param.particle_reload_dir + "/particles_source_" + speclist[i]->name + ".dat", param.src_fact);
+                }
         if (!param.magnetic_field_const) field.load_magnetic_field(param.magnetic_field_file.c_str());     // pic.cpp:148-149
         dist_reset();
         if (param.electric_field_from_file)
@@ -234,7 +239,12 @@ class Pic
     void print_field() { field.u_print((param.output_dir + "/potential.dat").c_str()); }
     void save()
     {
-        for (auto s : speclist) s->save(param.output_dir + "/particles_" + s->name + ".dat");
+        for (auto s : speclist)
+            if (s->particle)                        // pic.cpp:462-470
+            {
+                s->save(param.output_dir + "/particles_" + s->name + ".dat");
+                s->source5_save(param.output_dir + "/particles_source_" + s->name + ".dat");
+            }
     }
     double step_seconds() { return timer.get_real_time(); }
 

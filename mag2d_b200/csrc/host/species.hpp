@@ -112,6 +112,35 @@ class BaseSpecies
         upload();
     }
 
+    // the reservoir of the particle source (src/particles.cpp:109-139): int count + 64-byte t_particle records
+    void source5_save(const std::string& filename)
+    {
+        std::ofstream fw(filename.c_str(), std::ios::out | std::ios::binary);
+        if (!fw.is_open()) throw std::runtime_error("Species::source_save(): failed opening file");
+        int64_t n64 = 0;
+        gpu_check(mag2d_source_download(gpu, id, nullptr, 0, &n64));
+        std::vector<mag2d_particle> buf((size_t)std::max<int64_t>(n64, 1));
+        if (n64 > 0) gpu_check(mag2d_source_download(gpu, id, buf.data(), n64, &n64));
+        int n = (int)n64;
+        fw.write((char*)&n, sizeof(int));
+        fw.write((const char*)buf.data(), sizeof(mag2d_particle) * (size_t)n);
+    }
+    void source5_load(const std::string& filename, unsigned int factor)
+    {
+        std::ifstream fr(filename.c_str(), std::ios::in | std::ios::binary);
+        if (!fr.is_open())
+        {
+            std::cerr << " source5_load(): Warning: cannot open file " << filename << std::endl;
+            return;
+        }
+        int n = 0;
+        fr.read((char*)&n, sizeof(int));
+        std::vector<mag2d_particle> buf((size_t)std::max(n, 1));
+        fr.read((char*)buf.data(), sizeof(mag2d_particle) * (size_t)n);
+        if (!fr.good()) std::cerr << "Species::load(): read error\n";
+        gpu_check(mag2d_source_upload(gpu, id, factor, buf.data(), n));
+    }
+
     // ---- diagnostics (src/particles.cpp:367-414)
     void energy_dist_compute()
     {
