@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAG2D_ABI_VERSION 2
+#define MAG2D_ABI_VERSION 3
 #define MAG2D_MAX_SPECIES 16
 
 typedef struct mag2d_ctx mag2d_ctx;
