@@ -179,7 +179,8 @@ int mag2d_set_use_source(mag2d_ctx* ctx, int on);
 /* Species<CARTESIAN>::source5_refresh(factor) (src/particles.cpp:1053-1080): (unsigned)(density*V/factor) reservoir
  * particles, uniform in [0, x_max/factor] x [0, z_max/factor], Maxwellian at the species temperature, then the half
  * step back with the external fields.  V is Param::V (n_particles_total / density_total).  A species without particles
- * keeps an empty reservoir (:1063).  Device-side Philox generation. */
+ * keeps an empty reservoir (:1063).  Device-side Philox generation.  In a particle-sharded multi-GPU run every rank
+ * owns its own reservoir: pass this rank's share V / nranks, so that the ranks together inject the physical flux. */
 int mag2d_source_refresh(mag2d_ctx* ctx, int species, uint32_t factor, double V);
 /* BaseSpecies::source2_particles (src/particles.hpp:114) as the save/load files carry it (src/particles.cpp:115-138) */
 int mag2d_source_upload(mag2d_ctx* ctx, int species, uint32_t factor, const mag2d_particle* aos, int64_t n);
