@@ -615,3 +615,22 @@ def test_magnetic_field_table_must_cover_the_box(deckdir):
                    magnetic_field_file=os.path.join(deckdir, "no_such_file.txt"))
     with pytest.raises(RuntimeError, match="failed opening file"):
         _sim(d["config"], d["species_conf"], presolve=False)
+
+
+def test_magnetic_field_table_can_be_dropped_again(orc, deckdir):
+    """mag2d_set_magnetic_field(NULL): the context forgets the table; with magnetic_field_const = 0 the step then refuses
+    to run instead of silently using a constant"""
+    from common import write_btable
+    from mag2d_b200.api import Mag2dError
+    bfile = write_btable(os.path.join(deckdir, "btable_drop.txt"), 9, 9, 1.2e-2, 7.5e-2)
+    d = decks.deck("c3", deckdir + "_btdrop", n_particles=10, collisions=False, x_sampl=41, z_sampl=61, magnetic_field_const=0,
+                   magnetic_field_file=bfile, selfconsistent=0)
+    with _sim(d["config"], d["species_conf"], presolve=False) as sim:
+        e = sim.species_index("ELECTRON")
+        sim.set_particles(e, disk_particles(np.random.default_rng(2), 100, 0.6e-2, 3.7e-2, 2e-3, 4e5))
+        sim.species_advance(e)
+        B = sim.field_B(np.array([0.3e-2]), np.array([3.75e-2]))
+        assert B[1, 0] == pytest.approx(0.03 * (1 - 0.5 * 400.0 * 0.3e-2 ** 2), rel=1e-3) and B[2, 0] == 0.0
+        sim.set_magnetic_field(None)
+        with pytest.raises(Mag2dError, match="no table"):
+            sim.species_advance(e)

@@ -164,3 +164,25 @@ def test_source_is_cartesian_only(deckdir):
         sim.set_particles(e, disk_particles(np.random.default_rng(1), 10, 5e-3, 3e-2, 1e-3, 4e5))
         with pytest.raises(Mag2dError, match="CARTESIAN"):
             sim.source_refresh(e, 4)
+
+
+def test_source_edge_cases(orc, deckdir):
+    """empty store -> no reservoir (particles.cpp:1063); empty reservoir -> source() is a no-op; download of nothing"""
+    d = _deck(deckdir, "_srcedge", 4, False, extern_field=0.0)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        e = sim.species_index("ELECTRON")
+        sim.source_refresh(e, 4)                       # the species has no particles yet
+        assert sim.get_source_particles(e).shape[0] == 0
+        assert sim.species_source(e) == 0
+        sim.set_particles(e, disk_particles(np.random.default_rng(3), 10, 0.5 * L, 0.5 * L, 0.2 * L, 4e5))
+        sim.set_source_particles(e, 4, np.zeros((0, 7)))
+        assert sim.species_source(e) == 0 and sim.count(e)[0] == 10
+        # a reservoir particle that crosses a corner of its box in one step enters twice (x block, then z block)
+        w = L / 4
+        v = 0.5 * w / 1e-11                            # half a reservoir width per step, towards the corner
+        sim.set_source_particles(e, 4, np.array([[w * 0.9, 0, w * 0.9, v, 0.0, v, 0.0]]))
+        n = sim.species_source(e)
+        out = sim.get_particles(e)[10:]
+        assert n == out.shape[0] and n <= 2            # copies whose lateral shift leaves the box are dropped like in the reference
+        res = sim.get_source_particles(e)
+        assert 0 <= res[0, 0] <= w and 0 <= res[0, 2] <= w
