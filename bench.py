@@ -394,12 +394,12 @@ def bench_e2e(sim, part_species, args, torch, stream, world, dist, dev):
     for s in part_species:
         download(s)          # the host-side particle arrays the caller owns
     n_live = sum(sim.count(s)[0] for s in part_species)
-    streamed = (not sim.is3d) and int(sim.param["mover"]) == 0
+    streamed = int(sim.param["mover"]) == 0
     if streamed:
         # the device copy is dropped: from here on the particles live in the caller's (pinned) host arrays only
         for s in part_species:
             sim._chk(sim.L.mag2d_particles_clear(sim.h, s))
-        pointers = [[bufs[s][1][k].data_ptr() for k in ("x", "z", "vx", "vy", "vz")] for s in part_species]
+        pointers = [[bufs[s][1][k].data_ptr() for k in comps] for s in part_species]
         counts = [bufs[s][0] for s in part_species]
     # the host side of these boxes is a shared VM: one disturbed repeat can double the time of a PCIe-bound step, so the
     # leg is timed `repeats` times over `steps` steps each and the median repeat is reported (all are listed)
@@ -432,8 +432,8 @@ def bench_e2e(sim, part_species, args, torch, stream, world, dist, dev):
     return {"value": n_live * steps / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": dt / steps * 1e3,
             "repeats_ms_per_step": [round(r / steps * 1e3, 3) for r in repeats],
-            "path": ("mag2d_step_streamed: host SoA arrays (pinned) -> chunked H2D / fused step / D2H overlapped on three streams -> host arrays, "
-                     "+ mag2d_rho_download") if streamed else
+            "path": ("mag2d_step_streamed%s: host SoA arrays (pinned) -> chunked H2D / fused step / D2H overlapped on three streams -> host arrays, "
+                     "+ mag2d_rho_download") % ("3" if sim.is3d else "") if streamed else
                     "mag2d_particles_upload_soa (pinned host) -> mag2d_step -> mag2d_particles_download_soa + mag2d_rho_download"}
 
 

@@ -201,6 +201,10 @@ int mag2d_sort(mag2d_ctx* ctx, int species);
  * removed particles come back with x = NaN.  2-D Boris movers. */
 int mag2d_step_streamed(mag2d_ctx* ctx, int n_species, const int32_t* species, const int64_t* n_slots, double* const* x,
                         double* const* z, double* const* vx, double* const* vy, double* const* vz, int64_t chunk_slots);
+/* the same for CARTESIAN3D stores (six arrays: Species<CARTESIAN3D>::advance, src/species3d.cpp:3-93, on host-resident particles) */
+int mag2d_step_streamed3(mag2d_ctx* ctx, int n_species, const int32_t* species, const int64_t* n_slots, double* const* x,
+                         double* const* y, double* const* z, double* const* vx, double* const* vy, double* const* vz,
+                         int64_t chunk_slots);
 int mag2d_set_sort_interval(mag2d_ctx* ctx, int steps); /* 0 = never sort inside mag2d_step; -1 = per species from its thermal drift (v_th dt K ~ 0.35 cell, 2..64) */
 /* per-species override (-1 = use the context-wide interval): slow species (ions) need far fewer sorts than fast
  * ones.  With the Boris movers the sort is carried by the push kernels themselves (a COUNT step hands out cell

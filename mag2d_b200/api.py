@@ -109,6 +109,7 @@ def lib():
     L.mag2d_sort.argtypes = [vp, C.c_int]
     L.mag2d_set_sort_interval.argtypes = [vp, C.c_int]
     L.mag2d_step_streamed.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), i64p] + [C.POINTER(dp)] * 5 + [C.c_int64]
+    L.mag2d_step_streamed3.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), i64p] + [C.POINTER(dp)] * 6 + [C.c_int64]
     L.mag2d_set_species_sort_interval.argtypes = [vp, C.c_int, C.c_int]
     L.mag2d_advance_init.argtypes = [vp]
     L.mag2d_step.argtypes = [vp, C.c_int]
@@ -378,14 +379,18 @@ class Sim:
 
     def step_streamed(self, species, n_slots, pointers, chunk_slots=0):
         """one Pic::advance with HOST-resident particles: ``pointers[q]`` = five integer addresses (x, z, vx, vy, vz) of
-        species[q]'s host arrays (numpy ``.ctypes.data`` or torch ``.data_ptr()``, pinned for overlap)"""
+        species[q]'s host arrays (numpy ``.ctypes.data`` or torch ``.data_ptr()``, pinned for overlap); six
+        (x, y, z, vx, vy, vz) for CARTESIAN3D"""
         n = len(species)
         sp = (C.c_int32 * n)(*species)
         ns = (C.c_int64 * n)(*n_slots)
         cols = []
-        for a in range(5):
+        for a in range(6 if self.is3d else 5):
             cols.append((dp * n)(*[C.cast(pointers[q][a], dp) for q in range(n)]))
-        self._chk(self.L.mag2d_step_streamed(self.h, n, sp, ns, cols[0], cols[1], cols[2], cols[3], cols[4], chunk_slots))
+        if self.is3d:
+            self._chk(self.L.mag2d_step_streamed3(self.h, n, sp, ns, *cols, chunk_slots))
+        else:
+            self._chk(self.L.mag2d_step_streamed(self.h, n, sp, ns, *cols, chunk_slots))
 
     def species_advance(self, i):
         self._chk(self.L.mag2d_species_advance(self.h, i))

@@ -335,7 +335,7 @@ int mag2d_destroy(mag2d_ctx* c)
     cudaFree(c->d_gy);
     for (int b = 0; b < 3; b++)
     {
-        for (int a = 0; a < 5; a++) cudaFree(c->d_chunk[b][a]);
+        for (int a = 0; a < 6; a++) cudaFree(c->d_chunk[b][a]);
         if (c->ev_h2d[b]) { cudaEventDestroy(c->ev_h2d[b]); cudaEventDestroy(c->ev_comp[b]); cudaEventDestroy(c->ev_d2h[b]); }
     }
     if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h); }
@@ -1177,11 +1177,11 @@ int mag2d_step(mag2d_ctx* c, int nsteps)
 // i+1, the fused push/deposit kernel on chunk i and the D2H copy of chunk i-1 run concurrently on three streams, so
 // the step costs max(upload, compute, download) instead of their sum, and the particle set is not limited by HBM.
 // Blocks until the host arrays hold the pushed particles.  Removed particles come back with x = NaN.
-int mag2d_step_streamed(mag2d_ctx* c, int n_sp, const int32_t* species, const int64_t* n_slots, double* const* x, double* const* z,
-                        double* const* vx, double* const* vy, double* const* vz, int64_t chunk_slots)
+static int step_streamed_impl(mag2d_ctx* c, int n_sp, const int32_t* species, const int64_t* n_slots, double* const* x, double* const* y,
+                              double* const* z, double* const* vx, double* const* vy, double* const* vz, int64_t chunk_slots)
 {
-    CHECK_CTX(c);
-    if (is3d(c) || c->g.mover != MAG2D_ADVANCE_BORIS) { mag2d_set_error("mag2d_step_streamed: 2-D Boris movers only"); return 1; }
+    const bool three_d = is3d(c);
+    const int n_arr = three_d ? 6 : 5;
     if (chunk_slots <= 0) chunk_slots = 1 << 22;
     chunk_slots = (chunk_slots + 1023) / 1024 * 1024;
     if (!c->s_h2d)
@@ -1199,14 +1199,22 @@ int mag2d_step_streamed(mag2d_ctx* c, int n_sp, const int32_t* species, const in
     {
         CUDA_OK(cudaStreamSynchronize(c->s_d2h));
         for (int b = 0; b < 3; b++)
-            for (int a = 0; a < 5; a++)
+            for (int a = 0; a < n_arr; a++)
             {
                 cudaFree(c->d_chunk[b][a]);
                 CUDA_OK(cudaMalloc(&c->d_chunk[b][a], sizeof(double) * (size_t)chunk_slots));
             }
         c->chunk_capacity = chunk_slots;
     }
-    if (c->g.selfconsistent)
+    if (three_d)
+    {
+        if (c->g.selfconsistent)
+        {
+            if (solve3d(c, nullptr)) return 1;
+            if (mag2d_rho_reset(c, -1)) return 1;
+        }
+    }
+    else if (c->g.selfconsistent)
     {
         const bool direct = c->direct.ok && c->solver_kind != MAG2D_SOLVER_MULTIGRID;
         if (mg_solve(c, 0, c->solve_tol, c->max_cycles, direct && !c->cycles_per_step ? 1 : c->cycles_per_step, nullptr, nullptr)) return 1;
@@ -1221,28 +1229,29 @@ int mag2d_step_streamed(mag2d_ctx* c, int n_sp, const int32_t* species, const in
         CHECK_SPECIES(c, s);
         SpeciesStore& S = c->sp[s];
         if (refresh_pools(c, s)) return 1;
-        double* const host[5] = {x[q], z[q], vx[q], vy[q], vz[q]};
+        double* const host[6] = {x[q], z[q], vx[q], vy[q], vz[q], three_d ? y[q] : nullptr};      // staging order: y last
         for (long long off = 0; off < n_slots[q] && !rc; off += chunk_slots, ring++)
         {
             const int b = (int)(ring % 3);
             const long long cnt = std::min<long long>(chunk_slots, n_slots[q] - off);
             CUDA_OK(cudaStreamWaitEvent(c->s_h2d, c->ev_d2h[b], 0));       // the buffer's previous tenant has left
-            for (int a = 0; a < 5; a++)
+            for (int a = 0; a < n_arr; a++)
                 CUDA_OK(cudaMemcpyAsync(c->d_chunk[b][a], host[a] + off, sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, c->s_h2d));
             CUDA_OK(cudaEventRecord(c->ev_h2d[b], c->s_h2d));
             CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
             ParticlesDev view;
             memset(&view, 0, sizeof(view));
             view.x = c->d_chunk[b][0]; view.z = c->d_chunk[b][1]; view.vx = c->d_chunk[b][2]; view.vy = c->d_chunk[b][3]; view.vz = c->d_chunk[b][4];
+            view.y = three_d ? c->d_chunk[b][5] : nullptr;
             view.n = cnt;
             c->chunk_view = &view;
             c->chunk_slot0 = off;
-            rc = launch_species_advance(c, s, 0);
+            rc = three_d ? launch_species_advance3d(c, s, false, 0) : launch_species_advance(c, s, 0);
             c->chunk_view = nullptr;
             if (rc) break;
             CUDA_OK(cudaEventRecord(c->ev_comp[b], c->stream));
             CUDA_OK(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[b], 0));
-            for (int a = 0; a < 5; a++)
+            for (int a = 0; a < n_arr; a++)
                 CUDA_OK(cudaMemcpyAsync(host[a] + off, c->d_chunk[b][a], sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, c->s_d2h));
             CUDA_OK(cudaEventRecord(c->ev_d2h[b], c->s_d2h));
         }
@@ -1255,6 +1264,22 @@ int mag2d_step_streamed(mag2d_ctx* c, int n_sp, const int32_t* species, const in
     CUDA_OK(cudaStreamSynchronize(c->s_d2h));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+int mag2d_step_streamed(mag2d_ctx* c, int n_sp, const int32_t* species, const int64_t* n_slots, double* const* x, double* const* z,
+                        double* const* vx, double* const* vy, double* const* vz, int64_t chunk_slots)
+{
+    CHECK_CTX(c);
+    if (is3d(c) || c->g.mover != MAG2D_ADVANCE_BORIS) { mag2d_set_error("mag2d_step_streamed: 2-D Boris movers only"); return 1; }
+    return step_streamed_impl(c, n_sp, species, n_slots, x, nullptr, z, vx, vy, vz, chunk_slots);
+}
+
+int mag2d_step_streamed3(mag2d_ctx* c, int n_sp, const int32_t* species, const int64_t* n_slots, double* const* x, double* const* y,
+                         double* const* z, double* const* vx, double* const* vy, double* const* vz, int64_t chunk_slots)
+{
+    CHECK_CTX(c);
+    if (!is3d(c)) { mag2d_set_error("mag2d_step_streamed3: CARTESIAN3D only"); return 1; }
+    return step_streamed_impl(c, n_sp, species, n_slots, x, y, z, vx, vy, vz, chunk_slots);
 }
 
 int mag2d_energy_hist(mag2d_ctx* c, int s, int nbins, double emax, double* hist, double* stats)

@@ -174,7 +174,7 @@ struct mag2d_ctx
     // streamed step: the particle arrays a push works on are one chunk of a host-resident store (abi.cu)
     const ParticlesDev* chunk_view = nullptr;
     long long chunk_slot0 = 0;
-    double* d_chunk[3][5] = {};        // ring of device staging buffers (x, z, vx, vy, vz)
+    double* d_chunk[3][6] = {};        // ring of device staging buffers (x, z, vx, vy, vz; y for CARTESIAN3D)
     long long chunk_capacity = 0;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[3] = {}, ev_comp[3] = {}, ev_d2h[3] = {};

@@ -463,25 +463,36 @@ int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only, int sort_mo
 {
     SpeciesStore& S = c->sp[s];
     const mag2d_grid_desc& d = c->g;
-    if (S.n_slots > 0)
+    // streamed step (abi.cu): the particle arrays are one chunk of a host-resident store staged in device buffers
+    const bool chunked = c->chunk_view != nullptr && !deposit_only;
+    const long long n_active = chunked ? c->chunk_view->n : S.n_slots;
+    if (n_active > 0)
     {
         Push3Args A;
         A.g = grid3_view(c, s);
         A.s = species3_view(c, s);
-        A.p = particles3_view(S);
+        A.p = chunked ? *c->chunk_view : particles3_view(S);
         A.mcc = S.d_blob;
         A.counts = c->count_collisions ? S.d_counts : nullptr;
         A.removed = S.d_removed;
         A.seed = c->seed;
+        if (chunked && c->chunk_slot0)
+        {
+            // every chunk draws from its own Philox key (splitmix64 of its first global slot), as in the 2-D launcher
+            unsigned long long zz = (unsigned long long)c->chunk_slot0 + 0x9E3779B97F4A7C15ULL;
+            zz = (zz ^ (zz >> 30)) * 0xBF58476D1CE4E5B9ULL;
+            zz = (zz ^ (zz >> 27)) * 0x94D049BB133111EBULL;
+            A.seed ^= zz ^ (zz >> 31);
+        }
         A.coll_list = nullptr;
         A.coll_count = nullptr;
         A.permute = A.count = 0;
         A.key_in = A.rank_in = A.offset_in = nullptr;
         A.key_out = A.rank_out = A.count_out = nullptr;
         memset(&A.dst, 0, sizeof(A.dst));
-        const double per_cell = (double)S.n_slots / ((double)(d.M - 1) * (d.K - 1) * (d.N - 1));
+        const double per_cell = (double)n_active / ((double)(d.M - 1) * (d.K - 1) * (d.N - 1));
         A.deposit_runs = per_cell >= 32.0 ? 3 : 0;
-        const unsigned blocks = (unsigned)((S.n_slots + 2 * P3_THREADS - 1) / (2 * P3_THREADS));
+        const unsigned blocks = (unsigned)((n_active + 2 * P3_THREADS - 1) / (2 * P3_THREADS));
         const bool mcc = !deposit_only && S.h_blob && S.h_blob->has_collisions && std::isfinite(S.lifetime);
         const bool deposit = d.selfconsistent != 0;
         if (deposit_only)
@@ -490,10 +501,11 @@ int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only, int sort_mo
         }
         else
         {
-            if (update_edge_fields3d(c)) return 1;
+            // the potential does not change inside a step: later chunks of a streamed step reuse the edge fields
+            if (!(chunked && c->chunk_slot0 > 0) && update_edge_fields3d(c)) return 1;
             if (mcc)
             {
-                if (ensure_particle_scratch(c, S.capacity)) return 1;
+                if (ensure_particle_scratch(c, chunked ? std::max(n_active, S.capacity) : S.capacity)) return 1;
                 A.coll_list = c->d_key;
                 A.coll_count = c->d_coll_count;
                 CUDA_OK(cudaMemsetAsync(c->d_coll_count, 0, sizeof(unsigned), c->stream));
@@ -555,6 +567,7 @@ int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only, int sort_mo
         c->launches++;
         CUDA_OK(cudaGetLastError());
     }
+    if (chunked) return 0;          // the streamed step advances the species clock once per step, not per chunk
     if (!deposit_only)
     {
         S.niter++;

@@ -225,3 +225,39 @@ def test_sort_and_loader_3d(deckdir):
         alive, slots = sim.count(e)
         assert 0 < alive <= 50000
         assert np.isfinite(sim.get_field("u")).all()
+
+
+def test_streamed_step_3d_equals_the_resident_step(deckdir):
+    """mag2d_step_streamed3: host-resident six-array store pushed through the staging ring chunk by chunk; with
+    collisions off it leaves exactly the particles, the charge grid and the potential of mag2d_step"""
+    from mag2d_b200.api import Sim
+    d = decks.deck("c5", deckdir + "_str3", n_particles=10, collisions=False, x_sampl=17, y_sampl=15, z_sampl=13)
+    rng = np.random.default_rng(41)
+    n = 9000
+    with Sim(d["config"], d["species_conf"]) as ref, Sim(d["config"], d["species_conf"]) as sim:
+        e = sim.species_index("ELECTRON")
+        p = sim.param
+        a = np.zeros((n, 7))
+        a[:, 0] = rng.uniform(1e-7, p["x_max"] - 1e-7, n)
+        a[:, 1] = rng.uniform(1e-7, p["y_max"] - 1e-7, n)
+        a[:, 2] = rng.uniform(1e-7, p["z_max"] - 1e-7, n)
+        a[:, 3:6] = rng.normal(size=(n, 3)) * 8e5
+        ref.set_particles(e, a)
+        sim.set_particles(e, a)
+        ref.set_sort_interval(0)
+        ref.advance_init()
+        sim.advance_init()
+        got = sim.get_particles(e)
+        host = [np.ascontiguousarray(got[:, c]) for c in range(6)]
+        host[0][got[:, 7] == 0] = np.nan
+        sim._chk(sim.L.mag2d_particles_clear(sim.h, e))
+        for _ in range(4):
+            ref.advance(1)
+            sim.step_streamed([e], [n], [[c.ctypes.data for c in host]], chunk_slots=2048)     # 5 chunks: the ring wraps
+        want = ref.get_particles(e)
+        alive = want[:, 7] > 0
+        assert np.array_equal(~np.isnan(host[0]), alive) and 0 < alive.sum() < n
+        for c in range(6):
+            assert np.array_equal(host[c][alive], want[alive, c])
+        assert np.array_equal(sim.rho_fixed(e), ref.rho_fixed(e))
+        assert np.array_equal(sim.get_field("u"), ref.get_field("u"))
