@@ -411,7 +411,7 @@ def bench_e2e(sim, part_species, args, torch, stream, world, dist, dev):
         t0 = time.perf_counter()
         for _ in range(steps):
             if streamed:
-                sim.step_streamed(part_species, counts, pointers)
+                sim.step_streamed(part_species, counts, pointers, chunk_slots=args.e2e_chunk)
             else:
                 for s in part_species:
                     upload(s)
@@ -613,6 +613,7 @@ def main():
                     help="Poisson solver of the self-consistent step (auto: direct when the grid separates)")
     ap.add_argument("--solve-tol", type=float, default=1e-10)
     ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="slots per chunk of the streamed e2e step (0: the library default, 4 Mi)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
