@@ -250,11 +250,13 @@ struct Rhs3Args
 // Solver::solve's right-hand side + the reduction to the interior block
 __global__ void k_rhs3d(const __grid_constant__ Rhs3Args A)
 {
+    // one block per grid row (i, j), threads along k: no 64-bit divisions per node
     const size_t n = (size_t)A.M * A.K * A.N;
     const long long sj = A.N, si = (long long)A.K * A.N;
-    for (size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x; m < n; m += (size_t)gridDim.x * blockDim.x)
+    const int i = (int)(blockIdx.x / (unsigned)A.K), j = (int)(blockIdx.x % (unsigned)A.K);
+    for (int k = threadIdx.x; k < A.N; k += blockDim.x)
     {
-        const int k = (int)(m % A.N), j = (int)((m / A.N) % A.K), i = (int)(m / si);
+        const size_t m = ((size_t)i * A.K + j) * A.N + k;
         const bool fixed = A.mask[m] != MAG2D_FREE;
         double b;
         if (fixed) b = A.voltage[m];
@@ -316,15 +318,15 @@ __global__ void k_thomas_solve(int n_i, int plane, const double* __restrict__ in
         y = (v[e] - y) * inv[e];
         v[e] = y;
     }
+    // the two inverse transforms carry the factor 4 / ((n_j+1)(n_k+1)): it is folded into the stores of the back
+    // substitution (the recurrence itself runs on the unscaled x)
     double x = 0.0;
     for (int i = n_i - 1; i >= 0; i--)
     {
         const size_t e = (size_t)i * plane + mode;
         x = v[e] - inv[e] * x;
-        v[e] = x;
+        v[e] = x * scale;
     }
-    // the two inverse transforms carry the factor 4 / ((n_j+1)(n_k+1)); fold it in here
-    for (int i = 0; i < n_i; i++) v[(size_t)i * plane + mode] *= scale;
 }
 
 // alpha = Cinv (V_E - u0[E]);  one block
@@ -618,7 +620,7 @@ int solve3d(mag2d_ctx* c, double* resid_out)
     A.b = c->d_b;
     A.u = c->d_u;
     A.R = D.R;
-    k_rhs3d<<<148 * 8, 256, 0, c->stream>>>(A);
+    k_rhs3d<<<(unsigned)(M * K), std::min(256, (N + 31) / 32 * 32), 0, c->stream>>>(A);
     c->launches++;
     if (solve_interior(c, c->d_u)) return 1;
     if (D.ne > 0)

@@ -8,6 +8,7 @@
 //   Field3D::accumulate                         src/Field3D.hpp:40-65
 // Grids use the reference's Array3D layout a[(i*K + j)*N + k] (i along x, j along y, k along z; M, K, N nodes).
 // 96 B per particle-step (six fp64 components read and written once).
+#include <algorithm>
 #include <cstring>
 
 #include "ctx.hpp"
@@ -370,13 +371,17 @@ __global__ void __launch_bounds__(128) k_mcc_collide3d(const __grid_constant__ P
 __global__ void k_edge_fields3d(const double* __restrict__ u, int M, int K, int N, double* __restrict__ gx, double* __restrict__ gy,
                                 double* __restrict__ gz)
 {
-    const size_t sj = (size_t)N + 1, si = ((size_t)K + 1) * sj, n = ((size_t)M + 1) * si;
+    // one block per row (i, j) of the ghost-extended range, threads along k: no integer divisions per element
+    const size_t sj = (size_t)N + 1, si = ((size_t)K + 1) * sj;
     const size_t uj = N, ui = (size_t)K * N;
-    for (size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x; m < n; m += (size_t)gridDim.x * blockDim.x)
+    const int i = (int)(blockIdx.x / (unsigned)(K + 1)), j = (int)(blockIdx.x % (unsigned)(K + 1));
+    const int i0 = min(i, M - 1), j0 = min(j, K - 1);
+    const int i1 = max(i0, 1), j1 = max(j0, 1);
+    for (int k = threadIdx.x; k <= N; k += blockDim.x)
     {
-        const int k = (int)(m % sj), j = (int)((m / sj) % (K + 1)), i = (int)(m / si);
-        const int i0 = min(i, M - 1), j0 = min(j, K - 1), k0 = min(k, N - 1);
-        const int i1 = max(i0, 1), j1 = max(j0, 1), k1 = max(k0, 1);
+        const size_t m = (size_t)i * si + (size_t)j * sj + k;
+        const int k0 = min(k, N - 1);
+        const int k1 = max(k0, 1);
         gx[m] = u[i1 * ui + j0 * uj + k0] - u[(i1 - 1) * ui + j0 * uj + k0];
         gy[m] = u[i0 * ui + j1 * uj + k0] - u[i0 * ui + (j1 - 1) * uj + k0];
         gz[m] = u[i0 * ui + j0 * uj + k1] - u[i0 * ui + j0 * uj + k1 - 1];
@@ -452,7 +457,8 @@ ParticlesDev particles3_view(const SpeciesStore& S)
 
 int update_edge_fields3d(mag2d_ctx* c)
 {
-    k_edge_fields3d<<<148 * 8, 256, 0, c->stream>>>(c->d_u, c->g.M, c->g.K, c->g.N, c->d_gx, c->d_gy, c->d_gz);
+    k_edge_fields3d<<<(unsigned)((c->g.M + 1) * (c->g.K + 1)), std::min(256, (c->g.N + 32) / 32 * 32), 0, c->stream>>>(c->d_u, c->g.M, c->g.K, c->g.N, c->d_gx,
+                                                                                                                    c->d_gy, c->d_gz);
     c->launches++;
     CUDA_OK(cudaGetLastError());
     return 0;
