@@ -221,6 +221,18 @@ constexpr unsigned SORT_INVALID_KEY = 0xFFFFFFFFu;
 // warp-aggregated ticket: one atomic per (warp, cell), ranks handed out in lane order.  MATCH.ANY finds the lanes
 // that share a cell in one instruction, so all group leaders issue their atomics together: one memory round trip
 // per call, not one per distinct cell (the returning atomic is the long pole of a COUNT step).
+// The fused cell sort needs no stored tickets: a COUNT push only counts the particles per cell (one RED per warp and cell),
+// and the next (PERMUTE) push — which loads every particle at exactly the position it was counted at — recomputes the
+// cell and draws the slot from a per-cell cursor (the scanned counts).  Saves 16 bytes of ticket traffic per particle
+// and sort and the two key / rank arrays per species (16 bytes per slot).
+// count[key] += number of lanes holding key (one non-returning atomic per distinct key of the warp)
+__device__ __forceinline__ void warp_count(unsigned* __restrict__ count, bool valid, unsigned key)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned group = __match_any_sync(MAG2D_FULL_MASK, valid ? key : (0xFFFFFFE0u | lane));
+    if (valid && (int)lane == __ffs(group) - 1) atomicAdd(&count[key], (unsigned)__popc(group));
+}
+
 __device__ __forceinline__ unsigned warp_ticket(unsigned* __restrict__ count, bool valid, unsigned key)
 {
     const unsigned lane = lane_id();

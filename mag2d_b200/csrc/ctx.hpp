@@ -33,15 +33,11 @@ struct SpeciesStore
     unsigned long long niter = 0;     // BaseSpecies::niter
     double t = 0;                     // BaseSpecies::t
     int steps_since_sort = 0;
-    // cell sort fused into the push (sort.cu): tickets handed out by a COUNT step, consumed by the next PERMUTE step
-    unsigned* d_key[2] = {};          // [capacity] cell key per slot, two sets (a permuting step reads one, writes the other)
-    unsigned* d_rank[2] = {};
+    // cell sort fused into the push (sort.cu): cells counted by a COUNT step, cursors consumed by the next PERMUTE step
     unsigned* d_cell_count = nullptr; // [ncells]
     unsigned* d_cell_offset = nullptr;
     unsigned* d_sort_sums = nullptr;  // scan scratch + grand total
-    long long key_capacity = 0;
-    int kr = 0;                       // key/rank set holding the pending tickets
-    bool tickets_valid = false;       // a COUNT step has run and nothing has disturbed the slots since
+    bool tickets_valid = false;       // a COUNT step has run (cursors are pending) and nothing has disturbed the slots since
     int sort_interval = -1;           // pushes between permuting steps (-1: the context-wide setting)
     int pushes_since_permute = 1 << 20;
     // n_slots is only an upper bound after a fused permute (the live count stays on the device); every permute also

@@ -42,12 +42,8 @@ struct PushArgs
     int permute;                   // write every array to its sorted slot of the other slab (keys of an earlier COUNT step)
     int count;                     // hand every surviving particle a ticket of its new cell for the next permuting step
     int cell_cols;                 // N - 1
-    const unsigned* key_in;        // [slot] cell key / rank within the cell / exclusive offsets of the cells
-    const unsigned* rank_in;
-    const unsigned* offset_in;
+    unsigned* cursor;              // [cell] next free sorted slot of the cell (the scanned counts of the last COUNT push)
     ParticlesDev dst;              // the other slab
-    unsigned* key_out;             // [slot of this step's output]
-    unsigned* rank_out;
     unsigned* count_out;           // [cell]
 };
 
@@ -355,12 +351,19 @@ __global__ void __launch_bounds__(PUSH_THREADS, SORTING ? MAG2D_SORT_MIN_BLOCKS 
         dest[2 * p + 1] = k + 1;
         if (permute)
         {
-            // sorted slot = offset of the cell the particle was counted in + its ticket; slots that were dead when
-            // the tickets were handed out (or lie past n) have no destination: the permutation compacts
-            const uint2 ky = *reinterpret_cast<const uint2*>(A.key_in + k);
-            const uint2 rk = *reinterpret_cast<const uint2*>(A.rank_in + k);
-            dest[2 * p] = (k < n && ky.x != SORT_INVALID_KEY) ? (long long)__ldg(A.offset_in + ky.x) + rk.x : -1;
-            dest[2 * p + 1] = (k + 1 < n && ky.y != SORT_INVALID_KEY) ? (long long)__ldg(A.offset_in + ky.y) + rk.y : -1;
+            // dead slots and the slots past n have no destination: the permutation compacts
+            // the particle sits exactly where the COUNT push left it: recompute that cell (same operations as
+            // boundary_weights) and draw the next slot of the cell from the cursor array (the scanned counts)
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+            {
+                const double px = x[e], pz = z[e];
+                const bool alive = (k + e < n) && particle_alive(px);
+                const int ci = max(min((int)__dmul_rn(px, A.g.idx), A.g.M - 2), 0), cj = max(min((int)__dmul_rn(pz, A.g.idz), A.g.N - 2), 0);
+                const unsigned key = (unsigned)ci * (unsigned)(A.g.N - 1) + (unsigned)cj;
+                const unsigned slot = warp_ticket(A.cursor, alive, alive ? key : 0u);
+                dest[2 * p + e] = alive ? (long long)slot : -1;
+            }
         }
         bool keep[2];
         unsigned node[2], row[2] = {0, 0};
@@ -427,18 +430,12 @@ __global__ void __launch_bounds__(PUSH_THREADS, SORTING ? MAG2D_SORT_MIN_BLOCKS 
         }
         if (count)
         {
-            // tickets for the next permuting step, keyed by the cell the particle sits in now (node = i*N + j)
+            // cell counts for the next permuting step, keyed by the cell the particle sits in now (node = i*N + j)
 #pragma unroll
             for (int e = 0; e < 2; e++)
             {
                 const unsigned key = keep[e] ? node[e] - row[e] : SORT_INVALID_KEY;      // i*N + j - i = i*(N-1) + j
-                const unsigned rk = warp_ticket(A.count_out, keep[e], key);
-                const long long d = dest[2 * p + e];
-                if (d >= 0 && (permute || k + e < n))
-                {
-                    A.key_out[d] = key;
-                    A.rank_out[d] = rk;
-                }
+                warp_count(A.count_out, keep[e], key);
             }
         }
         if (DEPOSIT)
@@ -1391,8 +1388,7 @@ int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
         A.coll_list = nullptr;
         A.coll_count = nullptr;
         A.permute = A.count = A.cell_cols = 0;
-        A.key_in = A.rank_in = A.offset_in = nullptr;
-        A.key_out = A.rank_out = A.count_out = nullptr;
+        A.cursor = A.count_out = nullptr;
         memset(&A.dst, 0, sizeof(A.dst));
         const unsigned blocks = (unsigned)((n_active + PUSH_THREADS - 1) / PUSH_THREADS);
         const unsigned tile_blocks = (unsigned)((n_active + PUSH_THREADS * PPT - 1) / (PUSH_THREADS * PPT));
@@ -1449,12 +1445,7 @@ int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
                 A.permute = permute;
                 A.count = count;
                 A.cell_cols = d.N - 1;
-                A.key_in = S.d_key[S.kr];
-                A.rank_in = S.d_rank[S.kr];
-                A.offset_in = S.d_cell_offset;
-                // tickets of a permuting step describe the new slab: they go to the other key/rank set
-                A.key_out = S.d_key[permute ? S.kr ^ 1 : S.kr];
-                A.rank_out = S.d_rank[permute ? S.kr ^ 1 : S.kr];
+                A.cursor = S.d_cell_offset;
                 A.count_out = S.d_cell_count;
                 if (permute)
                 {

@@ -48,12 +48,8 @@ struct Push3Args
     int deposit_runs;   // distinct cells per warp call that get the REDUX merge (0: every lane scatters on its own)
     // cell sort fused into the step (sort.cu): COUNT hands out tickets, the next PERMUTE step stores sorted
     int permute, count;
-    const unsigned* key_in;
-    const unsigned* rank_in;
-    const unsigned* offset_in;
+    unsigned* cursor;   // [cell] next free sorted slot of the cell (the scanned counts of the last COUNT push)
     ParticlesDev dst;
-    unsigned* key_out;
-    unsigned* rank_out;
     unsigned* count_out;
 };
 
@@ -204,10 +200,18 @@ __global__ void __launch_bounds__(P3_THREADS, MAG3D_MIN_BLOCKS) k_push3d(const _
     long long dest[2] = {k, k + 1};
     if (permute)
     {
-        const uint2 ky = *reinterpret_cast<const uint2*>(A.key_in + k);
-        const uint2 rk = *reinterpret_cast<const uint2*>(A.rank_in + k);
-        dest[0] = (k < n && ky.x != SORT_INVALID_KEY) ? (long long)__ldg(A.offset_in + ky.x) + rk.x : -1;
-        dest[1] = (k + 1 < n && ky.y != SORT_INVALID_KEY) ? (long long)__ldg(A.offset_in + ky.y) + rk.y : -1;
+        // the particle sits exactly where the COUNT push left it: recompute that cell (same operations as boundary3)
+        // and draw the next slot of the cell from the cursor array (the scanned counts)
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+        {
+            const bool alive = (k + e < n) && particle_alive(x[e]);
+            const int ci = max(min((int)__dmul_rn(x[e], A.g.idx), A.g.M - 2), 0), cj = max(min((int)__dmul_rn(y[e], A.g.idy), A.g.K - 2), 0),
+                      ck = max(min((int)__dmul_rn(z[e], A.g.idz), A.g.N - 2), 0);
+            const unsigned key = ((unsigned)ci * (unsigned)(A.g.K - 1) + (unsigned)cj) * (unsigned)(A.g.N - 1) + (unsigned)ck;
+            const unsigned slot = warp_ticket(A.cursor, alive, alive ? key : 0u);
+            dest[e] = alive ? (long long)slot : -1;
+        }
     }
     const double dt = A.s.dt;
     bool keep[2];
@@ -283,13 +287,7 @@ __global__ void __launch_bounds__(P3_THREADS, MAG3D_MIN_BLOCKS) k_push3d(const _
         for (int e = 0; e < 2; e++)
         {
             const unsigned key = keep[e] ? cell[e] : SORT_INVALID_KEY;
-            const unsigned rk = warp_ticket(A.count_out, keep[e], key);
-            const long long d = dest[e];
-            if (d >= 0 && (permute || k + e < n))
-            {
-                A.key_out[d] = key;
-                A.rank_out[d] = rk;
-            }
+            warp_count(A.count_out, keep[e], key);
         }
     }
     if (DEPOSIT)
@@ -493,8 +491,7 @@ int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only, int sort_mo
         A.coll_list = nullptr;
         A.coll_count = nullptr;
         A.permute = A.count = 0;
-        A.key_in = A.rank_in = A.offset_in = nullptr;
-        A.key_out = A.rank_out = A.count_out = nullptr;
+        A.cursor = A.count_out = nullptr;
         memset(&A.dst, 0, sizeof(A.dst));
         const double per_cell = (double)n_active / ((double)(d.M - 1) * (d.K - 1) * (d.N - 1));
         A.deposit_runs = per_cell >= 32.0 ? 3 : 0;
@@ -523,11 +520,7 @@ int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only, int sort_mo
                 if (sort_fused_begin(c, s, permute, count)) return 1;
                 A.permute = permute;
                 A.count = count;
-                A.key_in = S.d_key[S.kr];
-                A.rank_in = S.d_rank[S.kr];
-                A.offset_in = S.d_cell_offset;
-                A.key_out = S.d_key[permute ? S.kr ^ 1 : S.kr];
-                A.rank_out = S.d_rank[permute ? S.kr ^ 1 : S.kr];
+                A.cursor = S.d_cell_offset;
                 A.count_out = S.d_cell_count;
                 if (permute)
                 {

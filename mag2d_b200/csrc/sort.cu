@@ -256,19 +256,15 @@ int launch_sort(mag2d_ctx* c, int s, bool trim)
 
 // ---- cell sort fused into the Boris push (push.cu, SORTING kernels) -----------------------------------------------
 // Instead of a stand-alone count + scatter pass every K steps (16 + 88 bytes per particle), the push itself does the
-// work of both: a COUNT step hands every surviving particle a ticket (cell key, rank in the cell) for the position it
-// has just been moved to; the counts are scanned; the next PERMUTE step reads the particles in slot order as always
-// but writes them to slot offset[key] + rank of the other slab, dropping dead slots on the way.  The store is then
-// sorted by the cell each particle occupied one step earlier, which is as good for the gather / scatter locality,
-// and the only extra traffic is the 8 bytes of ticket written and read per particle.
+// work of both: a COUNT step counts the surviving particles per cell at the position they have just been moved to
+// (one RED per warp and cell); the counts are scanned into per-cell cursors; the next PERMUTE step reads the particles
+// in slot order as always — each one at exactly the position it was counted at, so it recomputes its cell — draws its
+// slot from the cell's cursor (one returning atomic per warp and cell) and writes the particle there in the other
+// slab, dropping dead slots on the way.  The store is then sorted by the cell each particle occupied one step earlier,
+// which is as good for the gather / scatter locality, with no per-particle ticket arrays and no extra traffic
+// beyond the scattered stores themselves.
 void sort_fused_free(SpeciesStore& S)
 {
-    for (int q = 0; q < 2; q++)
-    {
-        cudaFree(S.d_key[q]);
-        cudaFree(S.d_rank[q]);
-        S.d_key[q] = S.d_rank[q] = nullptr;
-    }
     cudaFree(S.d_cell_count);
     cudaFree(S.d_cell_offset);
     cudaFree(S.d_sort_sums);
@@ -278,7 +274,6 @@ void sort_fused_free(SpeciesStore& S)
     S.ev_total = nullptr;
     S.total_pending = false;
     S.d_cell_count = S.d_cell_offset = S.d_sort_sums = nullptr;
-    S.key_capacity = 0;
     S.tickets_valid = false;
 }
 
@@ -292,22 +287,6 @@ int sort_fused_begin(mag2d_ctx* c, int s, bool permute, bool count)
         CUDA_OK(cudaMalloc(&S.d_cell_count, sizeof(unsigned) * (size_t)ncells));
         CUDA_OK(cudaMalloc(&S.d_cell_offset, sizeof(unsigned) * (size_t)ncells));
         CUDA_OK(cudaMalloc(&S.d_sort_sums, sizeof(unsigned) * (size_t)(ntiles + 8) + 16));
-    }
-    if (S.key_capacity < S.capacity)
-    {
-        if (S.tickets_valid)
-        {
-            mag2d_set_error("sort_fused_begin: the particle store grew while tickets were pending");
-            return 1;
-        }
-        for (int q = 0; q < 2; q++)
-        {
-            cudaFree(S.d_key[q]);
-            cudaFree(S.d_rank[q]);
-            CUDA_OK(cudaMalloc(&S.d_key[q], sizeof(unsigned) * (size_t)S.capacity));
-            CUDA_OK(cudaMalloc(&S.d_rank[q], sizeof(unsigned) * (size_t)S.capacity));
-        }
-        S.key_capacity = S.capacity;
     }
     if (count) CUDA_OK(cudaMemsetAsync(S.d_cell_count, 0, sizeof(unsigned) * (size_t)ncells, c->stream));
     // a live count sent home by an earlier permute has landed and nothing was appended since: everything behind it
@@ -339,7 +318,7 @@ int sort_fused_end(mag2d_ctx* c, int s, bool permute, bool count)
     if (permute)
     {
         // d_total still holds the number of particles the consumed tickets covered: everything behind is dead
-        k_fill_dead_keys<<<148 * 4, 256, 0, c->stream>>>(S.arr[S.cur ^ 1][ARR_X], count ? S.d_key[S.kr ^ 1] : nullptr, d_total, S.n_slots);
+        k_fill_dead_keys<<<148 * 4, 256, 0, c->stream>>>(S.arr[S.cur ^ 1][ARR_X], nullptr, d_total, S.n_slots);
         c->launches++;
         if (!S.total_pending)
         {
@@ -354,7 +333,6 @@ int sort_fused_end(mag2d_ctx* c, int s, bool permute, bool count)
             S.total_epoch = S.append_epoch;
         }
         S.cur ^= 1;
-        if (count) S.kr ^= 1;
         S.pushes_since_permute = 0;
         S.steps_since_sort = 0;
         S.tickets_valid = false;
