@@ -172,7 +172,7 @@ int refresh_pools(mag2d_ctx* c, int s)
 
 // pushes between two sorts of a species.  A context-wide interval of -1 picks it per species from the thermal drift:
 // the sort pays off while most particles of a warp still share their cell, i.e. until the thermal displacement
-// v_th * dt * K reaches about a third of a cell (measured on the C4 deck: electrons 6, optimum flat from 4 to 8);
+// v_th * dt * K reaches about a third of a cell (measured on the C4 deck: electrons 5, optimum flat from 4 to 6);
 // slow species (ions) are re-sorted every 64 pushes, which only serves to compact the removed slots.
 int effective_sort_interval(const mag2d_ctx* c, const SpeciesStore& S)
 {
@@ -184,7 +184,7 @@ int effective_sort_interval(const mag2d_ctx* c, const SpeciesStore& S)
     const double per_step = vth * S.desc.dt / h;
     if (!(per_step > 0)) return 64;
     // three axes to drift along: the same disorder is reached earlier in 3-D (C5: 5.67 ms with 4 pushes vs 5.77 with 6)
-    const double k = (is3d(c) ? 0.25 : 0.35) / per_step;
+    const double k = (is3d(c) ? 0.25 : 0.30) / per_step;
     return k >= 64 ? 64 : k <= 2 ? 2 : (int)(k + 0.5);
 }
 
