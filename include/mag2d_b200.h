@@ -207,8 +207,8 @@ int mag2d_step_streamed3(mag2d_ctx* ctx, int n_species, const int32_t* species, 
                          int64_t chunk_slots);
 int mag2d_set_sort_interval(mag2d_ctx* ctx, int steps); /* 0 = never sort inside mag2d_step; -1 = per species from its thermal drift (v_th dt K ~ 0.3 cell, 2..64) */
 /* per-species override (-1 = use the context-wide interval): slow species (ions) need far fewer sorts than fast
- * ones.  With the Boris movers the sort is carried by the push kernels themselves (a COUNT step hands out cell
- * tickets, the next step writes the particles to their sorted slots), so an interval of 1 is affordable. */
+ * ones.  With the Boris movers the sort is carried by the push kernels themselves (a COUNT step takes per-cell
+ * counts, the next step draws every particle's sorted slot from them and writes it there). */
 int mag2d_set_species_sort_interval(mag2d_ctx* ctx, int species, int steps);
 
 /* ---- stepping --------------------------------------------------------------------------------- */

@@ -1141,7 +1141,7 @@ int mag2d_step(mag2d_ctx* c, int nsteps)
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
         for (size_t s = 0; s < c->sp.size(); s++)
         {
-            // the source appends to the store after every push: pending sort tickets would never survive, so these runs
+            // the source appends to the store after every push: the pending cell counts of a fused sort would never survive, so these runs
             // use the stand-alone sort below (which also trims the slot range: the influx balances the wall losses)
             if (advance_one(c, (int)s, !c->use_source)) return 1;
             if (c->use_source && species_source(c, (int)s, nullptr)) return 1;      // pic.cpp:346-347

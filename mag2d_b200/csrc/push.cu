@@ -40,7 +40,7 @@ struct PushArgs
     unsigned* coll_count;
     // cell sort fused into the step (SORTING kernels; sort.cu describes the pipeline)
     int permute;                   // write every array to its sorted slot of the other slab (keys of an earlier COUNT step)
-    int count;                     // hand every surviving particle a ticket of its new cell for the next permuting step
+    int count;                     // count every surviving particle in its new cell for the next permuting step
     int cell_cols;                 // N - 1
     unsigned* cursor;              // [cell] next free sorted slot of the cell (the scanned counts of the last COUNT push)
     ParticlesDev dst;              // the other slab
@@ -1352,8 +1352,8 @@ static double rf_phase(const mag2d_ctx* c, const SpeciesStore& S)
     return c->g.rf_amplitude * cos(phase) + c->g.rf_U0;
 }
 
-// sort_mode: bit 0 = permute (write into the other slab at the sorted slots of the pending tickets), bit 1 = count
-// (hand out tickets for the next permuting step); Boris movers only
+// sort_mode: bit 0 = permute (write into the other slab at the sorted slots drawn from the pending cell cursors), bit 1 = count
+// (count the particles per cell for the next permuting step); Boris movers only
 int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
 {
     SpeciesStore& S = c->sp[s];

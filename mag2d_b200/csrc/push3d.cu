@@ -46,7 +46,7 @@ struct Push3Args
     unsigned* coll_list;
     unsigned* coll_count;
     int deposit_runs;   // distinct cells per warp call that get the REDUX merge (0: every lane scatters on its own)
-    // cell sort fused into the step (sort.cu): COUNT hands out tickets, the next PERMUTE step stores sorted
+    // cell sort fused into the step (sort.cu): COUNT counts per cell, the next PERMUTE step draws slots and stores sorted
     int permute, count;
     unsigned* cursor;   // [cell] next free sorted slot of the cell (the scanned counts of the last COUNT push)
     ParticlesDev dst;

@@ -185,7 +185,7 @@ __global__ void k_fill_dead(double* __restrict__ x, const unsigned long long* __
         x[k] = dead_marker();
 }
 
-// the same for a fused permuting step: the new tickets of the tail slots must read "no particle" as well
+// the same for a fused permuting step
 __global__ void k_fill_dead_keys(double* __restrict__ x, unsigned* __restrict__ key, const unsigned long long* __restrict__ total, long long n)
 {
     for (long long k = (long long)*total + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
@@ -317,7 +317,7 @@ int sort_fused_end(mag2d_ctx* c, int s, bool permute, bool count)
     unsigned long long* d_total = reinterpret_cast<unsigned long long*>(S.d_sort_sums + ((ntiles + 1) / 2 * 2 + 2));
     if (permute)
     {
-        // d_total still holds the number of particles the consumed tickets covered: everything behind is dead
+        // d_total still holds the number of particles the consumed cursors covered: everything behind is dead
         k_fill_dead_keys<<<148 * 4, 256, 0, c->stream>>>(S.arr[S.cur ^ 1][ARR_X], nullptr, d_total, S.n_slots);
         c->launches++;
         if (!S.total_pending)
