@@ -407,3 +407,36 @@ def test_particle_source_bit_exact(orc, deckdir, factor, collisions):
         assert np.array_equal(_sorted_rows(live_ref), _sorted_rows(live_orc))
         assert np.array_equal(rho_ref, rho)
         assert np.array_equal(ref.rng_draw("iuni", 3), orc.rng_draw(r, "iuni", 3))      # SHR3 streams stayed in step
+
+
+def test_magnetic_field_loader_error_texts_match_the_reference(orc, deckdir):
+    """Fields::load_magnetic_field's failure modes: the product's reader (mag2d_b200.config), the restatement and the
+    compiled reference refuse the same files with the same message"""
+    from common import write_btable
+    good = write_btable(os.path.join(deckdir, "bt_err_good.txt"), 7, 9, 1.2e-2, 7.5e-2)
+    rows = open(good).read().splitlines()
+    short = os.path.join(deckdir, "bt_err_short.txt")
+    with open(short, "w") as f:
+        f.write("\n".join(rows[:-1]) + "\n")                    # one node missing
+    cases = [(short, "wrong size of input vector"), (os.path.join(deckdir, "bt_err_none.txt"), "failed opening file")]
+    for path, text in cases:
+        with pytest.raises(RuntimeError, match=text):
+            cfg.load_magnetic_field(path)
+        d = decks.deck("c3", deckdir + "_bterr", n_particles=10, x_sampl=41, z_sampl=61, magnetic_field_const=0, magnetic_field_file=path,
+                       selfconsistent=0)
+        with pytest.raises(RuntimeError, match=text):
+            RefHarness(d["config"], d["species_conf"], seed=5)
+    with pytest.raises(RuntimeError, match="wrong size"):
+        orc.load_magnetic_field(short)
+    # a duplicated node instead of a missing one: the count is right, one node stays NaN -> "garbage loaded"
+    dup = os.path.join(deckdir, "bt_err_dup.txt")
+    with open(dup, "w") as f:
+        mid = len(rows) // 2
+        f.write("\n".join(rows[:mid] + [rows[mid - 1]] + rows[mid + 1:]) + "\n")
+    for loader in (cfg.load_magnetic_field, orc.load_magnetic_field):
+        with pytest.raises(RuntimeError, match="garbage loaded"):
+            loader(dup)
+    d = decks.deck("c3", deckdir + "_bterr2", n_particles=10, x_sampl=41, z_sampl=61, magnetic_field_const=0, magnetic_field_file=dup,
+                   selfconsistent=0)
+    with pytest.raises(RuntimeError, match="garbage loaded"):
+        RefHarness(d["config"], d["species_conf"], seed=5)
