@@ -43,6 +43,7 @@ def build(force=False, verbose=False, extra=(), out=None):
         OBJ = out + ".build"
     newest = max(os.path.getmtime(p) for p in _deps())
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
+        sys.stderr.write("mag2d_b200.build: reused %s (newer than every source; --force recompiles)\n" % LIB)
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     common = [_nvcc(), "-O3", "-std=c++17", "-lineinfo", "-ccbin", _ccbin(), "-Xcompiler", "-fPIC",
@@ -66,6 +67,7 @@ def build(force=False, verbose=False, extra=(), out=None):
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    sys.stderr.write("mag2d_b200.build: compiled %d translation units for sm_100a -> %s\n" % (len(SOURCES), LIB))
     return LIB
 
 

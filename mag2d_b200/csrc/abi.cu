@@ -112,24 +112,34 @@ int ensure_capacity(mag2d_ctx* c, SpeciesStore& S, long long need)
     if (need <= S.capacity) return 0;
     long long cap = std::max<long long>(need, (long long)(S.capacity * 1.5) + 1024);
     cap = (cap + 255) / 256 * 256;
-    double* old[N_ARR];
-    for (int a = 0; a < N_ARR; a++) old[a] = S.arr[S.cur][a];
     // drop the idle slab first (it is re-created lazily by the next sort)
     for (int a = 0; a < N_ARR; a++)
         if (S.arr[S.cur ^ 1][a]) { cudaFree(S.arr[S.cur ^ 1][a]); S.arr[S.cur ^ 1][a] = nullptr; }
-    for (int a = 0; a < N_ARR; a++) S.arr[S.cur][a] = nullptr;
-    const long long old_cap = S.capacity;
-    S.capacity = 0;
-    if (store_alloc_slab(c, S, S.cur, cap)) return 1;
+    // the larger slab goes into temporaries and is swapped in only when every array could be allocated: an
+    // out-of-memory failure leaves the store as it was
+    double* fresh[N_ARR] = {};
     for (int a = 0; a < N_ARR; a++)
-        if (old[a])
+    {
+        if (!needs_array(c, a)) continue;
+        if (cudaMalloc(&fresh[a], sizeof(double) * (size_t)cap) != cudaSuccess)
         {
-            if (S.n_slots > 0)
-                CUDA_OK(cudaMemcpyAsync(S.arr[S.cur][a], old[a], sizeof(double) * (size_t)S.n_slots, cudaMemcpyDeviceToDevice, c->stream));
-            CUDA_OK(cudaStreamSynchronize(c->stream));
-            CUDA_OK(cudaFree(old[a]));
+            cudaGetLastError();
+            for (int b = 0; b < N_ARR; b++)
+                if (fresh[b]) cudaFree(fresh[b]);
+            mag2d_set_error("ensure_capacity: out of device memory growing a particle store");
+            return 1;
         }
-    (void)old_cap;
+    }
+    for (int a = 0; a < N_ARR; a++)
+        if (fresh[a] && S.arr[S.cur][a] && S.n_slots > 0)
+            CUDA_OK(cudaMemcpyAsync(fresh[a], S.arr[S.cur][a], sizeof(double) * (size_t)S.n_slots, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    for (int a = 0; a < N_ARR; a++)
+    {
+        if (S.arr[S.cur][a]) cudaFree(S.arr[S.cur][a]);
+        S.arr[S.cur][a] = fresh[a];
+    }
+    S.capacity = cap;
     return 0;
 }
 
@@ -226,6 +236,13 @@ int species_source(mag2d_ctx* c, int s, long long* injected)
 }
 
 }  // namespace
+
+int refresh_pools_all(mag2d_ctx* c)
+{
+    for (size_t s = 0; s < c->sp.size(); s++)
+        if (refresh_pools(c, (int)s)) return 1;
+    return 0;
+}
 
 int store_alloc_slab(mag2d_ctx* c, SpeciesStore& S, int slab, long long capacity)
 {
@@ -942,6 +959,9 @@ int mag2d_source_upload(mag2d_ctx* c, int s, uint32_t factor, const mag2d_partic
     CHECK_SPECIES(c, s);
     if (factor == 0 || n < 0) { mag2d_set_error("mag2d_source_upload: bad arguments"); return 1; }
     SpeciesStore& S = c->sp[s];
+    // the copies below are blocking copies on the legacy stream, which does not order against the context's
+    // non-blocking stream: let the kernels that still read the old reservoir finish first
+    CUDA_OK(cudaStreamSynchronize(c->stream));
     if (source_alloc(c, S, n)) return 1;
     S.src_factor = factor;
     std::vector<double> col((size_t)std::max<int64_t>(n, 1));

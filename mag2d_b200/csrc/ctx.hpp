@@ -197,6 +197,7 @@ void mag2d_set_error(const std::string& msg);
     } while (0)
 
 // ---- store management (abi.cu)
+int refresh_pools_all(mag2d_ctx* c);   // partner pools of every species' collision model follow the particle arrays
 int store_alloc_slab(mag2d_ctx* c, SpeciesStore& S, int slab, long long capacity);
 
 // ---- launchers implemented in the kernel translation units

@@ -121,6 +121,8 @@ static __device__ __noinline__ int mcc_scatter(const MccBlob* __restrict__ B, Rn
             i = (long long)(rb.x % (unsigned long long)P.n);
             tries++;
         }
+        // no live partner found in 65 draws (a nearly emptied store): null collision instead of a dead slot's velocities
+        if (!particle_alive(P.x[i])) return -1;
         vr2 = P.vx[i];
         vz2 = P.vz[i];
         vt2 = P.vy[i];

@@ -51,8 +51,10 @@ struct PushArgs
 // The reference differences the potential around every particle; here the differences live in the
 // precomputed edge fields gx/gz (same operations, same rounding) and the particle only interpolates:
 // 8 loads instead of 12.  Edge cases of the reference (i == 0, i == jmax-1, j == 0, j == lmax-1) are
-// folded into the general formula by pinning the interpolation weight to 1 or 0 (the dropped terms are
-// exact zeros).  Float->int conversions are the expensive part on this pipe mix, so each axis is
+// folded into the general formula by ghost rows / columns that repeat the first / last difference: in the
+// first and last HALF cell of each axis the reference evaluates the one-sided form g (1 - fy), here the
+// same value comes out as g cx cy + g fx cy, which agrees to one or two ulp, not bit for bit (everywhere
+// else the operations and their order are the reference's).  Float->int conversions are the expensive part on this pipe mix, so each axis is
 // converted once: (int)(X + 0.5) is derived from (int)X and the fraction.  The two differ only when X
 // lies within one ulp below a half-integer, where both stencils interpolate the same edge value.
 __device__ __forceinline__ void gather_E(const GridDev& g, double x, double z, double& Ex, double& Ez)
@@ -1361,6 +1363,9 @@ int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
     // streamed step (abi.cu): the particle arrays are one chunk of a host-resident store staged in device buffers
     const bool chunked = c->chunk_view != nullptr;
     const long long n_active = chunked ? c->chunk_view->n : S.n_slots;
+    // a push that does not consume the pending cell cursors moves (or removes) particles away from the cells they were
+    // counted in: the cursors are stale from here on (a COUNT push re-validates them in sort_fused_end)
+    if (!chunked && !(sort_mode & 1)) S.tickets_valid = false;
     if (n_active > 0)
     {
         if (!d.magnetic_field_const && !c->d_btab_r)
@@ -1462,7 +1467,12 @@ int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
                 else
                     launch_boris_variant<MAG2D_CARTESIAN, true>(c, A, gather, bmode, mcc, d.selfconsistent != 0, tile_blocks);
                 if (sort_fused_end(c, s, permute, count)) return 1;
-                if (permute) A.p = particles_view(S);      // the collision pass works on the new slab
+                if (permute)
+                {
+                    A.p = particles_view(S);      // the collision pass works on the new slab
+                    // ... and so must its partner pools when this species is its own (or another species') target
+                    if (mcc && refresh_pools_all(c)) return 1;
+                }
             }
             else if (d.coord == MAG2D_CYLINDRICAL)
                 launch_boris_variant<MAG2D_CYLINDRICAL, false>(c, A, gather, bmode, mcc, d.selfconsistent != 0, tile_blocks);

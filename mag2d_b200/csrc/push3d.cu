@@ -470,6 +470,8 @@ int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only, int sort_mo
     // streamed step (abi.cu): the particle arrays are one chunk of a host-resident store staged in device buffers
     const bool chunked = c->chunk_view != nullptr && !deposit_only;
     const long long n_active = chunked ? c->chunk_view->n : S.n_slots;
+    // a push that does not consume the pending cell cursors invalidates them (see launch_species_advance)
+    if (!chunked && !deposit_only && !(sort_mode & 1)) S.tickets_valid = false;
     if (n_active > 0)
     {
         Push3Args A;
@@ -555,7 +557,11 @@ int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only, int sort_mo
             if (sorting)
             {
                 if (sort_fused_end(c, s, permute, count)) return 1;
-                if (permute) A.p = particles3_view(S);
+                if (permute)
+                {
+                    A.p = particles3_view(S);
+                    if (mcc && refresh_pools_all(c)) return 1;      // partner pools follow the slab flip
+                }
             }
             if (mcc)
             {

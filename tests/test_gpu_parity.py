@@ -407,6 +407,49 @@ def test_fused_cell_sort_keeps_the_particle_set_and_the_charge(orc, deckdir, int
         assert (np.diff(key) < 0).mean() < 0.35      # an unsorted store has ~0.5
 
 
+@pytest.mark.parametrize("interval", [2, 3])
+def test_per_species_pushes_between_steps_do_not_corrupt_the_fused_sort(deckdir, interval):
+    """a COUNT push leaves per-cell cursors for the next PERMUTE push; a per-species push in between
+    (mag2d_species_advance, the host layer's Species::advance) moves particles away from the cells they were counted
+    in, so the cursors must be dropped — otherwise the permute overflows cells and loses / duplicates particles.
+    Also: the interval switched off and on again between a COUNT and its PERMUTE."""
+    d = decks.deck("c4", deckdir, n_particles=30000, collisions=False, x_sampl=33, z_sampl=49, r_max=3.2e-3, z_max=4.8e-3)
+    rng = np.random.default_rng(77)
+    init = {}
+    for name, vth in (("ARGON_POS", 4e5), ("ELECTRON", 8e5)):
+        a = np.zeros((15000, 7))
+        a[:, 0] = rng.uniform(1e-7, 3.2e-3 - 1e-7, 15000)
+        a[:, 2] = rng.uniform(1e-7, 4.8e-3 - 1e-7, 15000)
+        a[:, 3:6] = rng.normal(size=(15000, 3)) * vth
+        init[name] = a
+    results = []
+    for k in (0, interval):
+        with _sim(d["config"], d["species_conf"]) as sim:
+            idx = [sim.species_index(n) for n in ("ARGON_POS", "ELECTRON")]
+            for n, i in zip(("ARGON_POS", "ELECTRON"), idx):
+                sim.set_particles(i, init[n])
+            sim.set_sort_interval(k)
+            sim.advance_init()
+            for _ in range(4):
+                sim.advance(1)                   # COUNT (first step of a period)
+                for i in idx:
+                    sim.species_advance(i)       # plain push between COUNT and PERMUTE
+                sim.advance(1)
+            sim.set_sort_interval(0)             # interval off ...
+            sim.advance(1)
+            sim.set_sort_interval(k)             # ... and on again
+            sim.advance(3)
+            out = {}
+            for n, i in zip(("ARGON_POS", "ELECTRON"), idx):
+                p = sim.get_particles(i)
+                alive = p[p[:, 7] > 0][:, [0, 2, 3, 4, 5]]
+                out[n] = (alive[np.lexsort(alive.T[::-1])], sim.count(i)[0])
+            results.append(out)
+    for n in ("ARGON_POS", "ELECTRON"):
+        assert results[0][n][1] == results[1][n][1] and 0 < results[0][n][1] < 15000
+        assert np.array_equal(results[0][n][0], results[1][n][0]), n
+
+
 def test_streamed_step_with_host_resident_particles_equals_the_resident_step(orc, deckdir):
     """mag2d_step_streamed pushes host SoA arrays through device staging buffers chunk by chunk; with collisions off
     it must leave exactly the particles, charge grids and potential of mag2d_step on a device-resident store"""
