@@ -41,14 +41,48 @@ DEFAULT_PARTICLES = {"c4": 100_000_000, "c2": 1_000_000, "c3": 10_000_000, "c1":
 BYTES = {"c4": 80.0, "c2": 80.0, "c3": 80.0, "c1": 96.0, "c5": 96.0}
 
 
+KERNEL_SOURCES = ("push.cu", "push3d.cu", "mcc.cuh", "common.cuh")
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r2_push_dram.json")
+
+
+def kernel_source_hash():
+    """sha1 over the kernel sources the profiled launches come from: a committed ncu capture only speaks for the code it profiled"""
+    import hashlib
+    h = hashlib.sha1()
+    for f in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "mag2d_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def _traffic_table():
+    with open(TRAFFIC_FILE) as f:
+        t = json.load(f)
+    if t.get("kernel_source_sha1") != kernel_source_hash():
+        return None, "stale: %s was captured from other kernel sources (profiles/make_traffic.py refreshes it)" % os.path.basename(TRAFFIC_FILE)
+    return t, None
+
+
 def measured_traffic(workload, n_particles):
-    """DRAM bytes per push launch from the committed `ncu --set full` capture (profiles/r1_push_dram.json holds
-    dram__bytes_read.sum + dram__bytes_write.sum per particle of the profiled launches), scaled to this run's
-    particles per launch; None when the workload was not profiled"""
+    """DRAM bytes per push launch from this round's `ncu --set full` capture (profiles/r2_push_dram.json holds
+    dram__bytes_read.sum + dram__bytes_write.sum per particle of the profiled launches, keyed by the sha1 of the kernel sources),
+    scaled to this run's particles per launch.  -> (bytes or None, note): a capture of other sources is refused, not reused"""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_push_dram.json")) as f:
-            t = json.load(f)
-        return float(t["dram_bytes_per_particle_step"][workload]) * n_particles
+        t, why = _traffic_table()
+        if t is None:
+            return None, why
+        v = t["dram_bytes_per_particle_step"].get(workload)
+        if v is None:
+            return None, "workload not profiled"
+        return float(v) * n_particles, "ncu --set full, %s" % t.get("captured", "this round")
+    except Exception as e:
+        return None, "no capture (%s)" % str(e)[:60]
+
+
+def measured_flops(workload):
+    try:
+        t, why = _traffic_table()
+        return float(t["fp64_flop_per_particle_step"][workload]) if t else None
     except Exception:
         return None
 
@@ -175,31 +209,28 @@ def load_particles(sim, workload, d, n):
         sim.run_initscript(d["initscript"])
 
 
-def bench_ours(args):
+def state_checksums(sim, part_species):
+    """64-bit digests of the potential and of every species' int64 charge grid (what the ranks must agree on bit for bit)"""
+    import hashlib
+
     import numpy as np
-    import torch
-    import torch.distributed as dist
+    out = []
+    for arr in [sim.get_field("u")] + [sim.rho_fixed(s) for s in part_species]:
+        h = hashlib.blake2b(np.ascontiguousarray(arr).tobytes(), digest_size=8).digest()
+        out.append(int.from_bytes(h, "little") >> 1)          # 63 bits: fits a signed int64 tensor
+    return out
+
+
+def run_workload(wl, args, env, steps, warmup, e2e_steps, with_cpu):
+    """one workload on this rank's GPU: load, warm up, time `steps` steps (device events on the launching stream, max over
+    ranks), phase times, roofline, solve, rank agreement, optionally the e2e leg and the CPU arm.  -> dict (rank 0 uses it)"""
+    import numpy as np
 
     from mag2d_b200.api import Sim
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    host_binding = bind_near_gpu(torch, local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    wl = args.workload
-    n = args.particles or DEFAULT_PARTICLES[wl]
+    torch, dist, world, rank, local_rank, dev, stream = (env[k] for k in ("torch", "dist", "world", "rank", "local_rank", "dev", "stream"))
+    n = (args.particles if wl == args.workload else 0) or DEFAULT_PARTICLES[wl]
     tmp = tempfile.mkdtemp(prefix="mag2d_bench_")
     d = make_deck(wl, n, world, tmp)
-    # a dedicated (non-default) stream: the context enqueues on it and the timing events are recorded on it
-    stream = torch.cuda.Stream(dev)
-    torch.cuda.set_stream(stream)
     sim = Sim(d["config"], d["species_conf"], device=local_rank, stream=stream.cuda_stream, seed=1234 + rank)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device=dev)
@@ -215,7 +246,7 @@ def bench_ours(args):
     sort_interval = args.sort_interval
     sim.set_sort_interval(sort_interval)
     species_sort = {}
-    if args.sort_intervals:
+    if args.sort_intervals and wl == args.workload:
         for item in args.sort_intervals.split(","):
             name, k = item.split("=")
             species_sort[name] = int(k)
@@ -226,7 +257,6 @@ def bench_ours(args):
     direct = selfconsistent and sim.solver_is_direct()
     three_d = wl == "c5"
     sim.advance_init()
-    n_live0 = sum(sim.count(s)[0] for s in part_species)
 
     def barrier():
         if world > 1:
@@ -234,7 +264,7 @@ def bench_ours(args):
         torch.cuda.synchronize()
 
     # ---- warm-up
-    sim.advance(args.warmup)
+    sim.advance(warmup)
     barrier()
     if selfconsistent:
         sim.solver_stats()      # reset the residual monitor
@@ -247,16 +277,27 @@ def bench_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    sim.advance(args.steps)
+    sim.advance(steps)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
     clock_info = clocks.stop() if rank == 0 else None
     monitored_resid = sim.solver_stats()["resid"] if selfconsistent else None
-    if three_d:
-        monitored_resid = sim.solve()["resid"]       # measured after the timed region (the 3-D step does not monitor)
     launches = sim.kernel_launches() - launches0
     n_live_end = sum(sim.count(s)[0] for s in part_species)
+    # ---- do the ranks hold the same potential and the same (all-reduced) charge grids, bit for bit?
+    ranks_agree = None
+    if selfconsistent:
+        digests = torch.tensor(state_checksums(sim, part_species), dtype=torch.int64, device=dev)
+        if world > 1:
+            lo, hi = digests.clone(), digests.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            ranks_agree = bool(torch.equal(lo, hi))
+        else:
+            ranks_agree = True
+    if three_d:
+        monitored_resid = sim.solve()["resid"]       # measured after the timed region (the 3-D step does not monitor)
     t = torch.tensor([ms, float(n_live), float(n_live_end)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
@@ -268,19 +309,53 @@ def bench_ours(args):
     else:
         n_live_all, n_live_end_all = float(n_live), float(n_live_end)
     # live particles decay slowly through wall losses: use the mean of the two counts
-    pstep = 0.5 * (n_live_all + n_live_end_all) * args.steps
+    pstep = 0.5 * (n_live_all + n_live_end_all) * steps
     value = pstep / (ms * 1e-3)
 
     # ---- per-phase device times (events around each phase; adds one sync per step, so it is a separate pass)
     sim.set_timing(True)
-    sim.advance(args.steps)
+    sim.advance(steps)
     tm = sim.timers()
     sim.set_timing(False)
-    push_ms = tm["push"] / args.steps
+    push_ms = tm["push"] / steps
     n_now = sum(sim.count(s)[0] for s in part_species)
     n_push_launches = len(part_species) * (2 if sim.param["rf"] else 1)
     peak, peak_src = measured_peaks()
     achieved = BYTES[wl] * n_now / (push_ms * 1e-3) / 1e9 if push_ms > 0 else 0.0
+    traffic, traffic_note = measured_traffic(wl, n_now / n_push_launches)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
+                # the same launches on the DRAM bytes ncu saw them move (frac uses the contract's algorithmic bytes)
+                "frac_moved": (traffic * n_push_launches / (push_ms * 1e-3) / 1e9 / peak) if traffic and push_ms > 0 else None,
+                "algorithmic_bytes_per_launch": BYTES[wl] * n_now / n_push_launches,
+                "kernel": "%s (fused gather+push+MCC+boundary+deposit), %d launches/step" % (
+                    "k_push3d / k_push3d_brick" if three_d else "k_push_multicoll" if wl == "c1" else "k_push_boris", n_push_launches),
+                "algorithmic_bytes_per_particle_step": BYTES[wl], "push_ms_per_step": push_ms,
+                "peak_source": peak_src}
+    extra = {}
+    if wl == "c1":
+        # the multi-collision mover is instruction-bound: report collision events/s and FP64 FLOP/s
+        he = [k for k, s in enumerate(sim.species) if s["type"] == 0]
+        e = part_species[0]
+        sim.set_collision_counting(True)
+        sim.collision_counts(e, reset=True)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        c0.record(stream)
+        sim.advance(steps)
+        c1.record(stream)
+        torch.cuda.synchronize()
+        cnt = sim.collision_counts(e, reset=True)
+        sim.set_collision_counting(False)
+        events = float(cnt.sum())
+        extra["collisions"] = {"events_per_s": events / (c0.elapsed_time(c1) * 1e-3), "events_per_particle_step": events / (n_now * steps),
+                               "real_collisions_per_particle_step": float(sum(cnt[k * 16:k * 16 + 16].sum() for k in he)) / (n_now * steps),
+                               "note": "null + real events of the null-collision method, counted in a separate pass (the counters are off in the timed region)"}
+        fl = measured_flops(wl)
+        if fl:
+            extra["fp64"] = {"flop_per_particle_step": fl, "achieved_tflops": fl * value / 1e12, "peak_tflops": 37.0,
+                             "note": "FP64 FLOP per particle-step from the committed ncu capture (DFMA = 2, DMUL/DADD = 1) x the measured rate; "
+                                     "peak = 148 SMs x 64 FP64 FMA lanes x 2 x 1.965 GHz"}
     solve_info = None
     if direct:
         solve_info = {"kind": ("direct: sine transforms along y and z (FP64 matrix products) x tridiagonal solve per mode along x, "
@@ -288,7 +363,7 @@ def bench_ours(args):
                       if three_d else
                       ("direct: sine transform along z (FP64 matrix product) x tridiagonal solve per mode along x "
                        "(the grid has no internal electrodes); exact to round-off like the reference's LU"),
-                      "ms_per_step": tm["solve"] / args.steps, "vcycles_per_step": 0,
+                      "ms_per_step": tm["solve"] / steps, "vcycles_per_step": 0,
                       "max_resid_over_timed_steps": monitored_resid,
                       "resid_def": "max|r_k/a_kk| / max|u| (largest Jacobi update relative to the potential)"}
     elif selfconsistent:
@@ -302,9 +377,9 @@ def bench_ours(args):
             need.append(sim.solver_stats()["cycles"])
         sim.set_solver(cycles_per_step=args.cycles, tol=1e-12, max_cycles=60)
         solve_info = {"kind": "geometric multigrid (Galerkin coarse operators), fixed V-cycles per step",
-                      "ms_per_step": tm["solve"] / args.steps, "vcycles_per_step": abs(args.cycles),
+                      "ms_per_step": tm["solve"] / steps, "vcycles_per_step": abs(args.cycles),
                       "first_guess": "2u_n - u_(n-1)" if args.cycles < 0 else "u_n",
-                      "ms_per_vcycle": tm["solve"] / args.steps / max(abs(args.cycles), 1),
+                      "ms_per_vcycle": tm["solve"] / steps / max(abs(args.cycles), 1),
                       "max_resid_over_timed_steps": monitored_resid,
                       "note": "relative error of u against the converged solve is ~5x resid (calibrated on this deck)",
                       "extra_cycles_to_1e-12": info["cycles"], "resid_after_extra": info["resid"],
@@ -315,54 +390,87 @@ def bench_ours(args):
     # memory, one Pic::advance runs, particles and the charge grid come back (what a host-resident caller
     # of Species::advance pays when it keeps the reference's host-side particle array)
     e2e = None
-    if args.e2e_steps > 0 and (rank == 0 or world > 1):
-        e2e = bench_e2e(sim, part_species, args, torch, stream, world, dist, dev)
-        e2e["host"] = host_binding
+    if e2e_steps > 0 and (rank == 0 or world > 1):
+        e2e = bench_e2e(sim, part_species, args, torch, stream, world, dist, dev, e2e_steps)
+        e2e["host"] = env["host_binding"]
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and with_cpu:
         try:
             cpu = cpu_baseline(wl, d, sim, part_species, args)
         except Exception as ex:     # the checker must never take the bench down
             cpu = {"value": None, "unit": "particle-steps/s", "cores": 1, "kind": "unavailable", "sample": repr(ex)}
+    rec = {
+        "value": value, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+        "config": {"workload": WORKLOADS[wl], "particles_per_gpu": n, "live_particles": n_live_all,
+                   "grid": list(sim.shape),
+                   "species": d["species"], "sort_interval": sort_interval, "species_sort_interval": species_sort,
+                   "l2": "inputs larger than L2 (%.1f GB of particle state per GPU)" % (n * 40 / 1e9)
+                   if n * 40 > 200e6 else "particle state fits L2: flush not applied, see roofline note",
+                   "parallelism": "particle shards, %d rank(s), NCCL all-reduce of the int64 charge grid" % world,
+                   "poisson": (("direct (2 sine transforms x tridiagonal + capacitance matrix)" if three_d else "direct (sine transform x tridiagonal)") if direct else "multigrid, %d V-cycles/step" % abs(args.cycles))
+                   if selfconsistent else "none (vacuum field solved once)"},
+        "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "ranks_agree": ranks_agree,
+        "phases_ms_per_step": {k: v / steps for k, v in tm.items()}, "solve": solve_info, "e2e": e2e, "cpu_baseline": cpu,
+    }
+    rec.update(extra)
+    sim.close()
+    return rec
+
+
+def bench_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    host_binding = bind_near_gpu(torch, local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    # a dedicated (non-default) stream: the context enqueues on it and the timing events are recorded on it
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    env = dict(torch=torch, dist=dist, world=world, rank=rank, local_rank=local_rank, dev=dev, stream=stream, host_binding=host_binding)
+    wl = args.workload
+    rec = run_workload(wl, args, env, args.steps, args.warmup, args.e2e_steps, not args.no_cpu_baseline)
+    secondary = None
+    if wl == "c4" and not args.no_secondary:
+        # BASELINE.json configs[4] (the named 8-GPU configuration: 256^3, 1.25e8 particles per GPU) rides on every line so that
+        # the driver's 1 -> 8 GPU scaling record carries it too; C4 stays the headline value
+        r5 = run_workload("c5", args, env, min(args.steps, args.secondary_steps), args.warmup, 0, False)
+        secondary = {"c5": {k: r5[k] for k in ("value", "ms_per_step", "steps", "warmup", "config", "gpu_launches", "roofline",
+                                               "ranks_agree", "phases_ms_per_step", "solve")}}
+        secondary["c5"].update(unit="particle-steps/s", n_gpus=world, scaling="weak", dtype="f64",
+                               allreduce_ms_per_step=r5["phases_ms_per_step"]["allreduce"])
     if rank == 0:
         out = {
             "metric": "particle-steps/sec (push+MCC+deposit, Poisson solve and periodic cell sort inside the step)",
-            "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "value": rec["value"], "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (device-side Philox loaders, seed 1234)",
-            "config": {"workload": WORKLOADS[wl], "particles_per_gpu": n, "live_particles": n_live_all,
-                       "grid": list(sim.shape),
-                       "species": d["species"], "sort_interval": sort_interval, "species_sort_interval": species_sort,
-                       "l2": "inputs larger than L2 (%.1f GB of particle state per GPU)" % (n * 40 / 1e9)
-                       if n * 40 > 200e6 else "particle state fits L2: flush not applied, see roofline note",
-                       "parallelism": "particle shards, %d rank(s), NCCL all-reduce of the int64 charge grid" % world,
-                       "poisson": (("direct (2 sine transforms x tridiagonal + capacitance matrix)" if three_d else "direct (sine transform x tridiagonal)") if direct else "multigrid, %d V-cycles/step" % abs(args.cycles))
-                       if selfconsistent else "none (vacuum field solved once)"},
-            "gpu_launches": int(launches),
-            "clocks": clock_info,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(wl, n_now / n_push_launches),
-                         "algorithmic_bytes_per_launch": BYTES[wl] * n_now / n_push_launches,
-                         "kernel": "%s (fused gather+push+MCC+boundary+deposit), %d launches/step" % ("k_push3d" if three_d else "k_push_boris", n_push_launches),
-                         "algorithmic_bytes_per_particle_step": BYTES[wl], "push_ms_per_step": push_ms,
-                         "peak_source": peak_src},
-            "phases_ms_per_step": {k: v / args.steps for k, v in tm.items()},
-            "solve": solve_info,
-            "e2e": e2e,
-            "cpu_baseline": cpu,
         }
+        for k in ("config", "gpu_launches", "clocks", "roofline", "ranks_agree", "phases_ms_per_step", "solve", "e2e", "cpu_baseline",
+                  "collisions", "fp64"):
+            if k in rec:
+                out[k] = rec[k]
+        if secondary:
+            out["secondary"] = secondary
         print(json.dumps(out))
-    sim.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def bench_e2e(sim, part_species, args, torch, stream, world, dist, dev):
+def bench_e2e(sim, part_species, args, torch, stream, world, dist, dev, e2e_steps):
     import ctypes as C
 
     import numpy as np
-    steps = max(1, args.e2e_steps)
+    steps = max(1, e2e_steps)
     bufs = {}
     h2d = d2h = 0
     for s in part_species:
@@ -619,6 +727,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-chunk", type=int, default=0, help="slots per chunk of the streamed e2e step (0: the library default, 4 Mi)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C5 record that rides on the C4 line")
+    ap.add_argument("--secondary-steps", type=int, default=16)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -301,6 +301,19 @@ class Sim:
         out[:, 7] = 1 - rec["empty"]
         return out
 
+    def get_particles_soa(self, i, what=("x", "y", "z", "vx", "vy", "vz")):
+        """-> dict of float64 arrays in device slot order (only the requested components are copied) + 'alive' (uint8)"""
+        n = self.count(i)[1]
+        want = set(what) | {"x"}
+        arrs = {k: (np.zeros(max(n, 1)) if k in want else None) for k in ("x", "y", "z", "vx", "vy", "vz", "ttd")}
+        alive = np.zeros(max(n, 1), dtype=np.uint8)
+        ns = C.c_int64()
+        ptr = [_d(arrs[k]) if arrs[k] is not None else None for k in ("x", "y", "z", "vx", "vy", "vz", "ttd")]
+        self._chk(self.L.mag2d_particles_download_soa(self.h, i, max(n, 1), *ptr, alive.ctypes.data_as(u8p), C.byref(ns)))
+        out = {k: v[:ns.value] for k, v in arrs.items() if v is not None}
+        out["alive"] = alive[:ns.value]
+        return out
+
     def count(self, i):
         a, b = C.c_int64(), C.c_int64()
         self._chk(self.L.mag2d_count(self.h, i, C.byref(a), C.byref(b)))

@@ -1,5 +1,15 @@
-"""Parity at BASELINE.json's full sizes through size-independent properties (the oracle cannot finish 1e8 particles in
-seconds): C4 (512 x 512, 1e8 particles, Poisson each step) and C5 (256^3, 1.25e8 particles on one GPU).
+"""Parity at BASELINE.json's full sizes: C4 (512 x 512, 1e8 particles, Poisson each step) and C5 (256^3, 1.25e8
+particles on one GPU) — against the CPU oracle where it finishes in seconds, through size-independent properties otherwise.
+
+Oracle-backed (test_c4_full_size_against_the_oracle, test_c5_full_size_against_the_oracle):
+  * the int64 charge grid of ALL 1e8 / 1.25e8 particles equals orc_deposit_fixed / orc3_deposit_fixed of the downloaded
+    positions bit for bit,
+  * a 1e6-particle sample pushed one step on the live 512^2 / 256^3 potential agrees with the oracle's Boris step to 1e-12,
+  * the live 512^2 right-hand side solved with scipy's sparse LU of the reference's matrix (probed from the oracle's operator;
+    SURVEY.md App. C: a valid stand-in for UMFPACK) agrees with the GPU potential to 1e-8; in 3-D (16.7 M unknowns: no
+    sparse LU in seconds) the oracle's operator applied to the GPU potential reproduces the oracle's right-hand side.
+
+Properties:
 
   * charge conservation of the fixed-point deposit: every live particle contributes 2^32 +- 2 units (2-D, four
     weights rounded to nearest) / +- 4 (3-D, eight weights), so |sum(rho_fixed) - n_live 2^32| <= 2 (4) n_live
@@ -11,6 +21,7 @@ seconds): C4 (512 x 512, 1e8 particles, Poisson each step) and C5 (256^3, 1.25e8
 import numpy as np
 import pytest
 
+from common import Particles, grid_from_param, model_from
 from mag2d_b200 import decks
 
 pytestmark = pytest.mark.gpu
@@ -90,3 +101,131 @@ def test_c5_full_size_properties(deckdir):
         sim.rho_reset(e)
         sim.species_accumulate(e)
         assert np.array_equal(sim.rho_fixed(e), g)
+
+
+# ------------------------------------------------------------------------------------------ against the oracle
+def _splu_of_oracle_operator(orc, g, mask):
+    """the reference's matrix (fields.cpp:133-259) as the oracle restates it, recovered by probing orc_apply_operator with the
+    nine (i mod 3, j mod 3) colourings (every row couples to its 3 x 3 neighbourhood at most), factorised by SuperLU"""
+    import scipy.sparse as sps
+    from scipy.sparse.linalg import splu
+    M, N = g.M, g.N
+    I, J = np.meshgrid(np.arange(M), np.arange(N), indexing="ij")
+    rows, cols, vals = [], [], []
+    for ci in range(3):
+        for cj in range(3):
+            probe = ((I % 3 == ci) & (J % 3 == cj)).astype(np.float64)
+            y = orc.apply_operator(g, mask, probe)
+            # row (i, j) sees exactly one probed column in its 3 x 3 neighbourhood: the one with (i', j') = colour
+            di = (ci - I % 3 + 1) % 3 - 1
+            dj = (cj - J % 3 + 1) % 3 - 1
+            ii, jj = I + di, J + dj
+            ok = (ii >= 0) & (ii < M) & (jj >= 0) & (jj < N) & (y != 0.0)
+            rows.append((I * N + J)[ok])
+            cols.append((ii * N + jj)[ok])
+            vals.append(y[ok])
+    A = sps.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(M * N, M * N))
+    return A, splu(A)
+
+
+def test_c4_full_size_against_the_oracle(orc, deckdir):
+    n, steps, n_sample = 100_000_000, 6, 1_000_000
+    sim = _run_c4(deckdir, "_full4o", n, steps)
+    try:
+        g = grid_from_param(sim.param)
+        mask, volt = orc.geometry(g, 0)
+        samples = {}
+        rng = np.random.default_rng(404)
+        for name in ("ARGON_POS", "ELECTRON"):
+            i = sim.species_index(name)
+            p = sim.get_particles_soa(i, ("x", "z", "vx", "vy", "vz"))
+            # (1) all 5e7 particles of the species: fixed-point deposit bit for bit
+            fixed, bad = orc.deposit_fixed(g, p["x"], p["z"], p["alive"])
+            assert bad == 0
+            assert np.array_equal(sim.rho_fixed(i), fixed), name
+            live = np.flatnonzero(p["alive"])
+            pick = np.sort(rng.choice(live, n_sample, replace=False))
+            a = np.zeros((n_sample, 7))
+            a[:, 0], a[:, 2], a[:, 3], a[:, 4], a[:, 5] = p["x"][pick], p["z"][pick], p["vx"][pick], p["vy"][pick], p["vz"][pick]
+            samples[name] = a
+            del p
+        # (3) the live right-hand side against a sparse LU of the reference's matrix
+        info = sim.solve(rf=False)
+        u = sim.get_field("u")
+        b = orc.rhs(g, mask, volt, sim.get_field("rho"))
+        A, lu = _splu_of_oracle_operator(orc, g, mask)
+        u_lu = lu.solve(b.ravel()).reshape(g.M, g.N)
+        assert np.abs(A @ u_lu.ravel() - b.ravel()).max() <= 1e-10 * np.abs(b).max()
+        assert np.abs(u - u_lu).max() <= 1e-8 * np.abs(u_lu).max(), (info, np.abs(u - u_lu).max(), np.abs(u_lu).max())
+    finally:
+        sim.close()
+    # (2) one collision-free Boris step of the 1e6 samples on that 512^2 potential, GPU against the oracle
+    d = decks.deck("c4", deckdir + "_full4p", n_particles=2 * n_sample, collisions=False)
+    with _sim(d["config"], d["species_conf"], presolve=False) as s2:
+        s2.set_field("u", u)
+        m, names = model_from(orc, d["species_conf"])
+        zero = np.zeros_like(u)
+        for name in ("ARGON_POS", "ELECTRON"):
+            i = s2.species_index(name)
+            s2.set_particles(i, samples[name])
+            s2.species_advance(i)
+            out = s2.get_particles(i)
+            P = Particles.from_aos7(samples[name])
+            orc.advance_boris(g, u, zero, m, names.index(name), P, niter=0, rng=None)
+            orc.advance_boundary(g, mask, m.get(names.index(name), "charge"), P)
+            ref = P.aos7()
+            assert np.array_equal(out[:, 7] > 0, P.alive > 0), name
+            both = P.alive > 0
+            cols = [0, 2, 3, 4, 5]
+            err = np.abs(out[both][:, cols] - ref[both][:, cols]).max(axis=0) / np.abs(ref[both][:, cols]).max(axis=0)
+            assert err.max() <= 1e-12, (name, err)
+
+
+def test_c5_full_size_against_the_oracle(deckdir):
+    from oracle import Oracle3, Orc3Grid
+    orc3 = Oracle3()
+    n, steps, n_sample = 125_000_000, 5, 1_000_000
+    d = decks.deck("c5", deckdir + "_full5o", n_particles=n)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        p = sim.param
+        g = Orc3Grid.make((int(p["x_sampl"]), int(p["y_sampl"]), int(p["z_sampl"])), p["idx"], p["idy"], p["idz"], p["x_max"],
+                          p["y_max"], p["z_max"], int(p["boundary"]), p["macroparticle_factor"])
+        e = sim.species_index("ELECTRON")
+        sim.run_initscript(d["initscript"])
+        sim.advance_init()
+        sim.advance(steps)
+        q = sim.get_particles_soa(e)
+        fixed, bad = orc3.deposit_fixed(g, q["x"], q["y"], q["z"], q["alive"])
+        assert bad == 0
+        assert np.array_equal(sim.rho_fixed(e), fixed)
+        del fixed
+        rng = np.random.default_rng(505)
+        pick = np.sort(rng.choice(np.flatnonzero(q["alive"]), n_sample, replace=False))
+        sample = {k: np.ascontiguousarray(q[k][pick]) for k in ("x", "y", "z", "vx", "vy", "vz")}
+        del q
+        # the live potential: what the next step would push with; the oracle's operator and right-hand side check it
+        sim.solve(rf=False)
+        u = sim.get_field("u")
+        mask, volt = orc3.geometry(g)
+        b = orc3.rhs(g, mask, volt, sim.get_field("rho"))
+        r = orc3.apply_operator(g, mask, u) - b
+        # rows are unit-diagonal-scaled 7-point stencils (|a_kk| = 6): the residual relative to the largest row sum
+        assert np.abs(r).max() <= 1e-9 * max(np.abs(b).max(), 6.0 * np.abs(u).max()), np.abs(r).max()
+        charge, mass, dt = -1.602189e-19, 9.11e-31, 1e-11
+    d2 = decks.deck("c5", deckdir + "_full5p", n_particles=n_sample, collisions=False)
+    with _sim(d2["config"], d2["species_conf"], presolve=False) as s2:
+        e = s2.species_index("ELECTRON")
+        s2.set_field("u", u)
+        aos = np.zeros((n_sample, 7))
+        for c, k in enumerate(("x", "y", "z", "vx", "vy", "vz")):
+            aos[:, c] = sample[k]
+        s2.set_particles(e, aos)
+        s2.species_advance(e)
+        out = s2.get_particles(e)
+        alive = np.ones(n_sample, dtype=np.uint8)
+        orc3.advance(g, u, mask, charge, mass, dt, (0.0, 0.0, 0.0), sample, alive)
+        assert np.array_equal(out[:, 7] > 0, alive > 0)
+        both = alive > 0
+        for c, k in enumerate(("x", "y", "z", "vx", "vy", "vz")):
+            err = np.abs(out[both, c] - sample[k][both]).max() / np.abs(sample[k][both]).max()
+            assert err <= 1e-12, (k, err)
