@@ -413,6 +413,8 @@ def run_workload(wl, args, env, steps, warmup, e2e_steps, with_cpu):
         "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "ranks_agree": ranks_agree,
         "phases_ms_per_step": {k: v / steps for k, v in tm.items()}, "solve": solve_info, "e2e": e2e, "cpu_baseline": cpu,
     }
+    if three_d:
+        rec["store"] = {d["species"][q]: sim.store_stats(s) for q, s in enumerate(part_species)}
     rec.update(extra)
     sim.close()
     return rec
@@ -445,7 +447,7 @@ def bench_ours(args):
         # the driver's 1 -> 8 GPU scaling record carries it too; C4 stays the headline value
         r5 = run_workload("c5", args, env, min(args.steps, args.secondary_steps), args.warmup, 0, False)
         secondary = {"c5": {k: r5[k] for k in ("value", "ms_per_step", "steps", "warmup", "config", "gpu_launches", "roofline",
-                                               "ranks_agree", "phases_ms_per_step", "solve")}}
+                                               "ranks_agree", "phases_ms_per_step", "solve", "store")}}
         secondary["c5"].update(unit="particle-steps/s", n_gpus=world, scaling="weak", dtype="f64",
                                allreduce_ms_per_step=r5["phases_ms_per_step"]["allreduce"])
     if rank == 0:
@@ -456,7 +458,7 @@ def bench_ours(args):
             "dtype": "f64", "data": "synthetic (device-side Philox loaders, seed 1234)",
         }
         for k in ("config", "gpu_launches", "clocks", "roofline", "ranks_agree", "phases_ms_per_step", "solve", "e2e", "cpu_baseline",
-                  "collisions", "fp64"):
+                  "collisions", "fp64", "store"):
             if k in rec:
                 out[k] = rec[k]
         if secondary:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAG2D_ABI_VERSION 3
+#define MAG2D_ABI_VERSION 4
 #define MAG2D_MAX_SPECIES 16
 
 typedef struct mag2d_ctx mag2d_ctx;
@@ -210,6 +210,18 @@ int mag2d_set_sort_interval(mag2d_ctx* ctx, int steps); /* 0 = never sort inside
  * ones.  With the Boris movers the sort is carried by the push kernels themselves (a COUNT step takes per-cell
  * counts, the next step draws every particle's sorted slot from them and writes it there). */
 int mag2d_set_species_sort_interval(mag2d_ctx* ctx, int species, int steps);
+/* Layout of a CARTESIAN3D store inside mag2d_step: MAG2D_LAYOUT_AUTO / MAG2D_LAYOUT_BRICKS bin the particles by 4 x 4 x 4-cell brick (one
+ * CTA per brick: field tile and charge tile in shared memory, leavers migrate between bins every step; push3d_brick.cu),
+ * MAG2D_LAYOUT_SLOTS keeps the slot-order kernel with the fused COUNT / PERMUTE cell sort.  2-D stores ignore it.  No reference
+ * counterpart: the reference's vector<t_particle> has no order (src/particles.hpp:223-247). */
+#define MAG2D_LAYOUT_AUTO 0
+#define MAG2D_LAYOUT_SLOTS 1
+#define MAG2D_LAYOUT_BRICKS 2
+int mag2d_set_store_layout(mag2d_ctx* ctx, int layout);
+/* out8 (species of a CARTESIAN3D context): re-binnings so far; since the last re-binning: guests that found their new bin full,
+ * leavers that did not fit the list; leavers listed by the last step; number of bins, index of the fullest bin, its free slots,
+ * slots in use over all bins (live particles + holes) */
+int mag2d_store_stats(mag2d_ctx* ctx, int species, int64_t* out8);
 
 /* ---- stepping --------------------------------------------------------------------------------- */
 /* Pic<D>::advance_init, src/pic.cpp:359-384 */

@@ -111,6 +111,8 @@ def lib():
     L.mag2d_step_streamed.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), i64p] + [C.POINTER(dp)] * 5 + [C.c_int64]
     L.mag2d_step_streamed3.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), i64p] + [C.POINTER(dp)] * 6 + [C.c_int64]
     L.mag2d_set_species_sort_interval.argtypes = [vp, C.c_int, C.c_int]
+    L.mag2d_set_store_layout.argtypes = [vp, C.c_int]
+    L.mag2d_store_stats.argtypes = [vp, C.c_int, i64p]
     L.mag2d_advance_init.argtypes = [vp]
     L.mag2d_step.argtypes = [vp, C.c_int]
     L.mag2d_species_advance.argtypes = [vp, C.c_int]
@@ -350,6 +352,16 @@ class Sim:
             self._chk(self.L.mag2d_set_sort_interval(self.h, steps))
         else:
             self._chk(self.L.mag2d_set_species_sort_interval(self.h, species, steps))
+
+    def set_store_layout(self, layout):
+        """'auto' / 'bricks': CARTESIAN3D stores are binned by 4 x 4 x 4-cell brick inside advance(); 'slots': slot order + fused cell sort"""
+        self._chk(self.L.mag2d_set_store_layout(self.h, {"auto": 0, "slots": 1, "bricks": 2}[layout]))
+
+    def store_stats(self, i):
+        out = np.zeros(8, dtype=np.int64)
+        self._chk(self.L.mag2d_store_stats(self.h, i, out.ctypes.data_as(i64p)))
+        return dict(rebinnings=int(out[0]), full_bins=int(out[1]), list_overflow=int(out[2]), leavers_last_step=int(out[3]),
+                    bins=int(out[4]), fullest_bin=int(out[5]), fullest_bin_room=int(out[6]), slots_in_use=int(out[7]))
 
     # ---- stepping
     def advance_init(self):

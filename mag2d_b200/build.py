@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmag2d_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["abi.cu", "push.cu", "sort.cu", "poisson.cu", "poisson_direct.cu", "push3d.cu", "poisson3d.cu", "comm.cu"]
+SOURCES = ["abi.cu", "push.cu", "sort.cu", "poisson.cu", "poisson_direct.cu", "push3d.cu", "push3d_brick.cu", "poisson3d.cu", "comm.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

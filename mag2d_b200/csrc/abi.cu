@@ -93,6 +93,7 @@ int free_store(SpeciesStore& S)
     if (S.d_blob) cudaFree(S.d_blob);
     delete S.h_blob;
     sort_fused_free(S);
+    brick_free(S);
     source_free(S);
     S = SpeciesStore();
     return 0;
@@ -108,6 +109,7 @@ bool needs_array(const mag2d_ctx* c, int a)
 int ensure_capacity(mag2d_ctx* c, SpeciesStore& S, long long need)
 {
     S.tickets_valid = false;      // every append goes through here: pending sort tickets do not cover the new slots
+    S.bins_valid = false;         // ... and neither do the brick bins
     S.append_epoch++;
     if (need <= S.capacity) return 0;
     long long cap = std::max<long long>(need, (long long)(S.capacity * 1.5) + 1024);
@@ -214,7 +216,17 @@ int fused_sort_mode(const mag2d_ctx* c, const SpeciesStore& S)
 int advance_one(mag2d_ctx* c, int s, bool in_step)
 {
     if (refresh_pools(c, s)) return 1;
-    if (is3d(c)) return launch_species_advance3d(c, s, false, in_step ? fused_sort_mode(c, c->sp[s]) : 0);
+    if (is3d(c))
+    {
+        // inside mag2d_step a 3-D species runs on the brick-binned store (push3d_brick.cu; mode bit 2) wherever the fused cell sort
+        // would be allowed to reorder it; MAG3D_BRICK=0 keeps the slot-order kernel with the fused sort
+        static const bool brick_env = !getenv("MAG3D_BRICK") || atoi(getenv("MAG3D_BRICK")) != 0;
+        const SpeciesStore& S = c->sp[s];
+        const bool bricks = c->store_layout == MAG2D_LAYOUT_BRICKS || (c->store_layout == MAG2D_LAYOUT_AUTO && brick_env);
+        if (in_step && bricks && c->fused_sort && !c->use_source && S.n_slots > 0 && effective_sort_interval(c, S) > 0)
+            return launch_species_advance3d(c, s, false, 4);
+        return launch_species_advance3d(c, s, false, in_step ? fused_sort_mode(c, c->sp[s]) : 0);
+    }
     return launch_species_advance(c, s, in_step ? fused_sort_mode(c, c->sp[s]) : 0);
 }
 
@@ -880,6 +892,7 @@ int mag2d_particles_clear(mag2d_ctx* c, int s)
     CHECK_SPECIES(c, s);
     c->sp[s].n_slots = 0;
     c->sp[s].tickets_valid = false;
+    c->sp[s].bins_valid = false;
     c->sp[s].append_epoch++;
     CUDA_OK(cudaMemsetAsync(c->sp[s].d_removed, 0, sizeof(unsigned long long), c->stream));
     return 0;
@@ -1025,6 +1038,51 @@ int mag2d_set_sort_interval(mag2d_ctx* c, int steps)
 {
     CHECK_CTX(c);
     c->sort_interval = steps;
+    return 0;
+}
+
+int mag2d_set_store_layout(mag2d_ctx* c, int layout)
+{
+    CHECK_CTX(c);
+    if (layout < MAG2D_LAYOUT_AUTO || layout > MAG2D_LAYOUT_BRICKS) { mag2d_set_error("mag2d_set_store_layout: unknown layout"); return 1; }
+    c->store_layout = layout;
+    return 0;
+}
+
+int mag2d_store_stats(mag2d_ctx* c, int s, int64_t* out8)
+{
+    CHECK_CTX(c);
+    CHECK_SPECIES(c, s);
+    SpeciesStore& S = c->sp[s];
+    for (int q = 0; q < 8; q++) out8[q] = 0;
+    out8[0] = S.rebinnings;
+    if (S.d_mig_count)
+    {
+        unsigned h[4] = {0, 0, 0, 0};
+        CUDA_OK(cudaMemcpyAsync(h, S.d_mig_count, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        out8[1] = h[2];
+        out8[2] = h[1];
+        out8[3] = h[0];
+    }
+    if (S.bins_valid && S.bin_nb > 0)
+    {
+        std::vector<unsigned> off((size_t)S.bin_nb + 1), cnt((size_t)S.bin_nb);
+        CUDA_OK(cudaMemcpyAsync(off.data(), S.d_bin_off, sizeof(unsigned) * off.size(), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaMemcpyAsync(cnt.data(), S.d_bin_cnt, sizeof(unsigned) * cnt.size(), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        long long worst = -1, room = 1LL << 40, used = 0;
+        for (int b = 0; b < S.bin_nb; b++)
+        {
+            const long long r = (long long)(off[b + 1] - off[b]) - cnt[b];
+            used += cnt[b];
+            if (r < room) { room = r; worst = b; }
+        }
+        out8[4] = S.bin_nb;
+        out8[5] = worst;
+        out8[6] = room;          // free slots of the fullest bin
+        out8[7] = used;          // slots in use (live particles + holes)
+    }
     return 0;
 }
 

@@ -46,6 +46,23 @@ struct SpeciesStore
     cudaEvent_t ev_total = nullptr;
     bool total_pending = false;
     long long append_epoch = 0, total_epoch = -1;
+    // brick-binned layout of a CARTESIAN3D store (push3d_brick.cu): brick b owns the slots [bin_off[b], bin_off[b+1]) of the current
+    // slab, the first bin_cnt[b] of them in use.  Anything that moves particles without going through the brick kernel, or appends
+    // to the store, drops bins_valid; the next step in brick mode re-bins.
+    bool bins_valid = false;
+    int bin_nb = 0;
+    unsigned* d_bin_off = nullptr;
+    unsigned* d_bin_cnt = nullptr;
+    unsigned* d_bin_scratch = nullptr;
+    uint2* d_mig_list = nullptr;          // leavers of the current step: (slot, destination brick)
+    unsigned* d_mig_count = nullptr;      // [0] listed this step, [1] did not fit the list, [2] found their new bin full (since the last re-binning)
+    long long mig_cap = 0;
+    unsigned* h_bin_flags = nullptr;      // pinned copy of d_mig_count, adopted without a synchronisation
+    cudaEvent_t ev_bin = nullptr;
+    bool bin_flags_pending = false;
+    unsigned bin_overflow_seen = 0;
+    double bin_slack = 0.125;             // spare slots behind every bin relative to the local mean fill (on top of 6 sigma + 32)
+    long long rebinnings = 0;
     // particle source (use_source): the reservoir BaseSpecies::source2_particles (particles.hpp:114), filled by
     // mag2d_source_refresh / mag2d_source_upload and pushed + sampled by mag2d_species_source.  x, z, vx, vy, vz, ttd
     double* src[6] = {};
@@ -155,6 +172,7 @@ struct mag2d_ctx
     double* d_charges = nullptr;  // [n_species]
     int sort_interval = 0;
     bool use_source = false;      // Param::use_source: mag2d_step calls Species::source() after every advance (pic.cpp:346-347)
+    int store_layout = MAG2D_LAYOUT_AUTO;   // mag2d_set_store_layout
     bool fused_sort = true;       // cell sort carried by the Boris push itself (MAG2D_FUSED_SORT=0: stand-alone passes)
     bool count_collisions = false;
 
@@ -243,6 +261,14 @@ int update_edge_fields3d(mag2d_ctx* c);
 int direct3d_setup(mag2d_ctx* c);
 void direct3d_free(mag2d_ctx* c);
 int solve3d(mag2d_ctx* c, double* resid_out);
+// push3d_brick.cu
+struct Grid3Dev;
+struct Push3Args;
+int brick_rebuild(mag2d_ctx* c, int s, const Grid3Dev& g);
+int launch_brick_push(mag2d_ctx* c, int s, const Push3Args& A, bool mcc, bool deposit);
+int launch_brick_migrate(mag2d_ctx* c, int s, const Push3Args& A);
+void brick_poll_overflow(SpeciesStore& S);
+void brick_free(SpeciesStore& S);
 inline bool is3d(const mag2d_ctx* c) { return c->g.coord == MAG2D_CARTESIAN3D; }
 inline size_t grid_nodes(const mag2d_ctx* c) { return (size_t)c->g.M * c->g.N * (is3d(c) ? (size_t)c->g.K : 1); }
 // comm.cu

@@ -11,8 +11,7 @@
 #include <algorithm>
 #include <cstring>
 
-#include "ctx.hpp"
-#include "mcc.cuh"
+#include "push3d.cuh"
 
 namespace {
 
@@ -20,120 +19,6 @@ constexpr int P3_THREADS = 256;
 #ifndef MAG3D_MIN_BLOCKS
 #define MAG3D_MIN_BLOCKS 3      // 80 registers, no spills (the weights are formed after the stores); C5: 5.77 ms vs 6.49 ms with 2
 #endif
-
-struct Grid3Dev
-{
-    int M, K, N;                    // nodes along x, y, z
-    int boundary, check_mask, deposit;
-    double x_max, y_max, z_max;
-    double idx, idy, idz;
-    const double* gx;               // edge differences u[m] - u[m - stride] along x / y / z
-    const double* gy;
-    const double* gz;
-    const unsigned char* cfree;     // per cell (indexed by its lowest node): any corner FREE
-    unsigned long long* rho;        // this species' fixed-point charge grid
-};
-
-struct Push3Args
-{
-    Grid3Dev g;
-    SpeciesDev s;
-    ParticlesDev p;
-    const MccBlob* mcc;
-    unsigned long long* counts;
-    unsigned long long* removed;
-    unsigned long long seed;
-    unsigned* coll_list;
-    unsigned* coll_count;
-    int deposit_runs;   // distinct cells per warp call that get the REDUX merge (0: every lane scatters on its own)
-    // cell sort fused into the step (sort.cu): COUNT counts per cell, the next PERMUTE step draws slots and stores sorted
-    int permute, count;
-    unsigned* cursor;   // [cell] next free sorted slot of the cell (the scanned counts of the last COUNT push)
-    ParticlesDev dst;
-    unsigned* count_out;
-};
-
-__device__ __forceinline__ unsigned long long q32_rn3(double w)
-{
-    const double magic = 6755399441055744.0;   // 1.5 * 2^52
-    const double t = __dadd_rn(__dmul_rn(w, 4294967296.0), magic);
-    return (unsigned long long)(__double_as_longlong(t) - __double_as_longlong(magic));
-}
-
-// one component of grad u at (X, Y, Z) in index units; DIR selects the differenced axis (0 x, 1 y, 2 z).
-// The edge-difference arrays carry ghost planes ([M+1][K+1][N+1], k_edge_fields3d): along the differenced axis plane 0
-// repeats plane 1 and plane M repeats plane M-1, which is exactly what Field3D::grad_component's clamp of the
-// coordinate to [0.5, xmax*idx - 0.5] produces; along the other axes the plane past the end repeats the last one.
-// No floating-point clamps remain in the particle loop (nine per particle before), only integer ones.
-template <int DIR>
-__device__ __forceinline__ double grad_component(const Grid3Dev& g, double X, double Y, double Z)
-{
-    const double xs = DIR == 0 ? X + 0.5 : X, ys = DIR == 1 ? Y + 0.5 : Y, zs = DIR == 2 ? Z + 0.5 : Z;
-    const int i = max(min((int)xs, g.M - 1), 0), j = max(min((int)ys, g.K - 1), 0), k = max(min((int)zs, g.N - 1), 0);
-    const double u = xs - i, v = ys - j, w = zs - k;
-    const unsigned sj = (unsigned)g.N + 1u, si = ((unsigned)g.K + 1u) * sj;
-    const double* f = (DIR == 0 ? g.gx : DIR == 1 ? g.gy : g.gz) + ((unsigned)i * si + (unsigned)j * sj + (unsigned)k);
-    const double g0 = __ldg(f), g1 = __ldg(f + si), g2 = __ldg(f + sj), g3 = __ldg(f + si + sj);
-    const double g4 = __ldg(f + 1), g5 = __ldg(f + si + 1), g6 = __ldg(f + sj + 1), g7 = __ldg(f + si + sj + 1);
-    const double cu = 1 - u, cv = 1 - v, cw = 1 - w;
-    const double r = cu * cv * cw * g0 + u * cv * cw * g1 + cu * v * cw * g2 + u * v * cw * g3 + cu * cv * w * g4 + u * cv * w * g5 +
-                     cu * v * w * g6 + u * v * w * g7;
-    return r * (DIR == 0 ? g.idx : DIR == 1 ? g.idy : g.idz);
-}
-
-// box boundary and electrode absorption; node = lowest node of the particle's cell
-__device__ __forceinline__ bool boundary3(const Grid3Dev& g, double& x, double& y, double& z, unsigned& node, unsigned* cell = nullptr)
-{
-    node = 0;
-    if (!(x >= 0.0 && x <= g.x_max && y >= 0.0 && y <= g.y_max && z >= 0.0 && z <= g.z_max))
-    {
-        if (g.boundary == MAG2D_BOUNDARY_FREE || !(x == x && y == y && z == z)) return false;
-        x = fmod(x, g.x_max); if (x < 0) x += g.x_max;
-        y = fmod(y, g.y_max); if (y < 0) y += g.y_max;
-        z = fmod(z, g.z_max); if (z < 0) z += g.z_max;
-    }
-    const double X = __dmul_rn(x, g.idx), Y = __dmul_rn(y, g.idy), Z = __dmul_rn(z, g.idz);
-    const int i = max(min((int)X, g.M - 2), 0), j = max(min((int)Y, g.K - 2), 0), k = max(min((int)Z, g.N - 2), 0);
-    const size_t m = ((size_t)i * g.K + j) * g.N + k;
-    node = (unsigned)m;
-    if (cell) *cell = ((unsigned)i * (unsigned)(g.K - 1) + (unsigned)j) * (unsigned)(g.N - 1) + (unsigned)k;
-    if (g.check_mask && !g.cfree[m]) return false;
-    return true;
-}
-
-// the eight Q32 weights of a particle that passed boundary3 (Field3D.hpp:56-64 order).  Computed right before the
-// deposit from the stored position, so that the sixteen weight registers are not live across the push.
-__device__ __forceinline__ void weights3(const Grid3Dev& g, double x, double y, double z, unsigned long long (&w)[8])
-{
-    const double X = __dmul_rn(x, g.idx), Y = __dmul_rn(y, g.idy), Z = __dmul_rn(z, g.idz);
-    const int i = max(min((int)X, g.M - 2), 0), j = max(min((int)Y, g.K - 2), 0), k = max(min((int)Z, g.N - 2), 0);
-    const double u = __dsub_rn(X, (double)i), v = __dsub_rn(Y, (double)j), t = __dsub_rn(Z, (double)k);
-    const double cu = __dsub_rn(1.0, u), cv = __dsub_rn(1.0, v), ct = __dsub_rn(1.0, t);
-    const double a00 = __dmul_rn(cu, cv), a10 = __dmul_rn(u, cv), a01 = __dmul_rn(cu, v), a11 = __dmul_rn(u, v);
-    w[0] = q32_rn3(__dmul_rn(a00, ct));
-    w[1] = q32_rn3(__dmul_rn(a10, ct));
-    w[2] = q32_rn3(__dmul_rn(a01, ct));
-    w[3] = q32_rn3(__dmul_rn(a11, ct));
-    w[4] = q32_rn3(__dmul_rn(a00, t));
-    w[5] = q32_rn3(__dmul_rn(a10, t));
-    w[6] = q32_rn3(__dmul_rn(a01, t));
-    w[7] = q32_rn3(__dmul_rn(a11, t));
-}
-
-// eight RED.ADD.64 of one lane
-__device__ __forceinline__ void scatter3(const Grid3Dev& g, unsigned node, const unsigned long long (&w)[8])
-{
-    const unsigned sj = (unsigned)g.N, si = (unsigned)(g.K * g.N);
-    unsigned long long* r = g.rho + node;
-    atomicAdd(r, w[0]);
-    atomicAdd(r + si, w[1]);
-    atomicAdd(r + sj, w[2]);
-    atomicAdd(r + si + sj, w[3]);
-    atomicAdd(r + 1, w[4]);
-    atomicAdd(r + si + 1, w[5]);
-    atomicAdd(r + sj + 1, w[6]);
-    atomicAdd(r + si + sj + 1, w[7]);
-}
 
 // warp-aggregated scatter: lanes that share a cell are summed with REDUX (two 16/17-bit pieces per weight), lanes
 // 0..7 issue one RED.ADD.64 each; after max_runs distinct cells the remaining lanes scatter on their own.  The merge
@@ -469,9 +354,19 @@ int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only, int sort_mo
     const mag2d_grid_desc& d = c->g;
     // streamed step (abi.cu): the particle arrays are one chunk of a host-resident store staged in device buffers
     const bool chunked = c->chunk_view != nullptr && !deposit_only;
-    const long long n_active = chunked ? c->chunk_view->n : S.n_slots;
     // a push that does not consume the pending cell cursors invalidates them (see launch_species_advance)
     if (!chunked && !deposit_only && !(sort_mode & 1)) S.tickets_valid = false;
+    // brick mode (sort_mode bit 2): the step runs on the brick-binned store; any other push of the resident store moves particles
+    // behind the bins' back
+    const bool brick = !chunked && !deposit_only && (sort_mode & 4) != 0;
+    if (!chunked && !deposit_only && !brick) S.bins_valid = false;
+    if (brick)
+    {
+        brick_poll_overflow(S);
+        if (!S.bins_valid && brick_rebuild(c, s, grid3_view(c, s))) return 1;
+        sort_mode = 0;
+    }
+    const long long n_active = chunked ? c->chunk_view->n : S.n_slots;
     if (n_active > 0)
     {
         Push3Args A;
@@ -517,6 +412,21 @@ int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only, int sort_mo
             }
             const bool permute = (sort_mode & 1) != 0, count = (sort_mode & 2) != 0;
             const bool sorting = permute || count;
+            if (brick)
+            {
+                if (launch_brick_push(c, s, A, mcc, deposit)) return 1;
+                if (mcc)
+                {
+                    k_mcc_collide3d<<<148 * 8, 128, 0, c->stream>>>(A);
+                    c->launches++;
+                }
+                if (launch_brick_migrate(c, s, A)) return 1;
+                CUDA_OK(cudaGetLastError());
+                S.niter++;
+                S.t += S.desc.dt;
+                S.steps_since_sort++;
+                return 0;
+            }
             if (sorting)
             {
                 if (sort_fused_begin(c, s, permute, count)) return 1;

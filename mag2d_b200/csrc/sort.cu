@@ -202,6 +202,7 @@ int launch_sort(mag2d_ctx* c, int s, bool trim)
     SpeciesStore& S = c->sp[s];
     const long long n = S.n_slots;
     S.tickets_valid = false;
+    S.bins_valid = false;
     if (n == 0) return 0;
     const int M = c->g.M, N = c->g.N;
     const bool three_d = is3d(c);

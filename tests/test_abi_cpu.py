@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
     L = C.CDLL(built)
     missing = [name for name in declared if not hasattr(L, name)]
     assert not missing, missing
-    assert L.mag2d_abi_version() == 3
+    assert L.mag2d_abi_version() == 4
 
 
 def test_struct_layouts_match_header(built):

@@ -170,10 +170,11 @@ def test_selfconsistent_loop_deposit_bit_exact(deckdir):
             assert np.array_equal(sim.rho_fixed(e), gfix)
 
 
-@pytest.mark.parametrize("interval", [1, 3])
-def test_fused_cell_sort_3d_keeps_the_particle_set_and_the_charge(deckdir, interval):
-    """the 3-D push carries the cell sort like the 2-D one: with collisions off the multiset of particles, the
-    integer charge grid and the potential must equal those of a run that never sorts"""
+@pytest.mark.parametrize("layout,interval", [("slots", 1), ("slots", 3), ("bricks", 4)])
+def test_fused_cell_sort_3d_keeps_the_particle_set_and_the_charge(deckdir, layout, interval):
+    """the 3-D step reorders the store — slot order with the fused COUNT / PERMUTE cell sort, or binned by brick —; with
+    collisions off the multiset of particles, the integer charge grid and the potential must equal those of a run that
+    never sorts (same operations on every particle: bit for bit)"""
     d = small_deck(deckdir, x_sampl=12, y_sampl=11, z_sampl=13, macroparticle_factor=2e6)
     rng = np.random.default_rng(41)
     results = []
@@ -186,6 +187,7 @@ def test_fused_cell_sort_3d_keeps_the_particle_set_and_the_charge(deckdir, inter
                 aos = box_particles(rng, 9001, g, 4e5)
             sim.set_particles(e, aos)
             sim.set_sort_interval(k)
+            sim.set_store_layout(layout)
             sim.advance_init()
             sim.advance(7)
             p = sim.get_particles(e)
@@ -197,7 +199,109 @@ def test_fused_cell_sort_3d_keeps_the_particle_set_and_the_charge(deckdir, inter
     assert np.array_equal(a[1], b[1])
     assert np.array_equal(a[2], b[2])
     n_alive = int(b[3].sum())
-    assert (b[3][:n_alive] == 0).sum() < 0.6 * (9001 - n_alive)      # dead slots were compacted away
+    if layout == "slots":
+        assert (b[3][:n_alive] == 0).sum() < 0.6 * (9001 - n_alive)      # dead slots were compacted away
+
+
+@pytest.mark.parametrize("B,boundary", [((0.0, 0.0, 0.0), "FREE"), ((0.3, -0.2, 0.5), "FREE"), ((0.0, 0.0, 0.0), "PERIODIC")])
+def test_brick_layout_equals_the_plain_step_bit_for_bit(deckdir, B, boundary):
+    """push3d_brick.cu against the slot-order kernel on a grid whose last bricks are partial (22 x 18 x 17 cells), with fast
+    particles (a third of a cell per step: every step a fifth of them changes brick, many leave the box or wrap around),
+    a magnetic field and a potential with structure: the same particles, charge grids and potentials, bit for bit"""
+    d = small_deck(deckdir, x_sampl=23, y_sampl=19, z_sampl=18, macroparticle_factor=5e6, boundary=boundary,
+                   Br=B[0], Bt=B[1], Bz=B[2])
+    rng = np.random.default_rng(4242)
+    results = []
+    aos = None
+    for layout in ("plain", "bricks"):
+        with _sim(d["config"], d["species_conf"]) as sim:
+            g = grid3(sim.param)
+            e = sim.species_index("ELECTRON")
+            if aos is None:
+                aos = box_particles(rng, 60013, g, 2.5e6)
+                aos[:7, 0] = g.x_max              # exactly on the far faces
+                aos[7:14, 1] = g.y_max
+                aos[14:21, 2] = g.z_max
+            sim.set_particles(e, aos)
+            sim.set_sort_interval(0 if layout == "plain" else 4)
+            sim.set_store_layout("bricks")
+            sim.advance_init()
+            snaps = []
+            for _ in range(3):
+                sim.advance(4)
+                p = sim.get_particles(e)
+                live = p[p[:, 7] > 0][:, :6]
+                snaps.append((live[np.lexsort(live.T[::-1])], sim.rho_fixed(e), sim.get_field("u")))
+            results.append(snaps)
+            if layout == "bricks":
+                st = sim.store_stats(e)
+                assert st["rebinnings"] >= 1 and st["list_overflow"] == 0
+    for a, b in zip(*results):
+        assert len(a[0]) == len(b[0]) and len(a[0]) > 1000
+        assert np.array_equal(a[0], b[0])
+        assert np.array_equal(a[1], b[1])
+        assert np.array_equal(a[2], b[2])
+    if boundary == "FREE":
+        assert len(results[0][-1][0]) < 60013
+    else:
+        assert len(results[0][-1][0]) == 60013
+
+
+def test_brick_bins_overflow_into_guests_and_rebin(deckdir):
+    """all particles start in one corner and stream into empty bricks whose bins only have the minimal slack: arrivals
+    that find a bin full stay guests of their old bin (global-memory path), the store is re-binned with more slack, and
+    nothing is lost or duplicated on the way"""
+    d = small_deck(deckdir, x_sampl=21, y_sampl=21, z_sampl=21, macroparticle_factor=5e6)
+    rng = np.random.default_rng(77)
+    results = []
+    aos = None
+    for layout in ("plain", "bricks"):
+        with _sim(d["config"], d["species_conf"]) as sim:
+            g = grid3(sim.param)
+            e = sim.species_index("ELECTRON")
+            if aos is None:
+                n = 40000
+                aos = np.zeros((n, 7))
+                aos[:, 0:3] = rng.uniform(0.02, 0.2, (n, 3)) * np.array([g.x_max, g.y_max, g.z_max])
+                aos[:, 3:6] = np.abs(rng.normal(size=(n, 3))) * 1.5e6 + 5e5       # all heading into the box
+            sim.set_particles(e, aos)
+            sim.set_sort_interval(0 if layout == "plain" else 4)
+            sim.advance_init()
+            sim.advance(25)
+            p = sim.get_particles(e)
+            live = p[p[:, 7] > 0][:, :6]
+            results.append((live[np.lexsort(live.T[::-1])], sim.rho_fixed(e), sim.count(e)[0]))
+            if layout == "bricks":
+                st = sim.store_stats(e)
+                assert st["rebinnings"] >= 2, st          # the first binning + at least one forced by full bins
+    a, b = results
+    assert a[2] == b[2] and a[2] > 1000
+    assert np.array_equal(a[0], b[0])
+    assert np.array_equal(a[1], b[1])
+
+
+def test_brick_layout_collision_rate(deckdir):
+    """collisions on the binned store: the Bernoulli test of the null-collision method fires with probability
+    1 - exp(-dt / lifetime) per particle-step, the collision pass changes velocities only (count conserved inside the box)"""
+    d = small_deck(deckdir, x_sampl=21, y_sampl=21, z_sampl=21, collisions=True, boundary="PERIODIC")
+    with _sim(d["config"], d["species_conf"]) as sim:
+        g = grid3(sim.param)
+        e = sim.species_index("ELECTRON")
+        n, steps = 200000, 20
+        sim.set_particles(e, box_particles(np.random.default_rng(5), n, g, 6e5))
+        sim.set_collision_counting(True)
+        sim.set_sort_interval(-1)
+        sim.advance_init()
+        e0 = (sim.get_particles(e)[:, 3:6] ** 2).sum()
+        sim.advance(steps)
+        assert sim.count(e)[0] == n
+        c = sim.collision_counts(e)
+        events = c.sum()
+        prob = sim.species_get(e, "prob")
+        expect = n * steps * prob
+        assert expect > 1000 and abs(events - expect) <= 5 * np.sqrt(expect), (events, expect)
+        assert (sim.get_particles(e)[:, 3:6] ** 2).sum() != e0
+        assert sim.store_stats(e)["rebinnings"] >= 1
 
 
 def test_sort_and_loader_3d(deckdir):
