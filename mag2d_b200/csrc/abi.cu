@@ -224,7 +224,7 @@ int advance_one(mag2d_ctx* c, int s, bool in_step)
         const SpeciesStore& S = c->sp[s];
         const bool bricks = c->store_layout == MAG2D_LAYOUT_BRICKS || (c->store_layout == MAG2D_LAYOUT_AUTO && brick_env);
         if (in_step && bricks && c->fused_sort && !c->use_source && S.n_slots > 0 && effective_sort_interval(c, S) > 0)
-            return launch_species_advance3d(c, s, false, 4);
+            return launch_species_advance3d(c, s, false, 4 | (std::min(effective_sort_interval(c, S), 1 << 20) << 3));
         return launch_species_advance3d(c, s, false, in_step ? fused_sort_mode(c, c->sp[s]) : 0);
     }
     return launch_species_advance(c, s, in_step ? fused_sort_mode(c, c->sp[s]) : 0);
@@ -1056,13 +1056,13 @@ int mag2d_store_stats(mag2d_ctx* c, int s, int64_t* out8)
     SpeciesStore& S = c->sp[s];
     for (int q = 0; q < 8; q++) out8[q] = 0;
     out8[0] = S.rebinnings;
-    if (S.d_mig_count)
+    if (S.d_ob_count)
     {
         unsigned h[4] = {0, 0, 0, 0};
-        CUDA_OK(cudaMemcpyAsync(h, S.d_mig_count, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaMemcpyAsync(h, S.d_ob_count, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(cudaStreamSynchronize(c->stream));
-        out8[1] = h[2];
-        out8[2] = h[1];
+        out8[1] = h[1];
+        out8[2] = h[2];
         out8[3] = h[0];
     }
     if (S.bins_valid && S.bin_nb > 0)

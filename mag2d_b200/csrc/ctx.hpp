@@ -54,9 +54,11 @@ struct SpeciesStore
     unsigned* d_bin_off = nullptr;
     unsigned* d_bin_cnt = nullptr;
     unsigned* d_bin_scratch = nullptr;
-    uint2* d_mig_list = nullptr;          // leavers of the current step: (slot, destination brick)
-    unsigned* d_mig_count = nullptr;      // [0] listed this step, [1] did not fit the list, [2] found their new bin full (since the last re-binning)
-    long long mig_cap = 0;
+    double* d_outbox[6] = {};             // this step's leavers (x, y, z, vx, vy, vz), placed into their new bins by k_place3d
+    unsigned* d_ob_dst = nullptr;         // their destination bricks
+    unsigned* d_ob_count = nullptr;       // [0] outbox entries of this step, [1] arrivals that found a bin full, [2] CTAs whose leavers did not fit (since the last re-binning)
+    long long ob_cap = 0;
+    int pushes_since_compact = 0;         // in-place steps since the last compacting one
     unsigned* h_bin_flags = nullptr;      // pinned copy of d_mig_count, adopted without a synchronisation
     cudaEvent_t ev_bin = nullptr;
     bool bin_flags_pending = false;
@@ -265,7 +267,8 @@ int solve3d(mag2d_ctx* c, double* resid_out);
 struct Grid3Dev;
 struct Push3Args;
 int brick_rebuild(mag2d_ctx* c, int s, const Grid3Dev& g);
-int launch_brick_push(mag2d_ctx* c, int s, const Push3Args& A, bool mcc, bool deposit);
+int launch_brick_push(mag2d_ctx* c, int s, const Push3Args& A, bool mcc, bool deposit, int compact_every);
+void brick_outbox_view(const SpeciesStore& S, ParticlesDev& v);
 int launch_brick_migrate(mag2d_ctx* c, int s, const Push3Args& A);
 void brick_poll_overflow(SpeciesStore& S);
 void brick_free(SpeciesStore& S);

@@ -232,18 +232,21 @@ __global__ void __launch_bounds__(128) k_mcc_collide3d(const __grid_constant__ P
     const unsigned n = *A.coll_count;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
     {
-        const long long k = A.coll_list[q];
-        double vx = A.p.vx[k], vy = A.p.vy[k], vz = A.p.vz[k];
-        Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)k);
+        // brick mode: entries with the high bit set are leavers waiting in the outbox (A.dst), see push3d_brick.cu
+        const unsigned raw = A.coll_list[q];
+        const ParticlesDev& P = (raw & 0x80000000u) ? A.dst : A.p;
+        const long long k = raw & 0x7FFFFFFFu;
+        double vx = P.vx[k], vy = P.vy[k], vz = P.vz[k];
+        Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)raw);
         rng.draw = 1;
         int target;
         const int proc = mcc_scatter(A.mcc, rng, vx, vy, vz, target);
         mcc_count(A.counts, A.mcc->n_targets, target, proc);
         if (proc >= 0)
         {
-            A.p.vx[k] = vx;
-            A.p.vy[k] = vy;
-            A.p.vz[k] = vz;
+            P.vx[k] = vx;
+            P.vy[k] = vy;
+            P.vz[k] = vz;
         }
     }
 }
@@ -359,6 +362,7 @@ int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only, int sort_mo
     // brick mode (sort_mode bit 2): the step runs on the brick-binned store; any other push of the resident store moves particles
     // behind the bins' back
     const bool brick = !chunked && !deposit_only && (sort_mode & 4) != 0;
+    const int brick_compact_every = std::max(1, sort_mode >> 3);     // bits 3..: steps between compacting (cell-sorting) passes
     if (!chunked && !deposit_only && !brick) S.bins_valid = false;
     if (brick)
     {
@@ -414,7 +418,8 @@ int launch_species_advance3d(mag2d_ctx* c, int s, bool deposit_only, int sort_mo
             const bool sorting = permute || count;
             if (brick)
             {
-                if (launch_brick_push(c, s, A, mcc, deposit)) return 1;
+                brick_outbox_view(S, A.dst);        // collision-list entries with the high bit set address the outbox
+                if (launch_brick_push(c, s, A, mcc, deposit, brick_compact_every)) return 1;
                 if (mcc)
                 {
                     k_mcc_collide3d<<<148 * 8, 128, 0, c->stream>>>(A);

@@ -44,31 +44,39 @@ constexpr int LIST_CAP = 128;            // leavers / collision hits of one pass
 #define MAG3D_BRICK_MIN_BLOCKS 4
 #endif
 
+struct Outbox
+{
+    double* arr[6];              // x, y, z, vx, vy, vz of this step's leavers
+    unsigned* dst;               // destination brick (OUTBOX_VOID: a reserved entry that was not filled)
+    unsigned* count;             // [0] entries reserved this step, [1] bins found full by arrivals (since the last re-binning), [2] CTAs whose leavers did not fit
+    unsigned cap;
+};
+constexpr unsigned OUTBOX_VOID = 0xFFFFFFFFu;
+
 struct BrickArgs
 {
     Push3Args A;
     const unsigned* bin_off;     // [nb + 1]
     unsigned* bin_cnt;           // [nb]
     int nbx, nby, nbz;
-    uint2* mig_list;             // (source slot, destination brick)
-    unsigned* mig_count;         // [0] entries appended this step, [1] entries that did not fit the list, [2] bins that were full
-    unsigned mig_cap;
+    int compact;                 // this step writes the stayers back compacted and cell-sorted (else: in place, holes stay)
+    Outbox ob;
 };
 
 struct __align__(128) BrickSmem
 {
     double P[6][BK_CHUNK];                       // x, y, z, vx, vy, vz of the staged slots
     double tile[3][TILE_LD];                     // edge differences gx [6][5][5], gy [5][6][5], gz [5][5][6]
-    unsigned long long cellsum[BCELLS][8];       // Q32 weight sums of every cell's eight corners
-    unsigned cnt[BCELLS + 4];                    // particles per class (64 cells + guests)
+    unsigned long long cellsum[8][BCELLS];       // Q32 weight sums, [corner][cell]: neighbouring cells sit in neighbouring banks
+    unsigned cnt[BCELLS + 4];                    // particles per class (64 cells + leavers)
     unsigned start[BCELLS + 4];                  // exclusive scan of cnt
     unsigned dstb[BK_CHUNK];                     // destination brick of a leaver
     unsigned short rank[BK_CHUNK];               // rank inside the class
     unsigned short perm[BK_CHUNK];               // sorted position -> staged slot (stayers)
     unsigned char cls[BK_CHUNK];                 // class (cell 0..63, CLS_GUEST) | 128 when the collision test fired; CLS_DEAD
-    uint2 leavers[LIST_CAP];                     // (slot, destination brick) of this pass' leavers, flushed with one atomic per CTA
     unsigned short hits[LIST_CAP];               // staged slots whose collision test fired
-    unsigned n_hit, hit_base, mig_base, pad;
+    unsigned short leave[LIST_CAP];              // staged slots of this pass' leavers, by rank
+    unsigned n_hit, hit_base, ob_base, pad;
     unsigned long long bar;
 };
 
@@ -101,6 +109,12 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // one component of grad u from the brick's tile: grad_component (push3d.cuh) with shared-memory operands.  (li, lj, lk)
@@ -151,6 +165,7 @@ __global__ void __launch_bounds__(BK_THREADS, MAG3D_BRICK_MIN_BLOCKS) k_push3d_b
     const unsigned n = B.bin_cnt[b];
     if (n == 0) return;
     const unsigned off = B.bin_off[b];
+    const bool compact = B.compact != 0;
     const int ci0 = bi * BR, cj0 = bj * BR, ck0 = bk * BR;
     double* const arr[6] = {A.p.x, A.p.y, A.p.z, A.p.vx, A.p.vy, A.p.vz};
     if (t == 0)
@@ -159,9 +174,12 @@ __global__ void __launch_bounds__(BK_THREADS, MAG3D_BRICK_MIN_BLOCKS) k_push3d_b
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue_load = [&](unsigned in) {
+    auto chunk_bytes = [&](unsigned in) {
         const unsigned m = min((unsigned)BK_CHUNK, n - in);
-        const unsigned bytes = ((m + 1u) & ~1u) * (unsigned)sizeof(double);      // bins are padded to 32 slots: the extra slot exists
+        return ((m + 1u) & ~1u) * (unsigned)sizeof(double);      // bins are padded to 32 slots: the extra slot exists
+    };
+    auto issue_load = [&](unsigned in) {
+        const unsigned bytes = chunk_bytes(in);
         mbar_expect_tx(&S.bar, 6 * bytes);
 #pragma unroll
         for (int a = 0; a < 6; a++) bulk_load(S.P[a], arr[a] + off + in, bytes, &S.bar);
@@ -187,7 +205,6 @@ __global__ void __launch_bounds__(BK_THREADS, MAG3D_BRICK_MIN_BLOCKS) k_push3d_b
             }
         }
     }
-    for (unsigned q = t; q < BCELLS * 8; q += BK_THREADS) (&S.cellsum[0][0])[q] = 0ULL;
     const double dt = A.s.dt;
     unsigned out = 0, removed = 0, parity = 0;
     for (unsigned in = 0; in < n; in += BK_CHUNK, parity ^= 1u)
@@ -225,7 +242,7 @@ __global__ void __launch_bounds__(BK_THREADS, MAG3D_BRICK_MIN_BLOCKS) k_push3d_b
                 }
                 else
                 {
-                    // a guest (its move to the right bin is still pending) or a particle exactly on the far face of the box
+                    // a guest (it found its own bin full) or a particle exactly on the far face of the box
                     Ex = -grad_component<0>(A.g, X, Y, Z);
                     Ey = -grad_component<1>(A.g, X, Y, Z);
                     Ez = -grad_component<2>(A.g, X, Y, Z);
@@ -266,7 +283,9 @@ __global__ void __launch_bounds__(BK_THREADS, MAG3D_BRICK_MIN_BLOCKS) k_push3d_b
                             scatter3(A.g, (unsigned)(((size_t)i * A.g.K + j) * A.g.N + k), w);
                         }
                     }
-                    S.rank[p] = (unsigned short)atomicAdd(&S.cnt[cls], 1u);
+                    const unsigned rk = atomicAdd(&S.cnt[cls], 1u);
+                    S.rank[p] = (unsigned short)rk;
+                    if (cls == CLS_GUEST && rk < (unsigned)LIST_CAP) S.leave[rk] = (unsigned short)p;
                     if (MCC)
                     {
                         const unsigned word = it == 0 ? rnd.x : it == 1 ? rnd.y : rnd.z;
@@ -274,14 +293,18 @@ __global__ void __launch_bounds__(BK_THREADS, MAG3D_BRICK_MIN_BLOCKS) k_push3d_b
                         {
                             const unsigned h = atomicAdd(&S.n_hit, 1u);
                             if (h < (unsigned)LIST_CAP) S.hits[h] = (unsigned short)p;
-                            else cls |= 128;              // list full: appended one by one in pass 2
+                            else cls |= 128;              // list full: appended one by one below
                         }
                     }
-                    S.P[0][p] = x; S.P[1][p] = y; S.P[2][p] = z;
+                    S.P[1][p] = y; S.P[2][p] = z;
                     S.P[3][p] = vx; S.P[4][p] = vy; S.P[5][p] = vz;
                 }
                 else
+                {
                     removed++;
+                    x = dead_marker();
+                }
+                S.P[0][p] = x;
             }
             S.cls[p] = cls;
         }
@@ -308,69 +331,21 @@ __global__ void __launch_bounds__(BK_THREADS, MAG3D_BRICK_MIN_BLOCKS) k_push3d_b
             }
         }
         __syncthreads();
-        const unsigned kept = S.start[65];
-        const unsigned n_leave = S.start[65] - S.start[64], n_hit = MCC ? min(S.n_hit, (unsigned)LIST_CAP) : 0u;
-        // one returning atomic per CTA and list (issued by two different warps; their results are only needed after pass 2)
-        if (t == 0 && n_leave) S.mig_base = atomicAdd(B.mig_count, min(n_leave, (unsigned)LIST_CAP));
+        const unsigned n_stay = S.start[64], n_leave = S.start[65] - S.start[64], n_hit = MCC ? min(S.n_hit, (unsigned)LIST_CAP) : 0u;
         if (MCC && t == 32 && n_hit) S.hit_base = atomicAdd(A.coll_count, n_hit);
-        // ---- pass 2: compacted, cell-sorted write-back; collision list; leavers' list
+        // ---- sorted index of the stayers (perm[sorted position] = staged slot)
 #pragma unroll 1
         for (int it = 0; it < BK_PPT; it++)
         {
             const unsigned p = t + (unsigned)it * BK_THREADS;
-            const unsigned char cf = p < m ? S.cls[p] : CLS_DEAD;
-            const bool alive = cf != CLS_DEAD;
-            const unsigned cls = cf & 127u;
-            unsigned dest = 0;
-            if (alive)
-            {
-                dest = S.start[cls] + S.rank[p];
-                if (cls < (unsigned)BCELLS) S.perm[dest] = (unsigned short)p;
-                const size_t d = (size_t)off + out + dest;
-#pragma unroll
-                for (int a = 0; a < 6; a++) arr[a][d] = S.P[a][p];
-            }
-            if (MCC && S.n_hit > (unsigned)LIST_CAP)
-            {
-                const bool hit = alive && (cf & 128);
-                const unsigned hm = __ballot_sync(MAG2D_FULL_MASK, hit);
-                if (hm)
-                {
-                    unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(A.coll_count, (unsigned)__popc(hm));
-                    base = __shfl_sync(MAG2D_FULL_MASK, base, 0);
-                    if (hit) A.coll_list[base + __popc(hm & ((1u << lane) - 1u))] = off + out + dest;
-                }
-            }
-            if (alive && cls == (unsigned)CLS_GUEST)
-            {
-                const unsigned r = S.rank[p];
-                const uint2 entry = make_uint2(off + out + dest, S.dstb[p]);
-                if (r < (unsigned)LIST_CAP) S.leavers[r] = entry;
-                else
-                {
-                    const unsigned q = atomicAdd(B.mig_count, 1u);
-                    if (q < B.mig_cap) B.mig_list[q] = entry;
-                    else atomicAdd(B.mig_count + 1, 1u);
-                }
-            }
+            if (p >= m) break;
+            const unsigned cls = S.cls[p] & 127u;
+            if (cls < (unsigned)BCELLS) S.perm[S.start[cls] + S.rank[p]] = (unsigned short)p;
         }
         __syncthreads();
-        // the two lists of this pass go out with coalesced stores
-        {
-            const unsigned nl = min(n_leave, (unsigned)LIST_CAP);
-            if (t < nl)
-            {
-                const unsigned q = S.mig_base + t;
-                if (q < B.mig_cap) B.mig_list[q] = S.leavers[t];
-                else atomicAdd(B.mig_count + 1, 1u);
-            }
-            if (MCC && t >= 128 && t - 128 < n_hit)
-            {
-                const unsigned p = S.hits[t - 128];
-                A.coll_list[S.hit_base + (t - 128)] = off + out + S.start[S.cls[p] & 127u] + S.rank[p];
-            }
-        }
+        // room in the outbox for this pass' leavers: one returning atomic per CTA, issued here and consumed after the deposit
+        unsigned ob_base = 0;
+        if (t == 0 && n_leave) ob_base = atomicAdd(B.ob.count, n_leave);
         // ---- charge of the stayers: four threads per cell walk the cell's particles, registers only
         if (DEPOSIT)
         {
@@ -387,29 +362,114 @@ __global__ void __launch_bounds__(BK_THREADS, MAG3D_BRICK_MIN_BLOCKS) k_push3d_b
 #pragma unroll
                 for (int e = 0; e < 8; e++) acc[e] += w[e];
             }
-            if (__any_sync(MAG2D_FULL_MASK, s1 > s0))
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+            {
+                acc[e] += __shfl_xor_sync(MAG2D_FULL_MASK, acc[e], 1);
+                acc[e] += __shfl_xor_sync(MAG2D_FULL_MASK, acc[e], 2);
+            }
+            if (q == 0)
             {
 #pragma unroll
-                for (int e = 0; e < 8; e++)
+                for (int e = 0; e < 8; e++) S.cellsum[e][c] = in == 0 ? acc[e] : S.cellsum[e][c] + acc[e];
+            }
+        }
+        if (t == 0 && n_leave) S.ob_base = ob_base;
+        __syncthreads();
+        // ---- leavers go to the outbox (all of this pass' leavers or none: a CTA that does not get room keeps them as guests)
+        const bool leavers_go = n_leave > 0 && S.ob_base + n_leave <= B.ob.cap;
+        if (n_leave)
+        {
+            if (!leavers_go && t == 0) atomicAdd(B.ob.count + 2, 1u);
+            // the first LIST_CAP leavers are listed by rank; a pass with more walks its slots for the rest
+            for (unsigned r = t; r < n_leave; r += BK_THREADS)
+            {
+                unsigned p;
+                if (r < (unsigned)LIST_CAP) p = S.leave[r];
+                else
                 {
-                    acc[e] += __shfl_xor_sync(MAG2D_FULL_MASK, acc[e], 1);
-                    acc[e] += __shfl_xor_sync(MAG2D_FULL_MASK, acc[e], 2);
+                    p = 0;
+                    for (unsigned k = 0; k < m; k++)
+                        if ((S.cls[k] & 127u) == (unsigned)CLS_GUEST && S.rank[k] == r) { p = k; break; }
                 }
-                if (q == 0 && s1 > s0)
+                const unsigned q = S.ob_base + r;
+                if (leavers_go)
                 {
 #pragma unroll
-                    for (int e = 0; e < 8; e++) S.cellsum[c][e] += acc[e];
+                    for (int a = 0; a < 6; a++) B.ob.arr[a][q] = S.P[a][p];
+                    B.ob.dst[q] = S.dstb[p];
+                    if (MCC && (S.cls[p] & 128)) A.coll_list[atomicAdd(A.coll_count, 1u)] = 0x80000000u | q;
+                    S.P[0][p] = dead_marker();
+                    S.cls[p] = CLS_DEAD;
+                }
+                else if (q < B.ob.cap) B.ob.dst[q] = OUTBOX_VOID;
+            }
+        }
+        if (!compact)
+        {
+            // ---- in place: the staged slots go back where they came from (holes included) with one bulk store per array
+            if (MCC)
+            {
+                if (t >= 128 && t - 128 < n_hit)
+                {
+                    const unsigned p = S.hits[t - 128];
+                    // a leaver collides where it is now: in the outbox (high bit: k_mcc_collide3d reads A.dst, the outbox view)
+                    A.coll_list[S.hit_base + (t - 128)] = S.cls[p] != CLS_DEAD ? off + in + p : 0x80000000u | (S.ob_base + S.rank[p]);
+                }
+                if (S.n_hit > (unsigned)LIST_CAP)
+                {
+                    for (unsigned p = t; p < m; p += BK_THREADS)
+                        if (S.cls[p] != CLS_DEAD && (S.cls[p] & 128)) A.coll_list[atomicAdd(A.coll_count, 1u)] = off + in + p;
                 }
             }
+            fence_proxy_async();
+            __syncthreads();
+            if (t == 0)
+            {
+                const unsigned bytes = chunk_bytes(in);
+#pragma unroll
+                for (int a = 0; a < 6; a++) bulk_store(arr[a] + off + in, S.P[a], bytes);
+                bulk_commit();
+                bulk_wait_read_all();           // shared memory may be overwritten (next pass) or released (exit)
+                if (in + BK_CHUNK < n) issue_load(in + BK_CHUNK);
+            }
+            out += m;
+            __syncthreads();
+            continue;
+        }
+        __syncthreads();
+        // ---- compacting pass: the stayers (and guests that could not leave) are written back cell-sorted, holes dropped
+        const unsigned kept = leavers_go ? n_stay : n_stay + n_leave;
+#pragma unroll 1
+        for (int it = 0; it < BK_PPT; it++)
+        {
+            const unsigned p = t + (unsigned)it * BK_THREADS;
+            if (p >= m) break;
+            const unsigned char cf = S.cls[p];
+            if (cf == CLS_DEAD) continue;
+            const unsigned dest = S.start[cf & 127u] + S.rank[p];
+            const size_t d = (size_t)off + out + dest;
+#pragma unroll
+            for (int a = 0; a < 6; a++) arr[a][d] = S.P[a][p];
+            if (MCC && (cf & 128)) A.coll_list[atomicAdd(A.coll_count, 1u)] = off + out + dest;
+        }
+        if (MCC && t >= 128 && t - 128 < n_hit)
+        {
+            const unsigned p = S.hits[t - 128];
+            const unsigned char cf = S.cls[p];
+            A.coll_list[S.hit_base + (t - 128)] = cf != CLS_DEAD ? off + out + S.start[cf & 127u] + S.rank[p] : 0x80000000u | (S.ob_base + S.rank[p]);
         }
         out += kept;
         fence_proxy_async();
         __syncthreads();
         if (t == 0 && in + BK_CHUNK < n) issue_load(in + BK_CHUNK);
     }
-    // the vacated tail of the bin becomes holes; the new fill level
-    for (unsigned k = out + t; k < n; k += BK_THREADS) A.p.x[(size_t)off + k] = dead_marker();
-    if (t == 0) B.bin_cnt[b] = out;
+    if (compact)
+    {
+        // the vacated tail of the bin becomes holes; the new fill level
+        for (unsigned k = out + t; k < n; k += BK_THREADS) A.p.x[(size_t)off + k] = dead_marker();
+        if (t == 0) B.bin_cnt[b] = out;
+    }
     if (DEPOSIT)
     {
         // one RED per node of the brick: node (ni, nj, nk) collects corner (a, b, c) of cell (ni - a, nj - b, nk - c)
@@ -421,7 +481,7 @@ __global__ void __launch_bounds__(BK_THREADS, MAG3D_BRICK_MIN_BLOCKS) k_push3d_b
             for (int e = 0; e < 8; e++)
             {
                 const int li = ni - (e & 1), lj = nj - ((e >> 1) & 1), lk = nk - (e >> 2);
-                if ((unsigned)li < (unsigned)BR && (unsigned)lj < (unsigned)BR && (unsigned)lk < (unsigned)BR) sum += S.cellsum[(li * BR + lj) * BR + lk][e];
+                if ((unsigned)li < (unsigned)BR && (unsigned)lj < (unsigned)BR && (unsigned)lk < (unsigned)BR) sum += S.cellsum[e][(li * BR + lj) * BR + lk];
             }
             if (sum) atomicAdd(A.g.rho + (((size_t)(ci0 + ni) * A.g.K + (cj0 + nj)) * A.g.N + (ck0 + nk)), sum);
         }
@@ -435,29 +495,32 @@ __global__ void __launch_bounds__(BK_THREADS, MAG3D_BRICK_MIN_BLOCKS) k_push3d_b
     }
 }
 
-// leavers move to the tail of their new brick's bin; a full bin leaves the particle where it is (a guest of its old bin)
-__global__ void __launch_bounds__(256) k_migrate3d(const __grid_constant__ BrickArgs B)
+// the outbox empties into the bins: every leaver takes the next free slot of its new brick's bin.  A full bin sends it on to
+// the following bins (any bin will do: a particle outside its bin's brick is a guest and goes through the global-memory path
+// until it leaves again), so nothing is ever dropped; the host re-bins with more slack when that happened.
+__global__ void __launch_bounds__(256) k_place3d(const __grid_constant__ BrickArgs B)
 {
-    const unsigned n = min(B.mig_count[0], B.mig_cap);
+    const unsigned n = min(B.ob.count[0], B.ob.cap);
+    const unsigned nb = (unsigned)(B.nbx * B.nby * B.nbz);
     double* const arr[6] = {B.A.p.x, B.A.p.y, B.A.p.z, B.A.p.vx, B.A.p.vy, B.A.p.vz};
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
     {
-        const uint2 e = B.mig_list[q];
-        const unsigned lo = B.bin_off[e.y], cap = B.bin_off[e.y + 1] - lo;
-        const unsigned pos = atomicAdd(&B.bin_cnt[e.y], 1u);
-        if (pos < cap)
+        unsigned dst = B.ob.dst[q];
+        if (dst == OUTBOX_VOID) continue;
+        for (unsigned probe = 0; probe < nb; probe++)
         {
-            const size_t d = (size_t)lo + pos;
-            // x last: the slot only turns live once the other five components are in place (nobody reads it before the
-            // next kernel anyway)
+            const unsigned lo = B.bin_off[dst], cap = B.bin_off[dst + 1] - lo;
+            const unsigned pos = atomicAdd(&B.bin_cnt[dst], 1u);
+            if (pos < cap)
+            {
+                const size_t d = (size_t)lo + pos;
 #pragma unroll
-            for (int a = 5; a >= 0; a--) arr[a][d] = arr[a][e.x];
-            arr[0][e.x] = dead_marker();
-        }
-        else
-        {
-            atomicSub(&B.bin_cnt[e.y], 1u);
-            atomicAdd(B.mig_count + 2, 1u);
+                for (int a = 0; a < 6; a++) arr[a][d] = B.ob.arr[a][q];
+                break;
+            }
+            atomicSub(&B.bin_cnt[dst], 1u);
+            if (probe == 0) atomicAdd(B.ob.count + 1, 1u);
+            dst = dst + 1 < nb ? dst + 1 : 0;
         }
     }
 }
@@ -576,12 +639,13 @@ void brick_free(SpeciesStore& S)
     cudaFree(S.d_bin_off);
     cudaFree(S.d_bin_cnt);
     cudaFree(S.d_bin_scratch);
-    cudaFree(S.d_mig_list);
-    cudaFree(S.d_mig_count);
+    for (int a = 0; a < 6; a++) { cudaFree(S.d_outbox[a]); S.d_outbox[a] = nullptr; }
+    cudaFree(S.d_ob_dst);
+    cudaFree(S.d_ob_count);
     if (S.h_bin_flags) cudaFreeHost(S.h_bin_flags);
     if (S.ev_bin) cudaEventDestroy(S.ev_bin);
-    S.d_bin_off = S.d_bin_cnt = S.d_bin_scratch = S.d_mig_count = nullptr;
-    S.d_mig_list = nullptr;
+    S.d_bin_off = S.d_bin_cnt = S.d_bin_scratch = S.d_ob_dst = S.d_ob_count = nullptr;
+    S.ob_cap = 0;
     S.h_bin_flags = nullptr;
     S.ev_bin = nullptr;
     S.bins_valid = false;
@@ -603,9 +667,9 @@ int brick_rebuild(mag2d_ctx* c, int s, const Grid3Dev& g)
         CUDA_OK(cudaMalloc(&S.d_bin_scratch, sizeof(unsigned) * (size_t)nb + 16));
         S.bin_nb = nb;
     }
-    if (!S.d_mig_count)
+    if (!S.d_ob_count)
     {
-        CUDA_OK(cudaMalloc(&S.d_mig_count, sizeof(unsigned) * 4));
+        CUDA_OK(cudaMalloc(&S.d_ob_count, sizeof(unsigned) * 4));
         CUDA_OK(cudaMallocHost(&S.h_bin_flags, sizeof(unsigned) * 4));
         CUDA_OK(cudaEventCreateWithFlags(&S.ev_bin, cudaEventDisableTiming));
     }
@@ -622,7 +686,7 @@ int brick_rebuild(mag2d_ctx* c, int s, const Grid3Dev& g)
     unsigned long long total = 0;
     CUDA_OK(cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    if (total >= 0xFFFFFFF0ULL) { mag2d_set_error("brick_rebuild: more than 2^32 slots"); return 1; }
+    if (total >= 0x7FFFFFF0ULL) { mag2d_set_error("brick_rebuild: more than 2^31 slots per species and GPU"); return 1; }
     const long long need = (long long)total;
     if (need > S.capacity)
     {
@@ -639,21 +703,29 @@ int brick_rebuild(mag2d_ctx* c, int s, const Grid3Dev& g)
     k_brick_scatter<<<pblocks, 256, 0, c->stream>>>(g, S.n_slots, P, nby, nbz, S.d_bin_off, S.d_bin_cnt);
     c->launches += 4;
     CUDA_OK(cudaGetLastError());
-    const long long mig_cap = std::max<long long>(need / 4, 4096);
-    if (S.mig_cap < mig_cap)
+    // the outbox takes one step's leavers: an eighth of the slots (a CTA whose leavers do not fit keeps them as guests)
+    const long long ob_cap = std::max<long long>(need / 8, 4096);
+    if (S.ob_cap < ob_cap)
     {
-        cudaFree(S.d_mig_list);
-        S.d_mig_list = nullptr;
-        CUDA_OK(cudaMalloc(&S.d_mig_list, sizeof(uint2) * (size_t)mig_cap));
-        S.mig_cap = mig_cap;
+        for (int a = 0; a < 6; a++)
+        {
+            cudaFree(S.d_outbox[a]);
+            S.d_outbox[a] = nullptr;
+            CUDA_OK(cudaMalloc(&S.d_outbox[a], sizeof(double) * (size_t)ob_cap));
+        }
+        cudaFree(S.d_ob_dst);
+        S.d_ob_dst = nullptr;
+        CUDA_OK(cudaMalloc(&S.d_ob_dst, sizeof(unsigned) * (size_t)ob_cap));
+        S.ob_cap = ob_cap;
     }
-    CUDA_OK(cudaMemsetAsync(S.d_mig_count, 0, sizeof(unsigned) * 4, c->stream));
+    CUDA_OK(cudaMemsetAsync(S.d_ob_count, 0, sizeof(unsigned) * 4, c->stream));
     CUDA_OK(cudaMemsetAsync(S.d_removed, 0, sizeof(unsigned long long), c->stream));
     S.cur ^= 1;
     S.n_slots = need;
     S.bins_valid = true;
     S.bin_flags_pending = false;
     S.bin_overflow_seen = 0;
+    S.pushes_since_compact = 0;
     S.tickets_valid = false;
     S.steps_since_sort = 0;
     S.append_epoch++;
@@ -662,21 +734,41 @@ int brick_rebuild(mag2d_ctx* c, int s, const Grid3Dev& g)
     return 0;
 }
 
-// one step of species s on its binned store: A is the argument block launch_species_advance3d has prepared
-int launch_brick_push(mag2d_ctx* c, int s, const Push3Args& A, bool mcc, bool deposit)
+static void brick_args(const mag2d_ctx* c, SpeciesStore& S, const Push3Args& A, BrickArgs& B)
 {
-    SpeciesStore& S = c->sp[s];
-    BrickArgs B;
+    memset(&B, 0, sizeof(B));
     B.A = A;
     B.bin_off = S.d_bin_off;
     B.bin_cnt = S.d_bin_cnt;
     B.nbx = (A.g.M - 1 + BR - 1) / BR;
     B.nby = (A.g.K - 1 + BR - 1) / BR;
     B.nbz = (A.g.N - 1 + BR - 1) / BR;
-    B.mig_list = S.d_mig_list;
-    B.mig_count = S.d_mig_count;
-    B.mig_cap = (unsigned)S.mig_cap;
-    CUDA_OK(cudaMemsetAsync(S.d_mig_count, 0, sizeof(unsigned), c->stream));
+    for (int a = 0; a < 6; a++) B.ob.arr[a] = S.d_outbox[a];
+    B.ob.dst = S.d_ob_dst;
+    B.ob.count = S.d_ob_count;
+    B.ob.cap = (unsigned)S.ob_cap;
+    (void)c;
+}
+
+// the outbox as a particle view: what k_mcc_collide3d reads for list entries with the high bit set (Push3Args::dst)
+void brick_outbox_view(const SpeciesStore& S, ParticlesDev& v)
+{
+    memset(&v, 0, sizeof(v));
+    v.x = S.d_outbox[0]; v.y = S.d_outbox[1]; v.z = S.d_outbox[2];
+    v.vx = S.d_outbox[3]; v.vy = S.d_outbox[4]; v.vz = S.d_outbox[5];
+    v.n = S.ob_cap;
+}
+
+// one step of species s on its binned store: A is the argument block launch_species_advance3d has prepared.  Every
+// compact_every-th step writes the bins back compacted and cell-sorted; the steps in between store them in place.
+int launch_brick_push(mag2d_ctx* c, int s, const Push3Args& A, bool mcc, bool deposit, int compact_every)
+{
+    SpeciesStore& S = c->sp[s];
+    BrickArgs B;
+    brick_args(c, S, A, B);
+    B.compact = S.pushes_since_compact + 1 >= compact_every ? 1 : 0;
+    S.pushes_since_compact = B.compact ? 0 : S.pushes_since_compact + 1;
+    CUDA_OK(cudaMemsetAsync(S.d_ob_count, 0, sizeof(unsigned), c->stream));
     const int smem = (int)sizeof(BrickSmem);
     static bool attr_set = false;
     if (!attr_set)
@@ -707,40 +799,35 @@ int launch_brick_push(mag2d_ctx* c, int s, const Push3Args& A, bool mcc, bool de
     return 0;
 }
 
-// after the collision pass: move the leavers, and send the overflow counters home (adopted by a later step, no sync)
+// after the collision pass: the outbox empties into the bins, and the overflow counters go home (adopted by a later step, no sync)
 int launch_brick_migrate(mag2d_ctx* c, int s, const Push3Args& A)
 {
     SpeciesStore& S = c->sp[s];
     BrickArgs B;
-    memset(&B, 0, sizeof(B));
-    B.A = A;
-    B.bin_off = S.d_bin_off;
-    B.bin_cnt = S.d_bin_cnt;
-    B.mig_list = S.d_mig_list;
-    B.mig_count = S.d_mig_count;
-    B.mig_cap = (unsigned)S.mig_cap;
-    k_migrate3d<<<148 * 4, 256, 0, c->stream>>>(B);
+    brick_args(c, S, A, B);
+    k_place3d<<<148 * 8, 256, 0, c->stream>>>(B);
     c->launches++;
     CUDA_OK(cudaGetLastError());
     if (!S.bin_flags_pending)
     {
-        CUDA_OK(cudaMemcpyAsync(S.h_bin_flags, S.d_mig_count, sizeof(unsigned) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaMemcpyAsync(S.h_bin_flags, S.d_ob_count, sizeof(unsigned) * 4, cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(cudaEventRecord(S.ev_bin, c->stream));
         S.bin_flags_pending = true;
     }
     return 0;
 }
 
-// a readback of the overflow counters has landed: guests that could not move mean the bins are too tight
+// a readback of the overflow counters has landed: arrivals that found their bin full (or CTAs whose leavers did not fit the
+// outbox) mean the bins are too tight
 void brick_poll_overflow(SpeciesStore& S)
 {
     if (!S.bin_flags_pending || cudaEventQuery(S.ev_bin) != cudaSuccess) return;
     S.bin_flags_pending = false;
-    const unsigned lost_list = S.h_bin_flags[1], full_bins = S.h_bin_flags[2];
-    if (lost_list + full_bins > S.bin_overflow_seen)
+    const unsigned full_bins = S.h_bin_flags[1], no_room = S.h_bin_flags[2];
+    if (no_room + full_bins > S.bin_overflow_seen)
     {
-        if (getenv("MAG3D_BRICK_DEBUG")) fprintf(stderr, "brick: overflow flags list=%u bins=%u (seen %u) -> re-bin with slack %.2f\n", lost_list, full_bins, S.bin_overflow_seen, S.bin_slack * 1.5 + 0.1);
-        S.bin_overflow_seen = lost_list + full_bins;
+        if (getenv("MAG3D_BRICK_DEBUG")) fprintf(stderr, "brick: overflow flags outbox=%u bins=%u (seen %u) -> re-bin with slack %.2f\n", no_room, full_bins, S.bin_overflow_seen, S.bin_slack * 1.5 + 0.1);
+        S.bin_overflow_seen = no_room + full_bins;
         S.bin_slack = std::min(S.bin_slack * 1.5 + 0.1, 4.0);
         S.bins_valid = false;            // re-bin with more slack at the next step
     }

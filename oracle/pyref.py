@@ -72,6 +72,10 @@ def _lib(variant):
     lib.ref_set_field.argtypes = [C.c_void_p, C.c_char_p, dp]
     lib.ref_field_op.argtypes = [C.c_void_p, C.c_char_p]
     lib.ref_field_E.argtypes = [C.c_void_p, C.c_int, dp, dp, C.c_double, dp, dp]
+    lib.ref_species_save.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    lib.ref_species_load.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    lib.ref_field2d_load.argtypes = [C.c_void_p, C.c_char_p, dp, dp, C.c_int]
+    lib.ref_energy_hist.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp]
     lib.ref_source_refresh.argtypes = [C.c_void_p, C.c_int, C.c_uint]
     lib.ref_source.argtypes = [C.c_void_p, C.c_int]
     lib.ref_source_n.argtypes = [C.c_void_p, C.c_int]
@@ -228,6 +232,28 @@ class RefHarness:
     def set_field(self, which, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
         self._chk(self.lib.ref_set_field(self.h, which.encode(), _dp(a)))
+
+    def species_save(self, i, path):
+        """BaseSpecies::save (src/particles.cpp:32-59)"""
+        self._chk(self.lib.ref_species_save(self.h, i, path.encode()))
+
+    def species_load(self, i, path):
+        """BaseSpecies::load (src/particles.cpp:61-93)"""
+        self._chk(self.lib.ref_species_load(self.h, i, path.encode()))
+
+    def field2d_load(self, path, max_values=1 << 22):
+        """Field2D::load (src/Field2D.cpp:46-130) -> dict(M, N, x_min, z_min, x_max, z_max, data)"""
+        info = np.zeros(6)
+        buf = np.zeros(max_values)
+        self._chk(self.lib.ref_field2d_load(self.h, path.encode(), _dp(info), _dp(buf), max_values))
+        M, N = int(info[0]), int(info[1])
+        return dict(M=M, N=N, x_min=info[2], z_min=info[3], x_max=info[4], z_max=info[5], data=buf[:M * N].reshape(M, N).copy())
+
+    def energy_hist(self, i, n_hist=200):
+        """BaseSpecies::energy_dist after reset + energy_dist_compute -> (bins, dict(n_val, mean, mean_tot, norm, min, max))"""
+        out, st = np.zeros(n_hist), np.zeros(6)
+        self._chk(self.lib.ref_energy_hist(self.h, i, n_hist, _dp(out), _dp(st)))
+        return out, dict(n_val=st[0], mean=st[1], mean_tot=st[2], norm=st[3], min=st[4], max=st[5])
 
     def field_op(self, op):
         self._chk(self.lib.ref_field_op(self.h, op.encode()))

@@ -431,6 +431,48 @@ int ref_field_op(void* hv, const char* op)
         else throw std::runtime_error("ref_field_op: unknown op " + w);
     });
 }
+// BaseSpecies::save / load (src/particles.cpp:32-93): the binary checkpoint either side of the path
+int ref_species_save(void* hv, int i, const char* path)
+{
+    Handle* h = (Handle*)hv;
+    return guarded(h, [&] { h->species(i)->save(path); });
+}
+int ref_species_load(void* hv, int i, const char* path)
+{
+    Handle* h = (Handle*)hv;
+    return guarded(h, [&] { h->species(i)->load(path); });
+}
+// Field2D::load (src/Field2D.cpp:46-130) into a scratch Field2D: dimensions, origin, spacing and values of what was read
+int ref_field2d_load(void* hv, const char* path, double* info6, double* values, int max_values)
+{
+    Handle* h = (Handle*)hv;
+    return guarded(h, [&] {
+        Field2D F(2, 2, 1.0, 1.0);
+        F.load(path);
+        info6[0] = F.jmax; info6[1] = F.lmax; info6[2] = F.GetXMin(); info6[3] = F.GetYMin(); info6[4] = F.GetXMax(); info6[5] = F.GetYMax();
+        if (F.jmax * F.lmax > max_values) throw std::runtime_error("ref_field2d_load: buffer too small");
+        for (int a = 0; a < F.jmax; a++) for (int b = 0; b < F.lmax; b++) values[a * F.lmax + b] = F[a][b];
+    });
+}
+// BaseSpecies::energy_dist_compute (src/particles.cpp:408-414) into a fresh Histogram of the species' own shape
+// (particles.hpp:169: 200 bins over [0, E_max)); out = n_hist bins, stats = n_val, mean, mean_tot, norm
+int ref_energy_hist(void* hv, int i, int n_hist, double* out, double* stats)
+{
+    Handle* h = (Handle*)hv;
+    return guarded(h, [&] {
+        BaseSpecies* S = h->species(i);
+        S->energy_dist.reset();
+        S->energy_dist_compute();
+        if (S->energy_dist.N_hist() != n_hist) throw std::runtime_error("ref_energy_hist: bin count differs");
+        for (int k = 0; k < n_hist; k++) out[k] = S->energy_dist[k];
+        stats[0] = S->energy_dist.N_val();
+        stats[1] = S->energy_dist.mean();
+        stats[2] = S->energy_dist.mean_tot();
+        stats[3] = S->energy_dist.norm();
+        stats[4] = S->energy_dist.Min();
+        stats[5] = S->energy_dist.Max();
+    });
+}
 int ref_field_E(void* hv, int n, const double* x, const double* z, double time, double* Ex, double* Ez)
 {
     Handle* h = (Handle*)hv;
