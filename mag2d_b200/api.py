@@ -191,7 +191,15 @@ class Sim:
             # plasma3d.cpp:44-46: the vacuum field of the electrodes is solved once at start-up
             if presolve:
                 self.solve_info["u"] = self.solve(rf=False)
-        elif presolve and not p["electric_field_from_file"]:
+        elif p["electric_field_from_file"]:
+            # Pic ctor: field.u.load(static file); if(rf) field.uRF.load(rf file)  (pic.cpp:154-177).  The reference adopts the
+            # file's own grid; here the file has to carry the grid of config.txt (as the C++ host layer requires too)
+            for which, key in (("u", "electric_field_static_file"),) + ((("uRF", "electric_field_rf_file"),) if p["rf"] else ()):
+                f = cfg.load_field2d(p[key])
+                if (f["M"], f["N"]) != (self.M, self.N) or abs(f["x_min"]) > 1e-9 * p["dx"] or abs(f["z_min"]) > 1e-9 * p["dz"]:
+                    raise Mag2dError("Pic: field file grid differs from x_sampl/z_sampl (regridding is not implemented)")
+                self.set_field(which, f["data"])
+        elif presolve:
             # Pic ctor: boundary_solve_rf(); if(!selfconsistent){ boundary_solve(); reset(); }  (pic.cpp:180-187)
             self.solve_info["uRF"] = self.solve(rf=True)
             if not p["selfconsistent"]:

@@ -300,3 +300,45 @@ def load_magnetic_field(fname):
     if np.isnan(Br).any() or np.isnan(Bz).any():
         raise RuntimeError("Fields::load_magnetic_field() garbage loaded")
     return dict(r_sampl=r_sampl, z_sampl=z_sampl, dr=float(dr), dz=float(dz), r_min=float(r_min), z_min=float(z_min), Br=Br, Bz=Bz)
+
+
+def load_field2d(fname):
+    """Field2D::load (reference src/Field2D.cpp:46-130): rows "x y value" on a regular grid in either order (other
+    lines are skipped) -> dict(M, N, dx, dz, x_min, z_min, data[M][N]); same error texts as the reference"""
+    try:
+        f = open(fname)
+    except OSError:
+        raise RuntimeError("Field2D::load(): failed opening file\n")
+    rows = []
+    with f:
+        for line in f:
+            t = line.split()
+            try:
+                rows.append((float(t[0]), float(t[1]), float(t[2])))
+            except (ValueError, IndexError):
+                continue
+    a = np.array(rows, dtype=np.float64).reshape(-1, 3)
+    n = a.shape[0]
+    if n < 2:
+        raise RuntimeError("Fields::load_magnetic_field() wrong size of input vector")
+
+    def axis(v):
+        lo, hi = v[0], v[-1]
+        nz = np.nonzero(np.diff(v) != 0.0)[0]
+        if nz.size == 0:
+            raise RuntimeError("Fields::load_magnetic_field() wrong size of input vector")
+        d = v[nz[0] + 1] - v[nz[0]]
+        if d < 0:
+            d, lo, hi = -d, v[-1], v[0]
+        return d, lo, _double2int((hi - lo) / d + 1, 1e-1)
+
+    dx, x_min, M = axis(a[:, 0])
+    dz, z_min, N = axis(a[:, 1])
+    if M * N != n:
+        raise RuntimeError("Fields::load_magnetic_field() wrong size of input vector")
+    data = np.full((M, N), np.nan)
+    for k in range(n):
+        data[_double2int((a[k, 0] - x_min) / dx, 1e-1), _double2int((a[k, 1] - z_min) / dz, 1e-1)] = a[k, 2]
+    if np.isnan(data).any():
+        raise RuntimeError("Fields::load_magnetic_field() garbage loaded")
+    return dict(M=M, N=N, dx=float(dx), dz=float(dz), x_min=float(x_min), z_min=float(z_min), data=data)

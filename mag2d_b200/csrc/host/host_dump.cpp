@@ -16,6 +16,19 @@ int main(int argc, char* argv[])
     try
     {
         GetPot cl(argc, argv);
+        const std::string field_file = cl("field2d", "");
+        if (!field_file.empty())
+        {
+            // Field2D::load (src/Field2D.cpp:46-130) alone: dimensions, origin, far corner and the values, row by row
+            Field2D F(2, 2, 1.0, 1.0);
+            F.load(field_file.c_str());
+            std::cout << std::setprecision(17) << "field2d " << F.jmax << " " << F.lmax << " " << F.GetXMin() << " " << F.GetYMin() << " " << F.GetXMax() << " "
+                      << F.GetYMax() << "\nvalues";
+            for (int i = 0; i < F.jmax; i++)
+                for (int j = 0; j < F.lmax; j++) std::cout << " " << F[i][j];
+            std::cout << "\n";
+            return 0;
+        }
         GetPot config(cl("config", "config.txt").c_str());
         Param p(config);
         std::cout << std::setprecision(17);

@@ -149,10 +149,21 @@ class BaseSpecies
         gpu_check(mag2d_energy_hist(gpu, id, energy_dist.N_hist(), energy_dist.Max(), counts.data(), stats));
         energy_dist.add_counts(counts.data(), stats);
     }
+    // this species' charge grid in coulombs, from the device's fixed-point grid: rho = charge * W * 2^-32 (the reference
+    // accumulates charge * weight per particle, Field2D.hpp:45-62; zero unless selfconsistent, particles.hpp:408)
+    void rho_download()
+    {
+        std::vector<int64_t> fixed((size_t)rho.jmax * rho.lmax);
+        gpu_check(mag2d_rho_fixed_download(gpu, id, fixed.data()));
+        for (int i = 0; i < rho.jmax; i++)
+            for (int j = 0; j < rho.lmax; j++) rho[i][j] = charge * ((double)fixed[(size_t)i * rho.lmax + j] * (1.0 / 4294967296.0));
+    }
     void dist_sample()
     {
         energy_dist_compute();
         probe_current_sum += probe_current;
+        rho_download();
+        rhoAverage.add(rho);          // particles.cpp:386-393
         nsampl++;
     }
     void dist_reset()
