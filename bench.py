@@ -232,6 +232,11 @@ def run_workload(wl, args, env, steps, warmup, e2e_steps, with_cpu):
     tmp = tempfile.mkdtemp(prefix="mag2d_bench_")
     d = make_deck(wl, n, world, tmp)
     sim = Sim(d["config"], d["species_conf"], device=local_rank, stream=stream.cuda_stream, seed=1234 + rank)
+    f32 = args.storage == "f32" and wl == args.workload
+    if f32:
+        sim.set_storage("f32")          # before any particle is loaded
+        e2e_steps = 0                   # the streamed step moves the caller's double arrays: fp64 storage only
+    bytes_per = BYTES[wl] / 2 if f32 else BYTES[wl]
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
@@ -321,16 +326,16 @@ def run_workload(wl, args, env, steps, warmup, e2e_steps, with_cpu):
     n_now = sum(sim.count(s)[0] for s in part_species)
     n_push_launches = len(part_species) * (2 if sim.param["rf"] else 1)
     peak, peak_src = measured_peaks()
-    achieved = BYTES[wl] * n_now / (push_ms * 1e-3) / 1e9 if push_ms > 0 else 0.0
-    traffic, traffic_note = measured_traffic(wl, n_now / n_push_launches)
+    achieved = bytes_per * n_now / (push_ms * 1e-3) / 1e9 if push_ms > 0 else 0.0
+    traffic, traffic_note = measured_traffic(wl + ("_f32" if f32 else ""), n_now / n_push_launches)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                 # the same launches on the DRAM bytes ncu saw them move (frac uses the contract's algorithmic bytes)
                 "frac_moved": (traffic * n_push_launches / (push_ms * 1e-3) / 1e9 / peak) if traffic and push_ms > 0 else None,
-                "algorithmic_bytes_per_launch": BYTES[wl] * n_now / n_push_launches,
+                "algorithmic_bytes_per_launch": bytes_per * n_now / n_push_launches,
                 "kernel": "%s (fused gather+push+MCC+boundary+deposit), %d launches/step" % (
                     "k_push3d / k_push3d_brick" if three_d else "k_push_multicoll" if wl == "c1" else "k_push_boris", n_push_launches),
-                "algorithmic_bytes_per_particle_step": BYTES[wl], "push_ms_per_step": push_ms,
+                "algorithmic_bytes_per_particle_step": bytes_per, "push_ms_per_step": push_ms,
                 "peak_source": peak_src}
     extra = {}
     if wl == "c1":
@@ -402,6 +407,7 @@ def run_workload(wl, args, env, steps, warmup, e2e_steps, with_cpu):
             cpu = {"value": None, "unit": "particle-steps/s", "cores": 1, "kind": "unavailable", "sample": repr(ex)}
     rec = {
         "value": value, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+        "dtype": "f32 storage of the particle arrays in HBM, f64 arithmetic" if f32 else "f64",
         "config": {"workload": WORKLOADS[wl], "particles_per_gpu": n, "live_particles": n_live_all,
                    "grid": list(sim.shape),
                    "species": d["species"], "sort_interval": sort_interval, "species_sort_interval": species_sort,
@@ -455,7 +461,7 @@ def bench_ours(args):
             "metric": "particle-steps/sec (push+MCC+deposit, Poisson solve and periodic cell sort inside the step)",
             "value": rec["value"], "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic (device-side Philox loaders, seed 1234)",
+            "dtype": rec["dtype"], "data": "synthetic (device-side Philox loaders, seed 1234)",
         }
         for k in ("config", "gpu_launches", "clocks", "roofline", "ranks_agree", "phases_ms_per_step", "solve", "e2e", "cpu_baseline",
                   "collisions", "fp64", "store"):
@@ -729,6 +735,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-chunk", type=int, default=0, help="slots per chunk of the streamed e2e step (0: the library default, 4 Mi)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--storage", default="f64", choices=["f64", "f32"],
+                    help="element type of the device-resident particle arrays (f32: 2-D Boris workloads; a separate line, never the headline)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C5 record that rides on the C4 line")
     ap.add_argument("--secondary-steps", type=int, default=16)
     args = ap.parse_args()

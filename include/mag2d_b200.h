@@ -214,6 +214,15 @@ int mag2d_set_species_sort_interval(mag2d_ctx* ctx, int species, int steps);
  * CTA per brick: field tile and charge tile in shared memory, leavers migrate between bins every step; push3d_brick.cu),
  * MAG2D_LAYOUT_SLOTS keeps the slot-order kernel with the fused COUNT / PERMUTE cell sort.  2-D stores ignore it.  No reference
  * counterpart: the reference's vector<t_particle> has no order (src/particles.hpp:223-247). */
+/* Element type of the device-resident particle arrays (north_star: "vectorised coalesced fp64/fp32 loads"; the reference's
+ * t_particle is all double, src/particles.hpp:26-33).  MAG2D_STORE_F32 keeps x, z, vx, vy, vz as floats in HBM (40 instead of 80 bytes
+ * per 2D3V particle-step); every operation is still carried out in fp64 on the widened values, positions are rounded to float BEFORE the
+ * boundary test and the deposit, so the charge grid is the exact fixed-point deposit of the stored positions.  Host-side interfaces
+ * (mag2d_particle, the SoA arrays) stay double.  2-D Boris movers; set it before any particle is loaded.  Not available with the
+ * multi-collision mover, CARTESIAN3D, the particle source, mag2d_step_streamed and particle-partner collisions. */
+#define MAG2D_STORE_F64 0
+#define MAG2D_STORE_F32 1
+int mag2d_set_storage(mag2d_ctx* ctx, int storage);
 #define MAG2D_LAYOUT_AUTO 0
 #define MAG2D_LAYOUT_SLOTS 1
 #define MAG2D_LAYOUT_BRICKS 2

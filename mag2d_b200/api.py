@@ -112,6 +112,7 @@ def lib():
     L.mag2d_step_streamed3.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), i64p] + [C.POINTER(dp)] * 6 + [C.c_int64]
     L.mag2d_set_species_sort_interval.argtypes = [vp, C.c_int, C.c_int]
     L.mag2d_set_store_layout.argtypes = [vp, C.c_int]
+    L.mag2d_set_storage.argtypes = [vp, C.c_int]
     L.mag2d_store_stats.argtypes = [vp, C.c_int, i64p]
     L.mag2d_advance_init.argtypes = [vp]
     L.mag2d_step.argtypes = [vp, C.c_int]
@@ -360,6 +361,10 @@ class Sim:
             self._chk(self.L.mag2d_set_sort_interval(self.h, steps))
         else:
             self._chk(self.L.mag2d_set_species_sort_interval(self.h, species, steps))
+
+    def set_storage(self, dtype):
+        """'f64' (default) or 'f32': element type of the device-resident particle arrays (2-D Boris movers; before any particle is loaded)"""
+        self._chk(self.L.mag2d_set_storage(self.h, {"f64": 0, "f32": 1}[dtype]))
 
     def set_store_layout(self, layout):
         """'auto' / 'bricks': CARTESIAN3D stores are binned by 4 x 4 x 4-cell brick inside advance(); 'slots': slot order + fused cell sort"""

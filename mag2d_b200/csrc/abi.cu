@@ -26,12 +26,13 @@ namespace {
 
 size_t grid_n(const mag2d_ctx* c) { return grid_nodes(c); }
 
+template <typename T>
 __global__ void k_count_alive(const double* __restrict__ x, long long n, unsigned long long* __restrict__ out2)
 {
     // out2[0] = live particles, out2[1] = 1 + highest live slot
     unsigned long long cnt = 0, hi = 0;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
-        if (particle_alive(x[k])) { cnt++; hi = (unsigned long long)k + 1; }
+        if (particle_alive(pld<T>(x, k))) { cnt++; hi = (unsigned long long)k + 1; }
     for (int o = 16; o > 0; o >>= 1)
     {
         cnt += __shfl_xor_sync(MAG2D_FULL_MASK, cnt, o);
@@ -123,7 +124,7 @@ int ensure_capacity(mag2d_ctx* c, SpeciesStore& S, long long need)
     for (int a = 0; a < N_ARR; a++)
     {
         if (!needs_array(c, a)) continue;
-        if (cudaMalloc(&fresh[a], sizeof(double) * (size_t)cap) != cudaSuccess)
+        if (cudaMalloc(&fresh[a], c->elem_size() * (size_t)cap) != cudaSuccess)
         {
             cudaGetLastError();
             for (int b = 0; b < N_ARR; b++)
@@ -134,7 +135,7 @@ int ensure_capacity(mag2d_ctx* c, SpeciesStore& S, long long need)
     }
     for (int a = 0; a < N_ARR; a++)
         if (fresh[a] && S.arr[S.cur][a] && S.n_slots > 0)
-            CUDA_OK(cudaMemcpyAsync(fresh[a], S.arr[S.cur][a], sizeof(double) * (size_t)S.n_slots, cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_OK(cudaMemcpyAsync(fresh[a], S.arr[S.cur][a], c->elem_size() * (size_t)S.n_slots, cudaMemcpyDeviceToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     for (int a = 0; a < N_ARR; a++)
     {
@@ -163,6 +164,11 @@ int refresh_pools(mag2d_ctx* c, int s)
         PoolDev want;
         memset(&want, 0, sizeof(want));
         const int pool = T.n_slots > 0 ? 1 : 0;   // speclist[k]->particles.size() == 0 -> continuum (particles.cpp:230)
+        if (pool && c->store_f32 && S.h_blob->t[k].n_inter > 0)
+        {
+            mag2d_set_error("fp32 particle storage: collisions with particle partners are not implemented (the partner pools are read as doubles)");
+            return 1;
+        }
         if (pool)
         {
             want.x = T.arr[T.cur][ARR_X];
@@ -236,6 +242,7 @@ int species_source(mag2d_ctx* c, int s, long long* injected)
     SpeciesStore& S = c->sp[s];
     if (injected) *injected = 0;
     if (S.src_n == 0) return 0;
+    if (c->store_f32) { mag2d_set_error("mag2d_species_source: fp64 particle storage only"); return 1; }
     if (c->g.coord != MAG2D_CARTESIAN || c->g.mover != MAG2D_ADVANCE_BORIS)
     {
         // Species<CYLINDRICAL>::source is declared but never defined in the reference (it does not link)
@@ -262,7 +269,7 @@ int store_alloc_slab(mag2d_ctx* c, SpeciesStore& S, int slab, long long capacity
     {
         if (!needs_array(c, a)) continue;
         if (S.arr[slab][a]) { cudaFree(S.arr[slab][a]); S.arr[slab][a] = nullptr; }
-        CUDA_OK(cudaMalloc(&S.arr[slab][a], sizeof(double) * (size_t)capacity));
+        CUDA_OK(cudaMalloc(&S.arr[slab][a], c->elem_size() * (size_t)capacity));
     }
     S.capacity = capacity;
     return 0;
@@ -832,10 +839,25 @@ int mag2d_particles_upload_soa(mag2d_ctx* c, int s, int64_t n, const double* x, 
     SpeciesStore& S = c->sp[s];
     if (ensure_capacity(c, S, S.n_slots + n)) return 1;
     const double* src[N_ARR] = {x, z, vx, vy, vz, y, ttd};
+    std::vector<float> narrow;
     for (int a = 0; a < N_ARR; a++)
     {
         double* dst = S.arr[S.cur][a];
         if (!dst) continue;
+        if (c->store_f32)
+        {
+            // fp32 storage: the host arrays stay double (the interface of the reference's t_particle), rounded here
+            float* dstf = reinterpret_cast<float*>(dst) + S.n_slots;
+            if (src[a])
+            {
+                narrow.resize((size_t)n);
+                for (int64_t k = 0; k < n; k++) narrow[(size_t)k] = (float)src[a][k];
+                CUDA_OK(cudaMemcpyAsync(dstf, narrow.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+                CUDA_OK(cudaStreamSynchronize(c->stream));
+            }
+            else CUDA_OK(cudaMemsetAsync(dstf, 0, sizeof(float) * (size_t)n, c->stream));
+            continue;
+        }
         if (src[a]) CUDA_OK(cudaMemcpyAsync(dst + S.n_slots, src[a], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
         else CUDA_OK(cudaMemsetAsync(dst + S.n_slots, 0, sizeof(double) * (size_t)n, c->stream));
     }
@@ -870,11 +892,19 @@ int mag2d_particles_download_soa(mag2d_ctx* c, int s, int64_t capacity, double* 
     if (S.n_slots == 0) return 0;
     if (capacity < S.n_slots) { mag2d_set_error("mag2d_particles_download_soa: buffer too small"); return 1; }
     double* dst[N_ARR] = {x, z, vx, vy, vz, y, ttd};
+    std::vector<float> narrow;
     for (int a = 0; a < N_ARR; a++)
     {
         if (!dst[a]) continue;
         const double* src = S.arr[S.cur][a];
-        if (src) CUDA_OK(cudaMemcpyAsync(dst[a], src, sizeof(double) * (size_t)S.n_slots, cudaMemcpyDeviceToHost, c->stream));
+        if (src && c->store_f32)
+        {
+            narrow.resize((size_t)S.n_slots);
+            CUDA_OK(cudaMemcpyAsync(narrow.data(), src, sizeof(float) * (size_t)S.n_slots, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_OK(cudaStreamSynchronize(c->stream));
+            for (long long k = 0; k < S.n_slots; k++) dst[a][k] = (double)narrow[(size_t)k];
+        }
+        else if (src) CUDA_OK(cudaMemcpyAsync(dst[a], src, sizeof(double) * (size_t)S.n_slots, cudaMemcpyDeviceToHost, c->stream));
         else memset(dst[a], 0, sizeof(double) * (size_t)S.n_slots);
     }
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -909,7 +939,8 @@ int mag2d_count(mag2d_ctx* c, int s, int64_t* n_alive, int64_t* n_slots)
         unsigned long long* d = reinterpret_cast<unsigned long long*>(c->d_scratch + 8);
         CUDA_OK(cudaMemsetAsync(d, 0, sizeof(h), c->stream));
         const unsigned blocks = (unsigned)std::min<long long>((S.n_slots + 255) / 256, 148 * 16);
-        k_count_alive<<<blocks, 256, 0, c->stream>>>(S.arr[S.cur][ARR_X], S.n_slots, d);
+        if (c->store_f32) k_count_alive<float><<<blocks, 256, 0, c->stream>>>(S.arr[S.cur][ARR_X], S.n_slots, d);
+        else k_count_alive<double><<<blocks, 256, 0, c->stream>>>(S.arr[S.cur][ARR_X], S.n_slots, d);
         c->launches++;
         CUDA_OK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -1038,6 +1069,21 @@ int mag2d_set_sort_interval(mag2d_ctx* c, int steps)
 {
     CHECK_CTX(c);
     c->sort_interval = steps;
+    return 0;
+}
+
+int mag2d_set_storage(mag2d_ctx* c, int storage)
+{
+    CHECK_CTX(c);
+    if (storage != MAG2D_STORE_F64 && storage != MAG2D_STORE_F32) { mag2d_set_error("mag2d_set_storage: unknown storage type"); return 1; }
+    if (storage == MAG2D_STORE_F32 && (is3d(c) || c->g.mover != MAG2D_ADVANCE_BORIS))
+    {
+        mag2d_set_error("mag2d_set_storage: fp32 particle storage is implemented for the 2-D Boris movers");
+        return 1;
+    }
+    for (const SpeciesStore& S : c->sp)
+        if (S.capacity > 0 || S.n_slots > 0) { mag2d_set_error("mag2d_set_storage: set the storage type before any particle is loaded"); return 1; }
+    c->store_f32 = storage == MAG2D_STORE_F32;
     return 0;
 }
 
@@ -1260,6 +1306,7 @@ static int step_streamed_impl(mag2d_ctx* c, int n_sp, const int32_t* species, co
 {
     const bool three_d = is3d(c);
     const int n_arr = three_d ? 6 : 5;
+    if (c->store_f32) { mag2d_set_error("mag2d_step_streamed: fp64 particle storage only (the host arrays are double)"); return 1; }
     if (chunk_slots <= 0) chunk_slots = 1 << 22;
     chunk_slots = (chunk_slots + 1023) / 1024 * 1024;
     if (!c->s_h2d)

@@ -85,6 +85,28 @@ struct ParticlesDev
     long long n;                // slots in use
 };
 
+// Element access of the particle arrays in their STORAGE type T: double, or float in the fp32 storage mode
+// (mag2d_set_storage; the arithmetic stays fp64, only what lives in HBM is rounded: 40 instead of 80 bytes per 2D3V
+// particle-step).  The array pointers keep the type double* everywhere; T says how the bytes behind them are laid out.
+template <typename T> __device__ __forceinline__ double pld(const double* base, long long k) { return (double)reinterpret_cast<const T*>(base)[k]; }
+template <typename T> __device__ __forceinline__ void pst(double* base, long long k, double v) { reinterpret_cast<T*>(base)[k] = (T)v; }
+template <typename T> __device__ __forceinline__ double2 pld2(const double* base, long long k);      // k even: one 128-bit / 64-bit load
+template <> __device__ __forceinline__ double2 pld2<double>(const double* base, long long k) { return *reinterpret_cast<const double2*>(base + k); }
+template <> __device__ __forceinline__ double2 pld2<float>(const double* base, long long k)
+{
+    const float2 f = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(base) + k);
+    return make_double2((double)f.x, (double)f.y);
+}
+template <typename T> __device__ __forceinline__ void pst2(double* base, long long k, double a, double b);
+template <> __device__ __forceinline__ void pst2<double>(double* base, long long k, double a, double b) { *reinterpret_cast<double2*>(base + k) = make_double2(a, b); }
+template <> __device__ __forceinline__ void pst2<float>(double* base, long long k, double a, double b)
+{
+    *reinterpret_cast<float2*>(reinterpret_cast<float*>(base) + k) = make_float2((float)a, (float)b);
+}
+// what a value becomes once it is stored (identity for double): positions are rounded BEFORE the boundary test and the
+// deposit, so that the charge grid is the exact fixed-point deposit of the stored positions
+template <typename T> __device__ __forceinline__ double stored(double v) { return (double)(T)v; }
+
 // A removed particle keeps its slot until the next sort; it is marked by x = NaN.
 __device__ __forceinline__ bool particle_alive(double x) { return x == x; }
 __device__ __forceinline__ double dead_marker() { return __longlong_as_double(0x7ff8000000000000LL); }

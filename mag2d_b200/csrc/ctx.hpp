@@ -175,6 +175,8 @@ struct mag2d_ctx
     int sort_interval = 0;
     bool use_source = false;      // Param::use_source: mag2d_step calls Species::source() after every advance (pic.cpp:346-347)
     int store_layout = MAG2D_LAYOUT_AUTO;   // mag2d_set_store_layout
+    bool store_f32 = false;                 // mag2d_set_storage: the particle arrays hold floats (2-D Boris movers; arithmetic stays fp64)
+    size_t elem_size() const { return store_f32 ? sizeof(float) : sizeof(double); }
     bool fused_sort = true;       // cell sort carried by the Boris push itself (MAG2D_FUSED_SORT=0: stand-alone passes)
     bool count_collisions = false;
 

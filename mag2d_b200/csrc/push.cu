@@ -310,7 +310,7 @@ constexpr int DEPOSIT_RUNS = MAG2D_DEPOSIT_RUNS;   // cells per warp call that g
 #ifndef MAG2D_SORT_MIN_BLOCKS
 #define MAG2D_SORT_MIN_BLOCKS MAG2D_PUSH_MIN_BLOCKS
 #endif
-template <int COORD, bool GATHER, int BMODE, bool MCC, bool DEPOSIT, bool SORTING>
+template <int COORD, bool GATHER, int BMODE, bool MCC, bool DEPOSIT, bool SORTING, typename T>
 __global__ void __launch_bounds__(PUSH_THREADS, SORTING ? MAG2D_SORT_MIN_BLOCKS : MAG2D_PUSH_MIN_BLOCKS) k_push_boris(const __grid_constant__ PushArgs A)
 {
     const unsigned lane = lane_id();
@@ -336,16 +336,16 @@ __global__ void __launch_bounds__(PUSH_THREADS, SORTING ? MAG2D_SORT_MIN_BLOCKS 
         const long long k = base + 64 * p;
         double x[2], z[2], vx[2], vz[2], vy[2];
         {
-            const double2 a = *reinterpret_cast<const double2*>(A.p.x + k);
-            const double2 b = *reinterpret_cast<const double2*>(A.p.z + k);
-            const double2 c = *reinterpret_cast<const double2*>(A.p.vx + k);
-            const double2 d = *reinterpret_cast<const double2*>(A.p.vz + k);
+            const double2 a = pld2<T>(A.p.x, k);
+            const double2 b = pld2<T>(A.p.z, k);
+            const double2 c = pld2<T>(A.p.vx, k);
+            const double2 d = pld2<T>(A.p.vz, k);
             x[0] = a.x; x[1] = a.y; z[0] = b.x; z[1] = b.y;
             vx[0] = c.x; vx[1] = c.y; vz[0] = d.x; vz[1] = d.y;
             vy[0] = vy[1] = 0.0;
             if (need_vy || permute)
             {
-                const double2 e = *reinterpret_cast<const double2*>(A.p.vy + k);
+                const double2 e = pld2<T>(A.p.vy, k);
                 vy[0] = e.x; vy[1] = e.y;
             }
         }
@@ -397,6 +397,12 @@ __global__ void __launch_bounds__(PUSH_THREADS, SORTING ? MAG2D_SORT_MIN_BLOCKS 
                 x[e] += vx[e] * dt;
                 z[e] += vz[e] * dt;
             }
+            if (sizeof(T) == 4)
+            {
+                // fp32 storage: the boundary test, the cell and the deposit see the position as it will be stored
+                x[e] = stored<T>(x[e]);
+                z[e] = stored<T>(z[e]);
+            }
             const bool inside = boundary_weights<DEPOSIT>(A.g, x[e], z[e], node[e], w[e], SORTING ? &row[e] : nullptr);
             keep[e] = live && inside;
             removed += (live && !inside) ? 1u : 0u;
@@ -415,20 +421,20 @@ __global__ void __launch_bounds__(PUSH_THREADS, SORTING ? MAG2D_SORT_MIN_BLOCKS 
             {
                 const long long d = dest[2 * p + e];
                 if (d < 0) continue;
-                A.dst.x[d] = x[e];
-                A.dst.z[d] = z[e];
-                A.dst.vx[d] = vx[e];
-                A.dst.vz[d] = vz[e];
-                A.dst.vy[d] = vy[e];
+                pst<T>(A.dst.x, d, x[e]);
+                pst<T>(A.dst.z, d, z[e]);
+                pst<T>(A.dst.vx, d, vx[e]);
+                pst<T>(A.dst.vz, d, vz[e]);
+                pst<T>(A.dst.vy, d, vy[e]);
             }
         }
         else
         {
-            *reinterpret_cast<double2*>(A.p.x + k) = make_double2(x[0], x[1]);
-            *reinterpret_cast<double2*>(A.p.z + k) = make_double2(z[0], z[1]);
-            *reinterpret_cast<double2*>(A.p.vx + k) = make_double2(vx[0], vx[1]);
-            *reinterpret_cast<double2*>(A.p.vz + k) = make_double2(vz[0], vz[1]);
-            if (need_vy) *reinterpret_cast<double2*>(A.p.vy + k) = make_double2(vy[0], vy[1]);
+            pst2<T>(A.p.x, k, x[0], x[1]);
+            pst2<T>(A.p.z, k, z[0], z[1]);
+            pst2<T>(A.p.vx, k, vx[0], vx[1]);
+            pst2<T>(A.p.vz, k, vz[0], vz[1]);
+            if (need_vy) pst2<T>(A.p.vy, k, vy[0], vy[1]);
         }
         if (count)
         {
@@ -726,13 +732,14 @@ __global__ void __launch_bounds__(PUSH_THREADS, MAG2D_TMA_CTAS_PER_SM) k_push_bo
 #endif  // MAG2D_WITH_TMA_PUSH
 
 // second pass of the Boris movers: BaseSpecies::scatter for the slots whose Bernoulli test fired
+template <typename T>
 __global__ void __launch_bounds__(128) k_mcc_collide(const __grid_constant__ PushArgs A)
 {
     const unsigned n = *A.coll_count;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
     {
         const long long k = A.coll_list[q];
-        double vx = A.p.vx[k], vy = A.p.vy[k], vz = A.p.vz[k];
+        double vx = pld<T>(A.p.vx, k), vy = pld<T>(A.p.vy, k), vz = pld<T>(A.p.vz, k);
         Rng rng = make_rng(A.seed, A.s.species, A.s.step, (unsigned long long)k);
         rng.draw = 1;     // block 0 was consumed by the Bernoulli test
         int target;
@@ -740,23 +747,23 @@ __global__ void __launch_bounds__(128) k_mcc_collide(const __grid_constant__ Pus
         mcc_count(A.counts, A.mcc->n_targets, target, proc);
         if (proc >= 0)
         {
-            A.p.vx[k] = vx;
-            A.p.vy[k] = vy;
-            A.p.vz[k] = vz;
+            pst<T>(A.p.vx, k, vx);
+            pst<T>(A.p.vy, k, vy);
+            pst<T>(A.p.vz, k, vz);
         }
     }
 }
 
 // ---- half step back: Species<D>::advance_boris_init ----------------------------------------------
-template <int COORD, bool GATHER>
+template <int COORD, bool GATHER, typename T>
 __global__ void __launch_bounds__(PUSH_THREADS) k_push_boris_init(const __grid_constant__ PushArgs A)
 {
     const long long k = (long long)blockIdx.x * PUSH_THREADS + threadIdx.x;
     if (k >= A.p.n) return;
-    const double x = A.p.x[k];
+    const double x = pld<T>(A.p.x, k);
     if (!particle_alive(x)) return;
-    const double z = A.p.z[k];
-    double vx = A.p.vx[k], vy = A.p.vy[k], vz = A.p.vz[k];
+    const double z = pld<T>(A.p.z, k);
+    double vx = pld<T>(A.p.vx, k), vy = pld<T>(A.p.vy, k), vz = pld<T>(A.p.vz, k);
     double Ex = 0.0, Ez = A.g.extern_field;
     if (GATHER) gather_E(A.g, x, z, Ex, Ez);
     // A.s holds the init constants: t = B*(-0.5*q*dt/(2m)), hq = (-q/m*dt)/2  (particles.cpp:1010,1028)
@@ -765,9 +772,9 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push_boris_init(const __grid_c
     else boris_rotate<COORD>(s.tx, s.ty, s.tz, s.sx, s.sy, s.sz, vx, vy, vz);
     vx += Ex * s.hq;
     vz += Ez * s.hq;
-    A.p.vx[k] = vx;
-    A.p.vy[k] = vy;
-    A.p.vz[k] = vz;
+    pst<T>(A.p.vx, k, vx);
+    pst<T>(A.p.vy, k, vy);
+    pst<T>(A.p.vz, k, vz);
 }
 
 // ---- multi-collision free-flight mover: Species<CARTESIAN>::advance_multicoll ---------------------
@@ -837,16 +844,17 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push_multicoll(const __grid_co
 }
 
 // ---- Species<D>::accumulate: deposit the current positions ----------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(PUSH_THREADS) k_accumulate(const __grid_constant__ PushArgs A)
 {
     const long long k = (long long)blockIdx.x * PUSH_THREADS + threadIdx.x;
-    double x = k < A.p.n ? A.p.x[k] : dead_marker();
+    double x = k < A.p.n ? pld<T>(A.p.x, k) : dead_marker();
     bool valid = particle_alive(x);
     unsigned node = 0;
     unsigned long long w[4] = {0, 0, 0, 0};
     if (valid)
     {
-        double z = A.p.z[k];
+        double z = pld<T>(A.p.z, k);
         GridDev g = A.g;
         g.check_mask = 0;
         g.boundary = MAG2D_BOUNDARY_PERIODIC;   // never drop here: accumulate() deposits every live particle
@@ -1052,6 +1060,7 @@ struct GenArgs
     int has_ttd;
 };
 
+template <typename T>
 __global__ void __launch_bounds__(PUSH_THREADS) k_generate(const __grid_constant__ GenArgs G)
 {
     const long long q = (long long)blockIdx.x * PUSH_THREADS + threadIdx.x;
@@ -1103,21 +1112,24 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_generate(const __grid_constant
         vy = (double)n1 * G.vth;
         vz = (double)n2 * G.vth;
     }
+    x = stored<T>(x);
+    z = stored<T>(z);
     const bool inside = x >= 0.0 && x <= G.x_max && z >= 0.0 && z <= G.z_max;
-    G.p.x[k] = inside ? x : dead_marker();
-    G.p.z[k] = z;
-    G.p.vx[k] = vx;
-    G.p.vy[k] = vy;
-    G.p.vz[k] = vz;
-    if (G.p.y) G.p.y[k] = y;
+    pst<T>(G.p.x, k, inside ? x : dead_marker());
+    pst<T>(G.p.z, k, z);
+    pst<T>(G.p.vx, k, vx);
+    pst<T>(G.p.vy, k, vy);
+    pst<T>(G.p.vz, k, vz);
+    if (G.p.y) pst<T>(G.p.y, k, y);
     if (G.has_ttd)
     {
         const uint4 r = rng.block();
-        G.p.ttd[k] = G.kind == 0 ? G.lifetime * rexp1(r.x) : 0.0;   // on_disk leaves time_to_death = 0
+        pst<T>(G.p.ttd, k, G.kind == 0 ? G.lifetime * rexp1(r.x) : 0.0);   // on_disk leaves time_to_death = 0
     }
 }
 
 // ---- energy histogram: BaseSpecies::energy_dist_compute + Histogram::add (strict bounds) ----------
+template <typename T>
 __global__ void __launch_bounds__(PUSH_THREADS) k_energy_hist(ParticlesDev p, double half_m_over_qe, int nbins, double emax,
                                                                unsigned long long* __restrict__ hist, double* __restrict__ sums)
 {
@@ -1128,8 +1140,8 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_energy_hist(ParticlesDev p, do
     unsigned long long n_in = 0, n_tot = 0;
     for (long long k = (long long)blockIdx.x * PUSH_THREADS + threadIdx.x; k < p.n; k += (long long)gridDim.x * PUSH_THREADS)
     {
-        if (!particle_alive(p.x[k])) continue;
-        const double vx = p.vx[k], vy = p.vy[k], vz = p.vz[k];
+        if (!particle_alive(pld<T>(p.x, k))) continue;
+        const double vx = pld<T>(p.vx, k), vy = pld<T>(p.vy, k), vz = pld<T>(p.vz, k);
         const double f = (vx * vx + vz * vz + vy * vy) * half_m_over_qe;
         if (f < emax && f > 0.0)
         {
@@ -1163,6 +1175,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_energy_hist(ParticlesDev p, do
 }
 
 // ---- AoS (reference t_particle, 64 B) <-> SoA converters ------------------------------------------
+template <typename T>
 __global__ void k_aos_to_soa(const mag2d_particle* __restrict__ aos, long long n_in, ParticlesDev p, long long first,
                              int has_y, int has_ttd)
 {
@@ -1171,36 +1184,38 @@ __global__ void k_aos_to_soa(const mag2d_particle* __restrict__ aos, long long n
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_in || aos[q].empty) return;
     const long long dst = first + q;
-    p.x[dst] = aos[q].x;
-    p.z[dst] = aos[q].z;
-    p.vx[dst] = aos[q].vx;
-    p.vy[dst] = aos[q].vy;
-    p.vz[dst] = aos[q].vz;
-    if (has_y) p.y[dst] = aos[q].y;
-    if (has_ttd) p.ttd[dst] = aos[q].time_to_death;
+    pst<T>(p.x, dst, aos[q].x);
+    pst<T>(p.z, dst, aos[q].z);
+    pst<T>(p.vx, dst, aos[q].vx);
+    pst<T>(p.vy, dst, aos[q].vy);
+    pst<T>(p.vz, dst, aos[q].vz);
+    if (has_y) pst<T>(p.y, dst, aos[q].y);
+    if (has_ttd) pst<T>(p.ttd, dst, aos[q].time_to_death);
 }
 
+template <typename T>
 __global__ void k_mark_dead(ParticlesDev p, const mag2d_particle* __restrict__ aos, long long n_in, long long first)
 {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < n_in && aos[q].empty) p.x[first + q] = dead_marker();
+    if (q < n_in && aos[q].empty) pst<T>(p.x, first + q, dead_marker());
 }
 
+template <typename T>
 __global__ void k_soa_to_aos(ParticlesDev p, mag2d_particle* __restrict__ aos, int has_y, int has_ttd)
 {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= p.n) return;
     mag2d_particle o;
     memset(&o, 0, sizeof(o));
-    const double x = p.x[q];
+    const double x = pld<T>(p.x, q);
     o.empty = particle_alive(x) ? 0 : 1;
     o.x = x;
-    o.z = p.z[q];
-    o.vx = p.vx[q];
-    o.vy = p.vy[q];
-    o.vz = p.vz[q];
-    o.y = has_y ? p.y[q] : 0.0;
-    o.time_to_death = has_ttd ? p.ttd[q] : 0.0;
+    o.z = pld<T>(p.z, q);
+    o.vx = pld<T>(p.vx, q);
+    o.vy = pld<T>(p.vy, q);
+    o.vz = pld<T>(p.vz, q);
+    o.y = has_y ? pld<T>(p.y, q) : 0.0;
+    o.time_to_death = has_ttd ? pld<T>(p.ttd, q) : 0.0;
     aos[q] = o;
 }
 
@@ -1295,29 +1310,43 @@ SpeciesDev species_view(const mag2d_ctx* c, int s, bool init)
     return v;
 }
 
-template <int COORD, bool SORTING, bool G, int B>
+// storage type of a species' particle arrays: T = float in the fp32 storage mode (mag2d_set_storage), else double
+#define DISPATCH_STORE(f32, ...)                 \
+    do {                                         \
+        if (f32) { using T = float; __VA_ARGS__; } \
+        else { using T = double; __VA_ARGS__; }  \
+    } while (0)
+
+template <int COORD, bool SORTING, bool G, int B, typename T>
 void launch_boris_gb(mag2d_ctx* c, const PushArgs& A, bool mcc, bool deposit, unsigned blocks)
 {
-#define LAUNCH(Mc, D) k_push_boris<COORD, G, B, Mc, D, SORTING><<<blocks, PUSH_THREADS, 0, c->stream>>>(A)
+#define LAUNCH(Mc, D) k_push_boris<COORD, G, B, Mc, D, SORTING, T><<<blocks, PUSH_THREADS, 0, c->stream>>>(A)
     if (mcc) { if (deposit) LAUNCH(true, true); else LAUNCH(true, false); }
     else { if (deposit) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
 }
 
-template <int COORD, bool SORTING>
-int launch_boris_variant(mag2d_ctx* c, const PushArgs& A, bool gather, int bmode, bool mcc, bool deposit, unsigned blocks)
+template <int COORD, bool SORTING, typename T>
+int launch_boris_variant_t(mag2d_ctx* c, const PushArgs& A, bool gather, int bmode, bool mcc, bool deposit, unsigned blocks)
 {
     switch ((gather ? 3 : 0) + bmode)
     {
-        case 0: launch_boris_gb<COORD, SORTING, false, B_NONE>(c, A, mcc, deposit, blocks); break;
-        case 1: launch_boris_gb<COORD, SORTING, false, B_CONST>(c, A, mcc, deposit, blocks); break;
-        case 2: launch_boris_gb<COORD, SORTING, false, B_TABLE>(c, A, mcc, deposit, blocks); break;
-        case 3: launch_boris_gb<COORD, SORTING, true, B_NONE>(c, A, mcc, deposit, blocks); break;
-        case 4: launch_boris_gb<COORD, SORTING, true, B_CONST>(c, A, mcc, deposit, blocks); break;
-        default: launch_boris_gb<COORD, SORTING, true, B_TABLE>(c, A, mcc, deposit, blocks); break;
+        case 0: launch_boris_gb<COORD, SORTING, false, B_NONE, T>(c, A, mcc, deposit, blocks); break;
+        case 1: launch_boris_gb<COORD, SORTING, false, B_CONST, T>(c, A, mcc, deposit, blocks); break;
+        case 2: launch_boris_gb<COORD, SORTING, false, B_TABLE, T>(c, A, mcc, deposit, blocks); break;
+        case 3: launch_boris_gb<COORD, SORTING, true, B_NONE, T>(c, A, mcc, deposit, blocks); break;
+        case 4: launch_boris_gb<COORD, SORTING, true, B_CONST, T>(c, A, mcc, deposit, blocks); break;
+        default: launch_boris_gb<COORD, SORTING, true, B_TABLE, T>(c, A, mcc, deposit, blocks); break;
     }
     c->launches++;
     return 0;
+}
+
+template <int COORD, bool SORTING>
+int launch_boris_variant(mag2d_ctx* c, const PushArgs& A, bool gather, int bmode, bool mcc, bool deposit, unsigned blocks)
+{
+    if (c->store_f32) return launch_boris_variant_t<COORD, SORTING, float>(c, A, gather, bmode, mcc, deposit, blocks);
+    return launch_boris_variant_t<COORD, SORTING, double>(c, A, gather, bmode, mcc, deposit, blocks);
 }
 
 }  // namespace
@@ -1480,7 +1509,7 @@ int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
                 launch_boris_variant<MAG2D_CARTESIAN, false>(c, A, gather, bmode, mcc, d.selfconsistent != 0, tile_blocks);
             if (mcc)
             {
-                k_mcc_collide<<<148 * 8, 128, 0, c->stream>>>(A);
+                DISPATCH_STORE(c->store_f32, k_mcc_collide<T><<<148 * 8, 128, 0, c->stream>>>(A));
                 c->launches++;
             }
         }
@@ -1520,13 +1549,13 @@ int launch_species_advance_init(mag2d_ctx* c, int s)
         if (update_ueff(c, d.rf ? rf_phase(c, S) : 0.0, d.rf != 0)) return 1;
     if (d.coord == MAG2D_CYLINDRICAL)
     {
-        if (gather) k_push_boris_init<MAG2D_CYLINDRICAL, true><<<blocks, PUSH_THREADS, 0, c->stream>>>(A);
-        else k_push_boris_init<MAG2D_CYLINDRICAL, false><<<blocks, PUSH_THREADS, 0, c->stream>>>(A);
+        if (gather) DISPATCH_STORE(c->store_f32, k_push_boris_init<MAG2D_CYLINDRICAL, true, T><<<blocks, PUSH_THREADS, 0, c->stream>>>(A));
+        else DISPATCH_STORE(c->store_f32, k_push_boris_init<MAG2D_CYLINDRICAL, false, T><<<blocks, PUSH_THREADS, 0, c->stream>>>(A));
     }
     else
     {
-        if (gather) k_push_boris_init<MAG2D_CARTESIAN, true><<<blocks, PUSH_THREADS, 0, c->stream>>>(A);
-        else k_push_boris_init<MAG2D_CARTESIAN, false><<<blocks, PUSH_THREADS, 0, c->stream>>>(A);
+        if (gather) DISPATCH_STORE(c->store_f32, k_push_boris_init<MAG2D_CARTESIAN, true, T><<<blocks, PUSH_THREADS, 0, c->stream>>>(A));
+        else DISPATCH_STORE(c->store_f32, k_push_boris_init<MAG2D_CARTESIAN, false, T><<<blocks, PUSH_THREADS, 0, c->stream>>>(A));
     }
     c->launches++;
     CUDA_OK(cudaGetLastError());
@@ -1542,7 +1571,7 @@ int launch_species_accumulate(mag2d_ctx* c, int s)
     A.g = grid_view(c, s);
     A.p = particles_view(S);
     const unsigned blocks = (unsigned)((S.n_slots + PUSH_THREADS - 1) / PUSH_THREADS);
-    k_accumulate<<<blocks, PUSH_THREADS, 0, c->stream>>>(A);
+    DISPATCH_STORE(c->store_f32, k_accumulate<T><<<blocks, PUSH_THREADS, 0, c->stream>>>(A));
     c->launches++;
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -1727,7 +1756,7 @@ int launch_generate(mag2d_ctx* c, int s, int kind, long long n, double a, double
     G.species = s;
     G.has_ttd = S.arr[S.cur][ARR_TTD] != nullptr;
     const unsigned blocks = (unsigned)((n + PUSH_THREADS - 1) / PUSH_THREADS);
-    k_generate<<<blocks, PUSH_THREADS, 0, c->stream>>>(G);
+    DISPATCH_STORE(c->store_f32, k_generate<T><<<blocks, PUSH_THREADS, 0, c->stream>>>(G));
     c->launches++;
     CUDA_OK(cudaGetLastError());
     S.n_slots += n;
@@ -1745,8 +1774,8 @@ int launch_energy_hist(mag2d_ctx* c, int s, int nbins, double emax, double* hist
     if (S.n_slots > 0)
     {
         const unsigned blocks = (unsigned)std::min<long long>((S.n_slots + PUSH_THREADS - 1) / PUSH_THREADS, 148 * 8);
-        k_energy_hist<<<blocks, PUSH_THREADS, sizeof(unsigned long long) * nbins, c->stream>>>(
-            particles_view(S), S.desc.mass * 0.5 / MAG2D_QE, nbins, emax, dh, ds);
+        DISPATCH_STORE(c->store_f32, k_energy_hist<T><<<blocks, PUSH_THREADS, sizeof(unsigned long long) * nbins, c->stream>>>(
+            particles_view(S), S.desc.mass * 0.5 / MAG2D_QE, nbins, emax, dh, ds));
         c->launches++;
         CUDA_OK(cudaGetLastError());
     }
@@ -1765,8 +1794,8 @@ int launch_aos_to_soa(mag2d_ctx* c, int s, const mag2d_particle* d_aos, long lon
     ParticlesDev p = particles_view(S);
     const unsigned blocks = (unsigned)((n_in + 255) / 256);
     const int has_y = S.arr[S.cur][ARR_Y] != nullptr, has_ttd = S.arr[S.cur][ARR_TTD] != nullptr;
-    k_aos_to_soa<<<blocks, 256, 0, c->stream>>>(d_aos, n_in, p, S.n_slots, has_y, has_ttd);
-    k_mark_dead<<<blocks, 256, 0, c->stream>>>(p, d_aos, n_in, S.n_slots);
+    DISPATCH_STORE(c->store_f32, k_aos_to_soa<T><<<blocks, 256, 0, c->stream>>>(d_aos, n_in, p, S.n_slots, has_y, has_ttd));
+    DISPATCH_STORE(c->store_f32, k_mark_dead<T><<<blocks, 256, 0, c->stream>>>(p, d_aos, n_in, S.n_slots));
     c->launches += 2;
     CUDA_OK(cudaGetLastError());
     *n_added = n_in;
@@ -1780,7 +1809,7 @@ int launch_soa_to_aos(mag2d_ctx* c, int s, mag2d_particle* d_aos)
     if (S.n_slots == 0) return 0;
     const unsigned blocks = (unsigned)((S.n_slots + 255) / 256);
     const int has_y = S.arr[S.cur][ARR_Y] != nullptr, has_ttd = S.arr[S.cur][ARR_TTD] != nullptr;
-    k_soa_to_aos<<<blocks, 256, 0, c->stream>>>(particles_view(S), d_aos, has_y, has_ttd);
+    DISPATCH_STORE(c->store_f32, k_soa_to_aos<T><<<blocks, 256, 0, c->stream>>>(particles_view(S), d_aos, has_y, has_ttd));
     c->launches++;
     CUDA_OK(cudaGetLastError());
     return 0;

@@ -16,24 +16,25 @@ constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_ITEMS = 4;   // per thread
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
+template <typename T>
 __global__ void k_sort_count(const double* __restrict__ x, const double* __restrict__ z, long long n, double idx, double idz,
                              int M, int N, unsigned* __restrict__ count, unsigned* __restrict__ key, unsigned* __restrict__ rank,
                              const double* __restrict__ y, double idy, int K)
 {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const double px = k < n ? x[k] : dead_marker();
+    const double px = k < n ? pld<T>(x, k) : dead_marker();
     const bool valid = particle_alive(px);
     unsigned ky = INVALID_KEY, rk = 0;
     if (valid)
     {
-        int i = (int)(px * idx), j = (int)(z[k] * idz);
+        int i = (int)(px * idx), j = (int)(pld<T>(z, k) * idz);
         i = max(min(i, M - 2), 0);
         j = max(min(j, N - 2), 0);
         ky = (unsigned)i * (unsigned)(N - 1) + (unsigned)j;
         if (y)
         {
             // CARTESIAN3D: cell (i, jy, k) in the Array3D order, x slowest
-            int jy = (int)(y[k] * idy);
+            int jy = (int)(pld<T>(y, k) * idy);
             jy = max(min(jy, K - 2), 0);
             ky = ((unsigned)i * (unsigned)(K - 1) + (unsigned)jy) * (unsigned)(N - 1) + (unsigned)j;
         }
@@ -165,6 +166,7 @@ struct PermArgs
     int n_arr;
 };
 
+template <typename T>
 __global__ void k_sort_scatter(const __grid_constant__ PermArgs P, long long n, const unsigned* __restrict__ key,
                                const unsigned* __restrict__ rank, const unsigned* __restrict__ offset)
 {
@@ -175,22 +177,24 @@ __global__ void k_sort_scatter(const __grid_constant__ PermArgs P, long long n, 
     const long long d = (long long)offset[ky] + rank[k];
 #pragma unroll
     for (int a = 0; a < N_ARR; a++)
-        if (a < P.n_arr) P.dst[a][d] = P.src[a][k];
+        if (a < P.n_arr) reinterpret_cast<T*>(P.dst[a])[d] = reinterpret_cast<const T*>(P.src[a])[k];
 }
 
 // slots behind the compacted particles become dead markers
+template <typename T>
 __global__ void k_fill_dead(double* __restrict__ x, const unsigned long long* __restrict__ total, long long n)
 {
     for (long long k = (long long)*total + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
-        x[k] = dead_marker();
+        pst<T>(x, k, dead_marker());
 }
 
 // the same for a fused permuting step
+template <typename T>
 __global__ void k_fill_dead_keys(double* __restrict__ x, unsigned* __restrict__ key, const unsigned long long* __restrict__ total, long long n)
 {
     for (long long k = (long long)*total + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
     {
-        x[k] = dead_marker();
+        pst<T>(x, k, dead_marker());
         if (key) key[k] = INVALID_KEY;
     }
 }
@@ -221,8 +225,12 @@ int launch_sort(mag2d_ctx* c, int s, bool trim)
     double* const* oth = S.arr[S.cur ^ 1];
     CUDA_OK(cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned) * (size_t)ncells, c->stream));
     const unsigned pblocks = (unsigned)((n + 255) / 256);
-    k_sort_count<<<pblocks, 256, 0, c->stream>>>(cur[ARR_X], cur[ARR_Z], n, c->g.idx, c->g.idz, M, N, c->d_cell_count, c->d_key, c->d_rank,
-                                                 three_d ? cur[ARR_Y] : nullptr, c->g.idy, c->g.K);
+    if (c->store_f32)
+        k_sort_count<float><<<pblocks, 256, 0, c->stream>>>(cur[ARR_X], cur[ARR_Z], n, c->g.idx, c->g.idz, M, N, c->d_cell_count, c->d_key, c->d_rank,
+                                                            three_d ? cur[ARR_Y] : nullptr, c->g.idy, c->g.K);
+    else
+        k_sort_count<double><<<pblocks, 256, 0, c->stream>>>(cur[ARR_X], cur[ARR_Z], n, c->g.idx, c->g.idz, M, N, c->d_cell_count, c->d_key, c->d_rank,
+                                                             three_d ? cur[ARR_Y] : nullptr, c->g.idy, c->g.K);
     k_scan_tiles<<<ntiles, SCAN_THREADS, 0, c->stream>>>(c->d_cell_count, c->d_cell_offset, c->d_block_sums, ncells);
     k_scan_sums<<<1, 1024, 0, c->stream>>>(c->d_block_sums, ntiles, d_total);
     k_scan_add<<<ntiles, SCAN_THREADS, 0, c->stream>>>(c->d_cell_offset, c->d_block_sums, ncells);
@@ -236,8 +244,16 @@ int launch_sort(mag2d_ctx* c, int s, bool trim)
             P.n_arr++;
         }
     for (int a = P.n_arr; a < N_ARR; a++) { P.src[a] = nullptr; P.dst[a] = nullptr; }
-    k_sort_scatter<<<pblocks, 256, 0, c->stream>>>(P, n, c->d_key, c->d_rank, c->d_cell_offset);
-    k_fill_dead<<<148 * 4, 256, 0, c->stream>>>(oth[ARR_X], d_total, n);
+    if (c->store_f32)
+    {
+        k_sort_scatter<float><<<pblocks, 256, 0, c->stream>>>(P, n, c->d_key, c->d_rank, c->d_cell_offset);
+        k_fill_dead<float><<<148 * 4, 256, 0, c->stream>>>(oth[ARR_X], d_total, n);
+    }
+    else
+    {
+        k_sort_scatter<double><<<pblocks, 256, 0, c->stream>>>(P, n, c->d_key, c->d_rank, c->d_cell_offset);
+        k_fill_dead<double><<<148 * 4, 256, 0, c->stream>>>(oth[ARR_X], d_total, n);
+    }
     c->launches += 6;
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemsetAsync(S.d_removed, 0, sizeof(unsigned long long), c->stream));
@@ -319,7 +335,8 @@ int sort_fused_end(mag2d_ctx* c, int s, bool permute, bool count)
     if (permute)
     {
         // d_total still holds the number of particles the consumed cursors covered: everything behind is dead
-        k_fill_dead_keys<<<148 * 4, 256, 0, c->stream>>>(S.arr[S.cur ^ 1][ARR_X], nullptr, d_total, S.n_slots);
+        if (c->store_f32) k_fill_dead_keys<float><<<148 * 4, 256, 0, c->stream>>>(S.arr[S.cur ^ 1][ARR_X], nullptr, d_total, S.n_slots);
+        else k_fill_dead_keys<double><<<148 * 4, 256, 0, c->stream>>>(S.arr[S.cur ^ 1][ARR_X], nullptr, d_total, S.n_slots);
         c->launches++;
         if (!S.total_pending)
         {
