@@ -375,6 +375,7 @@ int mag2d_destroy(mag2d_ctx* c)
         if (c->ev_h2d[b]) { cudaEventDestroy(c->ev_h2d[b]); cudaEventDestroy(c->ev_comp[b]); cudaEventDestroy(c->ev_d2h[b]); }
     }
     if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h); }
+    if (c->s_comm) { cudaStreamDestroy(c->s_comm); cudaEventDestroy(c->ev_comm_in); cudaEventDestroy(c->ev_comm_out); }
     cudaFree(c->d_mask);
     cudaFree(c->d_voltage);
     cudaFree(c->d_u);
@@ -1269,9 +1270,11 @@ int mag2d_step(mag2d_ctx* c, int nsteps)
             // use the stand-alone sort below (which also trims the slot range: the influx balances the wall losses)
             if (advance_one(c, (int)s, !c->use_source)) return 1;
             if (c->use_source && species_source(c, (int)s, nullptr)) return 1;      // pic.cpp:346-347
+            // this species' charge grid is complete: its all-reduce runs on the side stream under the next species' push
+            if (c->g.selfconsistent && comm_allreduce_species_async(c, (int)s)) return 1;
         }
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
-        if (c->g.selfconsistent && comm_allreduce_rho(c)) return 1;
+        if (c->g.selfconsistent && comm_allreduce_join(c)) return 1;
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
         // stand-alone sort: the multi-collision mover, or the fused sort switched off
         if (!c->fused_sort || c->g.mover == MAG2D_ADVANCE_MULTICOLL || c->use_source)

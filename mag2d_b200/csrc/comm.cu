@@ -111,6 +111,38 @@ extern "C" int mag2d_comm_destroy(mag2d_ctx* c)
     return 0;
 }
 
+// Species s has finished depositing (everything enqueued on c->stream so far): sum its grid over the ranks on the side stream,
+// so that the transfer runs under the NEXT species' push instead of after the last one.  comm_allreduce_join makes the
+// compute stream wait for all of them.  Every rank issues the same sequence of collectives (species order), as NCCL requires.
+int comm_allreduce_species_async(mag2d_ctx* c, int s)
+{
+    if (!c->nccl_comm || c->nranks <= 1 || c->sp[s].desc.charge == 0.0) return 0;
+    if (!c->s_comm)
+    {
+        CUDA_OK(cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&c->ev_comm_in, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&c->ev_comm_out, cudaEventDisableTiming));
+    }
+    CUDA_OK(cudaEventRecord(c->ev_comm_in, c->stream));
+    CUDA_OK(cudaStreamWaitEvent(c->s_comm, c->ev_comm_in, 0));
+    const size_t n = grid_nodes(c);
+    const int ncclInt64 = 4, ncclSum = 0;
+    unsigned long long* buf = c->d_rho + (size_t)s * n;
+    const int rc = g_nccl.AllReduce(buf, buf, n, ncclInt64, ncclSum, (NcclComm)c->nccl_comm, c->s_comm);
+    if (rc) return nccl_fail("ncclAllReduce", rc);
+    c->comm_pending = true;
+    return 0;
+}
+
+int comm_allreduce_join(mag2d_ctx* c)
+{
+    if (!c->comm_pending) return 0;
+    CUDA_OK(cudaEventRecord(c->ev_comm_out, c->s_comm));
+    CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_comm_out, 0));
+    c->comm_pending = false;
+    return 0;
+}
+
 // in-place sum of the fixed-point charge grids of all species over all ranks
 int comm_allreduce_rho(mag2d_ctx* c)
 {

@@ -200,6 +200,9 @@ struct mag2d_ctx
     // multi-GPU
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+    cudaStream_t s_comm = nullptr;      // side stream of the per-species charge all-reduce (overlaps the next species' push)
+    cudaEvent_t ev_comm_in = nullptr, ev_comm_out = nullptr;
+    bool comm_pending = false;
 
     // timing
     bool timing = false;
@@ -278,3 +281,5 @@ inline bool is3d(const mag2d_ctx* c) { return c->g.coord == MAG2D_CARTESIAN3D; }
 inline size_t grid_nodes(const mag2d_ctx* c) { return (size_t)c->g.M * c->g.N * (is3d(c) ? (size_t)c->g.K : 1); }
 // comm.cu
 int comm_allreduce_rho(mag2d_ctx* c);
+int comm_allreduce_species_async(mag2d_ctx* c, int s);
+int comm_allreduce_join(mag2d_ctx* c);
