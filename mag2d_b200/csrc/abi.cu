@@ -732,6 +732,7 @@ int mag2d_set_species(mag2d_ctx* c, int ns, const mag2d_species_desc* species, i
             T.density = species[k].density;
             T.mass = species[k].mass;
             T.vth = c->sp[k].v_max * M_SQRT1_2;
+            T.inv_M = 1.0 / (S.desc.mass + species[k].mass);
             T.first_inter = ii;
             T.n_inter = (int)by[i][k].size();
             for (const HostInter& I : by[i][k])
@@ -754,7 +755,15 @@ int mag2d_set_species(mag2d_ctx* c, int ns, const mag2d_species_desc* species, i
         B->n_inter_total = ii;
         B->n_tab = nt;
         B->has_collisions = rate > 0.0;
-        for (int q = 0; q < nt; q++) { B->tab[q] = tE[q]; B->tab[nt + q] = tS[q]; }
+        for (int q = 0; q < nt; q++)
+        {
+            B->tab[q] = tE[q];
+            B->tab[nt + q] = tS[q];
+            // the interpolation weight of vec_interpolate (tabulate.cpp:124-140) as a product instead of a division per look-up;
+            // the last point of a table (and of all tables) has no interval behind it
+            const double w = q + 1 < nt ? tE[q + 1] - tE[q] : 0.0;
+            B->tab[2 * nt + q] = w > 0.0 ? 1.0 / w : 0.0;
+        }
         S.h_blob = B;
         CUDA_OK(cudaMalloc(&S.d_blob, sizeof(MccBlob)));
         CUDA_OK(cudaMemcpyAsync(S.d_blob, B, sizeof(MccBlob), cudaMemcpyHostToDevice, c->stream));

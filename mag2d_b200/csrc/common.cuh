@@ -132,6 +132,7 @@ struct MccTarget
     int n_inter, first_inter;
     int pool;         // 1: partners are drawn from the target's particle array (particles.cpp:230-238)
     int pad;
+    double inv_M;     // 1 / (primary mass + target mass)
 };
 struct PoolDev
 {
@@ -148,7 +149,7 @@ struct MccBlob
     MccTarget t[MCC_MAX_T];
     MccInter in[MCC_MAX_I];
     PoolDev pool[MCC_MAX_T];
-    double tab[2 * MCC_MAX_TAB];   // energies [0, n_tab) then cross sections [n_tab, 2 n_tab)
+    double tab[3 * MCC_MAX_TAB];   // energies [0, n_tab), cross sections [n_tab, 2 n_tab), 1 / (E[j+1] - E[j]) [2 n_tab, 3 n_tab)
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -6,7 +6,10 @@
 #include "common.cuh"
 
 // vec_interpolate::operator(), src/tabulate.cpp:124-140: clamped ends, binary search, lerp
-__device__ __forceinline__ double table_lookup(const double* __restrict__ xd, const double* __restrict__ yd, int n, double x)
+// (the weight (x - x1) / (x2 - x1) is formed with the precomputed reciprocal interval width: one ulp off the division, which
+// only the statistics of the collisions see)
+__device__ __forceinline__ double table_lookup(const double* __restrict__ xd, const double* __restrict__ yd, const double* __restrict__ inv_w,
+                                               int n, double x)
 {
     if (x >= xd[n - 1]) return yd[n - 1];
     if (x <= xd[0]) return yd[0];
@@ -17,8 +20,7 @@ __device__ __forceinline__ double table_lookup(const double* __restrict__ xd, co
         if (x < xd[j3]) j2 = j3;
         else j1 = j3;
     }
-    double x1 = xd[j1];
-    double w = (x - x1) / (xd[j2] - x1);
+    const double w = (x - xd[j1]) * inv_w[j1];
     return yd[j1] * (1.0 - w) + yd[j2] * w;
 }
 
@@ -29,7 +31,7 @@ __device__ __forceinline__ double sigma_v(const MccBlob* B, const MccInter& I, d
     if (I.n_table > 0)
     {
         double EeV = I.half_mu * v * v * (1.0 / MAG2D_QE);
-        return table_lookup(B->tab + I.table_off, B->tab + B->n_tab + I.table_off, I.n_table, EeV) * v;
+        return table_lookup(B->tab + I.table_off, B->tab + B->n_tab + I.table_off, B->tab + 2 * B->n_tab + I.table_off, I.n_table, EeV) * v;
     }
     return I.rate;
 }
@@ -141,7 +143,7 @@ static __device__ __noinline__ int mcc_scatter(const MccBlob* __restrict__ B, Rn
     }
     if (intid == T.n_inter) return -1;
     const MccInter I = B->in[T.first_inter + intid];
-    const double inv_M = 1.0 / (mass + m2);
+    const double inv_M = T.inv_M;
     switch (I.type)
     {
         case 4:  // SUPERELASTIC: E' = E_rel + DE, isotropic in the centre-of-mass frame (particles.cpp:268-288)
