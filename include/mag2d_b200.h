@@ -201,6 +201,10 @@ int mag2d_sort(mag2d_ctx* ctx, int species);
  * removed particles come back with x = NaN.  2-D Boris movers. */
 int mag2d_step_streamed(mag2d_ctx* ctx, int n_species, const int32_t* species, const int64_t* n_slots, double* const* x,
                         double* const* z, double* const* vx, double* const* vy, double* const* vz, int64_t chunk_slots);
+/* bytes the streamed steps have copied host -> device / device -> host so far (reset != 0 clears the counters).  In a 2-D
+ * Cartesian run without magnetic field the out-of-plane velocity is not staged when the caller's vy arrays are pinned host memory:
+ * only the collision pass touches it, in place over PCIe (MAG2D_STREAM_VY=1 in the environment stages it like the others). */
+int mag2d_streamed_bytes(mag2d_ctx* ctx, int64_t* h2d_bytes, int64_t* d2h_bytes, int reset);
 /* the same for CARTESIAN3D stores (six arrays: Species<CARTESIAN3D>::advance, src/species3d.cpp:3-93, on host-resident particles) */
 int mag2d_step_streamed3(mag2d_ctx* ctx, int n_species, const int32_t* species, const int64_t* n_slots, double* const* x,
                          double* const* y, double* const* z, double* const* vx, double* const* vy, double* const* vz,

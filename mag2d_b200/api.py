@@ -111,6 +111,7 @@ def lib():
     L.mag2d_step_streamed.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), i64p] + [C.POINTER(dp)] * 5 + [C.c_int64]
     L.mag2d_step_streamed3.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), i64p] + [C.POINTER(dp)] * 6 + [C.c_int64]
     L.mag2d_set_species_sort_interval.argtypes = [vp, C.c_int, C.c_int]
+    L.mag2d_streamed_bytes.argtypes = [vp, i64p, i64p, C.c_int]
     L.mag2d_set_store_layout.argtypes = [vp, C.c_int]
     L.mag2d_set_storage.argtypes = [vp, C.c_int]
     L.mag2d_store_stats.argtypes = [vp, C.c_int, i64p]
@@ -429,6 +430,12 @@ class Sim:
             self._chk(self.L.mag2d_step_streamed3(self.h, n, sp, ns, *cols, chunk_slots))
         else:
             self._chk(self.L.mag2d_step_streamed(self.h, n, sp, ns, *cols, chunk_slots))
+
+    def streamed_bytes(self, reset=False):
+        """bytes the streamed steps have copied (host -> device, device -> host)"""
+        a, b = C.c_int64(), C.c_int64()
+        self._chk(self.L.mag2d_streamed_bytes(self.h, C.byref(a), C.byref(b), 1 if reset else 0))
+        return a.value, b.value
 
     def species_advance(self, i):
         self._chk(self.L.mag2d_species_advance(self.h, i))

@@ -1367,18 +1367,36 @@ static int step_streamed_impl(mag2d_ctx* c, int n_sp, const int32_t* species, co
         SpeciesStore& S = c->sp[s];
         if (refresh_pools(c, s)) return 1;
         double* const host[6] = {x[q], z[q], vx[q], vy[q], vz[q], three_d ? y[q] : nullptr};      // staging order: y last
+        // 2-D Cartesian push without a magnetic field: the push never touches the out-of-plane velocity (k_push_boris: need_vy), only
+        // the collision pass does, for the ~1 % of particles whose collision test fired.  When the caller's vy array is pinned (device-
+        // accessible) host memory, it is not copied at all: k_mcc_collide reads and writes those few elements in place over PCIe
+        // (zero-copy), which takes a fifth off the bytes of the step.  Pageable arrays are staged like the others.
+        double* vy_mapped = nullptr;
+        if (!three_d && c->g.coord == MAG2D_CARTESIAN && c->g.magnetic_field_const && c->g.Br == 0.0 && c->g.Bz == 0.0 && c->g.Bt == 0.0 && n_slots[q] > 0 &&
+            !(getenv("MAG2D_STREAM_VY") && atoi(getenv("MAG2D_STREAM_VY")) != 0))
+        {
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, vy[q]) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+                vy_mapped = static_cast<double*>(attr.devicePointer);
+            else cudaGetLastError();
+        }
         for (long long off = 0; off < n_slots[q] && !rc; off += chunk_slots, ring++)
         {
             const int b = (int)(ring % 3);
             const long long cnt = std::min<long long>(chunk_slots, n_slots[q] - off);
             CUDA_OK(cudaStreamWaitEvent(c->s_h2d, c->ev_d2h[b], 0));       // the buffer's previous tenant has left
             for (int a = 0; a < n_arr; a++)
+            {
+                if (a == 3 && vy_mapped) continue;
                 CUDA_OK(cudaMemcpyAsync(c->d_chunk[b][a], host[a] + off, sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, c->s_h2d));
+                c->streamed_h2d += sizeof(double) * (size_t)cnt;
+            }
             CUDA_OK(cudaEventRecord(c->ev_h2d[b], c->s_h2d));
             CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
             ParticlesDev view;
             memset(&view, 0, sizeof(view));
             view.x = c->d_chunk[b][0]; view.z = c->d_chunk[b][1]; view.vx = c->d_chunk[b][2]; view.vy = c->d_chunk[b][3]; view.vz = c->d_chunk[b][4];
+            if (vy_mapped) view.vy = vy_mapped + off;
             view.y = three_d ? c->d_chunk[b][5] : nullptr;
             view.n = cnt;
             c->chunk_view = &view;
@@ -1389,7 +1407,11 @@ static int step_streamed_impl(mag2d_ctx* c, int n_sp, const int32_t* species, co
             CUDA_OK(cudaEventRecord(c->ev_comp[b], c->stream));
             CUDA_OK(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[b], 0));
             for (int a = 0; a < n_arr; a++)
+            {
+                if (a == 3 && vy_mapped) continue;
                 CUDA_OK(cudaMemcpyAsync(host[a] + off, c->d_chunk[b][a], sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, c->s_d2h));
+                c->streamed_d2h += sizeof(double) * (size_t)cnt;
+            }
             CUDA_OK(cudaEventRecord(c->ev_d2h[b], c->s_d2h));
         }
         // Species<D>::advance: niter++, t += dt — once per step, not per chunk
@@ -1417,6 +1439,15 @@ int mag2d_step_streamed3(mag2d_ctx* c, int n_sp, const int32_t* species, const i
     CHECK_CTX(c);
     if (!is3d(c)) { mag2d_set_error("mag2d_step_streamed3: CARTESIAN3D only"); return 1; }
     return step_streamed_impl(c, n_sp, species, n_slots, x, y, z, vx, vy, vz, chunk_slots);
+}
+
+int mag2d_streamed_bytes(mag2d_ctx* c, int64_t* h2d, int64_t* d2h, int reset)
+{
+    if (!c) { mag2d_set_error("null context"); return 1; }
+    if (h2d) *h2d = (int64_t)c->streamed_h2d;
+    if (d2h) *d2h = (int64_t)c->streamed_d2h;
+    if (reset) c->streamed_h2d = c->streamed_d2h = 0;
+    return 0;
 }
 
 int mag2d_energy_hist(mag2d_ctx* c, int s, int nbins, double emax, double* hist, double* stats)

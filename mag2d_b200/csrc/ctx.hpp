@@ -195,6 +195,7 @@ struct mag2d_ctx
     double* d_chunk[3][6] = {};        // ring of device staging buffers (x, z, vx, vy, vz; y for CARTESIAN3D)
     long long chunk_capacity = 0;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    unsigned long long streamed_h2d = 0, streamed_d2h = 0;   // bytes the streamed steps have staged in each direction (mag2d_streamed_bytes)
     cudaEvent_t ev_h2d[3] = {}, ev_comp[3] = {}, ev_d2h[3] = {};
 
     // multi-GPU

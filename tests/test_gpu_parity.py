@@ -492,6 +492,53 @@ def test_streamed_step_with_host_resident_particles_equals_the_resident_step(orc
         assert np.array_equal(sim.get_field("u"), ref.get_field("u"))
 
 
+def test_streamed_step_leaves_vy_in_pinned_host_memory(deckdir):
+    """2-D Cartesian, B = 0: the push never reads the out-of-plane velocity, so a streamed step does not copy a PINNED vy array at
+    all — the collision pass reaches the few elements it needs in place over PCIe.  Checked here: the bytes the step copies
+    (four arrays instead of five), vy untouched bit for bit for every particle that did not collide, changed for a fraction
+    1 - exp(-dt / lifetime) of them (5 sigma), and the same particles / charge as with the staged copy when collisions are off."""
+    import torch
+    n = 60000
+    rng = np.random.default_rng(77)
+    out = {}
+    for collisions in (False, True):
+        d = decks.deck("c4", deckdir + "_zc%d" % collisions, n_particles=2 * n, collisions=collisions, x_sampl=33, z_sampl=49, r_max=3.2e-3,
+                       z_max=4.8e-3)
+        for pinned in (True, False):
+            with _sim(d["config"], d["species_conf"]) as sim:
+                e = sim.species_index("ELECTRON")
+                a = np.zeros((n, 5))
+                r2 = np.random.default_rng(5)
+                a[:, 0] = r2.uniform(1e-7, 3.2e-3 - 1e-7, n)
+                a[:, 1] = r2.uniform(1e-7, 4.8e-3 - 1e-7, n)
+                a[:, 2:5] = r2.normal(size=(n, 3)) * 8e5
+                sim.advance_init()
+                cols = [torch.from_numpy(np.ascontiguousarray(a[:, c])) for c in range(5)]
+                if pinned:
+                    cols = [t.pin_memory() for t in cols]
+                vy0 = cols[3].numpy().copy()
+                sim.streamed_bytes(reset=True)
+                sim.step_streamed([e], [n], [[t.data_ptr() for t in cols]], chunk_slots=16384)
+                h2d, d2h = sim.streamed_bytes()
+                assert h2d == d2h == (4 if pinned else 5) * 8 * n
+                vy1 = cols[3].numpy()
+                changed = vy1 != vy0
+                if collisions:
+                    prob = sim.species_get(e, "prob")
+                    assert abs(changed.sum() - n * prob) <= 5 * np.sqrt(n * prob) + 5, (changed.sum(), n * prob)
+                else:
+                    assert not changed.any()
+                out[(collisions, pinned)] = ([t.numpy().copy() for t in cols], sim.rho_fixed(e))
+    a, b = out[(False, True)], out[(False, False)]
+    for x, y in zip(a[0], b[0]):
+        assert np.array_equal(x, y, equal_nan=True)
+    assert np.array_equal(a[1], b[1])
+    # with collisions the two runs draw the same Philox streams (keyed by slot and chunk): identical, whichever way vy travels
+    a, b = out[(True, True)], out[(True, False)]
+    for x, y in zip(a[0], b[0]):
+        assert np.array_equal(x, y, equal_nan=True)
+
+
 @pytest.mark.skipif(not needs_ref, reason="oracle/_ref not present on this machine")
 def test_live_reference_rf_trap_100_steps(deckdir):
     from oracle import RefHarness
