@@ -555,11 +555,24 @@ def bench_e2e(sim, part_species, args, torch, stream, world, dist, dev, e2e_step
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dt, n_live = float(tmax[0]), float(tsum[1])
+    # per-rank link rates of this rank's own median repeat (min / max over the ranks): with N ranks on one host the sum of these is
+    # what the host's memory system and PCIe root complexes deliver in aggregate
+    own = sorted(repeats)[len(repeats) // 2] / steps
+    rate = torch.tensor([h2d / own / 1e9, d2h / own / 1e9], dtype=torch.float64, device=dev)
+    lo, hi, tot = rate.clone(), rate.clone(), rate.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    link = {"h2d_gb_per_s_per_rank_min_max": [round(float(lo[0]), 2), round(float(hi[0]), 2)],
+            "d2h_gb_per_s_per_rank_min_max": [round(float(lo[1]), 2), round(float(hi[1]), 2)],
+            "host_aggregate_gb_per_s_both_directions": round(float(tot[0] + tot[1]), 2)}
     return {"value": n_live * steps / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": dt / steps * 1e3,
+            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": dt / steps * 1e3, "link": link,
             "repeats_ms_per_step": [round(r / steps * 1e3, 3) for r in repeats],
             "path": ("mag2d_step_streamed%s: host SoA arrays (pinned) -> chunked H2D / fused step / D2H overlapped on three streams -> host arrays, "
-                     "+ mag2d_rho_download") % ("3" if sim.is3d else "") if streamed else
+                     "+ mag2d_rho_download; bytes as counted by the library (vy is not copied when the push does not read it: "
+                     "the collision pass reaches the pinned array in place)") % ("3" if sim.is3d else "") if streamed else
                     "mag2d_particles_upload_soa (pinned host) -> mag2d_step -> mag2d_particles_download_soa + mag2d_rho_download"}
 
 

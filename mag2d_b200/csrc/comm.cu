@@ -20,6 +20,10 @@ typedef int (*fn_GetUniqueId)(NcclUniqueId*);
 typedef int (*fn_CommInitRank)(NcclComm*, int, NcclUniqueId, int);
 typedef int (*fn_AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
 typedef int (*fn_CommDestroy)(NcclComm);
+typedef int (*fn_Send)(const void*, size_t, int, int, NcclComm, cudaStream_t);
+typedef int (*fn_Recv)(void*, size_t, int, int, NcclComm, cudaStream_t);
+typedef int (*fn_Group)();
+typedef int (*fn_Broadcast)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
 typedef const char* (*fn_GetErrorString)(int);
 
 struct NcclApi
@@ -30,6 +34,10 @@ struct NcclApi
     fn_AllReduce AllReduce = nullptr;
     fn_CommDestroy CommDestroy = nullptr;
     fn_GetErrorString GetErrorString = nullptr;
+    fn_Send Send = nullptr;
+    fn_Recv Recv = nullptr;
+    fn_Group GroupStart = nullptr, GroupEnd = nullptr;
+    fn_Broadcast Broadcast = nullptr;
 };
 
 NcclApi g_nccl;
@@ -60,6 +68,11 @@ int load_nccl()
     g_nccl.AllReduce = (fn_AllReduce)dlsym(h, "ncclAllReduce");
     g_nccl.CommDestroy = (fn_CommDestroy)dlsym(h, "ncclCommDestroy");
     g_nccl.GetErrorString = (fn_GetErrorString)dlsym(h, "ncclGetErrorString");
+    g_nccl.Send = (fn_Send)dlsym(h, "ncclSend");
+    g_nccl.Recv = (fn_Recv)dlsym(h, "ncclRecv");
+    g_nccl.GroupStart = (fn_Group)dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (fn_Group)dlsym(h, "ncclGroupEnd");
+    g_nccl.Broadcast = (fn_Broadcast)dlsym(h, "ncclBroadcast");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
     {
         mag2d_set_error("libnccl.so.2 lacks the expected symbols");
@@ -163,4 +176,32 @@ int comm_allreduce_rho(mag2d_ctx* c)
     const int rc = g_nccl.AllReduce(buf, buf, count, ncclInt64, ncclSum, (NcclComm)c->nccl_comm, c->stream);
     if (rc) return nccl_fail("ncclAllReduce", rc);
     return 0;
+}
+
+// ---- point-to-point pieces of the slab-parallel 3-D solve (poisson3d.cu); doubles, on the compute stream -----------------
+bool comm_has_p2p() { return g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd && g_nccl.Broadcast; }
+int comm_group_start()
+{
+    const int rc = g_nccl.GroupStart();
+    return rc ? nccl_fail("ncclGroupStart", rc) : 0;
+}
+int comm_group_end()
+{
+    const int rc = g_nccl.GroupEnd();
+    return rc ? nccl_fail("ncclGroupEnd", rc) : 0;
+}
+int comm_send(mag2d_ctx* c, const double* buf, size_t count, int peer)
+{
+    const int rc = g_nccl.Send(buf, count, 8 /* ncclFloat64 */, peer, (NcclComm)c->nccl_comm, c->stream);
+    return rc ? nccl_fail("ncclSend", rc) : 0;
+}
+int comm_recv(mag2d_ctx* c, double* buf, size_t count, int peer)
+{
+    const int rc = g_nccl.Recv(buf, count, 8, peer, (NcclComm)c->nccl_comm, c->stream);
+    return rc ? nccl_fail("ncclRecv", rc) : 0;
+}
+int comm_broadcast(mag2d_ctx* c, double* buf, size_t count, int root)
+{
+    const int rc = g_nccl.Broadcast(buf, buf, count, 8, root, (NcclComm)c->nccl_comm, c->stream);
+    return rc ? nccl_fail("ncclBroadcast", rc) : 0;
 }

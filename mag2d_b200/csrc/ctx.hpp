@@ -119,6 +119,14 @@ struct Direct3D
     double* cinv = nullptr;
     double* alpha = nullptr;
     double* green = nullptr;         // [ne][M*K*N] Green's functions of the electrode nodes
+    // slab-parallel solve on N ranks (solve_interior_slab): this rank transforms the x planes [pi0[r], pi0[r+1]) and runs the
+    // Thomas recurrences of the y rows [pj0[r], pj0[r+1]) of every plane
+    bool slab_ok = false;
+    std::vector<int> pi0, pj0;       // [nranks + 1]
+    double* V = nullptr;             // [n_i][rows of this rank][ldk] transformed right-hand side / solution, mode slab
+    double* inv_slab = nullptr;      // the same slab of the Thomas factors
+    double* Sb = nullptr;            // send / receive staging, one x slab each
+    double* Xb = nullptr;
 };
 
 struct mag2d_ctx
@@ -284,3 +292,9 @@ inline size_t grid_nodes(const mag2d_ctx* c) { return (size_t)c->g.M * c->g.N * 
 int comm_allreduce_rho(mag2d_ctx* c);
 int comm_allreduce_species_async(mag2d_ctx* c, int s);
 int comm_allreduce_join(mag2d_ctx* c);
+bool comm_has_p2p();
+int comm_group_start();
+int comm_group_end();
+int comm_send(mag2d_ctx* c, const double* buf, size_t count, int peer);
+int comm_recv(mag2d_ctx* c, double* buf, size_t count, int peer);
+int comm_broadcast(mag2d_ctx* c, double* buf, size_t count, int root);

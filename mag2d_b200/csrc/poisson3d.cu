@@ -34,8 +34,8 @@ struct Gemm3Args
     double* C; long long strideC; int ldc;
     int rows, cols, Kdim;                            // cols and Kdim are multiples of 32
     double scale;
-    // SCATTER epilogue: row r = il*ldj + jl of the interior block goes to node (il+1, jl+1, 1..) of the potential
-    int ldj, n_j, n_k, K, N;
+    // SCATTER epilogue: row r = il*ldj + jl of the interior block goes to node (i0+il+1, jl+1, 1..) of the potential
+    int ldj, n_j, n_k, K, N, i0;
 };
 
 __device__ __forceinline__ void cp16(void* smem, const void* gmem)
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(G3_THREADS) k_gemm3(const __grid_constant__ Ge
         if (r >= G.rows) continue;
         if (SCATTER)
         {
-            const int il = r / G.ldj, jl = r % G.ldj;
+            const int il = r / G.ldj + G.i0, jl = r % G.ldj;
             if (jl >= G.n_j) continue;
             double* out = C + ((size_t)(il + 1) * G.K + (jl + 1)) * G.N + 1;
 #pragma unroll
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(M3_THREADS) k_gemm3_mma(const __grid_constant_
         if (r >= G.rows) continue;
         if (SCATTER)
         {
-            const int il = r / G.ldj, jl = r % G.ldj;
+            const int il = r / G.ldj + G.i0, jl = r % G.ldj;
             if (jl >= G.n_j) continue;
             double* out = C + ((size_t)(il + 1) * G.K + (jl + 1)) * G.N + 1;
 #pragma unroll
@@ -438,6 +438,136 @@ int solve_interior(mag2d_ctx* c, double* u)
     return 0;
 }
 
+// ---- the same solve on N ranks (SURVEY.md §8e "optional later: reduce-scatter + slab-parallel ... + allgather") -------------
+// The sine transforms act inside an x plane, the Thomas recurrences along x inside a (y, z) mode: rank r transforms its slab of
+// x planes, the slabs are transposed over NVLink (ncclSend / ncclRecv, every pair exchanges 1/N^2 of the block) so that every
+// rank holds ALL planes of its slab of y rows, runs the recurrences of those modes, transposes back, applies the inverse
+// transforms to its planes and broadcasts them: every rank ends with the full potential.  Each number is produced by exactly the
+// kernels and operation order of the one-rank solve, so the potential is bit-identical for any N.
+int slab_setup(mag2d_ctx* c)
+{
+    Direct3D& D = c->direct3;
+    const int nr = c->nranks, me = c->rank;
+    D.pi0.assign(nr + 1, 0);
+    D.pj0.assign(nr + 1, 0);
+    const int pi = (D.n_i + nr - 1) / nr, pj = (D.ldj + nr - 1) / nr;
+    for (int q = 0; q <= nr; q++)
+    {
+        D.pi0[q] = std::min(q * pi, D.n_i);
+        D.pj0[q] = std::min(q * pj, D.ldj);
+    }
+    const size_t rows_me = (size_t)(D.pj0[me + 1] - D.pj0[me]);
+    const size_t slab_x = (size_t)std::max(D.pi0[me + 1] - D.pi0[me], 1) * D.ldj * D.ldk;
+    const size_t slab_m = std::max<size_t>((size_t)D.n_i * rows_me * D.ldk, 1);
+    CUDA_OK(cudaMalloc(&D.V, sizeof(double) * slab_m));
+    CUDA_OK(cudaMalloc(&D.inv_slab, sizeof(double) * slab_m));
+    CUDA_OK(cudaMalloc(&D.Sb, sizeof(double) * slab_x));
+    CUDA_OK(cudaMalloc(&D.Xb, sizeof(double) * slab_x));
+    if (rows_me > 0)
+        CUDA_OK(cudaMemcpy2DAsync(D.inv_slab, rows_me * D.ldk * sizeof(double), D.inv + (size_t)D.pj0[me] * D.ldk, (size_t)D.ldj * D.ldk * sizeof(double),
+                                  rows_me * D.ldk * sizeof(double), (size_t)D.n_i, cudaMemcpyDeviceToDevice, c->stream));
+    D.slab_ok = true;
+    return 0;
+}
+
+int solve_interior_slab(mag2d_ctx* c, double* u)
+{
+    Direct3D& D = c->direct3;
+    if (!D.slab_ok && slab_setup(c)) return 1;
+    const int nr = c->nranks, me = c->rank;
+    const int a = D.pi0[me], b = D.pi0[me + 1], np = b - a;
+    const size_t plane = (size_t)D.ldj * D.ldk;
+    const size_t rows_me = (size_t)(D.pj0[me + 1] - D.pj0[me]);
+    const size_t esz = sizeof(double);
+    Gemm3Args G;
+    memset(&G, 0, sizeof(G));
+    G.scale = 1.0;
+    if (np > 0)
+    {
+        // forward transforms of this rank's planes: T = R S_z, then R_i = S_y T_i
+        G.A = D.R + a * plane; G.lda = D.ldk; G.strideA = 0;
+        G.B = D.Sz; G.ldb = D.ldk; G.strideB = 0;
+        G.C = D.T + a * plane; G.ldc = D.ldk; G.strideC = 0;
+        G.rows = np * D.ldj; G.cols = D.ldk; G.Kdim = D.ldk;
+        gemm3(c, G, 1, false);
+        G.A = D.Sy; G.lda = D.ldj; G.strideA = 0;
+        G.B = D.T + a * plane; G.ldb = D.ldk; G.strideB = (long long)plane;
+        G.C = D.R + a * plane; G.ldc = D.ldk; G.strideC = (long long)plane;
+        G.rows = D.ldj; G.cols = D.ldk; G.Kdim = D.ldj;
+        gemm3(c, G, np, false);
+    }
+    // x slabs -> mode slabs: the rows [pj0[q], pj0[q+1]) of my planes go to rank q; their rows of my slab arrive from everybody
+    std::vector<size_t> off(nr + 1, 0);
+    for (int q = 0; q < nr; q++) off[q + 1] = off[q] + (size_t)np * (D.pj0[q + 1] - D.pj0[q]) * D.ldk;
+    for (int q = 0; q < nr && np > 0; q++)
+    {
+        const size_t rows_q = (size_t)(D.pj0[q + 1] - D.pj0[q]);
+        if (rows_q == 0) continue;
+        double* dst = q == me ? D.V + (size_t)a * rows_me * D.ldk : D.Sb + off[q];
+        CUDA_OK(cudaMemcpy2DAsync(dst, rows_q * D.ldk * esz, D.R + a * plane + (size_t)D.pj0[q] * D.ldk, plane * esz, rows_q * D.ldk * esz, (size_t)np,
+                                  cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (comm_group_start()) return 1;
+    for (int q = 0; q < nr; q++)
+    {
+        if (q == me) continue;
+        const size_t rows_q = (size_t)(D.pj0[q + 1] - D.pj0[q]), np_q = (size_t)(D.pi0[q + 1] - D.pi0[q]);
+        if (np > 0 && rows_q > 0 && comm_send(c, D.Sb + off[q], (size_t)np * rows_q * D.ldk, q)) return 1;
+        if (np_q > 0 && rows_me > 0 && comm_recv(c, D.V + (size_t)D.pi0[q] * rows_me * D.ldk, np_q * rows_me * D.ldk, q)) return 1;
+    }
+    if (comm_group_end()) return 1;
+    if (rows_me > 0)
+    {
+        const int plane_me = (int)(rows_me * D.ldk);
+        k_thomas_solve<<<(plane_me + 127) / 128, 128, 0, c->stream>>>(D.n_i, plane_me, D.inv_slab, D.V, 4.0 / ((double)(D.n_j + 1) * (double)(D.n_k + 1)));
+        c->launches++;
+    }
+    // mode slabs -> x slabs
+    if (comm_group_start()) return 1;
+    for (int q = 0; q < nr; q++)
+    {
+        if (q == me) continue;
+        const size_t rows_q = (size_t)(D.pj0[q + 1] - D.pj0[q]), np_q = (size_t)(D.pi0[q + 1] - D.pi0[q]);
+        if (np_q > 0 && rows_me > 0 && comm_send(c, D.V + (size_t)D.pi0[q] * rows_me * D.ldk, np_q * rows_me * D.ldk, q)) return 1;
+        if (np > 0 && rows_q > 0 && comm_recv(c, D.Xb + off[q], (size_t)np * rows_q * D.ldk, q)) return 1;
+    }
+    if (comm_group_end()) return 1;
+    for (int q = 0; q < nr && np > 0; q++)
+    {
+        const size_t rows_q = (size_t)(D.pj0[q + 1] - D.pj0[q]);
+        if (rows_q == 0) continue;
+        const double* src = q == me ? D.V + (size_t)a * rows_me * D.ldk : D.Xb + off[q];
+        CUDA_OK(cudaMemcpy2DAsync(D.R + a * plane + (size_t)D.pj0[q] * D.ldk, plane * esz, src, rows_q * D.ldk * esz, rows_q * D.ldk * esz, (size_t)np,
+                                  cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (np > 0)
+    {
+        // inverse transforms of this rank's planes, scattered into its planes of the potential
+        G.A = D.Sy; G.lda = D.ldj; G.strideA = 0;
+        G.B = D.R + a * plane; G.ldb = D.ldk; G.strideB = (long long)plane;
+        G.C = D.T + a * plane; G.ldc = D.ldk; G.strideC = (long long)plane;
+        G.rows = D.ldj; G.cols = D.ldk; G.Kdim = D.ldj;
+        gemm3(c, G, np, false);
+        G.A = D.T + a * plane; G.lda = D.ldk; G.strideA = 0;
+        G.B = D.Sz; G.ldb = D.ldk; G.strideB = 0;
+        G.C = u; G.strideC = 0;
+        G.rows = np * D.ldj; G.cols = D.ldk; G.Kdim = D.ldk;
+        G.ldj = D.ldj; G.n_j = D.n_j; G.n_k = D.n_k; G.K = c->g.K; G.N = c->g.N; G.i0 = a;
+        gemm3(c, G, 1, true);
+    }
+    // every rank's planes to everybody (the frame planes 0 and M-1 are Dirichlet values every rank has written itself)
+    const size_t node_plane = (size_t)c->g.K * c->g.N;
+    if (comm_group_start()) return 1;
+    for (int q = 0; q < nr; q++)
+    {
+        const size_t np_q = (size_t)(D.pi0[q + 1] - D.pi0[q]);
+        if (np_q > 0 && comm_broadcast(c, u + (size_t)(D.pi0[q] + 1) * node_plane, np_q * node_plane, q)) return 1;
+    }
+    if (comm_group_end()) return 1;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 std::vector<double> sine_matrix(int n, int ld)
 {
     std::vector<double> S((size_t)ld * ld, 0.0);
@@ -455,6 +585,7 @@ std::vector<double> sine_matrix(int n, int ld)
 
 void direct3d_free(mag2d_ctx* c)
 {
+    cudaFree(c->direct3.V); cudaFree(c->direct3.inv_slab); cudaFree(c->direct3.Sb); cudaFree(c->direct3.Xb);
     Direct3D& D = c->direct3;
     cudaFree(D.Sy); cudaFree(D.Sz); cudaFree(D.inv); cudaFree(D.R); cudaFree(D.T); cudaFree(D.interior_fixed);
     cudaFree(D.e_nodes); cudaFree(D.e_volts); cudaFree(D.cinv); cudaFree(D.alpha); cudaFree(D.green);
@@ -622,7 +753,13 @@ int solve3d(mag2d_ctx* c, double* resid_out)
     A.R = D.R;
     k_rhs3d<<<(unsigned)(M * K), std::min(256, (N + 31) / 32 * 32), 0, c->stream>>>(A);
     c->launches++;
-    if (solve_interior(c, c->d_u)) return 1;
+    // N ranks: the solve itself is shared out (MAG3D_SLAB_SOLVE=0 keeps it replicated); every rank must make this call
+    static const bool slab_env = !getenv("MAG3D_SLAB_SOLVE") || atoi(getenv("MAG3D_SLAB_SOLVE")) != 0;
+    if (c->nccl_comm && c->nranks > 1 && slab_env && comm_has_p2p())
+    {
+        if (solve_interior_slab(c, c->d_u)) return 1;
+    }
+    else if (solve_interior(c, c->d_u)) return 1;
     if (D.ne > 0)
     {
         k_capacitance<<<1, 64, 0, c->stream>>>(D.ne, D.e_nodes, D.e_volts, D.cinv, c->d_u, D.alpha);

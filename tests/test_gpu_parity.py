@@ -210,8 +210,17 @@ def test_cylindrical_selfconsistent_loop_vs_golden_reference(orc, deckdir):
         assert np.abs(sim.get_field("rho") - G["c3_rho5"]).max() <= 500 * 2.0 ** -33 * abs(qe) + 1e-6 * abs(qe)
 
 
-def test_cartesian_selfconsistent_loop_vs_oracle(orc, deckdir):
-    """two particle species, deposit + solve every step, collisions off (gas density 0)"""
+@pytest.mark.parametrize("deposit", ["fixed", "fp64"])
+def test_cartesian_selfconsistent_loop_vs_oracle(orc, deckdir, deposit):
+    """two particle species, deposit + solve every step, collisions off (gas density 0).
+
+    deposit = "fixed": the oracle loop deposits with the same Q32 fixed-point rule as the product (the bit-exactness contract
+    of the charge grid), so the two loops see the same right-hand side and differ only by the round-off of the solve and of the
+    push: trajectories within 1e-10 after 5 coupled steps, like the collision-free bar.
+    deposit = "fp64": the oracle deposits like the reference (sequential fp64 sums).  Each weight of the product is rounded at
+    2^-32 (2.3e-10), the charge of a node is a difference of two species' sums that nearly cancel (quasi-neutral plasma), so the
+    right-hand side differs by ~1e-8 of its size, the field by as much, and the trajectories after 5 steps by up to 1e-7 of the
+    largest coordinate: that is the price of an order-independent grid, not solver or push error (the "fixed" leg shows it)."""
     d = decks.deck("c4", deckdir + "_nc", n_particles=20000, collisions=False, x_sampl=33, z_sampl=33, r_max=3.2e-3, z_max=3.2e-3)
     with _sim(d["config"], d["species_conf"]) as sim:
         g = grid_from_param(sim.param)
@@ -226,9 +235,15 @@ def test_cartesian_selfconsistent_loop_vs_oracle(orc, deckdir):
         Pi, Pe = Particles.from_aos7(ai), Particles.from_aos7(ae)
         qi, qe = m.get(ii, "charge"), m.get(ie, "charge")
         sim.advance_init()
-        rho_i, _ = orc.deposit_fp64(g, qi, Pi.x, Pi.z)
-        rho_e, _ = orc.deposit_fp64(g, qe, Pe.x, Pe.z)
-        rho = rho_i + rho_e
+
+        def coulombs(q, P):
+            if deposit == "fp64":
+                return orc.deposit_fp64(g, q, P.x, P.z, P.alive.astype(np.uint8))[0]
+            return q * (orc.deposit_fixed(g, P.x, P.z, P.alive.astype(np.uint8))[0].astype(np.float64) * 2.0 ** -32)
+        rho = coulombs(qi, Pi) + coulombs(qe, Pe) if deposit == "fp64" else None
+        if deposit == "fixed":
+            # the product sums q_s W_s 2^-32 over the species in index order (k_rhs): so does this
+            rho = coulombs(qi, Pi) + coulombs(qe, Pe) if ii < ie else coulombs(qe, Pe) + coulombs(qi, Pi)
         u = orc.solve_direct(g, mask, orc.rhs(g, mask, volt, rho))
         urf = np.zeros_like(u)
         orc.advance_boris_init(g, u, urf, m, ii, Pi)
@@ -236,22 +251,22 @@ def test_cartesian_selfconsistent_loop_vs_oracle(orc, deckdir):
         for step in range(5):
             sim.advance(1)
             u = orc.solve_direct(g, mask, orc.rhs(g, mask, volt, rho))
-            rho_i[:] = 0
-            rho_e[:] = 0
             orc.advance_boris(g, u, urf, m, ii, Pi, niter=step, rng=None)
-            orc.advance_boundary(g, mask, qi, Pi, rho=rho_i)
+            orc.advance_boundary(g, mask, qi, Pi)
             orc.advance_boris(g, u, urf, m, ie, Pe, niter=step, rng=None)
-            orc.advance_boundary(g, mask, qe, Pe, rho=rho_e)
-            rho = rho_i + rho_e
+            orc.advance_boundary(g, mask, qe, Pe)
+            rho = coulombs(qi, Pi) + coulombs(qe, Pe) if ii < ie else coulombs(qe, Pe) + coulombs(qi, Pi)
         oi, oe = sim.get_particles(ii), sim.get_particles(ie)
         assert np.array_equal(oi[:, 7], Pi.alive) and np.array_equal(oe[:, 7], Pe.alive)
-        assert relerr(oe[:, [0, 2, 3, 4, 5]], Pe.aos7()[:, [0, 2, 3, 4, 5]]) <= 1e-7
-        assert relerr(oi[:, [0, 2, 3, 4, 5]], Pi.aos7()[:, [0, 2, 3, 4, 5]]) <= 1e-7
+        tol = 1e-10 if deposit == "fixed" else 1e-7
+        assert relerr(oe[:, [0, 2, 3, 4, 5]], Pe.aos7()[:, [0, 2, 3, 4, 5]]) <= tol
+        assert relerr(oi[:, [0, 2, 3, 4, 5]], Pi.aos7()[:, [0, 2, 3, 4, 5]]) <= tol
         # fixed-point grids are bit-exact for the device's own particle set
         for s, o in ((ii, oi), (ie, oe)):
             fixed, _ = orc.deposit_fixed(g, o[:, 0].copy(), o[:, 2].copy(), o[:, 7].astype(np.uint8))
             assert np.array_equal(sim.rho_fixed(s), fixed)
-        assert np.abs(sim.get_field("rho") - rho).max() <= 20000 * 2.0 ** -33 * abs(qe) + 1e-6 * abs(qe)
+        if deposit == "fp64":
+            assert np.abs(sim.get_field("rho") - rho).max() <= 20000 * 2.0 ** -33 * abs(qe) + 1e-6 * abs(qe)
 
 
 # ---------------------------------------------------------------------------------------- deposit
