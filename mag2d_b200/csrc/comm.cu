@@ -24,6 +24,7 @@ typedef int (*fn_Send)(const void*, size_t, int, int, NcclComm, cudaStream_t);
 typedef int (*fn_Recv)(void*, size_t, int, int, NcclComm, cudaStream_t);
 typedef int (*fn_Group)();
 typedef int (*fn_Broadcast)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
+typedef int (*fn_AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t);
 typedef const char* (*fn_GetErrorString)(int);
 
 struct NcclApi
@@ -38,6 +39,7 @@ struct NcclApi
     fn_Recv Recv = nullptr;
     fn_Group GroupStart = nullptr, GroupEnd = nullptr;
     fn_Broadcast Broadcast = nullptr;
+    fn_AllGather AllGather = nullptr;
 };
 
 NcclApi g_nccl;
@@ -73,6 +75,7 @@ int load_nccl()
     g_nccl.GroupStart = (fn_Group)dlsym(h, "ncclGroupStart");
     g_nccl.GroupEnd = (fn_Group)dlsym(h, "ncclGroupEnd");
     g_nccl.Broadcast = (fn_Broadcast)dlsym(h, "ncclBroadcast");
+    g_nccl.AllGather = (fn_AllGather)dlsym(h, "ncclAllGather");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
     {
         mag2d_set_error("libnccl.so.2 lacks the expected symbols");
@@ -179,7 +182,7 @@ int comm_allreduce_rho(mag2d_ctx* c)
 }
 
 // ---- point-to-point pieces of the slab-parallel 3-D solve (poisson3d.cu); doubles, on the compute stream -----------------
-bool comm_has_p2p() { return g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd && g_nccl.Broadcast; }
+bool comm_has_p2p() { return g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd && g_nccl.Broadcast && g_nccl.AllGather; }
 int comm_group_start()
 {
     const int rc = g_nccl.GroupStart();
@@ -204,4 +207,10 @@ int comm_broadcast(mag2d_ctx* c, double* buf, size_t count, int root)
 {
     const int rc = g_nccl.Broadcast(buf, buf, count, 8, root, (NcclComm)c->nccl_comm, c->stream);
     return rc ? nccl_fail("ncclBroadcast", rc) : 0;
+}
+// in-place all-gather: rank r's block of `count` doubles sits at buf + r * count
+int comm_allgather_inplace(mag2d_ctx* c, double* buf, size_t count)
+{
+    const int rc = g_nccl.AllGather(buf + (size_t)c->rank * count, buf, count, 8, (NcclComm)c->nccl_comm, c->stream);
+    return rc ? nccl_fail("ncclAllGather", rc) : 0;
 }

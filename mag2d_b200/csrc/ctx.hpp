@@ -298,3 +298,4 @@ int comm_group_end();
 int comm_send(mag2d_ctx* c, const double* buf, size_t count, int peer);
 int comm_recv(mag2d_ctx* c, double* buf, size_t count, int peer);
 int comm_broadcast(mag2d_ctx* c, double* buf, size_t count, int root);
+int comm_allgather_inplace(mag2d_ctx* c, double* buf, size_t count);

@@ -450,10 +450,12 @@ int slab_setup(mag2d_ctx* c)
     const int nr = c->nranks, me = c->rank;
     D.pi0.assign(nr + 1, 0);
     D.pj0.assign(nr + 1, 0);
-    const int pi = (D.n_i + nr - 1) / nr, pj = (D.ldj + nr - 1) / nr;
+    // planes are shared out by their index in the potential (interior plane i is plane i + 1 of u, the two frame planes ride along with
+    // the first and the last rank): when M divides by N every rank owns M / N whole planes of u and one all-gather spreads them
+    const int pu = (c->g.M + nr - 1) / nr, pj = (D.ldj + nr - 1) / nr;
     for (int q = 0; q <= nr; q++)
     {
-        D.pi0[q] = std::min(q * pi, D.n_i);
+        D.pi0[q] = q == nr ? D.n_i : std::min(std::max(q * pu - 1, 0), D.n_i);
         D.pj0[q] = std::min(q * pj, D.ldj);
     }
     const size_t rows_me = (size_t)(D.pj0[me + 1] - D.pj0[me]);
@@ -557,13 +559,20 @@ int solve_interior_slab(mag2d_ctx* c, double* u)
     }
     // every rank's planes to everybody (the frame planes 0 and M-1 are Dirichlet values every rank has written itself)
     const size_t node_plane = (size_t)c->g.K * c->g.N;
-    if (comm_group_start()) return 1;
-    for (int q = 0; q < nr; q++)
+    if (c->g.M % nr == 0)
     {
-        const size_t np_q = (size_t)(D.pi0[q + 1] - D.pi0[q]);
-        if (np_q > 0 && comm_broadcast(c, u + (size_t)(D.pi0[q] + 1) * node_plane, np_q * node_plane, q)) return 1;
+        if (comm_allgather_inplace(c, u, (size_t)(c->g.M / nr) * node_plane)) return 1;
     }
-    if (comm_group_end()) return 1;
+    else
+    {
+        if (comm_group_start()) return 1;
+        for (int q = 0; q < nr; q++)
+        {
+            const size_t np_q = (size_t)(D.pi0[q + 1] - D.pi0[q]);
+            if (np_q > 0 && comm_broadcast(c, u + (size_t)(D.pi0[q] + 1) * node_plane, np_q * node_plane, q)) return 1;
+        }
+        if (comm_group_end()) return 1;
+    }
     CUDA_OK(cudaGetLastError());
     return 0;
 }
