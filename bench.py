@@ -41,7 +41,7 @@ DEFAULT_PARTICLES = {"c4": 100_000_000, "c2": 1_000_000, "c3": 10_000_000, "c1":
 BYTES = {"c4": 80.0, "c2": 80.0, "c3": 80.0, "c1": 96.0, "c5": 96.0}
 
 
-KERNEL_SOURCES = ("push.cu", "push3d.cu", "mcc.cuh", "common.cuh")
+KERNEL_SOURCES = ("push.cu", "push3d.cu", "push3d.cuh", "push3d_brick.cu", "mcc.cuh", "common.cuh")
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r2_push_dram.json")
 
 
