@@ -106,10 +106,15 @@ struct Direct3D
 {
     bool ok = false;
     int n_i = 0, n_j = 0, n_k = 0;   // interior unknowns along x, y, z
-    int ldj = 0, ldk = 0;            // n_j, n_k rounded up to multiples of 32
+    int ldj = 0, ldk = 0;            // 2 * hpj, 2 * hpk: a folded row holds the symmetric half, then the antisymmetric half
+    int hpj = 0, hpk = 0;            // ceil(n / 2) rounded up to a multiple of 32
     int ne = 0;                      // electrode nodes inside the box (capacitance-matrix method)
-    double* Sy = nullptr;            // [ldj][ldj], [ldk][ldk] sine matrices
-    double* Sz = nullptr;
+    // half-size sine matrices of the folded transforms, [2][hp][hp] each (parity 0: odd mode numbers acting on the symmetric
+    // half, parity 1: even mode numbers on the antisymmetric half); _f forward, _i inverse (the transposes)
+    double* Sy_f = nullptr;
+    double* Sy_i = nullptr;
+    double* Sz_f = nullptr;
+    double* Sz_i = nullptr;
     double* inv = nullptr;           // [n_i][ldj][ldk] Thomas factors
     double* R = nullptr;             // [n_i][ldj][ldk] work arrays
     double* T = nullptr;

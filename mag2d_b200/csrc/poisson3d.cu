@@ -11,6 +11,13 @@
 //     U   = S_y (U^ S_z) * 4/((n_y+1)(n_z+1))
 // and interior electrode nodes are imposed exactly afterwards by the capacitance-matrix method (Green's functions
 // of the electrode nodes are precomputed with the same solver).  Exact to round-off like the reference's LU.
+//
+// The sine matrix S[j][k] = sin(pi (j+1)(k+1)/(n+1)) obeys S[j][n-1-k] = (-1)^j S[j][k]: modes with even j only see the
+// symmetric part x[k] + x[n-1-k] of a vector, modes with odd j the antisymmetric part x[k] - x[n-1-k].  Every transform is
+// therefore done FOLDED: a row of length ld = 2 hp holds the symmetric half [0, hp) and the antisymmetric half [hp, 2 hp),
+// the spectrum is kept in the same split order (even j, then odd j), and each of the four transforms becomes two products
+// with hp x hp matrices — half the flops of the full products.  k_fold3d folds the right-hand side along y and z at once,
+// k_unfold3d undoes both (x[k] = e + o, x[n-1-k] = e - o) while it writes the interior of the potential.
 // Geometries with extended internal electrodes need a 3-D multigrid (not built yet): set_grid refuses them.
 #include <cmath>
 #include <cstdlib>
@@ -29,13 +36,12 @@ constexpr int G3_SMEM = G3_STAGES * G3_STAGE_DOUBLES * (int)sizeof(double);
 
 struct Gemm3Args
 {
-    const double* A; long long strideA; int lda;     // [rows][Kdim]
-    const double* B; long long strideB; int ldb;     // [Kdim][cols]
-    double* C; long long strideC; int ldc;
-    int rows, cols, Kdim;                            // cols and Kdim are multiples of 32
+    // batch entry z = 2 * outer + parity: operand X starts at X + outer * strideX + parity * halfX (the two halves of a folded transform)
+    const double* A; long long strideA, halfA; int lda;     // [rows][Kdim]
+    const double* B; long long strideB, halfB; int ldb;     // [Kdim][cols]
+    double* C; long long strideC, halfC; int ldc;
+    int rows, cols, Kdim;                                   // cols and Kdim are multiples of 32
     double scale;
-    // SCATTER epilogue: row r = il*ldj + jl of the interior block goes to node (i0+il+1, jl+1, 1..) of the potential
-    int ldj, n_j, n_k, K, N, i0;
 };
 
 __device__ __forceinline__ void cp16(void* smem, const void* gmem)
@@ -47,15 +53,15 @@ __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_grou
 template <int W>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(W) : "memory"); }
 
-template <bool SCATTER>
 __global__ void __launch_bounds__(G3_THREADS) k_gemm3(const __grid_constant__ Gemm3Args G)
 {
     extern __shared__ __align__(16) double g3_smem[];
     const int t = threadIdx.x;
     const int r0 = blockIdx.y * G3_TM, c0 = blockIdx.x * G3_TN;
-    const double* A = G.A + (long long)blockIdx.z * G.strideA;
-    const double* B = G.B + (long long)blockIdx.z * G.strideB;
-    double* C = G.C + (long long)blockIdx.z * G.strideC;
+    const long long outer = blockIdx.z >> 1, par = blockIdx.z & 1;
+    const double* A = G.A + outer * G.strideA + par * G.halfA;
+    const double* B = G.B + outer * G.strideB + par * G.halfB;
+    double* C = G.C + outer * G.strideC + par * G.halfC;
     const int tr = (t / 8) * 4, tc = (t % 8) * 4;
     const int nk = G.Kdim / G3_KC;
     auto issue = [&](int kb) {
@@ -110,24 +116,9 @@ __global__ void __launch_bounds__(G3_THREADS) k_gemm3(const __grid_constant__ Ge
     {
         const int r = r0 + tr + p;
         if (r >= G.rows) continue;
-        if (SCATTER)
-        {
-            const int il = r / G.ldj + G.i0, jl = r % G.ldj;
-            if (jl >= G.n_j) continue;
-            double* out = C + ((size_t)(il + 1) * G.K + (jl + 1)) * G.N + 1;
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-            {
-                const int k = c0 + tc + q;
-                if (k < G.n_k) out[k] = acc[p][q] * G.scale;
-            }
-        }
-        else
-        {
-            double* out = C + (size_t)r * G.ldc + c0 + tc;
-            *reinterpret_cast<double2*>(out) = make_double2(acc[p][0] * G.scale, acc[p][1] * G.scale);
-            *reinterpret_cast<double2*>(out + 2) = make_double2(acc[p][2] * G.scale, acc[p][3] * G.scale);
-        }
+        double* out = C + (size_t)r * G.ldc + c0 + tc;
+        *reinterpret_cast<double2*>(out) = make_double2(acc[p][0] * G.scale, acc[p][1] * G.scale);
+        *reinterpret_cast<double2*>(out + 2) = make_double2(acc[p][2] * G.scale, acc[p][3] * G.scale);
     }
 }
 
@@ -146,15 +137,15 @@ __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b)
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
 
-template <bool SCATTER>
 __global__ void __launch_bounds__(M3_THREADS) k_gemm3_mma(const __grid_constant__ Gemm3Args G)
 {
     extern __shared__ __align__(16) double m3_smem[];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int r0 = blockIdx.y * M3_TM, c0 = blockIdx.x * M3_TN;
-    const double* A = G.A + (long long)blockIdx.z * G.strideA;
-    const double* B = G.B + (long long)blockIdx.z * G.strideB;
-    double* C = G.C + (long long)blockIdx.z * G.strideC;
+    const long long outer = blockIdx.z >> 1, par = blockIdx.z & 1;
+    const double* A = G.A + outer * G.strideA + par * G.halfA;
+    const double* B = G.B + outer * G.strideB + par * G.halfB;
+    double* C = G.C + outer * G.strideC + par * G.halfC;
     const int nk = G.Kdim / M3_KC;
     auto issue = [&](int kb) {
         double* sa = m3_smem + (kb % M3_STAGES) * M3_STAGE_DOUBLES;
@@ -211,24 +202,74 @@ __global__ void __launch_bounds__(M3_THREADS) k_gemm3_mma(const __grid_constant_
     {
         const int r = r0 + warp * 32 + p * 8 + fr;
         if (r >= G.rows) continue;
-        if (SCATTER)
-        {
-            const int il = r / G.ldj + G.i0, jl = r % G.ldj;
-            if (jl >= G.n_j) continue;
-            double* out = C + ((size_t)(il + 1) * G.K + (jl + 1)) * G.N + 1;
+        double* out = C + (size_t)r * G.ldc + c0 + 2 * fc;
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+        for (int q = 0; q < 4; q++) *reinterpret_cast<double2*>(out + q * 8) = make_double2(acc[p][q][0] * G.scale, acc[p][q][1] * G.scale);
+    }
+}
+
+// ---- folding --------------------------------------------------------------------------------------------------------
+// natural planes [ldj][ldk] (entries (jl, kl), jl < n_j, kl < n_k) -> folded planes: with s/a = symmetric / antisymmetric part
+// along an axis, the quadrants hold [ss | sa ; as | aa] (rows: y part, columns: z part).  The middle element of an odd
+// length is its own mirror image: it goes to the symmetric half as it is.  Every entry of the folded plane is written
+// (zeros in the padding).  One block per (pair of rows jj / n_j-1-jj, plane), threads along z.
+__global__ void __launch_bounds__(128) k_fold3d(int n_j, int n_k, int hpj, int hpk, const double* __restrict__ nat, double* __restrict__ fold)
+{
+    const int jj = blockIdx.x, jm = n_j - 1 - jj, ldk = 2 * hpk;
+    const size_t base = (size_t)blockIdx.y * (2 * hpj) * ldk;
+    const double* n0 = nat + base + (size_t)jj * ldk;
+    const double* n1 = nat + base + (size_t)max(jm, 0) * ldk;
+    double* f0 = fold + base + (size_t)jj * ldk;
+    double* f1 = fold + base + (size_t)(hpj + jj) * ldk;
+    const bool row_s = jj <= jm, row_a = jj < jm;
+    for (int kk = threadIdx.x; kk < hpk; kk += blockDim.x)
+    {
+        const int km = n_k - 1 - kk;
+        const bool col_s = kk <= km, col_a = kk < km;
+        double a = 0.0, b = 0.0, c = 0.0, d = 0.0;      // (j, k), (j, k~), (j~, k), (j~, k~)
+        if (row_s && col_s)
+        {
+            a = n0[kk];
+            if (col_a) b = n0[km];
+            if (row_a)
             {
-                const int k = c0 + q * 8 + 2 * fc;
-                if (k < G.n_k) out[k] = acc[p][q][0] * G.scale;
-                if (k + 1 < G.n_k) out[k + 1] = acc[p][q][1] * G.scale;
+                c = n1[kk];
+                if (col_a) d = n1[km];
             }
         }
-        else
+        const double s0 = a + b, a0 = col_a ? a - b : 0.0, s1 = c + d, a1 = col_a ? c - d : 0.0;
+        f0[kk] = s0 + s1;
+        f0[hpk + kk] = a0 + a1;
+        f1[kk] = row_a ? s0 - s1 : 0.0;
+        f1[hpk + kk] = row_a ? a0 - a1 : 0.0;
+    }
+}
+
+// folded planes [ee | eo ; oe | oo] of the inverse transforms -> interior nodes of the potential: plane il of the block is plane
+// i0 + il + 1 of u.  x[k] = e + o, x[n-1-k] = e - o along both axes.
+__global__ void __launch_bounds__(128) k_unfold3d(int n_j, int n_k, int hpj, int hpk, int K, int N, int i0, const double* __restrict__ fold,
+                                                  double* __restrict__ u)
+{
+    const int jj = blockIdx.x, jm = n_j - 1 - jj, ldk = 2 * hpk;
+    if (jj > jm) return;
+    const size_t base = (size_t)blockIdx.y * (2 * hpj) * ldk;
+    const double* f0 = fold + base + (size_t)jj * ldk;
+    const double* f1 = fold + base + (size_t)(hpj + jj) * ldk;
+    double* up = u + ((size_t)(i0 + (int)blockIdx.y + 1) * K + 1) * N + 1;       // node (i, 1, 1)
+    double* u0 = up + (size_t)jj * N;
+    double* u1 = up + (size_t)jm * N;
+    for (int kk = threadIdx.x; kk < hpk; kk += blockDim.x)
+    {
+        const int km = n_k - 1 - kk;
+        if (kk > km) break;
+        const double ee = f0[kk], eo = f0[hpk + kk], oe = f1[kk], oo = f1[hpk + kk];
+        const double p = ee + eo, q = oe + oo, r = ee - eo, t = oe - oo;
+        u0[kk] = p + q;
+        if (kk < km) u0[km] = r + t;
+        if (jj < jm)
         {
-            double* out = C + (size_t)r * G.ldc + c0 + 2 * fc;
-#pragma unroll
-            for (int q = 0; q < 4; q++) *reinterpret_cast<double2*>(out + q * 8) = make_double2(acc[p][q][0] * G.scale, acc[p][q][1] * G.scale);
+            u1[kk] = p - q;
+            if (kk < km) u1[km] = r - t;
         }
     }
 }
@@ -244,7 +285,7 @@ struct Rhs3Args
     const double* charges;
     double* b;                           // reference right-hand side (diagnostics, residual)
     double* u;                           // Dirichlet nodes receive their voltage
-    double* R;                           // [n_i][ldj][ldk] interior right-hand side with the frame values moved over
+    double* R;                           // [n_i][ldj][ldk] interior right-hand side with the frame values moved over (natural layout)
 };
 
 // Solver::solve's right-hand side + the reduction to the interior block
@@ -290,13 +331,16 @@ __global__ void k_rhs3d(const __grid_constant__ Rhs3Args A)
 }
 
 // Thomas factors of the Toeplitz systems [1, d, 1], d = -6 + lam_j + lam_k: inv[i][mode] = 1 / (d - inv[i-1][mode])
+// (a padding mode gets d = -6: its right-hand side is zero and stays zero)
 __global__ void k_thomas_setup(int n_i, int n_j, int n_k, int ldj, int ldk, double* __restrict__ inv)
 {
     const int mode = blockIdx.x * blockDim.x + threadIdx.x;
     if (mode >= ldj * ldk) return;
-    const int jl = mode / ldk, kl = mode % ldk;
+    // folded spectrum: entry l of a row is mode 2 l (l < hp) or mode 2 (l - hp) + 1 (counted from 0); the rest is padding
+    const int jl = mode / ldk, kl = mode % ldk, hpj = ldj / 2, hpk = ldk / 2;
+    const int mj = jl < hpj ? 2 * jl : 2 * (jl - hpj) + 1, mk = kl < hpk ? 2 * kl : 2 * (kl - hpk) + 1;
     double d = -6.0;
-    if (jl < n_j && kl < n_k) d += 2.0 * cospi((double)(jl + 1) / (double)(n_j + 1)) + 2.0 * cospi((double)(kl + 1) / (double)(n_k + 1));
+    if (mj < n_j && mk < n_k) d += 2.0 * cospi((double)(mj + 1) / (double)(n_j + 1)) + 2.0 * cospi((double)(mk + 1) / (double)(n_k + 1));
     double c = 0.0;
     for (int i = 0; i < n_i; i++)
     {
@@ -381,59 +425,81 @@ __global__ void k_residual3d(int M, int K, int N, const unsigned char* __restric
     }
 }
 
-int gemm3(mag2d_ctx* c, const Gemm3Args& G, int batch, bool scatter)
+// both halves of `outer` folded products in one launch
+int gemm3(mag2d_ctx* c, const Gemm3Args& G, int outer)
 {
     static const bool use_fma = getenv("MAG2D_GEMM") && !strcmp(getenv("MAG2D_GEMM"), "fma");
     if (use_fma)
     {
-        const dim3 grid(G.cols / G3_TN, (G.rows + G3_TM - 1) / G3_TM, batch);
-        if (scatter) k_gemm3<true><<<grid, G3_THREADS, G3_SMEM, c->stream>>>(G);
-        else k_gemm3<false><<<grid, G3_THREADS, G3_SMEM, c->stream>>>(G);
+        const dim3 grid(G.cols / G3_TN, (G.rows + G3_TM - 1) / G3_TM, 2 * outer);
+        k_gemm3<<<grid, G3_THREADS, G3_SMEM, c->stream>>>(G);
     }
     else
     {
-        const dim3 grid(G.cols / M3_TN, (G.rows + M3_TM - 1) / M3_TM, batch);
-        if (scatter) k_gemm3_mma<true><<<grid, M3_THREADS, M3_SMEM, c->stream>>>(G);
-        else k_gemm3_mma<false><<<grid, M3_THREADS, M3_SMEM, c->stream>>>(G);
+        const dim3 grid(G.cols / M3_TN, (G.rows + M3_TM - 1) / M3_TM, 2 * outer);
+        k_gemm3_mma<<<grid, M3_THREADS, M3_SMEM, c->stream>>>(G);
     }
     c->launches++;
     return 0;
 }
 
-// interior block R (in D.R) -> potential on the interior nodes of u (frame untouched)
+// x planes [a, a + np): natural right-hand side in D.T -> folded, transformed along z and y, in D.R
+int forward_planes(mag2d_ctx* c, int a, int np)
+{
+    Direct3D& D = c->direct3;
+    const long long plane = (long long)D.ldj * D.ldk;
+    k_fold3d<<<dim3((unsigned)D.hpj, (unsigned)np), 128, 0, c->stream>>>(D.n_j, D.n_k, D.hpj, D.hpk, D.T + a * plane, D.R + a * plane);
+    c->launches++;
+    Gemm3Args G;
+    memset(&G, 0, sizeof(G));
+    G.scale = 1.0;
+    // along z: T = R E_z, all rows of the np planes at once; the halves are the two column blocks
+    G.A = D.R + a * plane; G.lda = D.ldk; G.halfA = D.hpk;
+    G.B = D.Sz_f; G.ldb = D.hpk; G.halfB = (long long)D.hpk * D.hpk;
+    G.C = D.T + a * plane; G.ldc = D.ldk; G.halfC = D.hpk;
+    G.rows = np * D.ldj; G.cols = D.hpk; G.Kdim = D.hpk;
+    gemm3(c, G, 1);
+    // along y: R_i = E_y^T T_i for every plane; the halves are the two row blocks
+    G.A = D.Sy_f; G.lda = D.hpj; G.strideA = 0; G.halfA = (long long)D.hpj * D.hpj;
+    G.B = D.T + a * plane; G.ldb = D.ldk; G.strideB = plane; G.halfB = (long long)D.hpj * D.ldk;
+    G.C = D.R + a * plane; G.ldc = D.ldk; G.strideC = plane; G.halfC = (long long)D.hpj * D.ldk;
+    G.rows = D.hpj; G.cols = D.ldk; G.Kdim = D.hpj;
+    gemm3(c, G, np);
+    return 0;
+}
+
+// x planes [a, a + np): folded spectrum in D.R -> inverse transforms along y and z -> interior nodes of those planes of u
+int inverse_planes(mag2d_ctx* c, int a, int np, double* u)
+{
+    Direct3D& D = c->direct3;
+    const long long plane = (long long)D.ldj * D.ldk;
+    Gemm3Args G;
+    memset(&G, 0, sizeof(G));
+    G.scale = 1.0;
+    G.A = D.Sy_i; G.lda = D.hpj; G.strideA = 0; G.halfA = (long long)D.hpj * D.hpj;
+    G.B = D.R + a * plane; G.ldb = D.ldk; G.strideB = plane; G.halfB = (long long)D.hpj * D.ldk;
+    G.C = D.T + a * plane; G.ldc = D.ldk; G.strideC = plane; G.halfC = (long long)D.hpj * D.ldk;
+    G.rows = D.hpj; G.cols = D.ldk; G.Kdim = D.hpj;
+    gemm3(c, G, np);
+    G.A = D.T + a * plane; G.lda = D.ldk; G.strideA = 0; G.halfA = D.hpk;
+    G.B = D.Sz_i; G.ldb = D.hpk; G.strideB = 0; G.halfB = (long long)D.hpk * D.hpk;
+    G.C = D.R + a * plane; G.ldc = D.ldk; G.strideC = 0; G.halfC = D.hpk;
+    G.rows = np * D.ldj; G.cols = D.hpk; G.Kdim = D.hpk;
+    gemm3(c, G, 1);
+    k_unfold3d<<<dim3((unsigned)D.hpj, (unsigned)np), 128, 0, c->stream>>>(D.n_j, D.n_k, D.hpj, D.hpk, c->g.K, c->g.N, a, D.R + a * plane, u);
+    c->launches++;
+    return 0;
+}
+
+// interior right-hand side (natural layout, in D.T) -> potential on the interior nodes of u (frame untouched)
 int solve_interior(mag2d_ctx* c, double* u)
 {
     Direct3D& D = c->direct3;
     const int plane = D.ldj * D.ldk;
-    Gemm3Args G;
-    memset(&G, 0, sizeof(G));
-    G.scale = 1.0;
-    // along z: T = R S_z, rows = n_i * ldj
-    G.A = D.R; G.lda = D.ldk; G.strideA = 0;
-    G.B = D.Sz; G.ldb = D.ldk; G.strideB = 0;
-    G.C = D.T; G.ldc = D.ldk; G.strideC = 0;
-    G.rows = D.n_i * D.ldj; G.cols = D.ldk; G.Kdim = D.ldk;
-    gemm3(c, G, 1, false);
-    // along y: R_i = S_y T_i for every x plane
-    G.A = D.Sy; G.lda = D.ldj; G.strideA = 0;
-    G.B = D.T; G.ldb = D.ldk; G.strideB = plane;
-    G.C = D.R; G.ldc = D.ldk; G.strideC = plane;
-    G.rows = D.ldj; G.cols = D.ldk; G.Kdim = D.ldj;
-    gemm3(c, G, D.n_i, false);
+    if (forward_planes(c, 0, D.n_i)) return 1;
     k_thomas_solve<<<(plane + 127) / 128, 128, 0, c->stream>>>(D.n_i, plane, D.inv, D.R, 4.0 / ((double)(D.n_j + 1) * (double)(D.n_k + 1)));
     c->launches++;
-    // back: T_i = S_y R_i, then U = T S_z scattered into the potential
-    G.A = D.Sy; G.lda = D.ldj; G.strideA = 0;
-    G.B = D.R; G.ldb = D.ldk; G.strideB = plane;
-    G.C = D.T; G.ldc = D.ldk; G.strideC = plane;
-    G.rows = D.ldj; G.cols = D.ldk; G.Kdim = D.ldj;
-    gemm3(c, G, D.n_i, false);
-    G.A = D.T; G.lda = D.ldk; G.strideA = 0;
-    G.B = D.Sz; G.ldb = D.ldk; G.strideB = 0;
-    G.C = u; G.strideC = 0;
-    G.rows = D.n_i * D.ldj; G.cols = D.ldk; G.Kdim = D.ldk;
-    G.ldj = D.ldj; G.n_j = D.n_j; G.n_k = D.n_k; G.K = c->g.K; G.N = c->g.N;
-    gemm3(c, G, 1, true);
+    if (inverse_planes(c, 0, D.n_i, u)) return 1;
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -481,23 +547,8 @@ int solve_interior_slab(mag2d_ctx* c, double* u)
     const size_t plane = (size_t)D.ldj * D.ldk;
     const size_t rows_me = (size_t)(D.pj0[me + 1] - D.pj0[me]);
     const size_t esz = sizeof(double);
-    Gemm3Args G;
-    memset(&G, 0, sizeof(G));
-    G.scale = 1.0;
-    if (np > 0)
-    {
-        // forward transforms of this rank's planes: T = R S_z, then R_i = S_y T_i
-        G.A = D.R + a * plane; G.lda = D.ldk; G.strideA = 0;
-        G.B = D.Sz; G.ldb = D.ldk; G.strideB = 0;
-        G.C = D.T + a * plane; G.ldc = D.ldk; G.strideC = 0;
-        G.rows = np * D.ldj; G.cols = D.ldk; G.Kdim = D.ldk;
-        gemm3(c, G, 1, false);
-        G.A = D.Sy; G.lda = D.ldj; G.strideA = 0;
-        G.B = D.T + a * plane; G.ldb = D.ldk; G.strideB = (long long)plane;
-        G.C = D.R + a * plane; G.ldc = D.ldk; G.strideC = (long long)plane;
-        G.rows = D.ldj; G.cols = D.ldk; G.Kdim = D.ldj;
-        gemm3(c, G, np, false);
-    }
+    // forward transforms of this rank's planes
+    if (np > 0 && forward_planes(c, a, np)) return 1;
     // x slabs -> mode slabs: the rows [pj0[q], pj0[q+1]) of my planes go to rank q; their rows of my slab arrive from everybody
     std::vector<size_t> off(nr + 1, 0);
     for (int q = 0; q < nr; q++) off[q + 1] = off[q] + (size_t)np * (D.pj0[q + 1] - D.pj0[q]) * D.ldk;
@@ -542,21 +593,8 @@ int solve_interior_slab(mag2d_ctx* c, double* u)
         CUDA_OK(cudaMemcpy2DAsync(D.R + a * plane + (size_t)D.pj0[q] * D.ldk, plane * esz, src, rows_q * D.ldk * esz, rows_q * D.ldk * esz, (size_t)np,
                                   cudaMemcpyDeviceToDevice, c->stream));
     }
-    if (np > 0)
-    {
-        // inverse transforms of this rank's planes, scattered into its planes of the potential
-        G.A = D.Sy; G.lda = D.ldj; G.strideA = 0;
-        G.B = D.R + a * plane; G.ldb = D.ldk; G.strideB = (long long)plane;
-        G.C = D.T + a * plane; G.ldc = D.ldk; G.strideC = (long long)plane;
-        G.rows = D.ldj; G.cols = D.ldk; G.Kdim = D.ldj;
-        gemm3(c, G, np, false);
-        G.A = D.T + a * plane; G.lda = D.ldk; G.strideA = 0;
-        G.B = D.Sz; G.ldb = D.ldk; G.strideB = 0;
-        G.C = u; G.strideC = 0;
-        G.rows = np * D.ldj; G.cols = D.ldk; G.Kdim = D.ldk;
-        G.ldj = D.ldj; G.n_j = D.n_j; G.n_k = D.n_k; G.K = c->g.K; G.N = c->g.N; G.i0 = a;
-        gemm3(c, G, 1, true);
-    }
+    // inverse transforms of this rank's planes, unfolded into its planes of the potential
+    if (np > 0 && inverse_planes(c, a, np, u)) return 1;
     // every rank's planes to everybody (the frame planes 0 and M-1 are Dirichlet values every rank has written itself)
     const size_t node_plane = (size_t)c->g.K * c->g.N;
     if (c->g.M % nr == 0)
@@ -577,17 +615,23 @@ int solve_interior_slab(mag2d_ctx* c, double* u)
     return 0;
 }
 
-std::vector<double> sine_matrix(int n, int ld)
+// the two half matrices of a folded sine transform of length n: E_b[kk][m] = sin(pi (2m + b + 1)(kk + 1) / (n + 1)) for the
+// ceil(n/2) (b = 0) or floor(n/2) (b = 1) input pairs kk and modes m; [2][hp][hp], zero padding.  transposed: [b][m][kk].
+std::vector<double> half_sines(int n, int hp, bool transposed)
 {
-    std::vector<double> S((size_t)ld * ld, 0.0);
-    for (int j = 0; j < n; j++)
-        for (int k = j; k < n; k++)
-        {
-            const long long p = (long long)(j + 1) * (k + 1) % (2LL * (n + 1));
-            const double s = (double)sinl(M_PIl * (long double)p / (long double)(n + 1));
-            S[(size_t)j * ld + k] = S[(size_t)k * ld + j] = s;
-        }
-    return S;
+    std::vector<double> E(2 * (size_t)hp * hp, 0.0);
+    for (int b = 0; b < 2; b++)
+    {
+        const int h = b ? n / 2 : (n + 1) / 2;
+        for (int kk = 0; kk < h; kk++)
+            for (int m = 0; m < h; m++)
+            {
+                const long long p = (long long)(2 * m + b + 1) * (kk + 1) % (2LL * (n + 1));
+                const double v = (double)sinl(M_PIl * (long double)p / (long double)(n + 1));
+                E[(size_t)b * hp * hp + (transposed ? (size_t)m * hp + kk : (size_t)kk * hp + m)] = v;
+            }
+    }
+    return E;
 }
 
 }  // namespace
@@ -596,7 +640,7 @@ void direct3d_free(mag2d_ctx* c)
 {
     cudaFree(c->direct3.V); cudaFree(c->direct3.inv_slab); cudaFree(c->direct3.Sb); cudaFree(c->direct3.Xb);
     Direct3D& D = c->direct3;
-    cudaFree(D.Sy); cudaFree(D.Sz); cudaFree(D.inv); cudaFree(D.R); cudaFree(D.T); cudaFree(D.interior_fixed);
+    cudaFree(D.Sy_f); cudaFree(D.Sy_i); cudaFree(D.Sz_f); cudaFree(D.Sz_i); cudaFree(D.inv); cudaFree(D.R); cudaFree(D.T); cudaFree(D.interior_fixed);
     cudaFree(D.e_nodes); cudaFree(D.e_volts); cudaFree(D.cinv); cudaFree(D.alpha); cudaFree(D.green);
     D = Direct3D();
 }
@@ -641,8 +685,10 @@ int direct3d_setup(mag2d_ctx* c)
                     mag2d_set_error("3-D solver: a free k = N-1 face needs zero volts on the k = 0 face");
                     return 1;
                 }
-    D.ldj = (D.n_j + 31) / 32 * 32;
-    D.ldk = (D.n_k + 31) / 32 * 32;
+    D.hpj = ((D.n_j + 1) / 2 + 31) / 32 * 32;
+    D.hpk = ((D.n_k + 1) / 2 + 31) / 32 * 32;
+    D.ldj = 2 * D.hpj;
+    D.ldk = 2 * D.hpk;
     // electrode nodes inside the box
     std::vector<unsigned char> interior_fixed(n, 0);
     std::vector<int> e_nodes;
@@ -664,22 +710,26 @@ int direct3d_setup(mag2d_ctx* c)
         return 1;
     }
     const size_t block = (size_t)D.n_i * D.ldj * D.ldk;
-    const std::vector<double> Sy = sine_matrix(D.n_j, D.ldj), Sz = sine_matrix(D.n_k, D.ldk);
-    CUDA_OK(cudaMalloc(&D.Sy, sizeof(double) * Sy.size()));
-    CUDA_OK(cudaMalloc(&D.Sz, sizeof(double) * Sz.size()));
+    // y transforms multiply from the left (forward E^T, inverse E), z transforms from the right (forward E, inverse E^T)
+    const std::vector<double> Sy_f = half_sines(D.n_j, D.hpj, true), Sy_i = half_sines(D.n_j, D.hpj, false);
+    const std::vector<double> Sz_f = half_sines(D.n_k, D.hpk, false), Sz_i = half_sines(D.n_k, D.hpk, true);
+    CUDA_OK(cudaMalloc(&D.Sy_f, sizeof(double) * Sy_f.size()));
+    CUDA_OK(cudaMalloc(&D.Sy_i, sizeof(double) * Sy_i.size()));
+    CUDA_OK(cudaMalloc(&D.Sz_f, sizeof(double) * Sz_f.size()));
+    CUDA_OK(cudaMalloc(&D.Sz_i, sizeof(double) * Sz_i.size()));
     CUDA_OK(cudaMalloc(&D.inv, sizeof(double) * block));
     CUDA_OK(cudaMalloc(&D.R, sizeof(double) * block));
     CUDA_OK(cudaMalloc(&D.T, sizeof(double) * block));
     CUDA_OK(cudaMalloc(&D.interior_fixed, n));
-    CUDA_OK(cudaMemcpyAsync(D.Sy, Sy.data(), sizeof(double) * Sy.size(), cudaMemcpyHostToDevice, c->stream));
-    CUDA_OK(cudaMemcpyAsync(D.Sz, Sz.data(), sizeof(double) * Sz.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(D.Sy_f, Sy_f.data(), sizeof(double) * Sy_f.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(D.Sy_i, Sy_i.data(), sizeof(double) * Sy_i.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(D.Sz_f, Sz_f.data(), sizeof(double) * Sz_f.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(D.Sz_i, Sz_i.data(), sizeof(double) * Sz_i.size(), cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaMemcpyAsync(D.interior_fixed, interior_fixed.data(), n, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaMemsetAsync(D.R, 0, sizeof(double) * block, c->stream));
     CUDA_OK(cudaMemsetAsync(D.T, 0, sizeof(double) * block, c->stream));
-    CUDA_OK(cudaFuncSetAttribute(k_gemm3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
-    CUDA_OK(cudaFuncSetAttribute(k_gemm3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
-    CUDA_OK(cudaFuncSetAttribute(k_gemm3_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM));
-    CUDA_OK(cudaFuncSetAttribute(k_gemm3_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM));
+    CUDA_OK(cudaFuncSetAttribute(k_gemm3, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
+    CUDA_OK(cudaFuncSetAttribute(k_gemm3_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM));
     const int plane = D.ldj * D.ldk;
     k_thomas_setup<<<(plane + 127) / 128, 128, 0, c->stream>>>(D.n_i, D.n_j, D.n_k, D.ldj, D.ldk, D.inv);
     c->launches++;
@@ -695,9 +745,9 @@ int direct3d_setup(mag2d_ctx* c)
         {
             const int m = e_nodes[e];
             const int k = m % N, j = (m / N) % K, i = m / (K * N);
-            CUDA_OK(cudaMemsetAsync(D.R, 0, sizeof(double) * block, c->stream));
+            CUDA_OK(cudaMemsetAsync(D.T, 0, sizeof(double) * block, c->stream));
             const double one = 1.0;
-            CUDA_OK(cudaMemcpyAsync(D.R + ((size_t)(i - 1) * D.ldj + (j - 1)) * D.ldk + (k - 1), &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            CUDA_OK(cudaMemcpyAsync(D.T + ((size_t)(i - 1) * D.ldj + (j - 1)) * D.ldk + (k - 1), &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
             if (solve_interior(c, D.green + (size_t)e * n)) return 1;
             for (int q = 0; q < D.ne; q++)
                 CUDA_OK(cudaMemcpyAsync(&cmat[(size_t)q * D.ne + e], D.green + (size_t)e * n + e_nodes[q], sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -759,7 +809,7 @@ int solve3d(mag2d_ctx* c, double* resid_out)
     A.charges = c->d_charges;
     A.b = c->d_b;
     A.u = c->d_u;
-    A.R = D.R;
+    A.R = D.T;             // natural layout; solve_interior folds it into D.R
     k_rhs3d<<<(unsigned)(M * K), std::min(256, (N + 31) / 32 * 32), 0, c->stream>>>(A);
     c->launches++;
     // N ranks: the solve itself is shared out (MAG3D_SLAB_SOLVE=0 keeps it replicated); every rank must make this call
