@@ -127,28 +127,36 @@ __global__ void __launch_bounds__(G3_THREADS) k_gemm3(const __grid_constant__ Ge
 // 3-stage cp.async ring.  Per k4-step a warp loads 4 A and 4 B fragments (one double per lane each) for 16 DMMAs:
 // 16 FMAs per shared-memory double instead of 2 with the 4 x 4 register tile of k_gemm3, and 8x fewer issue slots.
 // Row strides of 20 / 36 doubles make both fragment loads bank-conflict free (lane/4 -> row * 8 banks, lane%4 -> 2 banks).
-constexpr int M3_TM = 128, M3_TN = 32, M3_KC = 16, M3_THREADS = 128, M3_STAGES = 3;
-constexpr int M3_LDA = M3_KC + 4, M3_LDB = M3_TN + 4;
-constexpr int M3_STAGE_DOUBLES = M3_TM * M3_LDA + M3_KC * M3_LDB;
-constexpr int M3_SMEM = M3_STAGES * M3_STAGE_DOUBLES * (int)sizeof(double);
+constexpr int M3_TM = 128, M3_KC = 16, M3_THREADS = 128, M3_STAGES = 3;
+constexpr int M3_LDA = M3_KC + 4;
+template <int TN>
+struct M3Cfg
+{
+    static constexpr int LDB = TN + 4;
+    static constexpr int STAGE_DOUBLES = M3_TM * M3_LDA + M3_KC * LDB;
+    static constexpr int SMEM = M3_STAGES * STAGE_DOUBLES * (int)sizeof(double);
+};
 
 __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
 
+// TN = 32 or 64 columns per CTA (32 x TN per warp)
+template <int TN>
 __global__ void __launch_bounds__(M3_THREADS) k_gemm3_mma(const __grid_constant__ Gemm3Args G)
 {
     extern __shared__ __align__(16) double m3_smem[];
+    constexpr int LDB = M3Cfg<TN>::LDB, STAGE = M3Cfg<TN>::STAGE_DOUBLES, NQ = TN / 8;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int r0 = blockIdx.y * M3_TM, c0 = blockIdx.x * M3_TN;
+    const int r0 = blockIdx.y * M3_TM, c0 = blockIdx.x * TN;
     const long long outer = blockIdx.z >> 1, par = blockIdx.z & 1;
     const double* A = G.A + outer * G.strideA + par * G.halfA;
     const double* B = G.B + outer * G.strideB + par * G.halfB;
     double* C = G.C + outer * G.strideC + par * G.halfC;
     const int nk = G.Kdim / M3_KC;
     auto issue = [&](int kb) {
-        double* sa = m3_smem + (kb % M3_STAGES) * M3_STAGE_DOUBLES;
+        double* sa = m3_smem + (kb % M3_STAGES) * STAGE;
         double* sb = sa + M3_TM * M3_LDA;
         const int k0 = kb * M3_KC;
         // A tile: 128 rows x 16 doubles = 1024 16-byte pieces (8 per row), 8 per thread
@@ -159,15 +167,15 @@ __global__ void __launch_bounds__(M3_THREADS) k_gemm3_mma(const __grid_constant_
             const int row = min(r0 + r, G.rows - 1);
             cp16(sa + r * M3_LDA + c2, A + (size_t)row * G.lda + k0 + c2);
         }
-        // B tile: 16 k x 32 columns = 256 pieces, 2 per thread
+        // B tile: 16 k x TN columns = 8 TN pieces, TN / 16 per thread
 #pragma unroll
-        for (int q = 0; q < 2; q++)
+        for (int q = 0; q < TN / 16; q++)
         {
-            const int e = t + q * M3_THREADS, r = e >> 4, c2 = (e & 15) * 2;
-            cp16(sb + r * M3_LDB + c2, B + (size_t)(k0 + r) * G.ldb + c0 + c2);
+            const int e = t + q * M3_THREADS, r = e / (TN / 2), c2 = (e % (TN / 2)) * 2;
+            cp16(sb + r * LDB + c2, B + (size_t)(k0 + r) * G.ldb + c0 + c2);
         }
     };
-    double acc[4][4][2] = {};
+    double acc[4][NQ][2] = {};
     for (int s = 0; s < M3_STAGES - 1; s++)
     {
         if (s < nk) issue(s);
@@ -180,20 +188,20 @@ __global__ void __launch_bounds__(M3_THREADS) k_gemm3_mma(const __grid_constant_
         __syncthreads();
         if (kb + M3_STAGES - 1 < nk) issue(kb + M3_STAGES - 1);
         cp_commit();
-        const double* sa = m3_smem + (kb % M3_STAGES) * M3_STAGE_DOUBLES + (warp * 32 + fr) * M3_LDA + fc;
-        const double* sb = m3_smem + (kb % M3_STAGES) * M3_STAGE_DOUBLES + M3_TM * M3_LDA + fc * M3_LDB + fr;
+        const double* sa = m3_smem + (kb % M3_STAGES) * STAGE + (warp * 32 + fr) * M3_LDA + fc;
+        const double* sb = m3_smem + (kb % M3_STAGES) * STAGE + M3_TM * M3_LDA + fc * LDB + fr;
 #pragma unroll
         for (int k4 = 0; k4 < M3_KC / 4; k4++)
         {
-            double a[4], b[4];
+            double a[4], b[NQ];
 #pragma unroll
             for (int p = 0; p < 4; p++) a[p] = sa[p * 8 * M3_LDA + k4 * 4];            // A[rb*8 + fr][k4*4 + fc]
 #pragma unroll
-            for (int q = 0; q < 4; q++) b[q] = sb[k4 * 4 * M3_LDB + q * 8];            // B[k4*4 + fc][cb*8 + fr]
+            for (int q = 0; q < NQ; q++) b[q] = sb[k4 * 4 * LDB + q * 8];              // B[k4*4 + fc][cb*8 + fr]
 #pragma unroll
             for (int p = 0; p < 4; p++)
 #pragma unroll
-                for (int q = 0; q < 4; q++) dmma884(acc[p][q], a[p], b[q]);
+                for (int q = 0; q < NQ; q++) dmma884(acc[p][q], a[p], b[q]);
         }
     }
     // D fragment: row fr, columns 2*fc, 2*fc+1 of every 8 x 8 block
@@ -204,7 +212,7 @@ __global__ void __launch_bounds__(M3_THREADS) k_gemm3_mma(const __grid_constant_
         if (r >= G.rows) continue;
         double* out = C + (size_t)r * G.ldc + c0 + 2 * fc;
 #pragma unroll
-        for (int q = 0; q < 4; q++) *reinterpret_cast<double2*>(out + q * 8) = make_double2(acc[p][q][0] * G.scale, acc[p][q][1] * G.scale);
+        for (int q = 0; q < NQ; q++) *reinterpret_cast<double2*>(out + q * 8) = make_double2(acc[p][q][0] * G.scale, acc[p][q][1] * G.scale);
     }
 }
 
@@ -274,59 +282,105 @@ __global__ void __launch_bounds__(128) k_unfold3d(int n_j, int n_k, int hpj, int
     }
 }
 
+constexpr int RHS_MAX_CHARGED = 8;
 struct Rhs3Args
 {
-    int M, K, N, n_i, n_j, n_k, ldj, ldk, n_species;
+    int M, K, N, n_i, n_j, n_k, hpj, hpk, n_species;
+    int ne;                              // electrode nodes inside the box (0: interior_fixed is all zero and is not read)
     double factor;                       // -macroparticle_factor / eps_0
     const unsigned char* mask;           // MAG2D_FREE or Dirichlet (anything else)
     const unsigned char* interior_fixed; // 1 on electrode nodes inside the box (capacitance method)
     const double* voltage;
     const unsigned long long* rho;       // [n_species][M*K*N] Q32 counts
-    const double* charges;
-    double* b;                           // reference right-hand side (diagnostics, residual)
+    int n_charged;                       // the species that carry charge, in species order
+    int charged[RHS_MAX_CHARGED];
+    double charge[RHS_MAX_CHARGED];
+    double* b;                           // reference right-hand side, or null (only the residual check reads it)
     double* u;                           // Dirichlet nodes receive their voltage
-    double* R;                           // [n_i][ldj][ldk] interior right-hand side with the frame values moved over (natural layout)
+    double* R;                           // [n_i][2 hpj][2 hpk] interior right-hand side with the frame values moved over, FOLDED along y and z
 };
 
-// Solver::solve's right-hand side + the reduction to the interior block
-__global__ void k_rhs3d(const __grid_constant__ Rhs3Args A)
+// Solver::solve's right-hand side + the reduction to the interior block, which leaves the kernel already FOLDED (k_fold3d's
+// layout).  A thread owns the four nodes (j, k), (j, k~), (j~, k), (j~, k~) that are mirror images of each other in the
+// interior block (j~ = K-1-j, k~ = n_k+1-k): it forms their right-hand sides and the four folded combinations in registers —
+// no shared memory, no barrier.  Block = 128 threads along k, grid = (row pairs, planes).
+__global__ void __launch_bounds__(128) k_rhs3d(const __grid_constant__ Rhs3Args A)
 {
-    // one block per grid row (i, j), threads along k: no 64-bit divisions per node
     const size_t n = (size_t)A.M * A.K * A.N;
     const long long sj = A.N, si = (long long)A.K * A.N;
-    const int i = (int)(blockIdx.x / (unsigned)A.K), j = (int)(blockIdx.x % (unsigned)A.K);
-    for (int k = threadIdx.x; k < A.N; k += blockDim.x)
+    const int i = (int)blockIdx.y, j0 = (int)blockIdx.x, j1 = A.K - 1 - j0;
+    const bool has_j1 = j1 > j0;                          // the middle row of an odd K is its own mirror image
+    const int il = i - 1, jj = j0 - 1;                    // interior plane; interior rows jj and n_j - 1 - jj
+    const bool plane_in = il >= 0 && il < A.n_i;
+    const int kpairs = (A.n_k + 3) / 2;
+    for (int kk = threadIdx.x; kk < kpairs; kk += blockDim.x)
     {
-        const size_t m = ((size_t)i * A.K + j) * A.N + k;
-        const bool fixed = A.mask[m] != MAG2D_FREE;
-        double b;
-        if (fixed) b = A.voltage[m];
-        else
-        {
-            double q = 0.0;
-            for (int s = 0; s < A.n_species; s++)
-            {
-                const double c = A.charges[s];
-                if (c != 0.0) q += c * ((double)(long long)A.rho[(size_t)s * n + m] * 2.3283064365386963e-10);
-            }
-            b = q * A.factor;
-        }
-        A.b[m] = b;
-        if (fixed) A.u[m] = b;
-        const int il = i - 1, jl = j - 1, kl = k - 1;
-        if (il < 0 || il >= A.n_i || jl < 0 || jl >= A.n_j || kl < 0 || kl >= A.n_k) continue;
-        double r = 0.0;
-        if (!A.interior_fixed[m])
-        {
-            r = b;
-            // neighbours by flat index, exactly as the reference's matrix rows address them (fields3d.cpp:61-67);
-            // Dirichlet neighbours on the frame contribute their value to the right-hand side
-            const long long nb[6] = {(long long)m - si, (long long)m - sj, (long long)m - 1, (long long)m + 1, (long long)m + sj, (long long)m + si};
+        const int kb = A.n_k + 1 - kk;
+        const bool has_kb = kb > kk && kb < A.N;          // a free k = N-1 face (n_k = N-1) leaves node k = 0 without a partner
+        size_t m[4];
+        bool valid[4];
+        unsigned char mk[4];
+        double q[4], r[4];
 #pragma unroll
-            for (int q = 0; q < 6; q++)
-                if (A.mask[nb[q]] != MAG2D_FREE && !A.interior_fixed[nb[q]]) r -= A.voltage[nb[q]];
+        for (int e = 0; e < 4; e++)
+        {
+            valid[e] = ((e & 1) == 0 || has_kb) && ((e & 2) == 0 || has_j1);
+            m[e] = ((size_t)i * A.K + (e & 2 ? j1 : j0)) * A.N + (e & 1 ? kb : kk);
+            mk[e] = valid[e] ? A.mask[m[e]] : (unsigned char)MAG2D_FIXED;
+            q[e] = 0.0;
+            r[e] = 0.0;
         }
-        A.R[((size_t)il * A.ldj + jl) * A.ldk + kl] = r;
+        // species outside, nodes inside: the four loads of a species are in flight together
+        for (int s = 0; s < A.n_charged; s++)
+        {
+            const unsigned long long* rho = A.rho + (size_t)A.charged[s] * n;
+            unsigned long long w[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) w[e] = valid[e] ? rho[m[e]] : 0ULL;
+#pragma unroll
+            for (int e = 0; e < 4; e++) q[e] += A.charge[s] * ((double)(long long)w[e] * 2.3283064365386963e-10);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+        {
+            if (!valid[e]) continue;
+            const int j = e & 2 ? j1 : j0, k = e & 1 ? kb : kk;
+            const bool fixed = mk[e] != MAG2D_FREE;
+            const double b = fixed ? A.voltage[m[e]] : q[e] * A.factor;
+            if (A.b) A.b[m[e]] = b;
+            if (fixed) A.u[m[e]] = b;
+            const int jl = j - 1, kl = k - 1;
+            if (plane_in && jl >= 0 && jl < A.n_j && kl >= 0 && kl < A.n_k && !(A.ne && A.interior_fixed[m[e]]))
+            {
+                double v = b;
+                // neighbours by flat index, exactly as the reference's matrix rows address them (fields3d.cpp:61-67);
+                // Dirichlet neighbours on the frame contribute their value to the right-hand side.  Only the outermost
+                // shell of the interior block has such neighbours (the flat-index neighbours of every other interior node
+                // are interior nodes themselves)
+                if (il == 0 || il == A.n_i - 1 || jl == 0 || jl == A.n_j - 1 || kl == 0 || kl == A.n_k - 1)
+                {
+                    const long long mm = (long long)m[e];
+#pragma unroll 1
+                    for (int t = 0; t < 6; t++)
+                    {
+                        const long long nb = mm + (t == 0 ? -si : t == 1 ? -sj : t == 2 ? -1LL : t == 3 ? 1LL : t == 4 ? sj : si);
+                        if (A.mask[nb] != MAG2D_FREE && !A.interior_fixed[nb]) v -= A.voltage[nb];
+                    }
+                }
+                r[e] = v;
+            }
+        }
+        if (!plane_in || jj < 0 || kk == 0) continue;
+        // interior column kl = kk - 1 and its mirror image n_k - 1 - kl (node kb); the padding of the folded block is never
+        // written: it is zero from set_grid on and every later stage of the solve maps zeros to zeros
+        const int kl = kk - 1, ldk = 2 * A.hpk;
+        double* f0 = A.R + ((size_t)il * (2 * A.hpj) + jj) * ldk;
+        double* f1 = f0 + (size_t)A.hpj * ldk;
+        const double s0 = r[0] + r[1], a0 = has_kb ? r[0] - r[1] : 0.0, s1 = r[2] + r[3], a1 = has_kb ? r[2] - r[3] : 0.0;
+        f0[kl] = s0 + s1;
+        f0[A.hpk + kl] = a0 + a1;
+        f1[kl] = has_j1 ? s0 - s1 : 0.0;
+        f1[A.hpk + kl] = has_j1 ? a0 - a1 : 0.0;
     }
 }
 
@@ -350,26 +404,72 @@ __global__ void k_thomas_setup(int n_i, int n_j, int n_k, int ldj, int ldk, doub
 }
 
 // y_i = (r_i - y_(i-1)) inv_i ; x_i = y_i - inv_i x_(i+1); one thread per (y,z) mode, coalesced across modes.
-// The 65k independent modes of a 256^3 grid hide the latency of the recurrence by themselves.
-__global__ void k_thomas_solve(int n_i, int plane, const double* __restrict__ inv, double* __restrict__ v, double scale)
+// A 256^3 grid has only 65k modes — 14 warps per SM — so the recurrence is fed through a register ring: the loads of the
+// next TH_U planes are in flight while the current TH_U are consumed (the recurrence itself is two flops per plane).
+constexpr int TH_U = 8;
+__global__ void __launch_bounds__(64) k_thomas_solve(int n_i, int plane, const double* __restrict__ inv, double* v, double scale)
 {
     const int mode = blockIdx.x * blockDim.x + threadIdx.x;
     if (mode >= plane) return;
+    double* vp = v + mode;
+    const double* cp = inv + mode;
+    double ra[TH_U], fa[TH_U], rb[TH_U], fb[TH_U];        // two register buffers, addressed statically
+    auto fetch = [&](double (&r)[TH_U], double (&f)[TH_U], int first, int dir) {
+#pragma unroll
+        for (int q = 0; q < TH_U; q++)
+        {
+            const int i = first + dir * q;
+            if (i >= 0 && i < n_i)
+            {
+                r[q] = vp[(size_t)i * plane];
+                f[q] = __ldg(cp + (size_t)i * plane);
+            }
+        }
+    };
     double y = 0.0;
-    for (int i = 0; i < n_i; i++)
+    auto forward = [&](const double (&r)[TH_U], const double (&f)[TH_U], int first) {
+#pragma unroll
+        for (int q = 0; q < TH_U; q++)
+        {
+            const int i = first + q;
+            if (i < n_i)
+            {
+                y = (r[q] - y) * f[q];
+                vp[(size_t)i * plane] = y;
+            }
+        }
+    };
+    // the planes fetched ahead have not been written yet in the running sweep
+    fetch(ra, fa, 0, 1);
+    for (int i0 = 0; i0 < n_i; i0 += 2 * TH_U)
     {
-        const size_t e = (size_t)i * plane + mode;
-        y = (v[e] - y) * inv[e];
-        v[e] = y;
+        fetch(rb, fb, i0 + TH_U, 1);
+        forward(ra, fa, i0);
+        fetch(ra, fa, i0 + 2 * TH_U, 1);
+        forward(rb, fb, i0 + TH_U);
     }
     // the two inverse transforms carry the factor 4 / ((n_j+1)(n_k+1)): it is folded into the stores of the back
     // substitution (the recurrence itself runs on the unscaled x)
     double x = 0.0;
-    for (int i = n_i - 1; i >= 0; i--)
+    auto backward = [&](const double (&r)[TH_U], const double (&f)[TH_U], int first) {
+#pragma unroll
+        for (int q = 0; q < TH_U; q++)
+        {
+            const int i = first - q;
+            if (i >= 0)
+            {
+                x = r[q] - f[q] * x;
+                vp[(size_t)i * plane] = x * scale;
+            }
+        }
+    };
+    fetch(ra, fa, n_i - 1, -1);
+    for (int i0 = n_i - 1; i0 >= 0; i0 -= 2 * TH_U)
     {
-        const size_t e = (size_t)i * plane + mode;
-        x = v[e] - inv[e] * x;
-        v[e] = x * scale;
+        fetch(rb, fb, i0 - TH_U, -1);
+        backward(ra, fa, i0);
+        fetch(ra, fa, i0 - 2 * TH_U, -1);
+        backward(rb, fb, i0 - TH_U);
     }
 }
 
@@ -436,20 +536,24 @@ int gemm3(mag2d_ctx* c, const Gemm3Args& G, int outer)
     }
     else
     {
-        const dim3 grid(G.cols / M3_TN, (G.rows + M3_TM - 1) / M3_TM, 2 * outer);
-        k_gemm3_mma<<<grid, M3_THREADS, M3_SMEM, c->stream>>>(G);
+        // 64 columns per CTA (210 registers, two CTAs per SM) measured slower on C5: 6.23 against 6.19 ms per step
+        const dim3 grid(G.cols / 32, (G.rows + M3_TM - 1) / M3_TM, 2 * outer);
+        k_gemm3_mma<32><<<grid, M3_THREADS, M3Cfg<32>::SMEM, c->stream>>>(G);
     }
     c->launches++;
     return 0;
 }
 
-// x planes [a, a + np): natural right-hand side in D.T -> folded, transformed along z and y, in D.R
-int forward_planes(mag2d_ctx* c, int a, int np)
+// x planes [a, a + np): folded right-hand side in D.R (natural: in D.T, folded here first) -> transformed along z and y, in D.R
+int forward_planes(mag2d_ctx* c, int a, int np, bool natural)
 {
     Direct3D& D = c->direct3;
     const long long plane = (long long)D.ldj * D.ldk;
-    k_fold3d<<<dim3((unsigned)D.hpj, (unsigned)np), 128, 0, c->stream>>>(D.n_j, D.n_k, D.hpj, D.hpk, D.T + a * plane, D.R + a * plane);
-    c->launches++;
+    if (natural)
+    {
+        k_fold3d<<<dim3((unsigned)D.hpj, (unsigned)np), 128, 0, c->stream>>>(D.n_j, D.n_k, D.hpj, D.hpk, D.T + a * plane, D.R + a * plane);
+        c->launches++;
+    }
     Gemm3Args G;
     memset(&G, 0, sizeof(G));
     G.scale = 1.0;
@@ -491,13 +595,13 @@ int inverse_planes(mag2d_ctx* c, int a, int np, double* u)
     return 0;
 }
 
-// interior right-hand side (natural layout, in D.T) -> potential on the interior nodes of u (frame untouched)
-int solve_interior(mag2d_ctx* c, double* u)
+// interior right-hand side (folded in D.R as k_rhs3d leaves it, or natural in D.T) -> potential on the interior nodes of u (frame untouched)
+int solve_interior(mag2d_ctx* c, double* u, bool natural)
 {
     Direct3D& D = c->direct3;
     const int plane = D.ldj * D.ldk;
-    if (forward_planes(c, 0, D.n_i)) return 1;
-    k_thomas_solve<<<(plane + 127) / 128, 128, 0, c->stream>>>(D.n_i, plane, D.inv, D.R, 4.0 / ((double)(D.n_j + 1) * (double)(D.n_k + 1)));
+    if (forward_planes(c, 0, D.n_i, natural)) return 1;
+    k_thomas_solve<<<(plane + 63) / 64, 64, 0, c->stream>>>(D.n_i, plane, D.inv, D.R, 4.0 / ((double)(D.n_j + 1) * (double)(D.n_k + 1)));
     c->launches++;
     if (inverse_planes(c, 0, D.n_i, u)) return 1;
     CUDA_OK(cudaGetLastError());
@@ -548,7 +652,7 @@ int solve_interior_slab(mag2d_ctx* c, double* u)
     const size_t rows_me = (size_t)(D.pj0[me + 1] - D.pj0[me]);
     const size_t esz = sizeof(double);
     // forward transforms of this rank's planes
-    if (np > 0 && forward_planes(c, a, np)) return 1;
+    if (np > 0 && forward_planes(c, a, np, false)) return 1;
     // x slabs -> mode slabs: the rows [pj0[q], pj0[q+1]) of my planes go to rank q; their rows of my slab arrive from everybody
     std::vector<size_t> off(nr + 1, 0);
     for (int q = 0; q < nr; q++) off[q + 1] = off[q] + (size_t)np * (D.pj0[q + 1] - D.pj0[q]) * D.ldk;
@@ -572,7 +676,7 @@ int solve_interior_slab(mag2d_ctx* c, double* u)
     if (rows_me > 0)
     {
         const int plane_me = (int)(rows_me * D.ldk);
-        k_thomas_solve<<<(plane_me + 127) / 128, 128, 0, c->stream>>>(D.n_i, plane_me, D.inv_slab, D.V, 4.0 / ((double)(D.n_j + 1) * (double)(D.n_k + 1)));
+        k_thomas_solve<<<(plane_me + 63) / 64, 64, 0, c->stream>>>(D.n_i, plane_me, D.inv_slab, D.V, 4.0 / ((double)(D.n_j + 1) * (double)(D.n_k + 1)));
         c->launches++;
     }
     // mode slabs -> x slabs
@@ -729,7 +833,7 @@ int direct3d_setup(mag2d_ctx* c)
     CUDA_OK(cudaMemsetAsync(D.R, 0, sizeof(double) * block, c->stream));
     CUDA_OK(cudaMemsetAsync(D.T, 0, sizeof(double) * block, c->stream));
     CUDA_OK(cudaFuncSetAttribute(k_gemm3, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
-    CUDA_OK(cudaFuncSetAttribute(k_gemm3_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM));
+    CUDA_OK(cudaFuncSetAttribute(k_gemm3_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, M3Cfg<32>::SMEM));
     const int plane = D.ldj * D.ldk;
     k_thomas_setup<<<(plane + 127) / 128, 128, 0, c->stream>>>(D.n_i, D.n_j, D.n_k, D.ldj, D.ldk, D.inv);
     c->launches++;
@@ -748,7 +852,7 @@ int direct3d_setup(mag2d_ctx* c)
             CUDA_OK(cudaMemsetAsync(D.T, 0, sizeof(double) * block, c->stream));
             const double one = 1.0;
             CUDA_OK(cudaMemcpyAsync(D.T + ((size_t)(i - 1) * D.ldj + (j - 1)) * D.ldk + (k - 1), &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-            if (solve_interior(c, D.green + (size_t)e * n)) return 1;
+            if (solve_interior(c, D.green + (size_t)e * n, true)) return 1;
             for (int q = 0; q < D.ne; q++)
                 CUDA_OK(cudaMemcpyAsync(&cmat[(size_t)q * D.ne + e], D.green + (size_t)e * n + e_nodes[q], sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -799,18 +903,26 @@ int solve3d(mag2d_ctx* c, double* resid_out)
     const size_t n = (size_t)M * K * N;
     Rhs3Args A;
     A.M = M; A.K = K; A.N = N;
-    A.n_i = D.n_i; A.n_j = D.n_j; A.n_k = D.n_k; A.ldj = D.ldj; A.ldk = D.ldk;
+    A.n_i = D.n_i; A.n_j = D.n_j; A.n_k = D.n_k; A.hpj = D.hpj; A.hpk = D.hpk;
     A.n_species = (int)c->sp.size();
+    A.n_charged = 0;
+    for (int s = 0; s < (int)c->sp.size(); s++)
+        if (c->sp[s].desc.charge != 0.0)
+        {
+            if (A.n_charged == RHS_MAX_CHARGED) { mag2d_set_error("3-D solver: more than 8 charged species"); return 1; }
+            A.charged[A.n_charged] = s;
+            A.charge[A.n_charged++] = c->sp[s].desc.charge;
+        }
     A.factor = -c->g.macroparticle_factor / MAG2D_EPS0;
     A.mask = c->d_mask;
     A.interior_fixed = D.interior_fixed;
     A.voltage = c->d_voltage;
     A.rho = c->d_rho;
-    A.charges = c->d_charges;
-    A.b = c->d_b;
+    A.ne = D.ne;
+    A.b = resid_out ? c->d_b : nullptr;
     A.u = c->d_u;
-    A.R = D.T;             // natural layout; solve_interior folds it into D.R
-    k_rhs3d<<<(unsigned)(M * K), std::min(256, (N + 31) / 32 * 32), 0, c->stream>>>(A);
+    A.R = D.R;
+    k_rhs3d<<<dim3((unsigned)((K + 1) / 2), (unsigned)M), 128, 0, c->stream>>>(A);
     c->launches++;
     // N ranks: the solve itself is shared out (MAG3D_SLAB_SOLVE=0 keeps it replicated); every rank must make this call
     static const bool slab_env = !getenv("MAG3D_SLAB_SOLVE") || atoi(getenv("MAG3D_SLAB_SOLVE")) != 0;
@@ -818,7 +930,7 @@ int solve3d(mag2d_ctx* c, double* resid_out)
     {
         if (solve_interior_slab(c, c->d_u)) return 1;
     }
-    else if (solve_interior(c, c->d_u)) return 1;
+    else if (solve_interior(c, c->d_u, false)) return 1;
     if (D.ne > 0)
     {
         k_capacitance<<<1, 64, 0, c->stream>>>(D.ne, D.e_nodes, D.e_volts, D.cinv, c->d_u, D.alpha);
