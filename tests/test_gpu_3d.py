@@ -85,6 +85,28 @@ def test_solve_with_charge_and_gather(deckdir):
         assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("shape", [(9, 8, 10), (8, 9, 9), (5, 70, 9), (5, 9, 69)])
+def test_folded_sine_transforms_every_parity_and_padding(deckdir, shape):
+    """the solver folds every grid line into its symmetric and antisymmetric halves (poisson3d.cu): even and odd interior
+    lengths along y and z (a middle element that is its own mirror image), half lengths below and above one 32-wide tile"""
+    orc = Oracle3()
+    d = small_deck(deckdir + "_fold%d_%d_%d" % shape, x_sampl=shape[0], y_sampl=shape[1], z_sampl=shape[2])
+    with _sim(d["config"], d["species_conf"]) as sim:
+        g = grid3(sim.param)
+        mask, volt = orc.geometry(g)
+        rng = np.random.default_rng(11)
+        e = sim.species_index("ELECTRON")
+        aos = box_particles(rng, 5000, g, 1e5)
+        sim.set_particles(e, aos)
+        sim.species_accumulate(e)
+        rho = sim.get_field("rho")
+        info = sim.solve()
+        u_ref = orc.solve_direct(g, mask, orc.rhs(g, mask, volt, rho))
+        u = sim.get_field("u")
+        assert np.abs(u - u_ref).max() <= 1e-9 * np.abs(u_ref).max(), info
+        assert info["resid"] < 1e-12
+
+
 def test_dense_deposit_uses_the_warp_merge_and_stays_bit_exact(deckdir):
     """>= 32 particles per cell switches the REDUX merge on (push3d.cu: warp_deposit3); sorted and unsorted stores,
     one and many particles per warp call must all give the oracle's integer grid"""
