@@ -434,7 +434,9 @@ __global__ void __launch_bounds__(BK_THREADS, MAG3D_BRICK_MIN_BLOCKS) k_push3d_b
                 if (in + BK_CHUNK < n) issue_load(in + BK_CHUNK);
             }
             out += m;
-            __syncthreads();
+            // the last pass of a bin: nobody writes the staging arrays any more, so only thread 0 waits for the bulk stores
+            // to have read them; everybody else goes on to the node flush
+            if (in + BK_CHUNK < n) __syncthreads();
             continue;
         }
         __syncthreads();
