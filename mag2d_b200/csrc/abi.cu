@@ -1253,6 +1253,10 @@ int mag2d_step(mag2d_ctx* c, int nsteps)
 {
     CHECK_CTX(c);
     if (c->sp.empty()) { mag2d_set_error("mag2d_step: no species"); return 1; }
+    // N ranks, 3-D: between the steps of one call nobody but the slab-parallel solve reads the summed charge, and it reads only
+    // this rank's planes: those steps reduce-scatter; the last step of the call all-reduces, so that every rank returns with
+    // the complete grids the ABI promises (mag2d_rho_download, mag2d_rho_fixed_download)
+    const bool own_slab = is3d(c) && c->g.selfconsistent && !c->use_source && solve3d_reads_own_planes_only(c);
     for (int it = 0; it < nsteps; it++)
     {
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
@@ -1280,7 +1284,7 @@ int mag2d_step(mag2d_ctx* c, int nsteps)
             if (advance_one(c, (int)s, !c->use_source)) return 1;
             if (c->use_source && species_source(c, (int)s, nullptr)) return 1;      // pic.cpp:346-347
             // this species' charge grid is complete: its all-reduce runs on the side stream under the next species' push
-            if (c->g.selfconsistent && comm_allreduce_species_async(c, (int)s)) return 1;
+            if (c->g.selfconsistent && comm_allreduce_species_async(c, (int)s, own_slab && it + 1 < nsteps)) return 1;
         }
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
         if (c->g.selfconsistent && comm_allreduce_join(c)) return 1;

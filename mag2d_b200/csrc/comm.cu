@@ -25,6 +25,7 @@ typedef int (*fn_Recv)(void*, size_t, int, int, NcclComm, cudaStream_t);
 typedef int (*fn_Group)();
 typedef int (*fn_Broadcast)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
 typedef int (*fn_AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t);
+typedef int (*fn_ReduceScatter)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
 typedef const char* (*fn_GetErrorString)(int);
 
 struct NcclApi
@@ -40,6 +41,7 @@ struct NcclApi
     fn_Group GroupStart = nullptr, GroupEnd = nullptr;
     fn_Broadcast Broadcast = nullptr;
     fn_AllGather AllGather = nullptr;
+    fn_ReduceScatter ReduceScatter = nullptr;
 };
 
 NcclApi g_nccl;
@@ -76,6 +78,7 @@ int load_nccl()
     g_nccl.GroupEnd = (fn_Group)dlsym(h, "ncclGroupEnd");
     g_nccl.Broadcast = (fn_Broadcast)dlsym(h, "ncclBroadcast");
     g_nccl.AllGather = (fn_AllGather)dlsym(h, "ncclAllGather");
+    g_nccl.ReduceScatter = (fn_ReduceScatter)dlsym(h, "ncclReduceScatter");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
     {
         mag2d_set_error("libnccl.so.2 lacks the expected symbols");
@@ -130,7 +133,9 @@ extern "C" int mag2d_comm_destroy(mag2d_ctx* c)
 // Species s has finished depositing (everything enqueued on c->stream so far): sum its grid over the ranks on the side stream,
 // so that the transfer runs under the NEXT species' push instead of after the last one.  comm_allreduce_join makes the
 // compute stream wait for all of them.  Every rank issues the same sequence of collectives (species order), as NCCL requires.
-int comm_allreduce_species_async(mag2d_ctx* c, int s)
+// own_slab_only: the only reader of the sum will be the slab-parallel 3-D solve, which takes rank r's block of M / nranks x planes
+// from rank r: an in-place reduce-scatter (half the traffic of the all-reduce) leaves exactly that block summed.
+int comm_allreduce_species_async(mag2d_ctx* c, int s, bool own_slab_only)
 {
     if (!c->nccl_comm || c->nranks <= 1 || c->sp[s].desc.charge == 0.0) return 0;
     if (!c->s_comm)
@@ -144,8 +149,17 @@ int comm_allreduce_species_async(mag2d_ctx* c, int s)
     const size_t n = grid_nodes(c);
     const int ncclInt64 = 4, ncclSum = 0;
     unsigned long long* buf = c->d_rho + (size_t)s * n;
-    const int rc = g_nccl.AllReduce(buf, buf, n, ncclInt64, ncclSum, (NcclComm)c->nccl_comm, c->s_comm);
-    if (rc) return nccl_fail("ncclAllReduce", rc);
+    if (own_slab_only && g_nccl.ReduceScatter && n % (size_t)c->nranks == 0)
+    {
+        const size_t per = n / (size_t)c->nranks;
+        const int rc = g_nccl.ReduceScatter(buf, buf + (size_t)c->rank * per, per, ncclInt64, ncclSum, (NcclComm)c->nccl_comm, c->s_comm);
+        if (rc) return nccl_fail("ncclReduceScatter", rc);
+    }
+    else
+    {
+        const int rc = g_nccl.AllReduce(buf, buf, n, ncclInt64, ncclSum, (NcclComm)c->nccl_comm, c->s_comm);
+        if (rc) return nccl_fail("ncclAllReduce", rc);
+    }
     c->comm_pending = true;
     return 0;
 }

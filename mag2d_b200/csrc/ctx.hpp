@@ -282,6 +282,7 @@ int update_edge_fields3d(mag2d_ctx* c);
 int direct3d_setup(mag2d_ctx* c);
 void direct3d_free(mag2d_ctx* c);
 int solve3d(mag2d_ctx* c, double* resid_out);
+bool solve3d_reads_own_planes_only(const mag2d_ctx* c);   // N ranks, slab-parallel solve, M divisible by N
 // push3d_brick.cu
 struct Grid3Dev;
 struct Push3Args;
@@ -295,7 +296,7 @@ inline bool is3d(const mag2d_ctx* c) { return c->g.coord == MAG2D_CARTESIAN3D; }
 inline size_t grid_nodes(const mag2d_ctx* c) { return (size_t)c->g.M * c->g.N * (is3d(c) ? (size_t)c->g.K : 1); }
 // comm.cu
 int comm_allreduce_rho(mag2d_ctx* c);
-int comm_allreduce_species_async(mag2d_ctx* c, int s);
+int comm_allreduce_species_async(mag2d_ctx* c, int s, bool own_slab_only = false);
 int comm_allreduce_join(mag2d_ctx* c);
 bool comm_has_p2p();
 int comm_group_start();

@@ -287,6 +287,7 @@ struct Rhs3Args
 {
     int M, K, N, n_i, n_j, n_k, hpj, hpk, n_species;
     int ne;                              // electrode nodes inside the box (0: interior_fixed is all zero and is not read)
+    int i_first;                         // first x plane of this launch (blockIdx.y counts from it)
     double factor;                       // -macroparticle_factor / eps_0
     const unsigned char* mask;           // MAG2D_FREE or Dirichlet (anything else)
     const unsigned char* interior_fixed; // 1 on electrode nodes inside the box (capacitance method)
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(128) k_rhs3d(const __grid_constant__ Rhs3Args 
 {
     const size_t n = (size_t)A.M * A.K * A.N;
     const long long sj = A.N, si = (long long)A.K * A.N;
-    const int i = (int)blockIdx.y, j0 = (int)blockIdx.x, j1 = A.K - 1 - j0;
+    const int i = A.i_first + (int)blockIdx.y, j0 = (int)blockIdx.x, j1 = A.K - 1 - j0;
     const bool has_j1 = j1 > j0;                          // the middle row of an odd K is its own mirror image
     const int il = i - 1, jj = j0 - 1;                    // interior plane; interior rows jj and n_j - 1 - jj
     const bool plane_in = il >= 0 && il < A.n_i;
@@ -894,6 +895,20 @@ int direct3d_setup(mag2d_ctx* c)
     return 0;
 }
 
+static bool slab_solve_active(const mag2d_ctx* c)
+{
+    // N ranks: the solve itself is shared out from three ranks on (every rank must make this call).  On two ranks the transposes
+    // and the all-gather cost more than half a solve saves (C5 at 256^3: 1.16 + 0.20 ms against 1.00 + 0.28 ms for the replicated
+    // solve and the all-reduce).  MAG3D_SLAB_SOLVE=1 shares it out on any N > 1, =0 keeps it replicated.
+    static const int slab_env = getenv("MAG3D_SLAB_SOLVE") ? atoi(getenv("MAG3D_SLAB_SOLVE")) : -1;
+    const bool want = slab_env < 0 ? c->nranks >= 3 : slab_env != 0;
+    return c->nccl_comm && c->nranks > 1 && want && comm_has_p2p();
+}
+
+// with M divisible by N, rank r owns the planes [r M/N, (r+1) M/N) of the potential (the all-gather path of solve_interior_slab):
+// it forms the right-hand side of those planes only, and only their charge has to be summed over the ranks
+bool solve3d_reads_own_planes_only(const mag2d_ctx* c) { return slab_solve_active(c) && c->g.M % c->nranks == 0; }
+
 // ElMag3D::solve / Solver::solve (src/fields3d.cpp:83-95, 170-181): rho of every species -> b -> u
 int solve3d(mag2d_ctx* c, double* resid_out)
 {
@@ -922,11 +937,14 @@ int solve3d(mag2d_ctx* c, double* resid_out)
     A.b = resid_out ? c->d_b : nullptr;
     A.u = c->d_u;
     A.R = D.R;
-    k_rhs3d<<<dim3((unsigned)((K + 1) / 2), (unsigned)M), 128, 0, c->stream>>>(A);
+    // the residual check needs the right-hand side of every plane (and the complete charge grids: mag2d_step's last step and
+    // mag2d_advance_init all-reduce)
+    const bool own_only = solve3d_reads_own_planes_only(c) && !resid_out;
+    const int planes = own_only ? M / c->nranks : M;
+    A.i_first = own_only ? c->rank * planes : 0;
+    k_rhs3d<<<dim3((unsigned)((K + 1) / 2), (unsigned)planes), 128, 0, c->stream>>>(A);
     c->launches++;
-    // N ranks: the solve itself is shared out (MAG3D_SLAB_SOLVE=0 keeps it replicated); every rank must make this call
-    static const bool slab_env = !getenv("MAG3D_SLAB_SOLVE") || atoi(getenv("MAG3D_SLAB_SOLVE")) != 0;
-    if (c->nccl_comm && c->nranks > 1 && slab_env && comm_has_p2p())
+    if (slab_solve_active(c))
     {
         if (solve_interior_slab(c, c->d_u)) return 1;
     }

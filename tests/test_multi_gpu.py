@@ -15,8 +15,11 @@ def test_two_ranks_match_one_rank_bit_for_bit():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     world = min(torch.cuda.device_count(), 4)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "mgpu_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "MGPU_RESULT ok" in r.stdout
+    # the slab-parallel 3-D solve is the default from three ranks on: force it, so that two ranks exercise it too (and then the
+    # replicated solve + all-reduce that two ranks get by default)
+    for slab in ("1", "0"):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+               "--master-addr", "127.0.0.1", "--master-port", str(29611 + int(slab)), os.path.join(ROOT, "tests", "mgpu_worker.py")]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MAG3D_SLAB_SOLVE=slab))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "MGPU_RESULT ok" in r.stdout
