@@ -240,7 +240,9 @@ int mag2d_store_stats(mag2d_ctx* ctx, int species, int64_t* out8);
 /* Pic<D>::advance_init, src/pic.cpp:359-384 */
 int mag2d_advance_init(mag2d_ctx* ctx);
 /* nsteps x Pic<D>::advance, src/pic.cpp:330-358: [solve] -> per species push+MCC+boundary+deposit ->
- * [rho all-reduce].  Asynchronous. */
+ * [rho all-reduce].  Asynchronous.  On N ranks every rank returns holding the complete summed charge grids; between the
+ * steps of ONE call a CARTESIAN3D context with the shared-out field solve only sums the planes each rank owns
+ * (reduce-scatter), so batching steps into one call is cheaper than calling with nsteps = 1. */
 int mag2d_step(mag2d_ctx* ctx, int nsteps);
 /* one Species<D>::advance (src/particles.hpp:342-349) of one species: fused advance_position +
  * advance_boundary (+ deposit into that species' rho when selfconsistent) */
