@@ -90,9 +90,10 @@ struct DirectSolver
 {
     bool ok = false;            // the grid separates (every row is an electrode or free between Dirichlet ends)
     int n = 0;                  // N - 2
-    int ld = 0;                 // n rounded up to a multiple of 32: leading dimension of every [.][n] array below
-    double* bp = nullptr;       // [M][ld] right-hand side of the interior columns (written by k_rhs)
-    double* S = nullptr;        // [n][n] sine matrix
+    int hp = 0;                 // ceil(n / 2) rounded up to a multiple of 32
+    int ld = 0;                 // 2 hp: leading dimension of every [.][n] array below; a row is FOLDED: [symmetric half | antisymmetric half]
+    double* bp = nullptr;       // [M][ld] folded right-hand side of the interior columns (written by k_rhs); then the inverse products' output
+    double* S = nullptr;        // [2][2][hp][hp] half-size sine matrices: forward (parity 0, 1), inverse (parity 0, 1)
     double* fwd = nullptr;      // [M][ld][2] forward sweep pairs (hat/den, lower/den)
     double* inv = nullptr;      // [M][ld] 1/den, applied in the forward product's epilogue
     double* bwd = nullptr;      // [M][ld][2] backward sweep pairs (y, upper/den)

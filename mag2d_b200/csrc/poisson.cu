@@ -338,8 +338,8 @@ struct RhsArgs
     double* b_mg;
     double* u;
     // direct solver (poisson_direct.cu): interior columns with the Dirichlet end nodes moved to the right-hand side
-    double* bp;
-    int ld;
+    double* bp;                      // FOLDED: [i][c] = v_c + v_(n-1-c), [i][hp + c] = v_c - v_(n-1-c), c = j - 1 the interior column
+    int ld, hp;
     const unsigned char* rowfree;
     const double* k2row;
 };
@@ -361,11 +361,9 @@ __device__ __forceinline__ double rho_coulomb(const unsigned long long* rho, con
     return q;
 }
 
-__global__ void k_rhs(const __grid_constant__ RhsArgs A)
+// right-hand side of node (i, j); returns the value the direct solver sees in interior column j - 1 (Dirichlet end nodes moved over)
+__device__ __forceinline__ double rhs_node(const RhsArgs& A, int i, int j)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= A.M || j >= A.N) return;
     const size_t n = (size_t)A.M * A.N, k = (size_t)i * A.N + j;
     const unsigned char m = A.mask[k];
     double b;
@@ -383,15 +381,11 @@ __global__ void k_rhs(const __grid_constant__ RhsArgs A)
             b = rho * (-(A.dx * A.dx) / MAG2D_EPS0 / A.dV);
     }
     A.b_ref[k] = b;
-    if (A.bp && j >= 1 && j <= A.N - 2)
+    double v = b;
+    if (A.bp && j >= 1 && j <= A.N - 2 && A.rowfree[i])
     {
-        double v = b;
-        if (A.rowfree[i])
-        {
-            if (j == 1) v -= A.k2row[i] * dirichlet_value(A.mask[k - 1], A.voltage[k - 1], A.rf);
-            if (j == A.N - 2) v -= A.k2row[i] * dirichlet_value(A.mask[k + 1], A.voltage[k + 1], A.rf);
-        }
-        A.bp[(size_t)i * A.ld + j - 1] = v;
+        if (j == 1) v -= A.k2row[i] * dirichlet_value(A.mask[k - 1], A.voltage[k - 1], A.rf);
+        if (j == A.N - 2) v -= A.k2row[i] * dirichlet_value(A.mask[k + 1], A.voltage[k + 1], A.rf);
     }
     if (m == MAG2D_FIXED || m == MAG2D_FIXED_RF)
     {
@@ -400,6 +394,25 @@ __global__ void k_rhs(const __grid_constant__ RhsArgs A)
     }
     else
         A.b_mg[k] = b * A.rowscale[i];
+    return v;
+}
+
+// one thread per pair of nodes (i, j), (i, N-1-j): mirror images of each other among the interior columns, so the direct
+// solver's right-hand side leaves the kernel folded (poisson_direct.cu)
+__global__ void k_rhs(const __grid_constant__ RhsArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int jm = A.N - 1 - j;
+    if (i >= A.M || j > jm) return;
+    const double v = rhs_node(A, i, j);
+    const double vm = j < jm ? rhs_node(A, i, jm) : 0.0;
+    if (A.bp && j >= 1)
+    {
+        double* row = A.bp + (size_t)i * A.ld;
+        row[j - 1] = v + vm;                                 // the middle column of an odd count is its own mirror image
+        row[A.hp + j - 1] = j < jm ? v - vm : 0.0;
+    }
 }
 
 __global__ void k_rho_total(const unsigned long long* __restrict__ rho, const double* __restrict__ charges, int ns, size_t n,
@@ -857,11 +870,12 @@ int mg_rhs(mag2d_ctx* c, int rf)
     const bool direct = c->direct.ok && c->solver_kind != MAG2D_SOLVER_MULTIGRID;
     A.bp = direct ? c->direct.bp : nullptr;
     A.ld = c->direct.ld;
+    A.hp = c->direct.hp;
     A.rowfree = c->direct.rowfree;
     A.k2row = c->direct.k2;
     A.u = rf ? c->d_uRF : c->d_u;
     const dim3 block(32, 8);
-    k_rhs<<<grid2d(g.N, g.M, block), block, 0, c->stream>>>(A);
+    k_rhs<<<grid2d((g.N + 1) / 2, g.M, block), block, 0, c->stream>>>(A);
     c->launches++;
     CUDA_OK(cudaGetLastError());
     return 0;

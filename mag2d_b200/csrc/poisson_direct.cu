@@ -8,9 +8,16 @@
 //      B^ = B' S            (sine transform of every row, one FP64 matrix product with the symmetric sine matrix S)
 //      T_k u^_k = b^_k      (one tridiagonal system in x / r per mode k; Thomas factors precomputed at set_grid)
 //      U  = (2/(N-1)) U^ S  (inverse transform)
-// which is exact up to round-off like the reference's LU, costs three kernels, and needs no convergence test.
+// which is exact up to round-off like the reference's LU and needs no convergence test.
+// The transforms are FOLDED, as in poisson3d.cu: S[j][n-1-k] = (-1)^j S[j][k], so modes with even j only see the symmetric
+// part of a row and modes with odd j the antisymmetric part.  k_rhs writes every row as [symmetric half | antisymmetric
+// half], the spectrum is kept in the same split order (the Thomas factors are stored by that order), each transform is two
+// products with n/2 x n/2 matrices (half the flops, and twice the CTAs per unit of work: these small products are bound by
+// the latency of a CTA, not by the FP64 pipe), and k_direct_unfold writes x[k] = e + o, x[n-1-k] = e - o into the potential.
 // Grids with internal electrodes keep the multigrid of poisson.cu.
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "ctx.hpp"
@@ -27,14 +34,11 @@ constexpr int GM_SMEM = GM_STAGES * GM_STAGE_DOUBLES * (int)sizeof(double);
 
 struct GemmArgs
 {
-    int M, ld, n;                   // rows, padded leading dimension of A / S / hat, live columns
-    const double* A;                // [M][ld]
-    const double* S;                // [ld][ld] sine matrix, zero padded
+    int M, ld, hp;                  // rows, leading dimension 2 hp of A / hat, half length (K and column count of one product)
+    const double* A;                // [M][ld]: parity p = blockIdx.z works on the columns [p hp, (p + 1) hp)
+    const double* S;                // [2][hp][hp] half-size sine matrices of the two parities, zero padded
     const double* inv;              // FORWARD: [M][ld] 1/den of the Thomas factorisation, folded into the epilogue
-    const unsigned char* rowfree;   // INVERSE: electrode rows keep the voltages k_rhs wrote
-    double* C;                      // FORWARD: value slots of the pair array [M][ld][2];  INVERSE: u + 1 with row stride ldc
-    int ldc;
-    double scale;
+    double* C;                      // FORWARD: value slots of the pair array [M][ld][2];  INVERSE: [M][ld]
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
@@ -53,7 +57,10 @@ __global__ void __launch_bounds__(GM_THREADS) k_direct_gemm(const __grid_constan
     const int t = threadIdx.x;
     const int i0 = blockIdx.y * GM_TM, j0 = blockIdx.x * GM_TN;
     const int tr = (t / 8) * 4, tc = (t % 8) * 4;
-    const int nk = G.ld / GM_KC;
+    const int nk = G.hp / GM_KC;
+    const int par = blockIdx.z;
+    const double* Ap = G.A + par * G.hp;
+    const double* Sp = G.S + (size_t)par * G.hp * G.hp;
     auto issue = [&](int kb) {
         double* sa = gm_smem + (kb % GM_STAGES) * GM_STAGE_DOUBLES;
         double* sb = sa + GM_TM * GM_LDA;
@@ -64,14 +71,14 @@ __global__ void __launch_bounds__(GM_THREADS) k_direct_gemm(const __grid_constan
         {
             const int e = t + q * GM_THREADS, r = e >> 4, c2 = (e & 15) * 2;
             const int i = min(i0 + r, G.M - 1);
-            cp_async16(sa + r * GM_LDA + c2, G.A + (size_t)i * G.ld + k0 + c2);
+            cp_async16(sa + r * GM_LDA + c2, Ap + (size_t)i * G.ld + k0 + c2);
         }
         // S tile: 32 k x 32 columns = 512 pieces, 4 per thread
 #pragma unroll
         for (int q = 0; q < 4; q++)
         {
             const int e = t + q * GM_THREADS, r = e >> 4, c2 = (e & 15) * 2;
-            cp_async16(sb + r * GM_TN + c2, G.S + (size_t)(k0 + r) * G.ld + j0 + c2);
+            cp_async16(sb + r * GM_TN + c2, Sp + (size_t)(k0 + r) * G.hp + j0 + c2);
         }
     };
     double acc[4][4] = {};
@@ -108,10 +115,10 @@ __global__ void __launch_bounds__(GM_THREADS) k_direct_gemm(const __grid_constan
     {
         const int i = i0 + tr + p;
         if (i >= G.M) continue;
+        const size_t e = (size_t)i * G.ld + par * G.hp + j0 + tc;
         if (FORWARD)
         {
             // p = hat / den goes into the value slots of the forward pair array [i][k][2]
-            const size_t e = (size_t)i * G.ld + j0 + tc;
             const double2 i01 = *reinterpret_cast<const double2*>(G.inv + e), i23 = *reinterpret_cast<const double2*>(G.inv + e + 2);
             G.C[2 * e] = acc[p][0] * i01.x;
             G.C[2 * e + 2] = acc[p][1] * i01.y;
@@ -120,15 +127,23 @@ __global__ void __launch_bounds__(GM_THREADS) k_direct_gemm(const __grid_constan
         }
         else
         {
-            if (!G.rowfree[i]) continue;
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-            {
-                const int j = j0 + tc + q;
-                if (j < G.n) G.C[(size_t)i * G.ldc + j] = acc[p][q] * G.scale;
-            }
+            *reinterpret_cast<double2*>(G.C + e) = make_double2(acc[p][0], acc[p][1]);
+            *reinterpret_cast<double2*>(G.C + e + 2) = make_double2(acc[p][2], acc[p][3]);
         }
     }
+}
+
+// the two halves [e | o] of the inverse products -> the interior columns of the potential: x[k] = e + o, x[n-1-k] = e - o.
+// Electrode rows keep the voltages k_rhs wrote.
+__global__ void k_direct_unfold(int M, int n, int hp, const double* __restrict__ eo, const unsigned char* __restrict__ rowfree, double scale,
+                                double* __restrict__ u, int ldc)
+{
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int km = n - 1 - kk;
+    if (i >= M || kk > km || !rowfree[i]) return;
+    const double e = eo[(size_t)i * (2 * hp) + kk], o = eo[(size_t)i * (2 * hp) + hp + kk];
+    u[(size_t)i * ldc + kk] = (e + o) * scale;
+    if (kk < km) u[(size_t)i * ldc + km] = (e - o) * scale;
 }
 
 // Thomas sweeps, one sine mode per lane of warp 0: y_i = p_i - lower_i y_(i-1) with p = hat/den already formed by the
@@ -218,6 +233,64 @@ __global__ void __launch_bounds__(TD_THREADS) k_direct_tridiag(int M, int ld, co
     tridiag_sweep<true, 1>(M, ld, k0, bwd, x, td_smem);
 }
 
+// ---- the same sweeps with the rows shared out over the warps of the CTA --------------------------------------------------
+// y_i = p_i - l_i y_(i-1) is an affine map of y_(i-1); a block of TS_ROWS consecutive rows is the affine map y_out = A + B y_in
+// with A = the block swept from y_in = 0 and B = prod(-l_i).  Warp w sweeps block w from zero (keeping its TS_ROWS local values in
+// registers), the warps exchange (A, B) through shared memory, every warp folds the blocks before its own into its y_in
+// (at most 15 steps) and corrects its rows: y_i = ylocal_i + (prod_(j<=i) -l_j) y_in.  The dependent chain is 2 TS_ROWS + M / TS_ROWS
+// operations instead of M; the lanes of a warp are 32 neighbouring modes, so every load and store is a full 512-byte (256-byte) line.
+constexpr int TS_ROWS = 32, TS_MAX_WARPS = 16;
+
+template <bool BACKWARD, int OUT_STRIDE>
+__device__ __forceinline__ void tridiag_sweep_blocked(int M, int ld, int k0, const double* __restrict__ pair, double* __restrict__ out,
+                                                       double (*sA)[33], double (*sB)[33])
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int q0 = w * TS_ROWS;
+    const double2* in = reinterpret_cast<const double2*>(pair) + k0 + lane;
+    double yl[TS_ROWS];
+    double y = 0.0, B = 1.0;
+#pragma unroll
+    for (int r = 0; r < TS_ROWS; r++)
+    {
+        const int q = q0 + r;
+        if (q < M)
+        {
+            const double2 pc = in[(size_t)(BACKWARD ? M - 1 - q : q) * ld];
+            y = fma(-pc.y, y, pc.x);
+            B *= -pc.y;
+        }
+        yl[r] = y;
+    }
+    sA[w][lane] = y;
+    sB[w][lane] = B;
+    __syncthreads();
+    double yin = 0.0;
+    for (int b = 0; b < w; b++) yin = fma(sB[b][lane], yin, sA[b][lane]);
+    double P = 1.0;
+#pragma unroll
+    for (int r = 0; r < TS_ROWS; r++)
+    {
+        const int q = q0 + r;
+        if (q < M)
+        {
+            const size_t row = (size_t)(BACKWARD ? M - 1 - q : q);
+            P *= -in[row * ld].y;                 // L2 / L1 hit: the line was read in the first pass
+            out[(row * ld + k0 + lane) * OUT_STRIDE] = fma(P, yin, yl[r]);
+        }
+    }
+    (void)nw;
+}
+
+__global__ void __launch_bounds__(TS_MAX_WARPS * 32) k_direct_tridiag_blocked(int M, int ld, const double* __restrict__ fwd, double* bwd, double* __restrict__ x)
+{
+    __shared__ double sA[TS_MAX_WARPS][33], sB[TS_MAX_WARPS][33];
+    const int k0 = blockIdx.x * 32;
+    tridiag_sweep_blocked<false, 2>(M, ld, k0, fwd, bwd, sA, sB);
+    __syncthreads();          // the backward sweep reads the y values other warps of this CTA have just written
+    tridiag_sweep_blocked<true, 1>(M, ld, k0, bwd, x, sA, sB);
+}
+
 }  // namespace
 
 void direct_free(mag2d_ctx* c)
@@ -281,20 +354,30 @@ int direct_setup(mag2d_ctx* c)
         if (i == 0) W[i] = 0.0;
         if (i == M - 1) E[i] = 0.0;
     }
-    // every [.][ld] array is zero padded to a multiple of 32 columns: the kernels then need no column bounds tests
-    const int ld = (n + 31) / 32 * 32;
-    std::vector<double> S((size_t)ld * ld, 0.0), lower((size_t)M * ld, 0.0), inv((size_t)M * ld, 0.0), upper((size_t)M * ld, 0.0);
-    for (int j = 0; j < n; j++)
-        for (int k = j; k < n; k++)
-        {
-            // reduce the argument exactly before calling sin: (j+1)(k+1) mod 2(n+1)
-            const long long p = (long long)(j + 1) * (k + 1) % (2LL * (n + 1));
-            const double s = (double)sinl(M_PIl * (long double)p / (long double)(n + 1));
-            S[(size_t)j * ld + k] = S[(size_t)k * ld + j] = s;
-        }
-    for (int k = 0; k < n; k++)
+    // every [.][ld] array holds two zero-padded halves of hp columns (a multiple of 32): the kernels need no column bounds tests
+    const int hp = ((n + 1) / 2 + 31) / 32 * 32, ld = 2 * hp;
+    // S: [forward | inverse][parity][hp][hp].  E_b[kk][m] = sin(pi (2m + b + 1)(kk + 1) / (n + 1)) for the ceil(n/2) (b = 0) or
+    // floor(n/2) (b = 1) folded columns kk and modes m; forward products take E_b, inverse products its transpose
+    std::vector<double> S(4 * (size_t)hp * hp, 0.0), lower((size_t)M * ld, 0.0), inv((size_t)M * ld, 0.0), upper((size_t)M * ld, 0.0);
+    for (int b = 0; b < 2; b++)
     {
-        const double lam = (double)(2.0L * cosl(M_PIl * (long double)(k + 1) / (long double)(n + 1)));
+        const int h = b ? n / 2 : (n + 1) / 2;
+        for (int kk = 0; kk < h; kk++)
+            for (int m = 0; m < h; m++)
+            {
+                // reduce the argument exactly before calling sin: (2m+b+1)(kk+1) mod 2(n+1)
+                const long long p = (long long)(2 * m + b + 1) * (kk + 1) % (2LL * (n + 1));
+                const double s = (double)sinl(M_PIl * (long double)p / (long double)(n + 1));
+                S[((size_t)b * hp + kk) * hp + m] = s;
+                S[((size_t)(2 + b) * hp + m) * hp + kk] = s;
+            }
+    }
+    for (int k = 0; k < ld; k++)
+    {
+        // column k of the folded spectrum is mode 2k (k < hp) or 2(k - hp) + 1, counted from 0; beyond n: padding (its
+        // right-hand side is zero and stays zero; the factors below are those of a well-posed dummy system)
+        const int mode = k < hp ? 2 * k : 2 * (k - hp) + 1;
+        const double lam = mode < n ? (double)(2.0L * cosl(M_PIl * (long double)(mode + 1) / (long double)(n + 1))) : 0.0;
         double cp_prev = 0.0;
         for (int i = 0; i < M; i++)
         {
@@ -310,6 +393,7 @@ int direct_setup(mag2d_ctx* c)
     }
     DirectSolver& D = c->direct;
     D.n = n;
+    D.hp = hp;
     D.ld = ld;
     CUDA_OK(cudaMalloc(&D.S, sizeof(double) * S.size()));
     // (value, coefficient) pairs of the two sweeps: the coefficient slots are filled once, here
@@ -350,22 +434,25 @@ int direct_solve(mag2d_ctx* c, double* u)
     GemmArgs G;
     G.M = c->g.M;
     G.ld = D.ld;
-    G.n = D.n;
-    G.S = D.S;
+    G.hp = D.hp;
     G.inv = D.inv;
-    G.rowfree = D.rowfree;
-    G.scale = 2.0 / (D.n + 1);
-    const dim3 grid(D.ld / GM_TN, (G.M + GM_TM - 1) / GM_TM);
+    const dim3 grid(D.hp / GM_TN, (G.M + GM_TM - 1) / GM_TM, 2);
     G.A = D.bp;
+    G.S = D.S;
     G.C = D.fwd;
-    G.ldc = D.ld;
     k_direct_gemm<true><<<grid, GM_THREADS, GM_SMEM, c->stream>>>(G);
-    k_direct_tridiag<<<D.ld / 32, TD_THREADS, TD_SMEM, c->stream>>>(G.M, D.ld, D.fwd, D.bwd, D.hat);
+    // rows shared out over up to 16 warps (M <= 512) (MAG2D_TRIDIAG=serial: one warp per 32 modes walks all rows)
+    static const bool serial_env = !(getenv("MAG2D_TRIDIAG") && !strcmp(getenv("MAG2D_TRIDIAG"), "blocked"));
+    const int warps = (G.M + TS_ROWS - 1) / TS_ROWS;
+    if (!serial_env && warps <= TS_MAX_WARPS) k_direct_tridiag_blocked<<<D.ld / 32, warps * 32, 0, c->stream>>>(G.M, D.ld, D.fwd, D.bwd, D.hat);
+    else k_direct_tridiag<<<D.ld / 32, TD_THREADS, TD_SMEM, c->stream>>>(G.M, D.ld, D.fwd, D.bwd, D.hat);
     G.A = D.hat;
-    G.C = u + 1;
-    G.ldc = c->g.N;
+    G.S = D.S + 2 * (size_t)D.hp * D.hp;
+    G.C = D.bp;              // the folded right-hand side has been consumed: its array takes the halves [e | o]
     k_direct_gemm<false><<<grid, GM_THREADS, GM_SMEM, c->stream>>>(G);
-    c->launches += 3;
+    const dim3 block(32, 8);
+    k_direct_unfold<<<dim3((D.hp + 31) / 32, (G.M + 7) / 8), block, 0, c->stream>>>(G.M, D.n, D.hp, D.bp, D.rowfree, 2.0 / (D.n + 1), u + 1, c->g.N);
+    c->launches += 4;
     CUDA_OK(cudaGetLastError());
     return 0;
 }
