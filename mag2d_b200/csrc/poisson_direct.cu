@@ -16,8 +16,6 @@
 // the latency of a CTA, not by the FP64 pipe), and k_direct_unfold writes x[k] = e + o, x[n-1-k] = e - o into the potential.
 // Grids with internal electrodes keep the multigrid of poisson.cu.
 #include <cmath>
-#include <cstdlib>
-#include <cstring>
 #include <vector>
 
 #include "ctx.hpp"
@@ -233,64 +231,6 @@ __global__ void __launch_bounds__(TD_THREADS) k_direct_tridiag(int M, int ld, co
     tridiag_sweep<true, 1>(M, ld, k0, bwd, x, td_smem);
 }
 
-// ---- the same sweeps with the rows shared out over the warps of the CTA --------------------------------------------------
-// y_i = p_i - l_i y_(i-1) is an affine map of y_(i-1); a block of TS_ROWS consecutive rows is the affine map y_out = A + B y_in
-// with A = the block swept from y_in = 0 and B = prod(-l_i).  Warp w sweeps block w from zero (keeping its TS_ROWS local values in
-// registers), the warps exchange (A, B) through shared memory, every warp folds the blocks before its own into its y_in
-// (at most 15 steps) and corrects its rows: y_i = ylocal_i + (prod_(j<=i) -l_j) y_in.  The dependent chain is 2 TS_ROWS + M / TS_ROWS
-// operations instead of M; the lanes of a warp are 32 neighbouring modes, so every load and store is a full 512-byte (256-byte) line.
-constexpr int TS_ROWS = 32, TS_MAX_WARPS = 16;
-
-template <bool BACKWARD, int OUT_STRIDE>
-__device__ __forceinline__ void tridiag_sweep_blocked(int M, int ld, int k0, const double* __restrict__ pair, double* __restrict__ out,
-                                                       double (*sA)[33], double (*sB)[33])
-{
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int q0 = w * TS_ROWS;
-    const double2* in = reinterpret_cast<const double2*>(pair) + k0 + lane;
-    double yl[TS_ROWS];
-    double y = 0.0, B = 1.0;
-#pragma unroll
-    for (int r = 0; r < TS_ROWS; r++)
-    {
-        const int q = q0 + r;
-        if (q < M)
-        {
-            const double2 pc = in[(size_t)(BACKWARD ? M - 1 - q : q) * ld];
-            y = fma(-pc.y, y, pc.x);
-            B *= -pc.y;
-        }
-        yl[r] = y;
-    }
-    sA[w][lane] = y;
-    sB[w][lane] = B;
-    __syncthreads();
-    double yin = 0.0;
-    for (int b = 0; b < w; b++) yin = fma(sB[b][lane], yin, sA[b][lane]);
-    double P = 1.0;
-#pragma unroll
-    for (int r = 0; r < TS_ROWS; r++)
-    {
-        const int q = q0 + r;
-        if (q < M)
-        {
-            const size_t row = (size_t)(BACKWARD ? M - 1 - q : q);
-            P *= -in[row * ld].y;                 // L2 / L1 hit: the line was read in the first pass
-            out[(row * ld + k0 + lane) * OUT_STRIDE] = fma(P, yin, yl[r]);
-        }
-    }
-    (void)nw;
-}
-
-__global__ void __launch_bounds__(TS_MAX_WARPS * 32) k_direct_tridiag_blocked(int M, int ld, const double* __restrict__ fwd, double* bwd, double* __restrict__ x)
-{
-    __shared__ double sA[TS_MAX_WARPS][33], sB[TS_MAX_WARPS][33];
-    const int k0 = blockIdx.x * 32;
-    tridiag_sweep_blocked<false, 2>(M, ld, k0, fwd, bwd, sA, sB);
-    __syncthreads();          // the backward sweep reads the y values other warps of this CTA have just written
-    tridiag_sweep_blocked<true, 1>(M, ld, k0, bwd, x, sA, sB);
-}
-
 }  // namespace
 
 void direct_free(mag2d_ctx* c)
@@ -441,11 +381,7 @@ int direct_solve(mag2d_ctx* c, double* u)
     G.S = D.S;
     G.C = D.fwd;
     k_direct_gemm<true><<<grid, GM_THREADS, GM_SMEM, c->stream>>>(G);
-    // rows shared out over up to 16 warps (M <= 512) (MAG2D_TRIDIAG=serial: one warp per 32 modes walks all rows)
-    static const bool serial_env = !(getenv("MAG2D_TRIDIAG") && !strcmp(getenv("MAG2D_TRIDIAG"), "blocked"));
-    const int warps = (G.M + TS_ROWS - 1) / TS_ROWS;
-    if (!serial_env && warps <= TS_MAX_WARPS) k_direct_tridiag_blocked<<<D.ld / 32, warps * 32, 0, c->stream>>>(G.M, D.ld, D.fwd, D.bwd, D.hat);
-    else k_direct_tridiag<<<D.ld / 32, TD_THREADS, TD_SMEM, c->stream>>>(G.M, D.ld, D.fwd, D.bwd, D.hat);
+    k_direct_tridiag<<<D.ld / 32, TD_THREADS, TD_SMEM, c->stream>>>(G.M, D.ld, D.fwd, D.bwd, D.hat);
     G.A = D.hat;
     G.S = D.S + 2 * (size_t)D.hp * D.hp;
     G.C = D.bp;              // the folded right-hand side has been consumed: its array takes the halves [e | o]
