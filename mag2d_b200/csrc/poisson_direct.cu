@@ -22,10 +22,16 @@
 
 namespace {
 
-// FP64 matrix product C = A x S on the CUDA cores: CTA tile 64 x 32, 4 x 4 outputs per thread, K in chunks of 32
+// FP64 matrix product C = A x S on the CUDA cores: CTA tile 64 x 32, GM_RPT x 4 outputs per thread, K in chunks of 32
 // streamed through a 3-stage cp.async ring (the operands are L2-resident, the ring hides the L2 latency).
 // All operands are padded to ld = a multiple of 32 columns with zeros, so the K loop has no bounds tests.
-constexpr int GM_TM = 64, GM_TN = 32, GM_KC = 32, GM_THREADS = 128, GM_STAGES = 3;
+// Measured on C4 (one CTA per SM at 512^2): 128 threads with 4 x 4 outputs each give a solve of 0.084 ms per step, 256 threads with
+// 2 x 4 (two warps per scheduler, -DMAG2D_GM_RPT=2) 0.096 ms: the shared-memory loads per FMA count, not the warps per scheduler.
+#ifndef MAG2D_GM_RPT
+#define MAG2D_GM_RPT 4
+#endif
+constexpr int GM_RPT = MAG2D_GM_RPT;                                  // output rows per thread
+constexpr int GM_TM = 64, GM_TN = 32, GM_KC = 32, GM_THREADS = 8 * GM_TM / GM_RPT, GM_STAGES = 3;
 constexpr int GM_LDA = GM_KC + 2;                                    // smem row stride of the A tile (doubles)
 constexpr int GM_STAGE_DOUBLES = GM_TM * GM_LDA + GM_KC * GM_TN;
 constexpr int GM_SMEM = GM_STAGES * GM_STAGE_DOUBLES * (int)sizeof(double);
@@ -54,7 +60,7 @@ __global__ void __launch_bounds__(GM_THREADS) k_direct_gemm(const __grid_constan
     extern __shared__ __align__(16) double gm_smem[];
     const int t = threadIdx.x;
     const int i0 = blockIdx.y * GM_TM, j0 = blockIdx.x * GM_TN;
-    const int tr = (t / 8) * 4, tc = (t % 8) * 4;
+    const int tr = (t / 8) * GM_RPT, tc = (t % 8) * 4;
     const int nk = G.hp / GM_KC;
     const int par = blockIdx.z;
     const double* Ap = G.A + par * G.hp;
@@ -63,23 +69,23 @@ __global__ void __launch_bounds__(GM_THREADS) k_direct_gemm(const __grid_constan
         double* sa = gm_smem + (kb % GM_STAGES) * GM_STAGE_DOUBLES;
         double* sb = sa + GM_TM * GM_LDA;
         const int k0 = kb * GM_KC;
-        // A tile: 64 rows x 32 doubles = 1024 16-byte pieces, 8 per thread (16 pieces per row)
+        // A tile: 64 rows x 32 doubles = 1024 16-byte pieces (16 pieces per row)
 #pragma unroll
-        for (int q = 0; q < 8; q++)
+        for (int q = 0; q < 1024 / GM_THREADS; q++)
         {
             const int e = t + q * GM_THREADS, r = e >> 4, c2 = (e & 15) * 2;
             const int i = min(i0 + r, G.M - 1);
             cp_async16(sa + r * GM_LDA + c2, Ap + (size_t)i * G.ld + k0 + c2);
         }
-        // S tile: 32 k x 32 columns = 512 pieces, 4 per thread
+        // S tile: 32 k x 32 columns = 512 pieces
 #pragma unroll
-        for (int q = 0; q < 4; q++)
+        for (int q = 0; q < 512 / GM_THREADS; q++)
         {
             const int e = t + q * GM_THREADS, r = e >> 4, c2 = (e & 15) * 2;
             cp_async16(sb + r * GM_TN + c2, Sp + (size_t)(k0 + r) * G.hp + j0 + c2);
         }
     };
-    double acc[4][4] = {};
+    double acc[GM_RPT][4] = {};
     for (int s = 0; s < GM_STAGES - 1; s++)
     {
         if (s < nk) issue(s);
@@ -96,20 +102,20 @@ __global__ void __launch_bounds__(GM_THREADS) k_direct_gemm(const __grid_constan
 #pragma unroll 8
         for (int k = 0; k < GM_KC; k++)
         {
-            double a[4], b[4];
+            double a[GM_RPT], b[4];
 #pragma unroll
-            for (int p = 0; p < 4; p++) a[p] = sa[(tr + p) * GM_LDA + k];
+            for (int p = 0; p < GM_RPT; p++) a[p] = sa[(tr + p) * GM_LDA + k];
             const double2 b01 = *reinterpret_cast<const double2*>(sb + k * GM_TN + tc);
             const double2 b23 = *reinterpret_cast<const double2*>(sb + k * GM_TN + tc + 2);
             b[0] = b01.x; b[1] = b01.y; b[2] = b23.x; b[3] = b23.y;
 #pragma unroll
-            for (int p = 0; p < 4; p++)
+            for (int p = 0; p < GM_RPT; p++)
 #pragma unroll
                 for (int q = 0; q < 4; q++) acc[p][q] = fma(a[p], b[q], acc[p][q]);
         }
     }
 #pragma unroll
-    for (int p = 0; p < 4; p++)
+    for (int p = 0; p < GM_RPT; p++)
     {
         const int i = i0 + tr + p;
         if (i >= G.M) continue;
