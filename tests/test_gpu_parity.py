@@ -56,6 +56,32 @@ def test_vacuum_solve_matches_direct_solver(orc, deckdir, deck, kw):
         assert sim.solve_info["u"]["cycles"] <= 40
 
 
+@pytest.mark.parametrize("coord_deck,M,N", [("c4", 33, 34), ("c4", 34, 35), ("c4", 21, 99), ("c4", 20, 130), ("c3", 30, 67)])
+def test_folded_direct_solver_every_parity_and_padding(orc, deckdir, coord_deck, M, N):
+    """the direct solver folds every row into its symmetric and antisymmetric halves (poisson_direct.cu): even and odd interior
+    column counts (a middle column that is its own mirror image), half lengths below, at and above one 32-wide tile, Cartesian
+    and cylindrical operator, with charge"""
+    kw = dict(x_sampl=M, z_sampl=N, r_max=1e-4 * (M - 1), z_max=1e-4 * (N - 1))
+    if coord_deck == "c3":
+        kw.update(geometry="EMPTY")
+    d = decks.deck(coord_deck, deckdir + "_fold%d_%d" % (M, N), n_particles=4000, **kw)
+    with _sim(d["config"], d["species_conf"]) as sim:
+        assert sim.solver_is_direct()
+        g = grid_from_param(sim.param)
+        ie = sim.species_index("ELECTRON")
+        rng = np.random.default_rng(M * 1000 + N)
+        a = np.zeros((4000, 7))
+        a[:, 0] = rng.uniform(0.05, 0.95, 4000) * g.x_max
+        a[:, 2] = rng.uniform(0.05, 0.95, 4000) * g.z_max
+        sim.set_particles(ie, a)
+        sim.species_accumulate(ie)
+        info = sim.solve(rf=False)
+        rho = sim.get_field("rho")
+        mask, volt = orc.geometry(g, int(sim.param["geometry"]))
+        u_ref = orc.solve_direct(g, mask, orc.rhs(g, mask, volt, rho))
+        assert np.abs(sim.get_field("u") - u_ref).max() <= 1e-8 * np.abs(u_ref).max(), info
+
+
 def test_solve_with_charge_matches_direct_solver(orc, deckdir):
     d = decks.deck("c4", deckdir, n_particles=40000, x_sampl=65, z_sampl=65, r_max=6.4e-3, z_max=6.4e-3)
     with _sim(d["config"], d["species_conf"]) as sim:
