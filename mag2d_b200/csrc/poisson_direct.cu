@@ -16,6 +16,8 @@
 // the latency of a CTA, not by the FP64 pipe), and k_direct_unfold writes x[k] = e + o, x[n-1-k] = e - o into the potential.
 // Grids with internal electrodes keep the multigrid of poisson.cu.
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "ctx.hpp"
@@ -133,6 +135,102 @@ __global__ void __launch_bounds__(GM_THREADS) k_direct_gemm(const __grid_constan
         {
             *reinterpret_cast<double2*>(G.C + e) = make_double2(acc[p][0], acc[p][1]);
             *reinterpret_cast<double2*>(G.C + e + 2) = make_double2(acc[p][2], acc[p][3]);
+        }
+    }
+}
+
+// ---- the same product on the FP64 tensor pipe (mma.sync m8n8k4, DMMA; poisson3d.cu has the large-grid version) ------------
+// CTA tile 64 x 32, four warps stacked along the rows (16 x 32 per warp = 2 x 4 DMMA tiles), K in chunks of 16 through a 3-stage
+// cp.async ring.  The FMA kernel above spends ~100 cycles per k step on its 16 dependent-load FMAs per thread (one CTA per SM, nothing
+// to hide the shared-memory latency with); here a warp issues 8 DMMAs per 6 fragment loads.  Row strides of 20 / 36 doubles keep the
+// fragment loads free of bank conflicts.
+constexpr int DM_KC = 16, DM_STAGES = 3, DM_LDA = DM_KC + 4, DM_LDB = GM_TN + 4;
+constexpr int DM_STAGE_DOUBLES = GM_TM * DM_LDA + DM_KC * DM_LDB;
+constexpr int DM_SMEM = DM_STAGES * DM_STAGE_DOUBLES * (int)sizeof(double);
+
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+template <bool FORWARD>
+__global__ void __launch_bounds__(128) k_direct_gemm_mma(const __grid_constant__ GemmArgs G)
+{
+    extern __shared__ __align__(16) double dm_smem[];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int i0 = blockIdx.y * GM_TM, j0 = blockIdx.x * GM_TN;
+    const int nk = G.hp / DM_KC;
+    const int par = blockIdx.z;
+    const double* Ap = G.A + par * G.hp;
+    const double* Sp = G.S + (size_t)par * G.hp * G.hp;
+    auto issue = [&](int kb) {
+        double* sa = dm_smem + (kb % DM_STAGES) * DM_STAGE_DOUBLES;
+        double* sb = sa + GM_TM * DM_LDA;
+        const int k0 = kb * DM_KC;
+        // A tile: 64 rows x 16 doubles = 512 16-byte pieces (8 per row), 4 per thread
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            const int e = t + q * 128, r = e >> 3, c2 = (e & 7) * 2;
+            const int i = min(i0 + r, G.M - 1);
+            cp_async16(sa + r * DM_LDA + c2, Ap + (size_t)i * G.ld + k0 + c2);
+        }
+        // S tile: 16 k x 32 columns = 256 pieces, 2 per thread
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+        {
+            const int e = t + q * 128, r = e >> 4, c2 = (e & 15) * 2;
+            cp_async16(sb + r * DM_LDB + c2, Sp + (size_t)(k0 + r) * G.hp + j0 + c2);
+        }
+    };
+    double acc[2][4][2] = {};
+    for (int s = 0; s < DM_STAGES - 1; s++)
+    {
+        if (s < nk) issue(s);
+        cp_async_commit();
+    }
+    const int fr = lane >> 2, fc = lane & 3;     // fragment row / column of this lane
+    for (int kb = 0; kb < nk; kb++)
+    {
+        cp_async_wait<DM_STAGES - 2>();
+        __syncthreads();
+        if (kb + DM_STAGES - 1 < nk) issue(kb + DM_STAGES - 1);
+        cp_async_commit();
+        const double* sa = dm_smem + (kb % DM_STAGES) * DM_STAGE_DOUBLES + (warp * 16 + fr) * DM_LDA + fc;
+        const double* sb = dm_smem + (kb % DM_STAGES) * DM_STAGE_DOUBLES + GM_TM * DM_LDA + fc * DM_LDB + fr;
+#pragma unroll
+        for (int k4 = 0; k4 < DM_KC / 4; k4++)
+        {
+            double a[2], b[4];
+#pragma unroll
+            for (int p = 0; p < 2; p++) a[p] = sa[p * 8 * DM_LDA + k4 * 4];            // A[rb*8 + fr][k4*4 + fc]
+#pragma unroll
+            for (int q = 0; q < 4; q++) b[q] = sb[k4 * 4 * DM_LDB + q * 8];            // S[k4*4 + fc][cb*8 + fr]
+#pragma unroll
+            for (int p = 0; p < 2; p++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) dmma884(acc[p][q], a[p], b[q]);
+        }
+    }
+    // D fragment: row fr, columns 2 fc, 2 fc + 1 of every 8 x 8 block
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+    {
+        const int i = i0 + warp * 16 + p * 8 + fr;
+        if (i >= G.M) continue;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            const size_t e = (size_t)i * G.ld + par * G.hp + j0 + q * 8 + 2 * fc;
+            if (FORWARD)
+            {
+                // p = hat / den goes into the value slots of the forward pair array [i][k][2]
+                const double2 iv = *reinterpret_cast<const double2*>(G.inv + e);
+                G.C[2 * e] = acc[p][q][0] * iv.x;
+                G.C[2 * e + 2] = acc[p][q][1] * iv.y;
+            }
+            else
+                *reinterpret_cast<double2*>(G.C + e) = make_double2(acc[p][q][0], acc[p][q][1]);
         }
     }
 }
@@ -358,6 +456,8 @@ int direct_setup(mag2d_ctx* c)
     CUDA_OK(cudaMemsetAsync(D.bp, 0, sizeof(double) * lower.size(), c->stream));
     CUDA_OK(cudaFuncSetAttribute(k_direct_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM));
     CUDA_OK(cudaFuncSetAttribute(k_direct_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM));
+    CUDA_OK(cudaFuncSetAttribute(k_direct_gemm_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM));
+    CUDA_OK(cudaFuncSetAttribute(k_direct_gemm_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM));
     CUDA_OK(cudaFuncSetAttribute(k_direct_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM));
     CUDA_OK(cudaMalloc(&D.rowfree, M));
     CUDA_OK(cudaMalloc(&D.k2, sizeof(double) * M));
@@ -383,15 +483,19 @@ int direct_solve(mag2d_ctx* c, double* u)
     G.hp = D.hp;
     G.inv = D.inv;
     const dim3 grid(D.hp / GM_TN, (G.M + GM_TM - 1) / GM_TM, 2);
+    // MAG2D_GEMM=fma: the products on the FP64 FMA pipe instead of the tensor pipe
+    static const bool use_fma = getenv("MAG2D_GEMM") && !strcmp(getenv("MAG2D_GEMM"), "fma");
     G.A = D.bp;
     G.S = D.S;
     G.C = D.fwd;
-    k_direct_gemm<true><<<grid, GM_THREADS, GM_SMEM, c->stream>>>(G);
+    if (use_fma) k_direct_gemm<true><<<grid, GM_THREADS, GM_SMEM, c->stream>>>(G);
+    else k_direct_gemm_mma<true><<<grid, 128, DM_SMEM, c->stream>>>(G);
     k_direct_tridiag<<<D.ld / 32, TD_THREADS, TD_SMEM, c->stream>>>(G.M, D.ld, D.fwd, D.bwd, D.hat);
     G.A = D.hat;
     G.S = D.S + 2 * (size_t)D.hp * D.hp;
     G.C = D.bp;              // the folded right-hand side has been consumed: its array takes the halves [e | o]
-    k_direct_gemm<false><<<grid, GM_THREADS, GM_SMEM, c->stream>>>(G);
+    if (use_fma) k_direct_gemm<false><<<grid, GM_THREADS, GM_SMEM, c->stream>>>(G);
+    else k_direct_gemm_mma<false><<<grid, 128, DM_SMEM, c->stream>>>(G);
     const dim3 block(32, 8);
     k_direct_unfold<<<dim3((D.hp + 31) / 32, (G.M + 7) / 8), block, 0, c->stream>>>(G.M, D.n, D.hp, D.bp, D.rowfree, 2.0 / (D.n + 1), u + 1, c->g.N);
     c->launches += 4;
