@@ -1168,6 +1168,7 @@ int mag2d_species_advance(mag2d_ctx* c, int s)
 {
     CHECK_CTX(c);
     CHECK_SPECIES(c, s);
+    c->edge_fields_fresh = c->edge_fields_fresh_armed = false;      // only mag2d_step shares the edge fields between species
     return advance_one(c, s, false);
 }
 
@@ -1277,6 +1278,8 @@ int mag2d_step(mag2d_ctx* c, int nsteps)
             if (mag2d_rho_reset(c, -1)) return 1;
         }
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
+        c->edge_fields_fresh = false;
+        c->edge_fields_fresh_armed = !is3d(c);
         for (size_t s = 0; s < c->sp.size(); s++)
         {
             // the source appends to the store after every push: the pending cell counts of a fused sort would never survive, so these runs
@@ -1286,6 +1289,7 @@ int mag2d_step(mag2d_ctx* c, int nsteps)
             // this species' charge grid is complete: its all-reduce runs on the side stream under the next species' push
             if (c->g.selfconsistent && comm_allreduce_species_async(c, (int)s, own_slab && it + 1 < nsteps)) return 1;
         }
+        c->edge_fields_fresh = c->edge_fields_fresh_armed = false;
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
         if (c->g.selfconsistent && comm_allreduce_join(c)) return 1;
         if (c->timing) CUDA_OK(cudaEventRecord(c->ev[3], c->stream));

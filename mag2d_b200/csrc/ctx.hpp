@@ -221,6 +221,9 @@ struct mag2d_ctx
 
     // timing
     bool timing = false;
+    // inside one iteration of mag2d_step, after the solve, nothing writes the potential: without an RF term the edge-difference
+    // fields the first species computed serve the following species too
+    bool edge_fields_fresh = false, edge_fields_fresh_armed = false;
     cudaEvent_t ev[8] = {};
     double timers[5] = {};
 };

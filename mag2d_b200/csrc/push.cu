@@ -1597,8 +1597,12 @@ int launch_species_advance(mag2d_ctx* c, int s, int sort_mode)
         {
             const bool gather = !A.g.const_E;
             const int bmode = A.g.b_r ? B_TABLE : A.s.has_B ? B_CONST : B_NONE;
-            if (gather)
+            if (gather && !(c->edge_fields_fresh && !d.rf))
+            {
                 if (update_ueff(c, d.rf ? rf_phase(c, S) : 0.0, d.rf != 0)) return 1;
+                // mag2d_step arms this flag per iteration (it is false everywhere else): the next species of the iteration skips the pass
+                if (c->edge_fields_fresh_armed) c->edge_fields_fresh = true;
+            }
             if (mcc)
             {
                 if (ensure_particle_scratch(c, chunked ? std::max(n_active, S.capacity) : S.capacity)) return 1;
